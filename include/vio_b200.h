@@ -1,0 +1,174 @@
+/*
+ * vio_b200.h -- C-ABI of the B200-native VIO hot path (libvio_b200.so).
+ *
+ * Drop-in boundary for the two reference classes that own the hot path
+ * (SURVEY.md section 8(b)); the reference has no FFI layer of its own, so every
+ * entry point cites the C++ member it replaces (paths relative to
+ * /root/reference/VINS_ios/):
+ *
+ *   FeatureTracker::readImage            feature_tracker.hpp:59,  feature_tracker.cpp:162-310
+ *   FeatureTracker::{setMask,rejectWithF,addPoints,updateID}
+ *                                        feature_tracker.cpp:36-103,311-321
+ *   VINS::processIMU                     VINS.hpp:164, VINS.cpp:333-375
+ *   VINS::processImage                   VINS.hpp:163, VINS.cpp:377-478
+ *   VINS::solve_ceres                    VINS.hpp:153, VINS.cpp:480-831
+ *   VINS::{clearState,setIMUModel,setExtrinsic}   VINS.hpp:157-159
+ *   setGlobalParam                       global_param.hpp:83, global_param.cpp:24-137
+ *
+ * Everything is BATCHED: a handle owns `batch` independent streams that advance in
+ * lock-step (one FeatureTracker + one VINS object per stream in reference terms);
+ * batch == 1 is the single-stream drop-in.  Plain pointers and sizes only; caller
+ * allocates every output; no ownership crosses the ABI; int return codes
+ * (0 = VIO_OK).  "dev" variants take/return DEVICE pointers and never touch the
+ * host; the plain variants take HOST pointers and do their own H2D/D2H copies.
+ *
+ * The library contains no CPU fallback: every entry point that computes needs a
+ * CUDA device and returns VIO_ERR_CUDA otherwise.
+ */
+#ifndef VIO_B200_H
+#define VIO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIO_OK 0
+#define VIO_ERR_ARG 1
+#define VIO_ERR_CUDA 2
+#define VIO_ERR_STATE 3
+#define VIO_ERR_CAPACITY 4
+
+/* Compile-time macros of the reference turned into run-time parameters
+ * (global_param.hpp:23-53, feature_tracker.hpp:24-29, feature_manager.hpp:22-25). */
+typedef struct vio_config {
+    int32_t rows, cols;          /* ROW 640, COL 480           feature_tracker.hpp:26-27 */
+    double fx, fy, cx, cy;       /* FOCUS_LENGTH_X/Y, PX, PY   global_param.cpp:29-32    */
+    double tic[3];               /* TIC_X/Y/Z                  global_param.cpp:37-39    */
+    double ric[9];               /* row-major; ypr2R(RIC_y,p,r) VINS.cpp:55               */
+    int32_t max_cnt;             /* MAX_CNT 70                 feature_tracker.hpp:24    */
+    int32_t min_dist;            /* MIN_DIST 30                feature_tracker.hpp:25    */
+    double f_threshold;          /* F_THRESHOLD 1.0            feature_tracker.hpp:28    */
+    int32_t freq;                /* FREQ 3                     global_param.cpp:35       */
+    int32_t window_size;         /* WINDOW_SIZE 10             global_param.hpp:28       */
+    int32_t num_of_f;            /* NUM_OF_F 1000              global_param.hpp:37       */
+    double acc_n, acc_w, gyr_n, gyr_w;  /* global_param.hpp:43-46 */
+    double gravity;              /* GRAVITY 9.805              global_param.hpp:42       */
+    int32_t max_iters;           /* options.max_num_iterations VINS.cpp:646              */
+    double min_parallax;         /* MIN_PARALLAX 10/549        feature_manager.hpp:24    */
+    double init_depth;           /* INIT_DEPTH 5.0             feature_manager.hpp:25    */
+    int32_t max_imu_per_frame;   /* capacity of dt_buf[] etc.  VINS.hpp:103-105          */
+    int32_t batch;               /* number of independent streams in the handle          */
+    int32_t device;              /* CUDA device ordinal                                   */
+} vio_config;
+
+/* Fills `cfg` with the reference's iPhone7P defaults (global_param.cpp:26-39) and the
+ * BASELINE.json bench values (max_cnt 150, window 10, freq 3). */
+void vio_config_default(vio_config *cfg);
+
+/* ------------------------------------------------------------------ front end */
+typedef struct vio_frontend vio_frontend;
+
+int vio_frontend_create(const vio_config *cfg, vio_frontend **out);
+void vio_frontend_destroy(vio_frontend *fe);
+
+/* FeatureTracker::readImage for every stream of the batch.
+ *   images : batch contiguous rows*cols u8 images (row-major, stride = cols)
+ * Detection / ID assignment / image_msg publication happen when the internal img_cnt == 0,
+ * then img_cnt = (img_cnt+1) % freq (ViewController.mm:494).  Returns VIO_OK; *published is
+ * set to 1 when this call produced a new image_msg. */
+int vio_frontend_read_images(vio_frontend *fe, const uint8_t *images_host, int *published);
+int vio_frontend_read_images_dev(vio_frontend *fe, const uint8_t *images_dev, int *published);
+/* Device buffer that the NEXT read_images_dev call will consume if the caller passes it back
+ * (zero-copy producer path): batch * rows * cols bytes. */
+uint8_t *vio_frontend_next_image_buffer(vio_frontend *fe);
+
+/* Tracker state after the last call, HOST outputs, per stream `s`:
+ *   n_out            number of tracked points
+ *   ids[n]           FeatureTracker::ids            (-1 between detect frames for fresh points never occurs: ids are assigned on detect frames)
+ *   pts_xy[2n]       FeatureTracker::cur_pts  (pixels)
+ *   track_cnt[n]     FeatureTracker::track_cnt
+ *   norm_xyz[3n]     image_msg values ((u-PX)/fx,(v-PY)/fy,1), only meaningful after a publishing call
+ * Any output pointer may be NULL.  Arrays must hold max_cnt entries. */
+int vio_frontend_get_stream(vio_frontend *fe, int s, int *n_out, int32_t *ids, float *pts_xy,
+                            int32_t *track_cnt, double *norm_xyz);
+/* readImage's UI outputs good_pts / track_len (feature_tracker.cpp:209-226,237-250,276-280). */
+int vio_frontend_get_ui(vio_frontend *fe, int s, int *n_out, float *good_pts_xy, double *track_len);
+/* Stage counters of the last call for stream s: [0] lk_in [1] lk_ok [2] f1_ok [3] f2_ok [4] kept [5] new [6] n_candidates [7] ransac iters */
+int vio_frontend_get_stats(vio_frontend *fe, int s, int32_t stats[8]);
+/* Device-resident SoA views (valid until the next call): counts[batch], ids[batch*max_cnt],
+ * norm_xyz[batch*max_cnt*3] -- what vio_backend_process_image_dev consumes. */
+int vio_frontend_image_msg_dev(vio_frontend *fe, const int32_t **counts, const int32_t **ids, const double **norm_xyz);
+/* Number of CUDA kernels launched by this handle since creation. */
+int64_t vio_frontend_launch_count(const vio_frontend *fe);
+/* Primitive entry points used by the parity tests (single image, host in/out).  */
+int vio_prim_pyramid(const vio_config *cfg, const uint8_t *img, uint8_t *l1, uint8_t *l2, uint8_t *l3);
+int vio_prim_min_eig_candidates(const vio_config *cfg, const uint8_t *img, const float *kept_xy, int n_kept,
+                                int max_corners, float *corners_xy, int *n_corners, float *max_val);
+int vio_prim_lk(const vio_config *cfg, const uint8_t *prev, const uint8_t *next, const float *pts_xy, int n,
+                float *next_xy, uint8_t *status);
+int vio_prim_ransac_f(const vio_config *cfg, const float *p1_xy, const float *p2_xy, int n, uint8_t *mask, int *iters);
+
+/* ------------------------------------------------------------------- back end */
+typedef struct vio_backend vio_backend;
+
+int vio_backend_create(const vio_config *cfg, vio_backend **out);
+void vio_backend_destroy(vio_backend *be);
+/* VINS::clearState for every stream. */
+int vio_backend_clear(vio_backend *be);
+
+/* VINS::processIMU, n_samples consecutive samples for every stream:
+ *   dt[n_samples*batch], acc[n_samples*batch*3], gyr[n_samples*batch*3]   (sample-major) */
+int vio_backend_process_imu(vio_backend *be, int n_samples, const double *dt, const double *acc, const double *gyr);
+int vio_backend_process_imu_dev(vio_backend *be, int n_samples, const double *dt, const double *acc, const double *gyr);
+
+/* External initialisation: the output of VINS::solveInitial/visualInitialAlign (VINS.cpp:833-1102,
+ * out of scope) supplied by the caller for frames 0..window_size:
+ * P[b][W+1][3], Q[b][W+1][4] (x,y,z,w), V[b][W+1][3], Ba[b][3], Bg[b][3].  Consumed by the
+ * process_image call that fills the window (frame_count == window_size, solver_flag INITIAL). */
+int vio_backend_set_init_window(vio_backend *be, const double *P, const double *Q, const double *V,
+                                const double *Ba, const double *Bg);
+
+/* VINS::processImage for every stream:  counts[batch], ids[batch*max_cnt], norm_xyz[batch*max_cnt*3],
+ * headers[batch].  Runs addFeatureCheckParallax, triangulate, solve_ceres (dogleg, <= max_iters),
+ * marginalisation, failureDetection and slideWindow on the device. */
+int vio_backend_process_image(vio_backend *be, const int32_t *counts, const int32_t *ids, const double *norm_xyz,
+                              const double *headers);
+int vio_backend_process_image_dev(vio_backend *be, const int32_t *counts, const int32_t *ids, const double *norm_xyz,
+                                  const double *headers_host);
+
+/* Window state of stream s (VINS::Ps/Rs/Vs/Bas/Bgs/Headers, VINS.hpp:73-77,107):
+ * P[(W+1)*3], Q[(W+1)*4] x,y,z,w, V[(W+1)*3], Ba[(W+1)*3], Bg[(W+1)*3], headers[W+1]. NULL = skip */
+int vio_backend_get_state(vio_backend *be, int s, double *P, double *Q, double *V, double *Ba, double *Bg, double *headers);
+/* Whole-batch device pointer to the packed state [batch][W+1][16] = P3,Q4(xyzw),V3,Ba3,Bg3 (for NCCL gathers). */
+int vio_backend_state_dev(vio_backend *be, const double **state, int64_t *n_doubles);
+/* info[0] solver_flag (0 INITIAL,1 NON_LINEAR) [1] marginalization_flag (0 OLD,1 SECOND_NEW) [2] frame_count
+ * [3] failure_occur [4] feature count in solve [5] projection factors [6] iterations run [7] last_track_num
+ * dinfo[0] initial cost [1] final cost [2] prior size n */
+int vio_backend_get_info(vio_backend *be, int s, int32_t info[8], double dinfo[4]);
+/* f_manager.feature of stream s: ids, start_frame, n_obs, estimated_depth, solve_flag; arrays sized `cap`. */
+int vio_backend_get_features(vio_backend *be, int s, int cap, int *n_out, int32_t *ids, int32_t *start_frame,
+                             int32_t *n_obs, double *depth, int32_t *solve_flag);
+/* Prior in information form over the canonical local layout [pose0(6) sb0(9) ... poseW sbW ex(6)],
+ * n = 15*(W+1)+6:  H[n*n] = J0^T J0, b[n] = J0^T r0, present[2*(W+1)+1] block mask.  For parity tests. */
+int vio_backend_get_prior(vio_backend *be, int s, double *H, double *b, int32_t *present, double *c0);
+int64_t vio_backend_launch_count(const vio_backend *be);
+
+/* Factor-level primitives for parity tests (host in/out, one factor each). */
+int vio_prim_preintegrate(const vio_config *cfg, int n, const double *dt, const double *acc, const double *gyr,
+                          const double acc0[3], const double gyr0[3], const double ba[3], const double bg[3],
+                          double *delta_pqv /*10: p3 q4(xyzw) v3*/, double *jacobian /*225*/, double *covariance /*225*/,
+                          double *sum_dt);
+int vio_prim_imu_factor(const vio_config *cfg, const double *delta_pqv, const double *jacobian, const double *covariance,
+                        double sum_dt, const double lin_ba[3], const double lin_bg[3],
+                        const double pose_i[7], const double sb_i[9], const double pose_j[7], const double sb_j[9],
+                        double *residual /*15*/, double *J /*15x30 row-major, local: [pi6 sbi9 pj6 sbj9]*/);
+int vio_prim_projection_factor(const vio_config *cfg, const double pts_i[3], const double pts_j[3],
+                               const double pose_i[7], const double pose_j[7], double inv_dep,
+                               double *residual /*2*/, double *J /*2x13 row-major: [pi6 pj6 lambda1]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIO_B200_H */

@@ -1,0 +1,142 @@
+"""ctypes loader for oracle/_ref/libvins_ref.so -- TEST INFRASTRUCTURE ONLY.
+
+The library is the reference's own factor code + vendored Ceres 1.12.0 driven by the restated
+estimator loop in oracle/backend_ref.cpp; it is built by oracle/Makefile from /root/reference and
+travels to the GPU box as a prebuilt file (oracle/_ref/ is git-ignored, not gpurun-ignored)."""
+import ctypes as C
+import importlib
+import os
+
+import numpy as np
+
+_abi = importlib.import_module("vins-mobile_b200.abi")
+DP, IP = _abi.DP, _abi.IP
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libvins_ref.so")
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.vref_create.restype = C.c_void_p
+        L.vref_create.argtypes = [C.POINTER(_abi.VioConfig)]
+        L.vref_destroy.argtypes = [C.c_void_p]
+        L.vref_clear.argtypes = [C.c_void_p]
+        L.vref_process_imu.argtypes = [C.c_void_p, C.c_double, DP, DP]
+        L.vref_set_init_window.argtypes = [C.c_void_p, DP, DP, DP, DP, DP]
+        L.vref_process_image.argtypes = [C.c_void_p, C.c_int, IP, DP, C.c_double]
+        L.vref_get_state.argtypes = [C.c_void_p, DP, DP, DP, DP, DP, DP]
+        L.vref_get_post_solve.argtypes = [C.c_void_p, DP]
+        L.vref_get_info.argtypes = [C.c_void_p, IP, DP]
+        L.vref_get_features.argtypes = [C.c_void_p, C.c_int, IP, IP, IP, IP, DP, IP]
+        L.vref_get_prior.argtypes = [C.c_void_p, DP, DP, IP, DP]
+        L.vref_preintegrate.argtypes = [C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
+        L.vref_imu_factor.argtypes = [DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP]
+        L.vref_projection_factor.argtypes = [C.c_double, DP, DP, DP, DP, DP, DP, C.c_double, DP, DP]
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+class RefEstimator:
+    """One VINS object (single stream) of the reference back end."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.W = cfg.window_size
+        self.h = lib().vref_create(C.byref(cfg))
+        if not self.h:
+            raise RuntimeError("vref_create failed")
+
+    def close(self):
+        if self.h:
+            lib().vref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process_imu(self, dt, acc, gyr):
+        a, g = _d(acc), _d(gyr)
+        lib().vref_process_imu(self.h, float(dt), _abi.ptr(a, C.c_double), _abi.ptr(g, C.c_double))
+
+    def set_init_window(self, P, Q, V, Ba, Bg):
+        arrs = [_d(x) for x in (P, Q, V, Ba, Bg)]
+        lib().vref_set_init_window(self.h, *[_abi.ptr(x, C.c_double) for x in arrs])
+
+    def process_image(self, ids, xyz, header):
+        ids = np.ascontiguousarray(ids, np.int32)
+        xyz = _d(xyz)
+        return lib().vref_process_image(self.h, len(ids), _abi.ptr(ids, C.c_int32), _abi.ptr(xyz, C.c_double), float(header))
+
+    def state(self):
+        n = self.W + 1
+        P, Q, V, Ba, Bg, H = (np.zeros((n, k)) for k in (3, 4, 3, 3, 3, 1))
+        lib().vref_get_state(self.h, *[_abi.ptr(x, C.c_double) for x in (P, Q, V, Ba, Bg, H)])
+        return dict(P=P, Q=Q, V=V, Ba=Ba, Bg=Bg, headers=H[:, 0])
+
+    def post_solve(self):
+        out = np.zeros((self.W + 1, 16))
+        rc = lib().vref_get_post_solve(self.h, _abi.ptr(out, C.c_double))
+        return None if rc else out
+
+    def info(self):
+        i = np.zeros(8, np.int32)
+        d = np.zeros(4)
+        lib().vref_get_info(self.h, _abi.ptr(i, C.c_int32), _abi.ptr(d, C.c_double))
+        return dict(solver_flag=int(i[0]), marg_flag=int(i[1]), frame_count=int(i[2]), failure=int(i[3]),
+                    n_feat=int(i[4]), n_proj=int(i[5]), iters=int(i[6]), last_track_num=int(i[7]),
+                    cost0=float(d[0]), cost1=float(d[1]), prior_n=int(d[2]))
+
+    def features(self, cap=4096):
+        n = C.c_int(0)
+        ids, st, no, fl = (np.zeros(cap, np.int32) for _ in range(4))
+        dep = np.zeros(cap)
+        lib().vref_get_features(self.h, cap, C.byref(n), _abi.ptr(ids, C.c_int32), _abi.ptr(st, C.c_int32),
+                                _abi.ptr(no, C.c_int32), _abi.ptr(dep, C.c_double), _abi.ptr(fl, C.c_int32))
+        k = n.value
+        return dict(ids=ids[:k], start=st[:k], n_obs=no[:k], depth=dep[:k], solve_flag=fl[:k])
+
+    def prior(self):
+        N = 15 * (self.W + 1) + 6
+        H = np.zeros((N, N)); b = np.zeros(N); pres = np.zeros(2 * (self.W + 1) + 1, np.int32); c0 = np.zeros(1)
+        rc = lib().vref_get_prior(self.h, _abi.ptr(H, C.c_double), _abi.ptr(b, C.c_double), _abi.ptr(pres, C.c_int32),
+                                  _abi.ptr(c0, C.c_double))
+        return None if rc else dict(H=H, b=b, present=pres, c0=float(c0[0]))
+
+
+def preintegrate(dt, acc, gyr, acc0, gyr0, ba, bg):
+    dt, acc, gyr, acc0, gyr0, ba, bg = (_d(x) for x in (dt, acc, gyr, acc0, gyr0, ba, bg))
+    pqv = np.zeros(10); jac = np.zeros((15, 15)); cov = np.zeros((15, 15)); sdt = np.zeros(1)
+    p = lambda a: _abi.ptr(a, C.c_double)
+    lib().vref_preintegrate(len(dt), p(dt), p(acc), p(gyr), p(acc0), p(gyr0), p(ba), p(bg), p(pqv), p(jac), p(cov), p(sdt))
+    return pqv, jac, cov, float(sdt[0])
+
+
+def imu_factor(pqv, jac, cov, sum_dt, lba, lbg, pi, sbi, pj, sbj):
+    a = [_d(x) for x in (pqv, jac, cov)]
+    b = [_d(x) for x in (lba, lbg, pi, sbi, pj, sbj)]
+    res = np.zeros(15); J = np.zeros((15, 30))
+    p = lambda x: _abi.ptr(x, C.c_double)
+    lib().vref_imu_factor(p(a[0]), p(a[1]), p(a[2]), float(sum_dt), *[p(x) for x in b], p(res), p(J))
+    return res, J
+
+
+def projection_factor(fx, tic, ric, pts_i, pts_j, pi, pj, inv_dep):
+    a = [_d(x) for x in (tic, ric, pts_i, pts_j, pi, pj)]
+    res = np.zeros(2); J = np.zeros((2, 13))
+    p = lambda x: _abi.ptr(x, C.c_double)
+    lib().vref_projection_factor(float(fx), *[p(x) for x in a], float(inv_dep), p(res), p(J))
+    return res, J

@@ -1,0 +1,344 @@
+// fe_kernels.cuh -- front-end CUDA kernels (sm_100a).  Every kernel is batched over streams (blockIdx.z or
+// blockIdx.y = stream).  The arithmetic contract is oracle/frontend_oracle.py (r_* functions), which is in turn
+// pinned to cv2 4.13; reference call sites are /root/reference/VINS_ios/feature_tracker.cpp:95,181,198,263.
+#pragma once
+#include "common.cuh"
+
+namespace fe {
+
+constexpr int LK_WIN = 21;
+constexpr int LK_LEVELS = 3;          // maxLevel (4 pyramid levels)
+constexpr int LK_MAX_ITERS = 30;
+constexpr int W_BITS = 14;
+constexpr int CAND_CAP = 16384;       // raw local maxima per stream
+constexpr int SORT_CAP = 8192;        // candidates above the quality threshold per stream
+
+struct PyrLevels {
+    const uint8_t *p[4];              // level base pointers for stream 0
+    int rows[4], cols[4];
+    size_t stride[4];                 // bytes between consecutive streams at this level
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// K1  pyrDown: 5-tap [1 4 6 4 1] x [1 4 6 4 1], REFLECT_101, (s + 128) >> 8, output ((H+1)/2,(W+1)/2)
+//     (cv::pyrDown inside calcOpticalFlowPyrLK; oracle r_pyr_down).  One thread -> 4 horizontally adjacent
+//     outputs (packed u8x4 store); the 5x11 input footprint is read as bytes through L1.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+                                                       int ir, int ic, int orows, int ocols, size_t in_stride,
+                                                       size_t out_stride) {
+    const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int oy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ox0 >= ocols || oy >= orows) return;
+    const uint8_t *src = in + (size_t)blockIdx.z * in_stride;
+    uint8_t *dst = out + (size_t)blockIdx.z * out_stride;
+    int acc[4] = {0, 0, 0, 0};
+    const int kw[5] = {1, 4, 6, 4, 1};
+    const bool interior = (2 * ox0 - 2 >= 0) && (2 * ox0 + 8 < ic);
+#pragma unroll
+    for (int dy = -2; dy <= 2; dy++) {
+        const int y = reflect101(2 * oy + dy, ir);
+        const uint8_t *row = src + (size_t)y * ic;
+        int v[11];
+        if (interior) {
+#pragma unroll
+            for (int k = 0; k < 11; k++) v[k] = row[2 * ox0 - 2 + k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 11; k++) v[k] = row[reflect101(2 * ox0 - 2 + k, ic)];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int h = v[2 * j] + 4 * v[2 * j + 1] + 6 * v[2 * j + 2] + 4 * v[2 * j + 3] + v[2 * j + 4];
+            acc[j] += kw[dy + 2] * h;
+        }
+    }
+    uint8_t *o = dst + (size_t)oy * ocols + ox0;
+    if (ox0 + 3 < ocols && ((ocols & 3) == 0)) {
+        uchar4 r;
+        r.x = (acc[0] + 128) >> 8; r.y = (acc[1] + 128) >> 8; r.z = (acc[2] + 128) >> 8; r.w = (acc[3] + 128) >> 8;
+        *reinterpret_cast<uchar4 *>(o) = r;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (ox0 + j < ocols) o[j] = (uint8_t)((acc[j] + 128) >> 8);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4  pyramidal LK, one warp per feature (cv::calcOpticalFlowPyrLK(Size(21,21), 3); oracle r_lk_track).
+//     Template: 24x24 u8 patch of I (REFLECT_101) staged in shared memory, Scharr gradients formed on the fly
+//     (zero outside the image), 14-bit fixed-point bilinear weights, int16-range template values held in
+//     registers (14 pixels per lane).  The 2x2 normal equations and the mismatch vector are reduced EXACTLY in
+//     integers with warp shuffles and converted to f32 once.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LK_WARPS = 4;
+constexpr int LK_PIX = (LK_WIN * LK_WIN + 31) / 32;     // 14 pixels per lane
+
+__device__ __forceinline__ void lk_weights(float fx, float fy, int &w00, int &w01, int &w10, int &w11) {
+    const float s = (float)(1 << W_BITS);
+    const float omx = fsub(1.f, fx), omy = fsub(1.f, fy);
+    w00 = __float2int_rn(fmul(fmul(omx, omy), s));
+    w01 = __float2int_rn(fmul(fmul(fx, omy), s));
+    w10 = __float2int_rn(fmul(fmul(omx, fy), s));
+    w11 = (1 << W_BITS) - w00 - w01 - w10;
+}
+
+__global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevels J, const float2 *__restrict__ prev_pts,
+                                                           float2 *__restrict__ next_pts, uint8_t *__restrict__ status,
+                                                           const int *__restrict__ n_pts, int maxp) {
+    __shared__ uint8_t sI[LK_WARPS][24 * 24];
+    __shared__ uint8_t sJ[LK_WARPS][22 * 24];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int f = blockIdx.x * LK_WARPS + warp;
+    if (f >= n_pts[b]) return;
+    const float2 pt = prev_pts[(size_t)b * maxp + f];
+    uint8_t *pI = sI[warp];
+    uint8_t *pJ = sJ[warp];
+    const float half = 10.f;
+    float nx = 0.f, ny = 0.f;          // nextPts[ptidx] (level coordinates, window centre)
+    bool ok = true;                    // status[ptidx]
+
+    for (int level = LK_LEVELS; level >= 0; level--) {
+        const int rows = I.rows[level], cols = I.cols[level];
+        const uint8_t *imI = I.p[level] + (size_t)b * I.stride[level];
+        const uint8_t *imJ = J.p[level] + (size_t)b * J.stride[level];
+        const float scale = 1.f / (float)(1 << level);
+        float px = fmul(pt.x, scale), py = fmul(pt.y, scale);
+        if (level == LK_LEVELS) { nx = px; ny = py; }
+        else { nx = fmul(nx, 2.f); ny = fmul(ny, 2.f); }
+        px = fsub(px, half); py = fsub(py, half);
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        if (ipx < -LK_WIN || ipx >= cols || ipy < -LK_WIN || ipy >= rows) {
+            if (level == 0) ok = false;
+            continue;
+        }
+        // stage the 24x24 template neighbourhood, rows ipy-1 .. ipy+22, cols ipx-1 .. ipx+22
+        __syncwarp();
+        for (int i = lane; i < 24 * 24; i += 32) {
+            const int r = i / 24, c = i - r * 24;
+            pI[i] = imI[(size_t)reflect101(ipy - 1 + r, rows) * cols + reflect101(ipx - 1 + c, cols)];
+        }
+        __syncwarp();
+        int w00, w01, w10, w11;
+        lk_weights(fsub(px, (float)ipx), fsub(py, (float)ipy), w00, w01, w10, w11);
+        short Iw[LK_PIX], gx[LK_PIX], gy[LK_PIX];
+        int a11 = 0, a12 = 0, a22 = 0;
+#pragma unroll
+        for (int k = 0; k < LK_PIX; k++) {
+            const int p = lane + 32 * k;
+            Iw[k] = gx[k] = gy[k] = 0;
+            if (p < LK_WIN * LK_WIN) {
+                const int y = p / LK_WIN, x = p - y * LK_WIN;
+                int iv = 0, dxv = 0, dyv = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int yy = y + (t >> 1), xx = x + (t & 1);       // window pixel (yy,xx) in 0..21
+                    const int wgt = t == 0 ? w00 : t == 1 ? w01 : t == 2 ? w10 : w11;
+                    const uint8_t *q = pI + (yy + 1) * 24 + (xx + 1);
+                    iv += wgt * q[0];
+                    const int gyi = ipy + yy, gxi = ipx + xx;
+                    if (gyi >= 0 && gyi < rows && gxi >= 0 && gxi < cols) {
+                        const int tl = q[-25], tc = q[-24], tr = q[-23], ml = q[-1], mr = q[1], bl = q[23], bc = q[24], br = q[25];
+                        dxv += wgt * (3 * (tr - tl) + 10 * (mr - ml) + 3 * (br - bl));
+                        dyv += wgt * (3 * (bl - tl) + 10 * (bc - tc) + 3 * (br - tr));
+                    }
+                }
+                const int ivs = (iv + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                const int gxs = (dxv + (1 << (W_BITS - 1))) >> W_BITS;
+                const int gys = (dyv + (1 << (W_BITS - 1))) >> W_BITS;
+                Iw[k] = (short)ivs; gx[k] = (short)gxs; gy[k] = (short)gys;
+                a11 += gxs * gxs; a12 += gxs * gys; a22 += gys * gys;
+            }
+        }
+        const float FLT_SCALE = 1.f / (float)(1 << 20);
+        const float A11 = fmul(__ll2float_rn(warp_sum_ll(a11)), FLT_SCALE);
+        const float A12 = fmul(__ll2float_rn(warp_sum_ll(a12)), FLT_SCALE);
+        const float A22 = fmul(__ll2float_rn(warp_sum_ll(a22)), FLT_SCALE);
+        const float D = fsub(fmul(A11, A22), fmul(A12, A12));
+        const float d12 = fsub(A11, A22);
+        const float mineig = __fdiv_rn(fsub(fadd(A22, A11), __fsqrt_rn(fadd(fmul(d12, d12), fmul(fmul(4.f, A12), A12)))),
+                                       (float)(2 * LK_WIN * LK_WIN));
+        if (mineig < 1e-4f || D < 1.1920929e-07f) {
+            if (level == 0) ok = false;
+            continue;
+        }
+        const float Dinv = __fdiv_rn(1.f, D);
+        float cx = fsub(nx, half), cy = fsub(ny, half);       // nextPt (window top-left, float)
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < LK_MAX_ITERS; j++) {
+            const int jx = (int)floorf(cx), jy = (int)floorf(cy);
+            if (jx < -LK_WIN || jx >= cols || jy < -LK_WIN || jy >= rows) {
+                if (level == 0) ok = false;
+                break;
+            }
+            __syncwarp();
+            for (int i = lane; i < 22 * 22; i += 32) {
+                const int r = i / 22, c = i - r * 22;
+                pJ[r * 24 + c] = imJ[(size_t)reflect101(jy + r, rows) * cols + reflect101(jx + c, cols)];
+            }
+            __syncwarp();
+            int v00, v01, v10, v11;
+            lk_weights(fsub(cx, (float)jx), fsub(cy, (float)jy), v00, v01, v10, v11);
+            int b1 = 0, b2 = 0;
+#pragma unroll
+            for (int k = 0; k < LK_PIX; k++) {
+                const int p = lane + 32 * k;
+                if (p < LK_WIN * LK_WIN) {
+                    const int y = p / LK_WIN, x = p - y * LK_WIN;
+                    const uint8_t *q = pJ + y * 24 + x;
+                    const int jv = (q[0] * v00 + q[1] * v01 + q[24] * v10 + q[25] * v11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                    const int diff = jv - Iw[k];
+                    b1 += diff * gx[k];
+                    b2 += diff * gy[k];
+                }
+            }
+            const float B1 = fmul(__ll2float_rn(warp_sum_ll(b1)), FLT_SCALE);
+            const float B2 = fmul(__ll2float_rn(warp_sum_ll(b2)), FLT_SCALE);
+            const float dx = fmul(fsub(fmul(A12, B2), fmul(A22, B1)), Dinv);
+            const float dy = fmul(fsub(fmul(A12, B1), fmul(A11, B2)), Dinv);
+            cx = fadd(cx, dx); cy = fadd(cy, dy);
+            nx = fadd(cx, half); ny = fadd(cy, half);
+            const double dd = (double)dx * (double)dx + (double)dy * (double)dy;
+            if (dd <= 0.01 * 0.01) break;
+            if (j > 0 && fabsf(fadd(dx, pdx)) < 0.01f && fabsf(fadd(dy, pdy)) < 0.01f) {
+                nx = fsub(nx, fmul(dx, 0.5f));
+                ny = fsub(ny, fmul(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (level == 0 && ok) {
+            const int fx = (int)floorf(fsub(nx, half)), fy = (int)floorf(fsub(ny, half));
+            if (fx < -LK_WIN || fx >= cols || fy < -LK_WIN || fy >= rows) ok = false;
+        }
+    }
+    if (lane == 0) {
+        next_pts[(size_t)b * maxp + f] = make_float2(nx, ny);
+        status[(size_t)b * maxp + f] = ok ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2  Shi-Tomasi response + 3x3 NMS + mask test, candidate compaction (cv::goodFeaturesToTrack front half;
+//     oracle r_min_eig_map / r_good_features).  The eig map is never written to HBM: a 32x32 tile computes
+//     Sobel (f32, the exact fma pattern cv2 uses), covariance products, 3x3 box sums in f64, min-eigenvalue,
+//     and emits (value, address) of every masked interior local maximum plus the masked global maximum.
+//     The min-distance mask of setMask() is evaluated analytically: a pixel is masked iff it lies within
+//     min_dist of a kept point's ROUNDED centre (cv::circle raster == Euclidean disc).
+//     NMS is threshold independent: (e > thr) && (e == dilate(threshold(e)))  <=>  (e > thr) && e >= 8 nbrs.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ET = 32;                 // tile edge
+__global__ void __launch_bounds__(256) eig_candidates_kernel(const uint8_t *__restrict__ img, size_t img_stride, int rows,
+                                                             int cols, const int2 *__restrict__ kept, const int *__restrict__ n_kept,
+                                                             int maxp, int min_dist, unsigned *__restrict__ max_bits,
+                                                             unsigned long long *__restrict__ cand, int *__restrict__ cand_cnt) {
+    __shared__ float sp[(ET + 6) * (ET + 6)];        // pixels as f32, origin (ty0-3, tx0-3)
+    __shared__ float sdx[(ET + 4) * (ET + 4)];       // origin (ty0-2, tx0-2)
+    __shared__ float sdy[(ET + 4) * (ET + 4)];
+    __shared__ float se[(ET + 2) * (ET + 2)];        // eig, origin (ty0-1, tx0-1)
+    __shared__ int2 sk[64];
+    __shared__ int nk;
+    const int b = blockIdx.z;
+    const int tx0 = blockIdx.x * ET, ty0 = blockIdx.y * ET;
+    const uint8_t *im = img + (size_t)b * img_stride;
+    const int tid = threadIdx.x;
+    if (tid == 0) nk = 0;
+    __syncthreads();
+    // kept points whose disc can touch this tile
+    {
+        const int n = n_kept[b];
+        for (int i = tid; i < n; i += 256) {
+            const int2 c = kept[(size_t)b * maxp + i];
+            if (c.x >= tx0 - min_dist && c.x < tx0 + ET + min_dist && c.y >= ty0 - min_dist && c.y < ty0 + ET + min_dist) {
+                const int s = atomicAdd(&nk, 1);
+                if (s < 64) sk[s] = c;
+            }
+        }
+    }
+    constexpr int PW = ET + 6, DW = ET + 4, EW = ET + 2;
+    for (int i = tid; i < PW * PW; i += 256) {
+        const int r = i / PW, c = i - r * PW;
+        const int y = reflect101(ty0 - 3 + r, rows), x = reflect101(tx0 - 3 + c, cols);
+        sp[i] = (y >= 0 && y < rows && x >= 0 && x < cols) ? (float)im[(size_t)y * cols + x] : 0.f;
+    }
+    __syncthreads();
+    const float a = (float)(1.0 / 3060.0);
+    const float a2 = fmul(2.f, a);
+    for (int i = tid; i < DW * DW; i += 256) {
+        const int r = i / DW, c = i - r * DW;
+        const float *q = sp + (r + 1) * PW + (c + 1);      // pixel (ty0-2+r, tx0-2+c)
+        // dx = fma(r[-1]+r[+1], a, r[0]*2a),  r[k] = p[k][+1]-p[k][-1]
+        const float rm = fsub(q[-PW + 1], q[-PW - 1]), r0 = fsub(q[1], q[-1]), rp = fsub(q[PW + 1], q[PW - 1]);
+        sdx[i] = ffma(fadd(rm, rp), a, fmul(r0, a2));
+        // dy = s[+1]-s[-1],  s[k] = fma(p[k][+1], a, fma(p[k][0], 2a, a*p[k][-1]))
+        const float sm = ffma(q[-PW + 1], a, ffma(q[-PW], a2, fmul(a, q[-PW - 1])));
+        const float spv = ffma(q[PW + 1], a, ffma(q[PW], a2, fmul(a, q[PW - 1])));
+        sdy[i] = fsub(spv, sm);
+    }
+    __syncthreads();
+    for (int i = tid; i < EW * EW; i += 256) {
+        const int r = i / EW, c = i - r * EW;
+        const int gy = ty0 - 1 + r, gx = tx0 - 1 + c;
+        float e = -1.f;
+        if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
+            double A[3], Bc[3], Cc[3];
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++) {
+                const int yy = reflect101(gy + dy, rows) - (ty0 - 2);
+                double ra[3], rb[3], rc[3];
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int xx = reflect101(gx + dx, cols) - (tx0 - 2);
+                    const float vx = sdx[yy * DW + xx], vy = sdy[yy * DW + xx];
+                    ra[dx + 1] = (double)fmul(vx, vx);
+                    rb[dx + 1] = (double)fmul(vx, vy);
+                    rc[dx + 1] = (double)fmul(vy, vy);
+                }
+                A[dy + 1] = __dadd_rn(__dadd_rn(ra[0], ra[1]), ra[2]);
+                Bc[dy + 1] = __dadd_rn(__dadd_rn(rb[0], rb[1]), rb[2]);
+                Cc[dy + 1] = __dadd_rn(__dadd_rn(rc[0], rc[1]), rc[2]);
+            }
+            const float fa = (float)__dadd_rn(__dadd_rn(A[0], A[1]), A[2]);
+            const float fb = (float)__dadd_rn(__dadd_rn(Bc[0], Bc[1]), Bc[2]);
+            const float fc = (float)__dadd_rn(__dadd_rn(Cc[0], Cc[1]), Cc[2]);
+            const float ha = fmul(fa, 0.5f), hc = fmul(fc, 0.5f);
+            const float t = fsub(ha, hc);
+            e = fsub(fadd(ha, hc), __fsqrt_rn(fadd(fmul(t, t), fmul(fb, fb))));
+        }
+        se[i] = e;
+    }
+    __syncthreads();
+    const int nkk = min(nk, 64);
+    const int md2 = min_dist * min_dist;
+    float local_max = 0.f;
+    for (int i = tid; i < ET * ET; i += 256) {
+        const int r = i / ET, c = i - r * ET;
+        const int gy = ty0 + r, gx = tx0 + c;
+        if (gy >= rows || gx >= cols) continue;
+        const float e = se[(r + 1) * EW + (c + 1)];
+        bool masked = false;
+        for (int k = 0; k < nkk; k++) {
+            const int ddx = gx - sk[k].x, ddy = gy - sk[k].y;
+            masked |= (ddx * ddx + ddy * ddy <= md2);
+        }
+        if (masked) continue;
+        local_max = fmaxf(local_max, e);
+        if (gy < 1 || gy >= rows - 1 || gx < 1 || gx >= cols - 1 || !(e > 0.f)) continue;
+        const float *q = se + (r + 1) * EW + (c + 1);
+        const float m = fmaxf(fmaxf(fmaxf(q[-EW - 1], q[-EW]), fmaxf(q[-EW + 1], q[-1])),
+                              fmaxf(fmaxf(q[1], q[EW - 1]), fmaxf(q[EW], q[EW + 1])));
+        if (e >= m) {
+            const int s = atomicAdd(&cand_cnt[b], 1);
+            if (s < CAND_CAP)
+                cand[(size_t)b * CAND_CAP + s] = ((unsigned long long)__float_as_uint(e) << 32) | (unsigned)(gy * cols + gx);
+        }
+    }
+    // masked global maximum (positive floats order like their bit patterns)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+    if ((tid & 31) == 0 && local_max > 0.f) atomicMax(&max_bits[b], __float_as_uint(local_max));
+}
+
+}  // namespace fe
