@@ -1,0 +1,457 @@
+// backend.cu -- C-ABI of the batched sliding-window estimator (include/vio_b200.h, vio_backend_*), replacing
+// VINS::processIMU / processImage / solve_ceres / slideWindow (/root/reference/VINS_ios/VINS.cpp:333-831,1149-1273) and
+// FeatureManager (feature_manager.cpp).  Every stream of the batch is one VINS object; all state lives in HBM and every
+// step is a fixed sequence of kernels with one CTA per stream -- no host round trip inside processImage.
+// No CPU fallback.
+#include "be_marg.cuh"
+
+#include <algorithm>
+#include <new>
+#include <vector>
+#include <string.h>
+
+using namespace be;
+
+struct vio_backend {
+    vio_config cfg;
+    BeState s;
+    cudaStream_t stream;
+    bool own_stream;
+    int64_t launches;
+    std::vector<void *> allocs;
+    // device staging for the host-pointer entry points
+    int *d_counts, *d_ids; double *d_xyz, *d_headers; double *d_imu; size_t imu_cap;
+    double *h_headers_pinned;
+};
+
+template <typename T>
+static int dalloc(vio_backend *be, T **p, size_t n) {
+    VIO_CUDA_TRY(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+    VIO_CUDA_TRY(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    be->allocs.push_back(*p);
+    return VIO_OK;
+}
+
+__global__ void init_state_kernel(BeState s, const double *tic, const double *ric) {
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) {
+        double *dv = S_dv(s, b);
+        for (int i = 0; i < 3; i++) dv[DV_TIC + i] = tic[i];
+        for (int i = 0; i < 9; i++) dv[DV_RIC + i] = ric[i];
+        stm(dv + DV_LAST_R, eye3()); stm(dv + DV_LAST_R_OLD, eye3()); stm(dv + DV_BACK_R0, eye3());
+        int *iv = S_iv(s, b);
+        for (int i = 0; i < IV_COUNT; i++) iv[i] = 0;
+        iv[IV_ACTION] = ACT_NONE;
+    }
+    __syncthreads();
+    clear_state_cta(s, b);
+}
+
+extern "C" int vio_backend_clear(vio_backend *be) {
+    if (!be) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    double h[12];
+    memcpy(h, be->cfg.tic, sizeof(double) * 3);
+    memcpy(h + 3, be->cfg.ric, sizeof(double) * 9);
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_xyz, h, sizeof(h), cudaMemcpyHostToDevice, be->stream));
+    init_state_kernel<<<be->s.B, 128, 0, be->stream>>>(be->s, be->d_xyz, be->d_xyz + 3);
+    be->launches++;
+    VIO_CUDA_TRY(cudaGetLastError());
+    return VIO_OK;
+}
+
+extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
+    if (!cfg || !out || cfg->batch < 1 || cfg->window_size < 4 || cfg->window_size > VIO_MAX_WIN || cfg->max_cnt < 1 || cfg->max_cnt > VIO_MAXP ||
+        cfg->num_of_f < 1 || cfg->max_imu_per_frame < 1)
+        return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(cfg->device));
+    vio_backend *be = new (std::nothrow) vio_backend();
+    if (!be) return VIO_ERR_ARG;
+    be->cfg = *cfg; be->launches = 0; be->own_stream = true;
+    VIO_CUDA_TRY(cudaStreamCreateWithFlags(&be->stream, cudaStreamNonBlocking));
+    BeState &s = be->s;
+    memset(&s, 0, sizeof(s));
+    s.B = cfg->batch; s.W = cfg->window_size; s.NF = s.W + 1; s.NP = 15 * s.NF; s.NPX = s.NP + 6; s.NPW = 6 * s.NF;
+    s.MAXCNT = cfg->max_cnt;
+    s.FCAP = std::min(8192, (s.NF + 1) * cfg->max_cnt);
+    s.LCAP = cfg->num_of_f;
+    s.PCAP = std::min(cfg->num_of_f * s.W, 16384);
+    s.MAXIMU = cfg->max_imu_per_frame;
+    s.gravity = cfg->gravity; s.min_parallax = cfg->min_parallax; s.init_depth = cfg->init_depth;
+    s.sqrt_info = cfg->fx / 1.5;                                   // ProjectionFactor::sqrt_info, VINS.cpp:29-32
+    s.noise[0] = s.noise[2] = cfg->acc_n * cfg->acc_n; s.noise[1] = s.noise[3] = cfg->gyr_n * cfg->gyr_n;
+    s.noise[4] = cfg->acc_w * cfg->acc_w; s.noise[5] = cfg->gyr_w * cfg->gyr_w;
+    s.max_iters = cfg->max_iters;
+    const size_t B = s.B, NF = s.NF;
+    int rc = VIO_OK;
+    if (!rc) rc = dalloc(be, &s.Ps, B * NF * 3);
+    if (!rc) rc = dalloc(be, &s.Rs, B * NF * 9);
+    if (!rc) rc = dalloc(be, &s.Vs, B * NF * 3);
+    if (!rc) rc = dalloc(be, &s.Bas, B * NF * 3);
+    if (!rc) rc = dalloc(be, &s.Bgs, B * NF * 3);
+    if (!rc) rc = dalloc(be, &s.Headers, B * NF);
+    if (!rc) rc = dalloc(be, &s.pre, B * NF * PR_STRIDE);
+    if (!rc) rc = dalloc(be, &s.imu_buf, B * NF * s.MAXIMU * 7);
+    if (!rc) rc = dalloc(be, &s.imu_cnt, B * NF);
+    if (!rc) rc = dalloc(be, &s.iv, B * IV_COUNT);
+    if (!rc) rc = dalloc(be, &s.dv, B * DV_COUNT);
+    if (!rc) rc = dalloc(be, &s.init_state, B * (NF * 10 + 6));
+    if (!rc) rc = dalloc(be, &s.f_id, B * s.FCAP);
+    if (!rc) rc = dalloc(be, &s.f_start, B * s.FCAP);
+    if (!rc) rc = dalloc(be, &s.f_nobs, B * s.FCAP);
+    if (!rc) rc = dalloc(be, &s.f_flag, B * s.FCAP);
+    if (!rc) rc = dalloc(be, &s.f_depth, B * s.FCAP);
+    if (!rc) rc = dalloc(be, &s.f_obs, B * s.FCAP * NF * 2);
+    if (!rc) rc = dalloc(be, &s.Hp, B * s.NPX * s.NPX);
+    if (!rc) rc = dalloc(be, &s.bp, B * s.NPX);
+    if (!rc) rc = dalloc(be, &s.x0, B * (NF * 16 + 7));
+    if (!rc) rc = dalloc(be, &s.present, B * (2 * NF + 1));
+    if (!rc) rc = dalloc(be, &s.par, B * (NF * 16 + s.LCAP));
+    if (!rc) rc = dalloc(be, &s.cand, B * (NF * 16 + s.LCAP));
+    if (!rc) rc = dalloc(be, &s.lm_slot, B * s.LCAP);
+    if (!rc) rc = dalloc(be, &s.fac_lm, B * s.PCAP);
+    if (!rc) rc = dalloc(be, &s.fac_j, B * s.PCAP);
+    if (!rc) rc = dalloc(be, &s.post_solve, B * NF * 16);
+    if (!rc) rc = dalloc(be, &s.state_out, B * NF * 16);
+    size_t sc = solve_scratch_doubles(s.NP, s.NPX, s.NPW, s.LCAP, s.W);
+    sc = std::max(sc, marg_scratch_doubles(s.NPX, s.LCAP, cfg->max_cnt));
+    sc = std::max(sc, (size_t)s.FCAP * (5 + 2 * NF));
+    s.scratch_stride = (sc + 15) & ~(size_t)15;
+    if (!rc) rc = dalloc(be, &s.scratch, B * s.scratch_stride);
+    if (!rc) rc = dalloc(be, &be->d_counts, B);
+    if (!rc) rc = dalloc(be, &be->d_ids, B * cfg->max_cnt);
+    if (!rc) rc = dalloc(be, &be->d_xyz, B * cfg->max_cnt * 3 + 16);
+    if (!rc) rc = dalloc(be, &be->d_headers, B);
+    be->imu_cap = 64;
+    if (!rc) rc = dalloc(be, &be->d_imu, be->imu_cap * B * 7);
+    if (!rc && cudaMallocHost((void **)&be->h_headers_pinned, B * sizeof(double)) != cudaSuccess) rc = VIO_ERR_CUDA;
+    if (rc) { vio_backend_destroy(be); return rc; }
+    VIO_CUDA_TRY(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s.FCAP + 64));
+    rc = vio_backend_clear(be);
+    if (rc) { vio_backend_destroy(be); return rc; }
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    *out = be;
+    return VIO_OK;
+}
+
+extern "C" void vio_backend_destroy(vio_backend *be) {
+    if (!be) return;
+    cudaSetDevice(be->cfg.device);
+    cudaStreamSynchronize(be->stream);
+    for (void *p : be->allocs) cudaFree(p);
+    if (be->h_headers_pinned) cudaFreeHost(be->h_headers_pinned);
+    cudaStreamDestroy(be->stream);
+    delete be;
+}
+
+extern "C" int vio_backend_process_imu_dev(vio_backend *be, int n, const double *dt, const double *acc, const double *gyr) {
+    if (!be || n < 0) return VIO_ERR_ARG;
+    if (n == 0) return VIO_OK;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    imu_kernel<<<(be->s.B + 3) / 4, 128, 0, be->stream>>>(be->s, n, dt, acc, gyr);
+    be->launches++;
+    VIO_CUDA_TRY(cudaGetLastError());
+    return VIO_OK;
+}
+
+extern "C" int vio_backend_process_imu(vio_backend *be, int n, const double *dt, const double *acc, const double *gyr) {
+    if (!be || n < 0 || (n > 0 && (!dt || !acc || !gyr))) return VIO_ERR_ARG;
+    if (n == 0) return VIO_OK;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    const size_t B = be->s.B;
+    if ((size_t)n > be->imu_cap) {
+        VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+        double *p;
+        VIO_CUDA_TRY(cudaMalloc((void **)&p, (size_t)n * B * 7 * sizeof(double)));
+        be->allocs.push_back(p);
+        be->d_imu = p; be->imu_cap = n;
+    }
+    double *d_dt = be->d_imu, *d_acc = d_dt + (size_t)n * B, *d_gyr = d_acc + (size_t)n * B * 3;
+    VIO_CUDA_TRY(cudaMemcpyAsync(d_dt, dt, (size_t)n * B * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(d_acc, acc, (size_t)n * B * 3 * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(d_gyr, gyr, (size_t)n * B * 3 * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    return vio_backend_process_imu_dev(be, n, d_dt, d_acc, d_gyr);
+}
+
+__global__ void set_init_kernel(BeState s, const double *P, const double *Q, const double *V, const double *Ba, const double *Bg) {
+    const int b = blockIdx.x;
+    double *o = s.init_state + (size_t)b * (s.NF * 10 + 6);
+    for (int i = threadIdx.x; i < s.NF; i += blockDim.x) {
+        const size_t k = (size_t)b * s.NF + i;
+        for (int c = 0; c < 3; c++) { o[10 * i + c] = P[3 * k + c]; o[10 * i + 7 + c] = V[3 * k + c]; }
+        for (int c = 0; c < 4; c++) o[10 * i + 3 + c] = Q[4 * k + c];
+    }
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 3; c++) { o[10 * s.NF + c] = Ba[3 * b + c]; o[10 * s.NF + 3 + c] = Bg[3 * b + c]; }
+        S_iv(s, b)[IV_INIT_PENDING] = 1;
+    }
+}
+
+extern "C" int vio_backend_set_init_window(vio_backend *be, const double *P, const double *Q, const double *V, const double *Ba, const double *Bg) {
+    if (!be || !P || !Q || !V || !Ba || !Bg) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    const size_t B = be->s.B, NF = be->s.NF;
+    double *d;
+    const size_t tot = B * NF * 10 + B * 6;
+    VIO_CUDA_TRY(cudaMalloc((void **)&d, tot * sizeof(double)));
+    double *dP = d, *dQ = dP + B * NF * 3, *dV = dQ + B * NF * 4, *dBa = dV + B * NF * 3, *dBg = dBa + B * 3;
+    cudaMemcpyAsync(dP, P, B * NF * 3 * sizeof(double), cudaMemcpyHostToDevice, be->stream);
+    cudaMemcpyAsync(dQ, Q, B * NF * 4 * sizeof(double), cudaMemcpyHostToDevice, be->stream);
+    cudaMemcpyAsync(dV, V, B * NF * 3 * sizeof(double), cudaMemcpyHostToDevice, be->stream);
+    cudaMemcpyAsync(dBa, Ba, B * 3 * sizeof(double), cudaMemcpyHostToDevice, be->stream);
+    cudaMemcpyAsync(dBg, Bg, B * 3 * sizeof(double), cudaMemcpyHostToDevice, be->stream);
+    set_init_kernel<<<be->s.B, 32, 0, be->stream>>>(be->s, dP, dQ, dV, dBa, dBg);
+    be->launches++;
+    cudaError_t e = cudaStreamSynchronize(be->stream);
+    cudaFree(d);
+    return e == cudaSuccess ? VIO_OK : VIO_ERR_CUDA;
+}
+
+__global__ void clear_init_pending_kernel(BeState s) {
+    int *iv = S_iv(s, blockIdx.x);
+    if (threadIdx.x == 0 && iv[IV_ACTION] == ACT_INIT_SOLVE) iv[IV_INIT_PENDING] = 0;
+}
+
+static int run_process_image(vio_backend *be, const int32_t *counts, const int32_t *ids, const double *xyz, const double *headers_dev) {
+    BeState &s = be->s;
+    cudaStream_t st = be->stream;
+    addfeat_kernel<<<s.B, 256, 0, st>>>(s, counts, ids, xyz, headers_dev);
+    triangulate_kernel<<<s.B, 128, 0, st>>>(s);
+    prepare_kernel<<<s.B, 256, 0, st>>>(s);
+    solve_kernel<<<s.B, SOLVE_T, 0, st>>>(s);
+    post_solve_kernel<<<s.B, 256, 0, st>>>(s);
+    marg_kernel<<<s.B, MARG_T, sizeof(MargSmem), st>>>(s);
+    finish_kernel<<<s.B, 256, s.FCAP + 64, st>>>(s);
+    clear_init_pending_kernel<<<s.B, 32, 0, st>>>(s);
+    be->launches += 8;
+    VIO_CUDA_TRY(cudaGetLastError());
+    return VIO_OK;
+}
+
+extern "C" int vio_backend_process_image_dev(vio_backend *be, const int32_t *counts, const int32_t *ids, const double *xyz, const double *headers_host) {
+    if (!be || !counts || !ids || !xyz || !headers_host) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));          // pinned header staging is reused
+    memcpy(be->h_headers_pinned, headers_host, be->s.B * sizeof(double));
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_headers, be->h_headers_pinned, be->s.B * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    return run_process_image(be, counts, ids, xyz, be->d_headers);
+}
+
+extern "C" int vio_backend_process_image(vio_backend *be, const int32_t *counts, const int32_t *ids, const double *xyz, const double *headers) {
+    if (!be || !counts || !ids || !xyz || !headers) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    const size_t B = be->s.B, P = be->cfg.max_cnt;
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_counts, counts, B * sizeof(int), cudaMemcpyHostToDevice, be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_ids, ids, B * P * sizeof(int), cudaMemcpyHostToDevice, be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_xyz, xyz, B * P * 3 * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_headers, headers, B * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    return run_process_image(be, be->d_counts, be->d_ids, be->d_xyz, be->d_headers);
+}
+
+static int stream_err(vio_backend *be, int s) {
+    int e = 0;
+    VIO_CUDA_TRY(cudaMemcpyAsync(&e, be->s.iv + (size_t)s * IV_COUNT + IV_ERR, sizeof(int), cudaMemcpyDeviceToHost, be->stream));
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    return e;
+}
+
+template <typename T>
+static int bd2h(vio_backend *be, T *dst, const T *src, size_t n) {
+    if (!dst || n == 0) return VIO_OK;
+    VIO_CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, be->stream));
+    return VIO_OK;
+}
+
+extern "C" int vio_backend_get_state(vio_backend *be, int s, double *P, double *Q, double *V, double *Ba, double *Bg, double *headers) {
+    if (!be || s < 0 || s >= be->s.B) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    const int NF = be->s.NF;
+    std::vector<double> h((size_t)NF * 16), R((size_t)NF * 9);
+    int rc = bd2h(be, h.data(), be->s.state_out + (size_t)s * NF * 16, (size_t)NF * 16);
+    if (!rc) rc = bd2h(be, headers, be->s.Headers + (size_t)s * NF, NF);
+    if (rc) return rc;
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    for (int i = 0; i < NF; i++) {
+        const double *o = &h[16 * i];
+        for (int c = 0; c < 3; c++) { if (P) P[3 * i + c] = o[c]; if (V) V[3 * i + c] = o[7 + c]; if (Ba) Ba[3 * i + c] = o[10 + c]; if (Bg) Bg[3 * i + c] = o[13 + c]; }
+        if (Q) for (int c = 0; c < 4; c++) Q[4 * i + c] = o[3 + c];
+    }
+    return stream_err(be, s);
+}
+
+extern "C" int vio_backend_get_post_solve(vio_backend *be, int s, double *out) {
+    if (!be || s < 0 || s >= be->s.B || !out) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    int rc = bd2h(be, out, be->s.post_solve + (size_t)s * be->s.NF * 16, (size_t)be->s.NF * 16);
+    if (rc) return rc;
+    return stream_err(be, s);
+}
+
+extern "C" int vio_backend_state_dev(vio_backend *be, const double **state, int64_t *n_doubles) {
+    if (!be) return VIO_ERR_ARG;
+    if (state) *state = be->s.state_out;
+    if (n_doubles) *n_doubles = (int64_t)be->s.B * be->s.NF * 16;
+    return VIO_OK;
+}
+
+extern "C" int vio_backend_get_info(vio_backend *be, int s, int32_t info[8], double dinfo[4]) {
+    if (!be || s < 0 || s >= be->s.B) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    int iv[IV_COUNT]; double dv[DV_COUNT];
+    int rc = bd2h(be, iv, be->s.iv + (size_t)s * IV_COUNT, IV_COUNT);
+    if (!rc) rc = bd2h(be, dv, be->s.dv + (size_t)s * DV_COUNT, DV_COUNT);
+    if (rc) return rc;
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    if (info) { info[0] = iv[IV_SOLVER_FLAG]; info[1] = iv[IV_MARG_FLAG]; info[2] = iv[IV_FRAME_COUNT]; info[3] = iv[IV_FAILURE];
+                info[4] = iv[IV_N_LM]; info[5] = iv[IV_N_FAC]; info[6] = iv[IV_ITERS]; info[7] = iv[IV_LAST_TRACK]; }
+    if (dinfo) { dinfo[0] = dv[DV_COST0]; dinfo[1] = dv[DV_COST1]; dinfo[2] = iv[IV_PRIOR_VALID] ? iv[IV_PRIOR_N] : 0; dinfo[3] = iv[IV_ERR]; }
+    return VIO_OK;
+}
+
+extern "C" int vio_backend_get_features(vio_backend *be, int s, int cap, int *n_out, int32_t *ids, int32_t *start, int32_t *nobs, double *depth,
+                                        int32_t *flag) {
+    if (!be || s < 0 || s >= be->s.B || !n_out) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    int nf = 0;
+    VIO_CUDA_TRY(cudaMemcpyAsync(&nf, be->s.iv + (size_t)s * IV_COUNT + IV_NFEAT, sizeof(int), cudaMemcpyDeviceToHost, be->stream));
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    const int n = std::min(nf, cap);
+    const size_t fo = (size_t)s * be->s.FCAP;
+    int rc = bd2h(be, ids, be->s.f_id + fo, n);
+    if (!rc) rc = bd2h(be, start, be->s.f_start + fo, n);
+    if (!rc) rc = bd2h(be, nobs, be->s.f_nobs + fo, n);
+    if (!rc) rc = bd2h(be, depth, be->s.f_depth + fo, n);
+    if (!rc) rc = bd2h(be, flag, be->s.f_flag + fo, n);
+    if (rc) return rc;
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    *n_out = nf;
+    return nf <= cap ? VIO_OK : VIO_ERR_CAPACITY;
+}
+
+extern "C" int vio_backend_get_prior(vio_backend *be, int s, double *H, double *b, int32_t *present, double *c0) {
+    if (!be || s < 0 || s >= be->s.B) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    const size_t N = be->s.NPX;
+    int valid = 0;
+    VIO_CUDA_TRY(cudaMemcpyAsync(&valid, be->s.iv + (size_t)s * IV_COUNT + IV_PRIOR_VALID, sizeof(int), cudaMemcpyDeviceToHost, be->stream));
+    int rc = bd2h(be, H, be->s.Hp + (size_t)s * N * N, N * N);
+    if (!rc) rc = bd2h(be, b, be->s.bp + (size_t)s * N, N);
+    if (!rc) rc = bd2h(be, present, be->s.present + (size_t)s * (2 * be->s.NF + 1), 2 * be->s.NF + 1);
+    if (!rc && c0) rc = bd2h(be, c0, be->s.dv + (size_t)s * DV_COUNT + DV_PRIOR_C0, 1);
+    if (rc) return rc;
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    return valid ? VIO_OK : VIO_ERR_STATE;
+}
+
+extern "C" int64_t vio_backend_launch_count(const vio_backend *be) { return be ? be->launches : 0; }
+extern "C" int vio_backend_sync(vio_backend *be) {
+    if (!be) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    return VIO_OK;
+}
+// run the back end on another stream (e.g. the front end's) so that device-to-device hand-over needs no host sync
+extern "C" int vio_backend_use_stream(vio_backend *be, void *cuda_stream) {
+    if (!be || !cuda_stream) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    if (be->own_stream) cudaStreamDestroy(be->stream);
+    be->stream = (cudaStream_t)cuda_stream; be->own_stream = false;
+    return VIO_OK;
+}
+
+// ------------------------------------------------------------------ factor-level primitives for the parity tests
+__global__ void prim_preint_kernel(int n, const double *dt, const double *acc, const double *gyr, const double *init, const double *noise, double *pr) {
+    __shared__ PreScratch scr;
+    if (threadIdx.x == 0) pre_init(pr, ld3(init), ld3(init + 3), ld3(init + 6), ld3(init + 9));
+    __syncwarp();
+    for (int i = 0; i < n; i++) pre_propagate_warp(pr, dt[i], ld3(acc + 3 * i), ld3(gyr + 3 * i), noise, scr);
+}
+
+extern "C" int vio_prim_preintegrate(const vio_config *cfg, int n, const double *dt, const double *acc, const double *gyr, const double acc0[3],
+                                     const double gyr0[3], const double ba[3], const double bg[3], double *pqv, double *jac, double *cov, double *sum_dt) {
+    VIO_CUDA_TRY(cudaSetDevice(cfg->device));
+    double *d;
+    const size_t tot = (size_t)n * 7 + 12 + 6 + PR_STRIDE;
+    VIO_CUDA_TRY(cudaMalloc((void **)&d, tot * sizeof(double)));
+    double *d_dt = d, *d_acc = d + n, *d_gyr = d_acc + 3 * n, *d_init = d_gyr + 3 * n, *d_noise = d_init + 12, *d_pr = d_noise + 6;
+    double init[12], noise[6];
+    memcpy(init, acc0, 24); memcpy(init + 3, gyr0, 24); memcpy(init + 6, ba, 24); memcpy(init + 9, bg, 24);
+    noise[0] = noise[2] = cfg->acc_n * cfg->acc_n; noise[1] = noise[3] = cfg->gyr_n * cfg->gyr_n; noise[4] = cfg->acc_w * cfg->acc_w; noise[5] = cfg->gyr_w * cfg->gyr_w;
+    cudaMemcpy(d_dt, dt, n * 8, cudaMemcpyHostToDevice); cudaMemcpy(d_acc, acc, n * 24, cudaMemcpyHostToDevice); cudaMemcpy(d_gyr, gyr, n * 24, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_init, init, sizeof(init), cudaMemcpyHostToDevice); cudaMemcpy(d_noise, noise, sizeof(noise), cudaMemcpyHostToDevice);
+    cudaMemset(d_pr, 0, PR_STRIDE * 8);
+    prim_preint_kernel<<<1, 32>>>(n, d_dt, d_acc, d_gyr, d_init, d_noise, d_pr);
+    std::vector<double> h(PR_STRIDE);
+    cudaError_t e = cudaMemcpy(h.data(), d_pr, PR_STRIDE * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return VIO_ERR_CUDA;
+    memcpy(pqv, &h[PR_DP], 10 * 8); memcpy(jac, &h[PR_JAC], 225 * 8); memcpy(cov, &h[PR_COV], 225 * 8); *sum_dt = h[PR_SUMDT];
+    return VIO_OK;
+}
+
+__global__ void prim_imu_factor_kernel(double *pr, double g, const double *x, double *res, double *J) {
+    if (threadIdx.x != 0) return;
+    double rr[15], Jr[450];
+    imu_sqrt_info(pr + PR_COV, pr + PR_SQI);
+    imu_residual(pr, g, x, x + 7, x + 16, x + 23, rr, Jr);
+    const double *U = pr + PR_SQI;
+    for (int r = 0; r < 15; r++) {
+        double t = 0;
+        for (int k = r; k < 15; k++) t += U[r * 15 + k] * rr[k];
+        res[r] = t;
+        for (int c = 0; c < 30; c++) { double u = 0; for (int k = r; k < 15; k++) u += U[r * 15 + k] * Jr[k * 30 + c]; J[r * 30 + c] = u; }
+    }
+}
+
+extern "C" int vio_prim_imu_factor(const vio_config *cfg, const double *pqv, const double *jac, const double *cov, double sum_dt, const double lba[3],
+                                   const double lbg[3], const double pi[7], const double sbi[9], const double pj[7], const double sbj[9], double *res,
+                                   double *J) {
+    VIO_CUDA_TRY(cudaSetDevice(cfg->device));
+    std::vector<double> h(PR_STRIDE, 0.0);
+    memcpy(&h[PR_DP], pqv, 80); memcpy(&h[PR_LBA], lba, 24); memcpy(&h[PR_LBG], lbg, 24); h[PR_SUMDT] = sum_dt; h[PR_VALID] = 1;
+    memcpy(&h[PR_JAC], jac, 225 * 8); memcpy(&h[PR_COV], cov, 225 * 8);
+    double x[32];
+    memcpy(x, pi, 56); memcpy(x + 7, sbi, 72); memcpy(x + 16, pj, 56); memcpy(x + 23, sbj, 72);
+    double *d;
+    VIO_CUDA_TRY(cudaMalloc((void **)&d, (PR_STRIDE + 32 + 15 + 450) * 8));
+    cudaMemcpy(d, h.data(), PR_STRIDE * 8, cudaMemcpyHostToDevice); cudaMemcpy(d + PR_STRIDE, x, sizeof(x), cudaMemcpyHostToDevice);
+    prim_imu_factor_kernel<<<1, 32>>>(d, cfg->gravity, d + PR_STRIDE, d + PR_STRIDE + 32, d + PR_STRIDE + 47);
+    cudaMemcpy(res, d + PR_STRIDE + 32, 15 * 8, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(J, d + PR_STRIDE + 47, 450 * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? VIO_OK : VIO_ERR_CUDA;
+}
+
+__global__ void prim_proj_kernel(ProjConst K, const double *in, double *out) {
+    if (threadIdx.x != 0) return;
+    double r2[2], Ji[12], Jj[12], Jl[2], sq;
+    proj_eval(K, ld3(in), ld3(in + 3), in + 6, in + 13, in[20], r2, Ji, Jj, Jl, &sq);
+    // undo the robust correction so that the raw ProjectionFactor::Evaluate output can be compared: r = r2 / sqrt(rho1)
+    const double sr = sqrt(fmax(2.2250738585072014e-308, 1.0 / (1.0 + sq)));
+    out[0] = r2[0] / sr; out[1] = r2[1] / sr;
+    for (int r = 0; r < 2; r++) {
+        for (int c = 0; c < 6; c++) { out[2 + r * 13 + c] = Ji[6 * r + c] / sr; out[2 + r * 13 + 6 + c] = Jj[6 * r + c] / sr; }
+        out[2 + r * 13 + 12] = Jl[r] / sr;
+    }
+    out[28] = 0.5 * log(1.0 + sq);
+}
+
+extern "C" int vio_prim_projection_factor(const vio_config *cfg, const double pts_i[3], const double pts_j[3], const double pose_i[7],
+                                          const double pose_j[7], double inv_dep, double *res, double *J) {
+    VIO_CUDA_TRY(cudaSetDevice(cfg->device));
+    ProjConst K;
+    memcpy(K.ric.m, cfg->ric, 72);
+    K.tic.x = cfg->tic[0]; K.tic.y = cfg->tic[1]; K.tic.z = cfg->tic[2];
+    K.sqrt_info = cfg->fx / 1.5;
+    double in[21], out[29];
+    memcpy(in, pts_i, 24); memcpy(in + 3, pts_j, 24); memcpy(in + 6, pose_i, 56); memcpy(in + 13, pose_j, 56); in[20] = inv_dep;
+    double *d;
+    VIO_CUDA_TRY(cudaMalloc((void **)&d, 50 * 8));
+    cudaMemcpy(d, in, sizeof(in), cudaMemcpyHostToDevice);
+    prim_proj_kernel<<<1, 32>>>(K, d, d + 21);
+    cudaError_t e = cudaMemcpy(out, d + 21, sizeof(out), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return VIO_ERR_CUDA;
+    memcpy(res, out, 16); memcpy(J, out + 2, 26 * 8);
+    return VIO_OK;
+}

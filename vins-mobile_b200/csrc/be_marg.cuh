@@ -1,0 +1,372 @@
+// be_marg.cuh -- K13: window marginalisation, one CTA per stream.
+// Replaces MarginalizationInfo::{addResidualBlockInfo,preMarginalize,marginalize,getParameterBlocks} and the two call sites
+// in VINS::solve_ceres (marginalization_factor.cpp:11-322; VINS.cpp:690-830):
+//   A = sum J^T J, b = sum J^T r over {old prior, IMUFactor(0->1), ProjectionFactors of landmarks that start in frame 0} (MARGIN_OLD)
+//       or over {old prior} (MARGIN_SECOND_NEW);   Amm^+ by symmetric eigendecomposition with eigenvalue threshold eps = 1e-8;
+//   A_r = Arr - Arm Amm^+ Amr, b_r = brr - Arm Amm^+ bmm;   second eigendecomposition, eigenvalues <= eps dropped:
+//   J0 = S^{1/2} V^T, r0 = S^{-1/2} V^T b_r.
+// The new prior is kept in information form over the canonical layout: Hp = J0^T J0 = V S+ V^T, bp = J0^T r0 = V+ V+^T b_r,
+// c0 = |r0|^2 -- everything MarginalizationFactor::Evaluate contributes to the next solve (cost, gradient, J^T J).
+// The reference orders blocks by unordered_map iteration over pointer values (quirk Q10); here the order is canonical.
+#pragma once
+#include "be_solve.cuh"
+
+namespace be {
+
+constexpr int MARG_T = 512;
+constexpr double MARG_EPS = 1e-8;      // MarginalizationInfo::eps, marginalization_factor.hpp:75
+
+// Cyclic two-sided Jacobi eigensolver, parallel (round-robin) ordering, A symmetric n x n (ld), destroyed: on exit its diagonal
+// holds the eigenvalues and V (n x n, ld = n) the eigenvectors as columns.  cs = shared scratch for 2*(n/2+1) doubles.
+__device__ inline void eig_sym_jacobi(double *A, int n, int ld, double *V, double *cs, int *pq, double *sh_red) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int e = tid; e < n * n; e += T) { const int i = e / n, j = e - i * n; V[e] = (i == j) ? 1.0 : 0.0; }
+    __syncthreads();
+    if (n < 2) return;
+    const int ne = (n + 1) & ~1, np = ne / 2;
+    for (int sweep = 0; sweep < 40; sweep++) {
+        double off = 0, dg = 0;
+        for (int e = tid; e < n * n; e += T) { const int i = e / n, j = e - i * n; const double a = A[(size_t)i * ld + j]; if (i == j) dg += a * a; else off += a * a; }
+        off = block_sum_d(off, sh_red);
+        dg = block_sum_d(dg, sh_red);
+        if (off <= 1e-30 * dg || off == 0.0) break;
+        for (int round = 0; round < ne - 1; round++) {
+            for (int k = tid; k < np; k += T) {
+                int p = (k == 0) ? ne - 1 : (round + k) % (ne - 1);
+                int q = (round + ne - 1 - k) % (ne - 1);
+                if (p > q) { const int t = p; p = q; q = t; }
+                double c = 1.0, sn = 0.0;
+                if (q < n) {
+                    const double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
+                    if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * sqrt(fabs(app * aqq))) {
+                        const double zeta = (aqq - app) / (2.0 * apq);
+                        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        c = 1.0 / sqrt(1.0 + t * t); sn = c * t;
+                    }
+                } else { p = -1; }
+                pq[2 * k] = p; pq[2 * k + 1] = q; cs[2 * k] = c; cs[2 * k + 1] = sn;
+            }
+            __syncthreads();
+            // rows:  B = J^T A
+            for (int e = tid; e < np * n; e += T) {
+                const int k = e / n, j = e - k * n;
+                const int p = pq[2 * k], q = pq[2 * k + 1];
+                if (p < 0) continue;
+                const double c = cs[2 * k], sn = cs[2 * k + 1];
+                const double x = A[(size_t)p * ld + j], y = A[(size_t)q * ld + j];
+                A[(size_t)p * ld + j] = c * x - sn * y; A[(size_t)q * ld + j] = sn * x + c * y;
+            }
+            __syncthreads();
+            // columns:  A' = B J ,  V' = V J
+            for (int e = tid; e < np * n; e += T) {
+                const int i = e / np, k = e - i * np;
+                const int p = pq[2 * k], q = pq[2 * k + 1];
+                if (p < 0) continue;
+                const double c = cs[2 * k], sn = cs[2 * k + 1];
+                double x = A[(size_t)i * ld + p], y = A[(size_t)i * ld + q];
+                A[(size_t)i * ld + p] = c * x - sn * y; A[(size_t)i * ld + q] = sn * x + c * y;
+                x = V[(size_t)i * n + p]; y = V[(size_t)i * n + q];
+                V[(size_t)i * n + p] = c * x - sn * y; V[(size_t)i * n + q] = sn * x + c * y;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ProjectionFactor Jacobian wrt para_Ex_Pose (projection_facor.cpp:73-84), corrected by sqrt(rho'): 2x6
+__device__ inline void proj_jac_ex(const ProjConst &K, V3 pts_i, const double *pi, const double *pj, double inv_dep, double *Jex) {
+    const V3 Pi = ld3(pi), Pj = ld3(pj);
+    const M3 Ri = q2R(ldq(pi + 3)), Rj = q2R(ldq(pj + 3));
+    const V3 pc_i = pts_i * (1.0 / inv_dep);
+    const V3 p_imu_i = K.ric * pc_i + K.tic;
+    const V3 pw = Ri * p_imu_i + Pi;
+    const M3 RjT = tr(Rj), ricT = tr(K.ric);
+    const V3 p_imu_j = RjT * (pw - Pj);
+    const V3 pc_j = ricT * (p_imu_j - K.tic);
+    const double dep = pc_j.z;
+    double red[6];
+    red[0] = K.sqrt_info / dep; red[1] = 0; red[2] = -K.sqrt_info * pc_j.x / (dep * dep);
+    red[3] = 0; red[4] = K.sqrt_info / dep; red[5] = -K.sqrt_info * pc_j.y / (dep * dep);
+    const M3 L = ricT * (RjT * Ri - eye3());
+    const M3 tmp_r = ricT * RjT * Ri * K.ric;
+    const M3 Rr = (-1.0 * (tmp_r * skew(pc_i))) + skew(tmp_r * pc_i) + skew(ricT * (RjT * (Ri * K.tic + Pi - Pj) - K.tic));
+    for (int r = 0; r < 2; r++)
+        for (int c = 0; c < 3; c++) {
+            double a = 0, bb = 0;
+            for (int k = 0; k < 3; k++) { a += red[3 * r + k] * L.m[3 * k + c]; bb += red[3 * r + k] * Rr.m[3 * k + c]; }
+            Jex[6 * r + c] = a; Jex[6 * r + 3 + c] = bb;
+        }
+}
+
+struct MargSmem {
+    int c2w[VIO_MAX_WIN * 15 + 15 + 6 + 8];      // canonical dof -> work index (-1 = absent)
+    int kept[VIO_MAX_WIN * 15 + 15 + 6 + 8];     // kept work position -> canonical dof
+    int pq[2 * 256];
+    double cs[2 * 256];
+    double red[32];
+    int scan[33];
+    int n_eff, m, L0, mc;
+};
+
+__global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    MargSmem &sm = *reinterpret_cast<MargSmem *>(smraw);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int *iv = S_iv(s, b);
+    const int act = iv[IV_ACTION];
+    if (act != ACT_INIT_SOLVE && act != ACT_NL_SOLVE) return;
+    const int W = s.W, NF = s.NF, NP = s.NP, NPX = s.NPX;
+    const int marg = iv[IV_MARG_FLAG];
+    int *pres = s.present + (size_t)b * (2 * NF + 1);
+    const int prior_valid = iv[IV_PRIOR_VALID];
+    if (marg == 1 && !(prior_valid && pres[2 * (W - 1)])) return;         // VINS.cpp:779-780: nothing to do
+    double *dvs = S_dv(s, b);
+    double *par = s.par + (size_t)b * (NF * 16 + s.LCAP);
+    const size_t fo = (size_t)b * s.FCAP;
+    const int nl = iv[IV_N_LM], nfac = iv[IV_N_FAC];
+    // old2new() after new2old(): repack the (re-anchored) state; inverse depths come back from the feature table
+    for (int i = tid; i < NF; i += MARG_T) {
+        double *p = par + 16 * i;
+        st3(p, ld3(S_Ps(s, b, i))); stq(p + 3, R2q(ldm(S_Rs(s, b, i))));
+        st3(p + 7, ld3(S_Vs(s, b, i))); st3(p + 10, ld3(S_Bas(s, b, i))); st3(p + 13, ld3(S_Bgs(s, b, i)));
+    }
+    for (int l = tid; l < nl; l += MARG_T) par[16 * NF + l] = 1.0 / s.f_depth[fo + s.lm_slot[(size_t)b * s.LCAP + l]];
+    // ---- which canonical dofs are marginalised / kept --------------------------------------------------------
+    // new "present" set = blocks touched by any factor of this marginalisation
+    __shared__ int touched[2 * (VIO_MAX_WIN + 1) + 1];
+    __shared__ int lm_m[1];                                             // unused placeholder to keep layout explicit
+    for (int i = tid; i < 2 * NF + 1; i += MARG_T) touched[i] = prior_valid ? pres[i] : 0;
+    __syncthreads();
+    int *lm_work = (int *)(s.scratch + (size_t)b * s.scratch_stride);    // [LCAP] work index of landmark l (or -1)
+    double *base = s.scratch + (size_t)b * s.scratch_stride + ((s.LCAP + 7) / 2);
+    if (marg == 0) {
+        if (tid == 0) { touched[0] = touched[1] = touched[2] = touched[3] = 1; }
+        __syncthreads();
+        // landmarks that start in frame 0, in list order
+        int lbase = 0;
+        for (int c0 = 0; c0 < nl; c0 += MARG_T) {
+            const int l = c0 + tid;
+            int is = 0;
+            if (l < nl) is = s.f_start[fo + s.lm_slot[(size_t)b * s.LCAP + l]] == 0;
+            int tot;
+            const int r = lbase + block_excl_scan(is, sm.scan, &tot);
+            __syncthreads();
+            if (l < nl) lm_work[l] = is ? 15 + r : -1;
+            lbase += tot;
+        }
+        if (tid == 0) { sm.L0 = lbase; sm.mc = 15; }
+        for (int f = tid; f < nfac; f += MARG_T) {
+            const int l = s.fac_lm[(size_t)b * s.PCAP + f];
+            if (s.f_start[fo + s.lm_slot[(size_t)b * s.LCAP + l]] == 0) { touched[2 * s.fac_j[(size_t)b * s.PCAP + f]] = 1; touched[2 * NF] = 1; }
+        }
+    } else {
+        if (tid == 0) { sm.L0 = 0; sm.mc = 6; }
+    }
+    __syncthreads();
+    const int L0 = sm.L0, mc = sm.mc, m = mc + L0;
+    if (tid == 0) {
+        // work order: [marginalised canonical dofs | landmarks | kept canonical dofs (present only)]
+        int k = 0;
+        for (int c = 0; c < NPX; c++) {
+            const int blk = c < NP ? 2 * (c / 15) + ((c % 15) >= 6) : 2 * NF;
+            bool is_marg;
+            if (marg == 0) is_marg = c < 15;
+            else is_marg = (c >= 15 * (W - 1) && c < 15 * (W - 1) + 6);
+            if (is_marg) { sm.c2w[c] = (marg == 0) ? c : c - 15 * (W - 1); continue; }
+            if (touched[blk]) { sm.c2w[c] = m + k; sm.kept[k] = c; k++; } else sm.c2w[c] = -1;
+        }
+        sm.n_eff = k; sm.m = m;
+    }
+    __syncthreads();
+    const int n = sm.n_eff, pos = m + n;
+    // scratch carve: A[pos*pos] b[pos] Vm[m*m] T[m*(n+1)] Ar[n*n] br[n] Vr[n*n] dx[NPX] tvec[NPX]
+    double *A = base;
+    double *bv = A + (size_t)pos * pos;
+    double *Vm = bv + pos;
+    double *Tm = Vm + (size_t)m * m;
+    double *Zm = Tm + (size_t)m * (n + 1);
+    double *Ar = Zm + (size_t)m * (n + 1);
+    double *br = Ar + (size_t)n * n;
+    double *Vr = br + n;
+    double *dx = Vr + (size_t)n * n;
+    double *tv = dx + NPX;
+    for (size_t e = tid; e < (size_t)pos * pos + pos; e += MARG_T) A[e] = 0.0;      // A and b are contiguous
+    __syncthreads();
+    // ---- accumulate A, b ---------------------------------------------------------------------------------------
+    if (prior_valid) {                                      // MarginalizationFactor of the previous prior, evaluated at the current point
+        const double *Hp = s.Hp + (size_t)b * NPX * NPX, *bp = s.bp + (size_t)b * NPX;
+        prior_dx(s, b, par, dx);
+        __syncthreads();
+        for (int i = tid; i < NPX; i += MARG_T) {
+            double t = 0;
+            for (int j = 0; j < NPX; j++) t += Hp[(size_t)i * NPX + j] * dx[j];
+            const int wi = sm.c2w[i];
+            if (wi >= 0) bv[wi] += t + bp[i];
+        }
+        for (int e = tid; e < NPX * NPX; e += MARG_T) {
+            const int i = e / NPX, j = e - i * NPX;
+            const int wi = sm.c2w[i], wj = sm.c2w[j];
+            if (wi >= 0 && wj >= 0) A[(size_t)wi * pos + wj] += Hp[e];
+        }
+        __syncthreads();
+    }
+    if (marg == 0) {
+        // IMUFactor(pre_integrations[1]) on {Pose0, SpeedBias0, Pose1, SpeedBias1}: one warp
+        if (tid < 32) {
+            const int lane = tid;
+            const double *pr = S_pre(s, b, 1);
+            double *J = tv + NPX;                           // 930 doubles of scratch after tv
+            double *Jw = J + 450, *rr = J + 900, *rw = J + 915;
+            if (lane == 0) imu_residual(pr, s.gravity, par, par + 7, par + 16, par + 23, rr, J);
+            __syncwarp();
+            const double *U = pr + PR_SQI;
+            if (lane < 15) { double t = 0; for (int k = lane; k < 15; k++) t += U[lane * 15 + k] * rr[k]; rw[lane] = t; }
+            for (int e = lane; e < 450; e += 32) {
+                const int r = e / 30, c = e - r * 30;
+                double t = 0;
+                for (int k = r; k < 15; k++) t += U[r * 15 + k] * J[k * 30 + c];
+                Jw[e] = t;
+            }
+            __syncwarp();
+            for (int e = lane; e < 900; e += 32) {
+                const int r = e / 30, c = e - r * 30;
+                double t = 0;
+                for (int k = 0; k < 15; k++) t += Jw[k * 30 + r] * Jw[k * 30 + c];
+                atomic_add(&A[(size_t)sm.c2w[r] * pos + sm.c2w[c]], t);
+            }
+            for (int c = lane; c < 30; c += 32) {
+                double t = 0;
+                for (int k = 0; k < 15; k++) t += Jw[k * 30 + c] * rw[k];
+                atomic_add(&bv[sm.c2w[c]], t);
+            }
+        }
+        // ProjectionFactors of the landmarks that start in frame 0: blocks {Pose0, Pose_j, Ex_Pose, Feature}
+        ProjConst K; K.ric = ldm(dvs + DV_RIC); K.tic = ld3(dvs + DV_TIC); K.sqrt_info = s.sqrt_info;
+        for (int f = tid; f < nfac; f += MARG_T) {
+            const int l = s.fac_lm[(size_t)b * s.PCAP + f], j = s.fac_j[(size_t)b * s.PCAP + f];
+            const int lw = lm_work[l];
+            if (lw < 0) continue;
+            const int k = s.lm_slot[(size_t)b * s.LCAP + l];
+            const double *o = S_obs(s, b, k);
+            const V3 pi = v3(o[0], o[1], 1.0), pj = v3(o[2 * j], o[2 * j + 1], 1.0);
+            double r2[2], J[2][19], Ji[12], Jj[12], Jl[2], Jex[12], sq;
+            proj_eval(K, pi, pj, par, par + 16 * j, par[16 * NF + l], r2, Ji, Jj, Jl, &sq);
+            proj_jac_ex(K, pi, par, par + 16 * j, par[16 * NF + l], Jex);
+            const double sr = sqrt(fmax(2.2250738585072014e-308, 1.0 / (1.0 + sq)));
+            int idx[19];
+            for (int a = 0; a < 6; a++) { idx[a] = sm.c2w[a]; idx[6 + a] = sm.c2w[15 * j + a]; idx[12 + a] = sm.c2w[NP + a]; }
+            idx[18] = lw;
+            for (int r = 0; r < 2; r++) {
+                for (int a = 0; a < 6; a++) { J[r][a] = Ji[6 * r + a]; J[r][6 + a] = Jj[6 * r + a]; J[r][12 + a] = sr * Jex[6 * r + a]; }
+                J[r][18] = Jl[r];
+            }
+            for (int a = 0; a < 19; a++) {
+                for (int c = 0; c < 19; c++) atomic_add(&A[(size_t)idx[a] * pos + idx[c]], J[0][a] * J[0][c] + J[1][a] * J[1][c]);
+                atomic_add(&bv[idx[a]], J[0][a] * r2[0] + J[1][a] * r2[1]);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- Amm^+ via eigendecomposition (0.5*(Amm + Amm^T) first, marginalization_factor.cpp:268) -----------------
+    for (int e = tid; e < m * m; e += MARG_T) { const int i = e / m, j = e - i * m; if (j < i) { const double v = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]); A[(size_t)i * pos + j] = v; A[(size_t)j * pos + i] = v; } }
+    __syncthreads();
+    // Tm = [Amr | bmm] must be saved before A's mm block is destroyed?  (only the mm block is rotated: rows/cols < m with ld = pos)
+    eig_sym_jacobi(A, m, pos, Vm, sm.cs, sm.pq, sm.red);
+    __syncthreads();
+    // Tm = Lambda^+ Vm^T [Amr | bmm]      (m x (n+1))
+    for (int e = tid; e < m * (n + 1); e += MARG_T) {
+        const int k = e / (n + 1), c = e - k * (n + 1);
+        const double lam = A[(size_t)k * pos + k];
+        double t = 0;
+        if (lam > MARG_EPS) {
+            for (int i = 0; i < m; i++) t += Vm[(size_t)i * m + k] * (c < n ? A[(size_t)i * pos + m + c] : bv[i]);
+            t /= lam;
+        }
+        Tm[e] = t;
+    }
+    __syncthreads();
+    // Z = Vm Tm = Amm^+ [Amr | bmm]   (m x (n+1)) ;  A_r = Arr - Amr^T Z ,  b_r = brr - Amr^T z_b
+    for (int e = tid; e < m * (n + 1); e += MARG_T) {
+        const int i = e / (n + 1), c = e - i * (n + 1);
+        double t = 0;
+        for (int k = 0; k < m; k++) t += Vm[(size_t)i * m + k] * Tm[(size_t)k * (n + 1) + c];
+        Zm[e] = t;
+    }
+    __syncthreads();
+    for (int e = tid; e < n * (n + 1); e += MARG_T) {
+        const int r = e / (n + 1), c = e - r * (n + 1);
+        double acc = 0;
+        for (int i = 0; i < m; i++) acc += A[(size_t)i * pos + m + r] * Zm[(size_t)i * (n + 1) + c];
+        if (c < n) Ar[(size_t)r * n + c] = A[(size_t)(m + r) * pos + m + c] - acc;
+        else br[r] = bv[m + r] - acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += MARG_T) { const int i = e / n, j = e - i * n; if (j < i) { const double v = 0.5 * (Ar[(size_t)i * n + j] + Ar[(size_t)j * n + i]); Ar[(size_t)i * n + j] = v; Ar[(size_t)j * n + i] = v; } }
+    __syncthreads();
+    eig_sym_jacobi(Ar, n, n, Vr, sm.cs, sm.pq, sm.red);
+    __syncthreads();
+    // tv[k] = v_k . b_r ;  c0 = sum_{lam>eps} tv^2 / lam
+    for (int k = tid; k < n; k += MARG_T) {
+        double t = 0;
+        for (int i = 0; i < n; i++) t += Vr[(size_t)i * n + k] * br[i];
+        tv[k] = t;
+    }
+    __syncthreads();
+    double c0p = 0;
+    for (int k = tid; k < n; k += MARG_T) { const double lam = Ar[(size_t)k * n + k]; if (lam > MARG_EPS) c0p += tv[k] * tv[k] / lam; }
+    const double c0 = block_sum_d(c0p, sm.red);
+    // ---- write the new prior in canonical layout, shifted like addr_shift (VINS.cpp:759-774 / 806-829) ---------------
+    double *Hp = s.Hp + (size_t)b * NPX * NPX, *bp = s.bp + (size_t)b * NPX;
+    for (int e = tid; e < NPX * NPX; e += MARG_T) Hp[e] = 0.0;
+    for (int e = tid; e < NPX; e += MARG_T) bp[e] = 0.0;
+    __syncthreads();
+    auto shift = [&](int c) {
+        if (c >= NP) return c;                                            // para_Ex_Pose stays
+        if (marg == 0) return c - 15;                                     // frame i -> i-1
+        return c >= 15 * W ? c - 15 : c;                                  // frame W -> W-1
+    };
+    for (int e = tid; e < n * n; e += MARG_T) {
+        const int i = e / n, j = e - i * n;
+        double t = 0;
+        for (int k = 0; k < n; k++) { const double lam = Ar[(size_t)k * n + k]; if (lam > MARG_EPS) t += Vr[(size_t)i * n + k] * lam * Vr[(size_t)j * n + k]; }
+        Hp[(size_t)shift(sm.kept[i]) * NPX + shift(sm.kept[j])] = t;
+    }
+    for (int i = tid; i < n; i += MARG_T) {
+        double t = 0;
+        for (int k = 0; k < n; k++) { const double lam = Ar[(size_t)k * n + k]; if (lam > MARG_EPS) t += Vr[(size_t)i * n + k] * tv[k]; }
+        bp[shift(sm.kept[i])] = t;
+    }
+    // linearisation point = current values of every kept block (preMarginalize memcpy), re-addressed
+    double *x0 = s.x0 + (size_t)b * (NF * 16 + 7);
+    __syncthreads();
+    if (tid == 0) {
+        int np[2 * (VIO_MAX_WIN + 1) + 1];
+        for (int i = 0; i < 2 * NF + 1; i++) np[i] = 0;
+        for (int blk = 0; blk < 2 * NF; blk++) {
+            if (!touched[blk]) continue;
+            const int fr = blk / 2;
+            int nf2;
+            if (marg == 0) { if (fr == 0) continue; nf2 = fr - 1; }
+            else { if (blk == 2 * (W - 1)) continue; nf2 = (fr == W) ? W - 1 : fr; }
+            np[2 * nf2 + (blk & 1)] = 1;
+        }
+        np[2 * NF] = touched[2 * NF];
+        for (int fr = 0; fr < NF; fr++) {
+            int src;
+            if (marg == 0) src = fr + 1; else src = (fr == W - 1) ? W : fr;
+            if (src > W) continue;
+            if (np[2 * fr]) for (int k = 0; k < 7; k++) x0[16 * fr + k] = par[16 * src + k];
+            if (np[2 * fr + 1]) for (int k = 0; k < 9; k++) x0[16 * fr + 7 + k] = par[16 * src + 7 + k];
+        }
+        for (int i = 0; i < 2 * NF + 1; i++) pres[i] = np[i];
+        iv[IV_PRIOR_VALID] = 1; iv[IV_PRIOR_N] = n;
+        dvs[DV_PRIOR_C0] = c0;
+    }
+}
+
+__host__ inline size_t marg_scratch_doubles(int NPX, int LCAP, int max_cnt) {
+    const size_t m = 15 + (size_t)max_cnt, n = NPX, pos = m + n;
+    return (LCAP + 7) / 2 + pos * pos + pos + m * m + 2 * m * (n + 1) + n * n + n + n * n + 2 * (size_t)NPX + 1024;
+}
+
+}  // namespace be

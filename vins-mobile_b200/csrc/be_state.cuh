@@ -1,0 +1,62 @@
+// be_state.cuh -- device-resident state of the batched estimator (one VINS object per stream, VINS.hpp:51-172).
+// All arrays are [batch][...] with the per-stream extent given by the stride fields; a kernel gets the struct by value and
+// indexes with blockIdx.x = stream.
+#pragma once
+#include "be_factors.cuh"
+
+namespace be {
+
+// per-stream integer scalars (BeState::iv)
+enum { IV_FRAME_COUNT = 0, IV_FIRST_IMU, IV_SOLVER_FLAG, IV_MARG_FLAG, IV_FAILURE, IV_NFEAT, IV_LAST_TRACK, IV_ACTION, IV_INIT_PENDING,
+       IV_PRIOR_VALID, IV_N_LM, IV_N_FAC, IV_ITERS, IV_PRIOR_N, IV_ERR, IV_COUNT = 16 };
+// per-stream double scalars (BeState::dv)
+enum { DV_ACC0 = 0, DV_GYR0 = 3, DV_LAST_P = 6, DV_LAST_P_OLD = 9, DV_BACK_P0 = 12, DV_LAST_R = 15, DV_LAST_R_OLD = 24, DV_BACK_R0 = 33,
+       DV_COST0 = 42, DV_COST1 = 43, DV_PRIOR_C0 = 44, DV_TIC = 45, DV_RIC = 48, DV_COUNT = 64 };
+// IV_ACTION values decided by the feature kernel (VINS::processImage control flow, VINS.cpp:377-478)
+enum { ACT_ACCUMULATE = 0, ACT_INIT_SOLVE = 1, ACT_SLIDE_ONLY = 2, ACT_NL_SOLVE = 3, ACT_NONE = 4 };
+
+struct BeState {
+    int B, W, NF;            // NF = W + 1 frames
+    int NP;                  // 15 * NF   pose+speed-bias local size
+    int NPX;                 // NP + 6    (+ ex_pose)
+    int NPW;                 // 6 * NF    pose-only local size (landmark coupling rows)
+    int FCAP, LCAP, PCAP, MAXIMU, MAXCNT;
+    double gravity, min_parallax, init_depth, sqrt_info;
+    double noise[6];         // acc_n^2, gyr_n^2, acc_n^2, gyr_n^2, acc_w^2, gyr_w^2   (integration_base.h:37-43)
+    int max_iters;
+    // window state
+    double *Ps, *Rs, *Vs, *Bas, *Bgs, *Headers;       // [B][NF][3|9|3|3|3|1]
+    double *pre;                                      // [B][NF][PR_STRIDE]
+    double *imu_buf; int *imu_cnt;                    // [B][NF][MAXIMU][7], [B][NF]
+    int *iv; double *dv;                              // [B][IV_COUNT], [B][DV_COUNT]
+    double *init_state;                               // [B][NF*10 + 6]  P3 Q4 V3 per frame, Ba3 Bg3
+    // feature table (FeatureManager::feature, always sorted by feature id)
+    int *f_id, *f_start, *f_nobs, *f_flag; double *f_depth; double *f_obs;   // [B][FCAP], obs [B][FCAP][NF][2]
+    // prior (MarginalizationInfo in information form, canonical layout [pose_i(6) sb_i(9)]_i ex(6))
+    double *Hp, *bp; double *x0;                      // [B][NPX*NPX], [B][NPX], [B][NF*16+7]
+    int *present;                                     // [B][2*NF+1]
+    // solve workspace
+    double *par, *cand;                               // [B][NF*16 + LCAP]   pose7 sb9 per frame, then inverse depths
+    int *lm_slot, *fac_lm, *fac_j;                    // [B][LCAP], [B][PCAP], [B][PCAP]
+    double *scratch; size_t scratch_stride;           // [B][scratch_stride] doubles
+    double *post_solve;                               // [B][NF][16]
+    double *state_out;                                // [B][NF][16] packed P,Q,V,Ba,Bg after the step
+};
+
+__device__ __forceinline__ double *S_Ps(const BeState &s, int b, int i) { return s.Ps + ((size_t)b * s.NF + i) * 3; }
+__device__ __forceinline__ double *S_Rs(const BeState &s, int b, int i) { return s.Rs + ((size_t)b * s.NF + i) * 9; }
+__device__ __forceinline__ double *S_Vs(const BeState &s, int b, int i) { return s.Vs + ((size_t)b * s.NF + i) * 3; }
+__device__ __forceinline__ double *S_Bas(const BeState &s, int b, int i) { return s.Bas + ((size_t)b * s.NF + i) * 3; }
+__device__ __forceinline__ double *S_Bgs(const BeState &s, int b, int i) { return s.Bgs + ((size_t)b * s.NF + i) * 3; }
+__device__ __forceinline__ double *S_pre(const BeState &s, int b, int i) { return s.pre + ((size_t)b * s.NF + i) * PR_STRIDE; }
+__device__ __forceinline__ double *S_imu(const BeState &s, int b, int i) { return s.imu_buf + ((size_t)b * s.NF + i) * s.MAXIMU * 7; }
+__device__ __forceinline__ int *S_iv(const BeState &s, int b) { return s.iv + (size_t)b * IV_COUNT; }
+__device__ __forceinline__ double *S_dv(const BeState &s, int b) { return s.dv + (size_t)b * DV_COUNT; }
+__device__ __forceinline__ double *S_obs(const BeState &s, int b, int slot) { return s.f_obs + ((size_t)b * s.FCAP + slot) * s.NF * 2; }
+__device__ __forceinline__ double *S_par_pose(const BeState &s, double *par, int i) { return par + 16 * i; }
+__device__ __forceinline__ double *S_par_sb(const BeState &s, double *par, int i) { return par + 16 * i + 7; }
+
+// the predicate repeated throughout the reference: used_num >= 2 && start_frame < WINDOW_SIZE - 2
+__device__ __forceinline__ bool in_solve(const BeState &s, int nobs, int start) { return nobs >= 2 && start < s.W - 2; }
+
+}  // namespace be
