@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- VIO frames/sec (640x480, 150 feats, 10-KF window) on B200 vs the reference CPU path.
+
+A "step" is ONE camera frame for every stream of the batch: FeatureTracker::readImage on all streams and, on every FREQ-th
+frame, 20 IMU samples through VINS::processIMU + one VINS::processImage (triangulate, <=10 dogleg iterations, marginalisation,
+slideWindow).  Workload at N GPUs: 128 independent streams per GPU (BASELINE.json configs[2]; configs[3] is the same shape at
+N=8), weak scaling, streams sharded by rank with no data-path collective; the only collective is an NCCL all-gather of the
+packed window states after each solve when N > 1.
+
+  python bench.py --gpus 1 --steps 30 --warmup 6          # ours
+  python bench.py --impl reference --steps 30 --warmup 6  # reference CPU arm (cv2 KLT/RANSAC/GFTT + reference factors + Ceres)
+
+Timed region: CUDA events on the stream the kernels run on, barrier + synchronize on both sides, max over ranks.  Inputs of
+successive steps are different frames (39 MB per step at B=128) and the working set (pyramids, windows, scratch ~0.6 GB) is
+larger than the 126 MB L2, so no explicit L2 flush is needed (config.l2 says so).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FREQ = 3
+IMU_PER_KF = 20
+ALGO_BYTES_PER_FRAME = 1_247_562          # 640x480, N=150, FREQ=3
+ALGO_BYTES_PYR = 407_962                  # 1.328*HW read L0 + write L1..L3
+ALGO_BYTES_DETECT = 614_400               # 2*HW on a detect frame
+ALGO_BYTES_KLT = 634_800                  # 4232*N
+
+
+def _rank_world():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class Clocks(threading.Thread):
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev, self.stop_flag, self.rows = dev, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------------- data
+def make_data(synth, B, n_frames, stream0, device, cam=None):
+    """(n_frames, B, rows, cols) u8 frames on `device`, IMU (n_kf-1, 20, B, .) and ground-truth init windows."""
+    import torch
+    cam = cam or synth.Camera()
+    surf = synth.Surface(1000, device=device)                        # one texture, per-stream trajectories
+    frames = torch.empty((n_frames, B, cam.rows, cam.cols), dtype=torch.uint8, device=device)
+    n_kf = (n_frames + FREQ - 1) // FREQ
+    dt = np.full((n_kf - 1, IMU_PER_KF, B), 1.0 / 200.0)
+    acc = np.zeros((n_kf - 1, IMU_PER_KF, B, 3))
+    gyr = np.zeros((n_kf - 1, IMU_PER_KF, B, 3))
+    gt = []
+    for b in range(B):
+        s = synth.make_stream(stream0 + b, n_frames, cam=cam, device=device, surface=surf)
+        frames[:, b] = s.images
+        m = (n_kf - 1) * IMU_PER_KF
+        acc[:, :, b] = s.acc[:m].reshape(n_kf - 1, IMU_PER_KF, 3)
+        gyr[:, :, b] = s.gyr[:m].reshape(n_kf - 1, IMU_PER_KF, 3)
+        gt.append((s.P[::FREQ], synth.rot_to_quat_xyzw(s.R[::FREQ]), s.V[::FREQ]))
+    return frames, dt, acc, gyr, gt, cam
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+class Pipeline:
+    """One FeatureTracker + VINS pair per stream, batched, both on one CUDA stream (front end hands image_msg to the back end
+    in device memory)."""
+
+    def __init__(self, api, cfg, stream_handle, gt, host_inputs):
+        self.api, self.cfg, self.W, self.B = api, cfg, cfg.window_size, cfg.batch
+        self.fe = api.FrontEnd(cfg)
+        self.be = api.BackEnd(cfg)
+        self.fe.use_stream(stream_handle)
+        self.be.use_stream(stream_handle)
+        self.msg = self.fe.image_msg_dev()
+        self.gt, self.host = gt, host_inputs
+        self.kf = 0
+        self.frame = 0
+        self.state_host = None
+
+    def step(self, img, imu):
+        """img: device pointer (device-resident run) or pinned host ndarray (e2e run).  imu(kf) -> (dt, acc, gyr) device pointers
+        or host arrays."""
+        pub = self.fe.read_images(img) if self.host else self.fe.read_images_dev(img)
+        if pub:
+            k = self.kf
+            if k > 0:
+                d, a, g = imu(k - 1)
+                if self.host:
+                    self.be.process_imu(d, a, g)
+                else:
+                    self.be.process_imu_dev(IMU_PER_KF, d, a, g)
+            if k == self.W:
+                P = np.stack([g[0][:self.W + 1] for g in self.gt]); Q = np.stack([g[1][:self.W + 1] for g in self.gt])
+                V = np.stack([g[2][:self.W + 1] for g in self.gt])
+                self.be.set_init_window(P, Q, V, np.zeros((self.B, 3)), np.zeros((self.B, 3)))
+            self.be.process_image_dev(self.msg[0], self.msg[1], self.msg[2], np.full(self.B, self.frame / 30.0))
+            if self.host:
+                self.state_host = self.be.state_all()          # device -> host read of the step's result
+            self.kf += 1
+        self.frame += 1
+        return pub
+
+    def close(self):
+        self.fe.close()
+        self.be.close()
+
+
+def run_ours(args):
+    import torch
+    rank, local, world = _rank_world()
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    abi = importlib.import_module("vins-mobile_b200.abi")
+    api = importlib.import_module("vins-mobile_b200.api")
+    synth = importlib.import_module("vins-mobile_b200.synth")
+    B = args.batch
+    cfg = abi.default_config(batch=B, max_cnt=150, window_size=10, device=local)
+    W = cfg.window_size
+    prologue = FREQ * (W + 1)                       # fills the window and runs the first (initialising) solve
+    n_frames = prologue + args.warmup + args.steps + FREQ
+    t0 = time.time()
+    frames, dt, acc, gyr, gt, cam = make_data(synth, B, n_frames, rank * B, dev)
+    t_data = time.time() - t0
+    dt_d, acc_d, gyr_d = (torch.as_tensor(x, device=dev).contiguous() for x in (dt, acc, gyr))
+    stream = torch.cuda.Stream(device=dev)
+    sh = stream.cuda_stream
+
+    def imu_dev(k):
+        return dt_d[k].data_ptr(), acc_d[k].data_ptr(), gyr_d[k].data_ptr()
+
+    def imu_host(k):
+        return dt[k], acc[k], gyr[k]
+
+    gather_buf = None
+    if world > 1:
+        gather_buf = torch.empty((world, B, W + 1, 16), dtype=torch.float64, device=dev)
+        send_buf = torch.empty((B, W + 1, 16), dtype=torch.float64, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_run(host_inputs):
+        pipe = Pipeline(api, cfg, sh, gt, host_inputs)
+        src = frames.cpu().pin_memory().numpy() if host_inputs else None
+        with torch.cuda.stream(stream):
+            def one(i):
+                pub = pipe.step(src[i] if host_inputs else frames[i].data_ptr(), imu_host if host_inputs else imu_dev)
+                if pub and world > 1:
+                    pipe.be.copy_state(send_buf.data_ptr(), True)
+                    dist.all_gather_into_tensor(gather_buf.view(world * B, W + 1, 16), send_buf)
+            for i in range(prologue + args.warmup):
+                one(i)
+            barrier()
+            l0 = pipe.fe.launch_count() + pipe.be.launch_count()
+            clocks = Clocks(local)
+            if rank == 0:
+                clocks.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(prologue + args.warmup, prologue + args.warmup + args.steps):
+                one(i)
+            e1.record(stream)
+            barrier()
+            clocks.stop_flag = True
+            ms = e0.elapsed_time(e1)
+            launches = pipe.fe.launch_count() + pipe.be.launch_count() - l0
+            # per-kernel CUDA-event pass (separate, untimed): 2 more keyframe periods
+            pipe.fe.profile(True); pipe.be.profile(True)
+            base = prologue + args.warmup + args.steps
+            for i in range(base, base + FREQ):
+                one(i)
+            prof = {}
+            prof.update(pipe.fe.profile(False)); prof.update(pipe.be.profile(False))
+            info = [pipe.be.info(b) for b in range(min(B, 4))]
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        pipe.close()
+        return ms, launches, prof, info, clocks.summary() if rank == 0 else None
+
+    ms, launches, prof, info, clk = timed_run(False)
+    ms_e2e, _, _, _, _ = timed_run(True)
+    if rank != 0:
+        return
+    total_frames = args.steps * B * world
+    value = total_frames / (ms * 1e-3)
+    e2e = total_frames / (ms_e2e * 1e-3)
+    n_kf_steps = len([i for i in range(args.steps) if (prologue + args.warmup + i) % FREQ == 0])
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    # roofline of the dominant HBM-bound kernel of the front end (per launch = one batch of B images)
+    kern = {k: {"launches": c, "ms_per_launch": t / c} for k, (c, t) in prof.items() if c}
+    cand = {"pyr_down_kernel": ALGO_BYTES_PYR / 3.0, "eig_candidates_kernel": ALGO_BYTES_DETECT, "lk_kernel": ALGO_BYTES_KLT}
+    dom = max((k for k in cand if k in kern), key=lambda k: kern[k]["ms_per_launch"] * (3 if k == "pyr_down_kernel" else 1), default=None)
+    roof = None
+    if dom:
+        bytes_per_launch = cand[dom] * B
+        ach = bytes_per_launch / (kern[dom]["ms_per_launch"] * 1e-3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
+                "algorithmic_bytes_per_launch": bytes_per_launch}
+    for k in kern:
+        if k in cand:
+            kern[k]["achieved_GBps"] = cand[k] * B / (kern[k]["ms_per_launch"] * 1e-3) / 1e9
+    cpu = cpu_baseline(args, frames[:, :min(B, os.cpu_count() or 1)].cpu().numpy(), dt, acc, gyr, gt, prologue) if world == 1 and not args.no_cpu else None
+    line = {
+        "metric": "VIO frames/sec (640x480, 150 feats, 10-KF window)", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/f32 front end, f64 back end", "data": "synthetic",
+        "config": {"workload": f"batch {B} independent streams per GPU, 640x480@30fps + 200 Hz IMU, 150 feats, 10-KF window, FREQ=3 "
+                               "(BASELINE.json configs[2]; configs[3] at 8 GPUs)", "batch_per_gpu": B, "streams": B * world, "freq": FREQ,
+                   "keyframe_steps_timed": n_kf_steps, "l2": "inputs change every step and the working set exceeds L2; no explicit flush",
+                   "prologue_frames_untimed": prologue, "data_gen_s": round(t_data, 1)},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * cam.rows * cam.cols + B * IMU_PER_KF * 7 * 8 / FREQ),
+                "d2h_bytes_per_step": int(B * (W + 1) * 16 * 8 / FREQ), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
+        "solve_info_stream0": info[0] if info else None,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+class Quiet:
+    """fd-level silencer for the reference's printf chatter (marginalization_factor.cpp prints on every call)."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.null)
+        os.close(self.saved)
+
+
+def _cpu_worker(payload):
+    """One stream through the CPU reference path: cv2 (OpenCV binary) KLT / RANSAC-F / goodFeaturesToTrack driven by the restated
+    readImage, then the reference's factors + vendored Ceres 1.12 driven by the restated estimator loop."""
+    frames, dt, acc, gyr, gt, prologue, n_time, threads = payload
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cv2
+    cv2.setNumThreads(threads)
+    import frontend_oracle as fo
+    import backend_oracle as bo
+    abi = importlib.import_module("vins-mobile_b200.abi")
+    cfg = abi.default_config(batch=1, max_cnt=150)
+    W = cfg.window_size
+    tr = fo.FeatureTrackerOracle(max_cnt=150, backend="cv2")
+    est = bo.RefEstimator(cfg)
+    kf = 0
+    t_start = None
+    with Quiet():
+        for i in range(prologue + n_time):
+            if i == prologue:
+                t_start = time.perf_counter()
+            _, _, pub = tr.read_image(frames[i])
+            if pub:
+                if kf > 0:
+                    for j in range(IMU_PER_KF):
+                        est.process_imu(dt[kf - 1][j], acc[kf - 1][j], gyr[kf - 1][j])
+                if kf == W:
+                    est.set_init_window(gt[0][:W + 1], gt[1][:W + 1], gt[2][:W + 1], np.zeros(3), np.zeros(3))
+                ids = np.array(sorted(tr.image_msg.keys()), np.int32)
+                xyz = np.array([tr.image_msg[k] for k in ids])
+                est.process_image(ids, xyz, i / 30.0)
+                kf += 1
+    return time.perf_counter() - t_start
+
+
+def cpu_baseline(args, frames_cpu, dt, acc, gyr, gt, prologue, n_time=None):
+    """Throughput-fair CPU baseline: one single-threaded stream per host core, aggregate frames/s."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_streams = min(cores, frames_cpu.shape[1])
+    n_time = n_time or min(args.steps + args.warmup, frames_cpu.shape[0] - prologue)
+    n_time -= n_time % FREQ
+    payloads = [(frames_cpu[:, b], dt[:, :, b], acc[:, :, b], gyr[:, :, b], gt[b], prologue, n_time, 1) for b in range(n_streams)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(n_streams) as pool:
+        times = pool.map(_cpu_worker, payloads)
+    v = n_streams * n_time / max(times)
+    return {"value": v, "unit": "frames/s", "cores": n_streams, "kind": "reference",
+            "sample": f"{n_streams} streams x {n_time} frames (same frames/IMU as GPU streams 0..{n_streams - 1}), one process per core, "
+                      "cv2.setNumThreads(1); front end = OpenCV 4.13 binary (the reference's OpenCV fork is not vendored) driven by the "
+                      "restated readImage, back end = reference factor code + vendored Ceres 1.12 (oracle/_ref)",
+            "per_stream_frames_per_s": n_time / (sum(times) / len(times))}
+
+
+def run_reference(args):
+    rank, local, world = _rank_world()
+    if rank != 0:
+        return
+    synth = importlib.import_module("vins-mobile_b200.synth")
+    cores = os.cpu_count() or 1
+    prologue = FREQ * 11
+    n_time = args.steps + args.warmup
+    n_time -= n_time % FREQ
+    n_time = max(n_time, FREQ)
+    n_frames = prologue + n_time + FREQ
+    import torch
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    frames, dt, acc, gyr, gt, cam = make_data(synth, cores, n_frames, 0, dev)
+    cpu = cpu_baseline(args, frames.cpu().numpy(), dt, acc, gyr, gt, prologue, n_time)
+    line = {"impl": "reference", "metric": "VIO frames/sec (640x480, 150 feats, 10-KF window)", "value": cpu["value"], "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cores / cpu["value"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32 front end, f64 back end", "data": "synthetic",
+            "config": {"workload": "independent streams, 640x480@30fps + 200 Hz IMU, 150 feats, 10-KF window, FREQ=3 "
+                                   "(one stream per host core)", "streams": cores, "freq": FREQ},
+            "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -153,7 +153,22 @@ int vio_backend_get_features(vio_backend *be, int s, int cap, int *n_out, int32_
 /* Prior in information form over the canonical local layout [pose0(6) sb0(9) ... poseW sbW ex(6)],
  * n = 15*(W+1)+6:  H[n*n] = J0^T J0, b[n] = J0^T r0, present[2*(W+1)+1] block mask.  For parity tests. */
 int vio_backend_get_prior(vio_backend *be, int s, double *H, double *b, int32_t *present, double *c0);
+/* Packed state of the whole batch [batch][W+1][16] (P3,Q4 xyzw,V3,Ba3,Bg3) copied to caller memory (host: synchronous; device:
+ * stream-ordered, e.g. the send buffer of an NCCL gather). */
+int vio_backend_copy_state(vio_backend *be, double *dst, int dst_is_device);
+/* State right after new2old() of the last solve, before marginalisation / slideWindow: [W+1][16] of stream s (parity tests). */
+int vio_backend_get_post_solve(vio_backend *be, int s, double *out);
 int64_t vio_backend_launch_count(const vio_backend *be);
+int vio_backend_sync(vio_backend *be);
+/* Run the handle's kernels on a caller-owned cudaStream_t (passed as void*), e.g. to chain front end -> back end without a host
+ * synchronisation or to time with the caller's CUDA events. */
+int vio_backend_use_stream(vio_backend *be, void *cuda_stream);
+int vio_frontend_use_stream(vio_frontend *fe, void *cuda_stream);
+int vio_frontend_sync(vio_frontend *fe);
+/* Per-kernel CUDA-event timing: returns "name:launches:total_ms;..." accumulated since the previous call and switches the
+ * timer on/off for subsequent launches. */
+int vio_frontend_profile(vio_frontend *fe, int enable, char *out, int cap);
+int vio_backend_profile(vio_backend *be, int enable, char *out, int cap);
 
 /* Factor-level primitives for parity tests (host in/out, one factor each). */
 int vio_prim_preintegrate(const vio_config *cfg, int n, const double *dt, const double *acc, const double *gyr,

@@ -685,11 +685,20 @@ def r_set_mask(pts, track_cnt, rows, cols, min_dist):
     order = sorted(range(n), key=lambda i: (-int(track_cnt[i]), i))
     mask = np.full((rows, cols), 255, np.uint8)
     keep = []
+    rx = np.rint(pts[:, 0]).astype(np.int64) if n else np.zeros(0, np.int64)
+    ry = np.rint(pts[:, 1]).astype(np.int64) if n else np.zeros(0, np.int64)
+    if cv2 is not None:                     # what the reference itself calls (feature_tracker.cpp:73,80)
+        for i in order:
+            cx, cy = int(rx[i]), int(ry[i])
+            if mask[cy, cx] != 255:
+                continue
+            keep.append(i)
+            cv2.circle(mask, (cx, cy), min_dist, 0, -1)
+        return keep, mask
     yy, xx = np.mgrid[-min_dist:min_dist + 1, -min_dist:min_dist + 1]
     disc = (xx * xx + yy * yy) <= min_dist * min_dist
     for i in order:
-        cx = int(np.rint(pts[i, 0]))
-        cy = int(np.rint(pts[i, 1]))
+        cx, cy = int(rx[i]), int(ry[i])
         if mask[cy, cx] != 255:
             continue
         keep.append(i)
@@ -763,17 +772,17 @@ class FeatureTrackerOracle:
 
     def _parallax_update(self, div):
         """feature_tracker.cpp:209-226 / :237-250 (UI-only outputs good_pts, track_len)."""
-        track_len = []
-        for i in range(len(self.forw_pts)):
-            p = self.forw_pts[i]
-            if p[0] < self.pmin[i, 0] or p[1] < self.pmin[i, 1]:
-                self.pmin[i] = p
-            elif p[0] > self.pmax[i, 0] or p[1] > self.pmax[i, 1]:
-                self.pmax[i] = p
-            d = self.pmax[i].astype(f64) - self.pmin[i].astype(f64)
-            nrm = float(np.sqrt(d[0] * d[0] + d[1] * d[1]))
-            parallax = 0.0 if nrm < 2.0 else nrm
-            track_len.append(min(1.0, 1.0 * parallax / div))
+        p = self.forw_pts
+        if len(p) == 0:
+            return []
+        lo = (p[:, 0] < self.pmin[:, 0]) | (p[:, 1] < self.pmin[:, 1])
+        hi = ~lo & ((p[:, 0] > self.pmax[:, 0]) | (p[:, 1] > self.pmax[:, 1]))
+        self.pmin[lo] = p[lo]
+        self.pmax[hi] = p[hi]
+        d = self.pmax.astype(f64) - self.pmin.astype(f64)
+        nrm = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
+        parallax = np.where(nrm < 2.0, 0.0, nrm)
+        track_len = np.minimum(1.0, 1.0 * parallax / div).tolist()
         return track_len
 
     def read_image(self, img):

@@ -1,0 +1,59 @@
+"""Shared drivers for the back-end parity tests: feed identical IMU samples / image_msg / initial window to the reference
+estimator (oracle/_ref/libvins_ref.so) and to the CUDA back end (C-ABI)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+synth = importlib.import_module("vins-mobile_b200.synth")
+
+
+class Quiet:
+    """Silence the reference's printf chatter (marginalization_factor.cpp prints on every call) at the fd level."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.null)
+        os.close(self.saved)
+
+
+def drive(est, tr, k, W, single=True):
+    """Advance estimator `est` (RefEstimator or api.BackEnd batch 1) by keyframe k of track set `tr`."""
+    per = tr["per"]
+    if k > 0:
+        sl = slice((k - 1) * per, k * per)
+        dts = np.diff(np.concatenate([[tr["t_kf"][k - 1]], tr["imu_t"][sl]]))
+        if hasattr(est, "B"):
+            est.process_imu(dts[:, None], tr["acc"][sl][:, None, :], tr["gyr"][sl][:, None, :])
+        else:
+            for d, a, g in zip(dts, tr["acc"][sl], tr["gyr"][sl]):
+                est.process_imu(d, a, g)
+    if k == W:
+        fr = list(range(W + 1))
+        Q = synth.rot_to_quat_xyzw(tr["R"][fr])
+        if hasattr(est, "B"):
+            est.set_init_window(tr["P"][fr][None], Q[None], tr["V"][fr][None], np.zeros((1, 3)), np.zeros((1, 3)))
+        else:
+            est.set_init_window(tr["P"][fr], Q, tr["V"][fr], np.zeros(3), np.zeros(3))
+    ids, xyz = tr["frames"][k]
+    if hasattr(est, "B"):
+        est.process_image_single(ids, xyz, tr["t_kf"][k])
+    else:
+        est.process_image(ids, xyz, tr["t_kf"][k])
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.abs(a - b).max() / max(1e-12, np.abs(b).max()))
+
+
+def quat_err(qa, qb):
+    """max over frames of min(|qa-qb|, |qa+qb|) (q and -q are the same rotation)."""
+    qa, qb = np.asarray(qa), np.asarray(qb)
+    return float(np.minimum(np.abs(qa - qb).max(-1), np.abs(qa + qb).max(-1)).max())

@@ -50,6 +50,8 @@ def lib():
         L.vio_frontend_launch_count.argtypes = [vp]
         L.vio_frontend_launch_count.restype = C.c_int64
         L.vio_frontend_sync.argtypes = [vp]
+        L.vio_frontend_use_stream.argtypes = [vp, vp]
+        L.vio_frontend_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
         L.vio_prim_pyramid.argtypes = [cfgp, UP, UP, UP, UP]
         L.vio_prim_min_eig_candidates.argtypes = [cfgp, UP, FP, C.c_int, C.c_int, FP, C.POINTER(C.c_int), FP]
         L.vio_prim_lk.argtypes = [cfgp, UP, UP, FP, C.c_int, FP, UP]
@@ -72,11 +74,23 @@ def lib():
             L.vio_backend_launch_count.argtypes = [vp]
             L.vio_backend_launch_count.restype = C.c_int64
             L.vio_backend_sync.argtypes = [vp]
+            L.vio_backend_use_stream.argtypes = [vp, vp]
+            L.vio_backend_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
+            L.vio_backend_copy_state.argtypes = [vp, vp, C.c_int]
             L.vio_prim_preintegrate.argtypes = [cfgp, C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
             L.vio_prim_imu_factor.argtypes = [cfgp, DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP]
             L.vio_prim_projection_factor.argtypes = [cfgp, DP, DP, DP, DP, C.c_double, DP, DP]
         _lib = L
     return _lib
+
+
+def _parse_profile(txt):
+    out = {}
+    for item in txt.split(";"):
+        if item:
+            name, cnt, ms = item.split(":")
+            out[name] = (int(cnt), float(ms))
+    return out
 
 
 def exported_symbols():
@@ -144,6 +158,14 @@ class FrontEnd:
         keys = ["lk_in", "lk_ok", "f1_ok", "f2_ok", "kept", "new", "n_cand", "ransac_iters"]
         return dict(zip(keys, st.tolist()))
 
+    def use_stream(self, cuda_stream: int):
+        _check(lib().vio_frontend_use_stream(self.h, cuda_stream), "vio_frontend_use_stream")
+
+    def profile(self, enable: bool) -> dict:
+        buf = C.create_string_buffer(4096)
+        _check(lib().vio_frontend_profile(self.h, int(enable), buf, 4096), "vio_frontend_profile")
+        return _parse_profile(buf.value.decode())
+
     def image_msg_dev(self):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(lib().vio_frontend_image_msg_dev(self.h, C.byref(a), C.byref(b), C.byref(c)), "vio_frontend_image_msg_dev")
@@ -196,3 +218,155 @@ def prim_ransac_f(cfg, p1, p2):
         return None, it.value
     _check(rc, "vio_prim_ransac_f")
     return m, it.value
+
+
+class BackEnd:
+    """Batched VINS estimator (VINS.hpp:51-172): `batch` sliding windows advancing in lock-step."""
+
+    def __init__(self, cfg: VioConfig):
+        self.cfg = cfg
+        self.B, self.W, self.maxp = cfg.batch, cfg.window_size, cfg.max_cnt
+        self.h = C.c_void_p()
+        _check(lib().vio_backend_create(C.byref(cfg), C.byref(self.h)), "vio_backend_create")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().vio_backend_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self):
+        _check(lib().vio_backend_clear(self.h), "vio_backend_clear")
+
+    def process_imu(self, dt, acc, gyr):
+        """processIMU for n consecutive samples: dt (n,B), acc (n,B,3), gyr (n,B,3) HOST arrays."""
+        dt = np.ascontiguousarray(dt, np.float64).reshape(-1, self.B)
+        n = dt.shape[0]
+        acc = np.ascontiguousarray(acc, np.float64).reshape(n, self.B, 3)
+        gyr = np.ascontiguousarray(gyr, np.float64).reshape(n, self.B, 3)
+        _check(lib().vio_backend_process_imu(self.h, n, ptr(dt, C.c_double), ptr(acc, C.c_double), ptr(gyr, C.c_double)), "vio_backend_process_imu")
+
+    def process_imu_dev(self, n, dt_ptr, acc_ptr, gyr_ptr):
+        _check(lib().vio_backend_process_imu_dev(self.h, n, dt_ptr, acc_ptr, gyr_ptr), "vio_backend_process_imu_dev")
+
+    def set_init_window(self, P, Q, V, Ba, Bg):
+        n = self.W + 1
+        P = np.ascontiguousarray(P, np.float64).reshape(self.B, n, 3); Q = np.ascontiguousarray(Q, np.float64).reshape(self.B, n, 4)
+        V = np.ascontiguousarray(V, np.float64).reshape(self.B, n, 3)
+        Ba = np.ascontiguousarray(Ba, np.float64).reshape(self.B, 3); Bg = np.ascontiguousarray(Bg, np.float64).reshape(self.B, 3)
+        _check(lib().vio_backend_set_init_window(self.h, *[ptr(x, C.c_double) for x in (P, Q, V, Ba, Bg)]), "vio_backend_set_init_window")
+
+    def process_image(self, counts, ids, xyz, headers):
+        """processImage: counts (B,), ids (B,max_cnt), xyz (B,max_cnt,3), headers (B,) HOST arrays."""
+        counts = np.ascontiguousarray(counts, np.int32).reshape(self.B)
+        ids = np.ascontiguousarray(ids, np.int32).reshape(self.B, self.maxp)
+        xyz = np.ascontiguousarray(xyz, np.float64).reshape(self.B, self.maxp, 3)
+        headers = np.ascontiguousarray(headers, np.float64).reshape(self.B)
+        _check(lib().vio_backend_process_image(self.h, ptr(counts, C.c_int32), ptr(ids, C.c_int32), ptr(xyz, C.c_double), ptr(headers, C.c_double)),
+               "vio_backend_process_image")
+
+    def process_image_dev(self, counts_ptr, ids_ptr, xyz_ptr, headers):
+        headers = np.ascontiguousarray(headers, np.float64).reshape(self.B)
+        _check(lib().vio_backend_process_image_dev(self.h, counts_ptr, ids_ptr, xyz_ptr, ptr(headers, C.c_double)), "vio_backend_process_image_dev")
+
+    def process_image_single(self, ids, xyz, header):
+        """convenience for batch 1: variable-length ids/xyz"""
+        assert self.B == 1
+        n = len(ids)
+        I = np.zeros((1, self.maxp), np.int32); X = np.zeros((1, self.maxp, 3)); X[..., 2] = 1.0
+        I[0, :n] = ids; X[0, :n] = xyz
+        self.process_image([n], I, X, [header])
+
+    def state(self, s=0):
+        n = self.W + 1
+        P, Q, V, Ba, Bg, H = (np.zeros((n, k)) for k in (3, 4, 3, 3, 3, 1))
+        _check(lib().vio_backend_get_state(self.h, s, *[ptr(x, C.c_double) for x in (P, Q, V, Ba, Bg, H)]), "vio_backend_get_state")
+        return dict(P=P, Q=Q, V=V, Ba=Ba, Bg=Bg, headers=H[:, 0])
+
+    def post_solve(self, s=0):
+        out = np.zeros((self.W + 1, 16))
+        _check(lib().vio_backend_get_post_solve(self.h, s, ptr(out, C.c_double)), "vio_backend_get_post_solve")
+        return out
+
+    def state_dev(self):
+        p = C.c_void_p(); n = C.c_int64(0)
+        _check(lib().vio_backend_state_dev(self.h, C.byref(p), C.byref(n)), "vio_backend_state_dev")
+        return p.value, n.value
+
+    def info(self, s=0):
+        i = np.zeros(8, np.int32); d = np.zeros(4)
+        _check(lib().vio_backend_get_info(self.h, s, ptr(i, C.c_int32), ptr(d, C.c_double)), "vio_backend_get_info")
+        return dict(solver_flag=int(i[0]), marg_flag=int(i[1]), frame_count=int(i[2]), failure=int(i[3]), n_feat=int(i[4]), n_proj=int(i[5]),
+                    iters=int(i[6]), last_track_num=int(i[7]), cost0=float(d[0]), cost1=float(d[1]), prior_n=int(d[2]), err=int(d[3]))
+
+    def features(self, s=0, cap=8192):
+        n = C.c_int(0)
+        ids, st, no, fl = (np.zeros(cap, np.int32) for _ in range(4)); dep = np.zeros(cap)
+        _check(lib().vio_backend_get_features(self.h, s, cap, C.byref(n), ptr(ids, C.c_int32), ptr(st, C.c_int32), ptr(no, C.c_int32),
+                                              ptr(dep, C.c_double), ptr(fl, C.c_int32)), "vio_backend_get_features")
+        k = n.value
+        return dict(ids=ids[:k], start=st[:k], n_obs=no[:k], depth=dep[:k], solve_flag=fl[:k])
+
+    def prior(self, s=0):
+        N = 15 * (self.W + 1) + 6
+        H = np.zeros((N, N)); b = np.zeros(N); pres = np.zeros(2 * (self.W + 1) + 1, np.int32); c0 = np.zeros(1)
+        rc = lib().vio_backend_get_prior(self.h, s, ptr(H, C.c_double), ptr(b, C.c_double), ptr(pres, C.c_int32), ptr(c0, C.c_double))
+        if rc == 3:
+            return None
+        _check(rc, "vio_backend_get_prior")
+        return dict(H=H, b=b, present=pres, c0=float(c0[0]))
+
+    def use_stream(self, cuda_stream: int):
+        _check(lib().vio_backend_use_stream(self.h, cuda_stream), "vio_backend_use_stream")
+
+    def profile(self, enable: bool) -> dict:
+        buf = C.create_string_buffer(4096)
+        _check(lib().vio_backend_profile(self.h, int(enable), buf, 4096), "vio_backend_profile")
+        return _parse_profile(buf.value.decode())
+
+    def copy_state(self, dst_ptr: int, is_device: bool):
+        _check(lib().vio_backend_copy_state(self.h, dst_ptr, int(is_device)), "vio_backend_copy_state")
+
+    def state_all(self):
+        out = np.zeros((self.B, self.W + 1, 16))
+        self.copy_state(out.ctypes.data, False)
+        return out
+
+    def launch_count(self):
+        return lib().vio_backend_launch_count(self.h)
+
+    def sync(self):
+        _check(lib().vio_backend_sync(self.h), "vio_backend_sync")
+
+
+def prim_preintegrate(cfg, dt, acc, gyr, acc0, gyr0, ba, bg):
+    d = lambda a: np.ascontiguousarray(a, np.float64)
+    dt, acc, gyr, acc0, gyr0, ba, bg = (d(x) for x in (dt, acc, gyr, acc0, gyr0, ba, bg))
+    pqv = np.zeros(10); jac = np.zeros((15, 15)); cov = np.zeros((15, 15)); sdt = np.zeros(1)
+    p = lambda a: ptr(a, C.c_double)
+    _check(lib().vio_prim_preintegrate(C.byref(cfg), len(dt), p(dt), p(acc), p(gyr), p(acc0), p(gyr0), p(ba), p(bg), p(pqv), p(jac), p(cov), p(sdt)),
+           "vio_prim_preintegrate")
+    return pqv, jac, cov, float(sdt[0])
+
+
+def prim_imu_factor(cfg, pqv, jac, cov, sum_dt, lba, lbg, pi, sbi, pj, sbj):
+    d = lambda a: np.ascontiguousarray(a, np.float64)
+    a = [d(x) for x in (pqv, jac, cov)]; b = [d(x) for x in (lba, lbg, pi, sbi, pj, sbj)]
+    res = np.zeros(15); J = np.zeros((15, 30))
+    p = lambda x: ptr(x, C.c_double)
+    _check(lib().vio_prim_imu_factor(C.byref(cfg), p(a[0]), p(a[1]), p(a[2]), float(sum_dt), *[p(x) for x in b], p(res), p(J)), "vio_prim_imu_factor")
+    return res, J
+
+
+def prim_projection_factor(cfg, pts_i, pts_j, pi, pj, inv_dep):
+    d = lambda a: np.ascontiguousarray(a, np.float64)
+    a = [d(x) for x in (pts_i, pts_j, pi, pj)]
+    res = np.zeros(2); J = np.zeros((2, 13))
+    p = lambda x: ptr(x, C.c_double)
+    _check(lib().vio_prim_projection_factor(C.byref(cfg), *[p(x) for x in a], float(inv_dep), p(res), p(J)), "vio_prim_projection_factor")
+    return res, J

@@ -17,6 +17,7 @@ struct vio_backend {
     BeState s;
     cudaStream_t stream;
     bool own_stream;
+    KernelTimer timer;
     int64_t launches;
     std::vector<void *> allocs;
     // device staging for the host-pointer entry points
@@ -140,7 +141,7 @@ extern "C" void vio_backend_destroy(vio_backend *be) {
     cudaStreamSynchronize(be->stream);
     for (void *p : be->allocs) cudaFree(p);
     if (be->h_headers_pinned) cudaFreeHost(be->h_headers_pinned);
-    cudaStreamDestroy(be->stream);
+    if (be->own_stream) cudaStreamDestroy(be->stream);
     delete be;
 }
 
@@ -148,7 +149,7 @@ extern "C" int vio_backend_process_imu_dev(vio_backend *be, int n, const double 
     if (!be || n < 0) return VIO_ERR_ARG;
     if (n == 0) return VIO_OK;
     VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
-    imu_kernel<<<(be->s.B + 3) / 4, 128, 0, be->stream>>>(be->s, n, dt, acc, gyr);
+    VIO_LAUNCH(be->timer, be->stream, "imu_kernel", (imu_kernel<<<(be->s.B + 3) / 4, 128, 0, be->stream>>>(be->s, n, dt, acc, gyr)));
     be->launches++;
     VIO_CUDA_TRY(cudaGetLastError());
     return VIO_OK;
@@ -215,14 +216,14 @@ __global__ void clear_init_pending_kernel(BeState s) {
 static int run_process_image(vio_backend *be, const int32_t *counts, const int32_t *ids, const double *xyz, const double *headers_dev) {
     BeState &s = be->s;
     cudaStream_t st = be->stream;
-    addfeat_kernel<<<s.B, 256, 0, st>>>(s, counts, ids, xyz, headers_dev);
-    triangulate_kernel<<<s.B, 128, 0, st>>>(s);
-    prepare_kernel<<<s.B, 256, 0, st>>>(s);
-    solve_kernel<<<s.B, SOLVE_T, 0, st>>>(s);
-    post_solve_kernel<<<s.B, 256, 0, st>>>(s);
-    marg_kernel<<<s.B, MARG_T, sizeof(MargSmem), st>>>(s);
-    finish_kernel<<<s.B, 256, s.FCAP + 64, st>>>(s);
-    clear_init_pending_kernel<<<s.B, 32, 0, st>>>(s);
+    VIO_LAUNCH(be->timer, st, "addfeat_kernel", (addfeat_kernel<<<s.B, 256, 0, st>>>(s, counts, ids, xyz, headers_dev)));
+    VIO_LAUNCH(be->timer, st, "triangulate_kernel", (triangulate_kernel<<<s.B, 128, 0, st>>>(s)));
+    VIO_LAUNCH(be->timer, st, "prepare_kernel", (prepare_kernel<<<s.B, 256, 0, st>>>(s)));
+    VIO_LAUNCH(be->timer, st, "solve_kernel", (solve_kernel<<<s.B, SOLVE_T, 0, st>>>(s)));
+    VIO_LAUNCH(be->timer, st, "post_solve_kernel", (post_solve_kernel<<<s.B, 256, 0, st>>>(s)));
+    VIO_LAUNCH(be->timer, st, "marg_kernel", (marg_kernel<<<s.B, MARG_T, sizeof(MargSmem), st>>>(s)));
+    VIO_LAUNCH(be->timer, st, "finish_kernel", (finish_kernel<<<s.B, 256, s.FCAP + 64, st>>>(s)));
+    VIO_LAUNCH(be->timer, st, "clear_init_pending_kernel", (clear_init_pending_kernel<<<s.B, 32, 0, st>>>(s)));
     be->launches += 8;
     VIO_CUDA_TRY(cudaGetLastError());
     return VIO_OK;
@@ -231,9 +232,8 @@ static int run_process_image(vio_backend *be, const int32_t *counts, const int32
 extern "C" int vio_backend_process_image_dev(vio_backend *be, const int32_t *counts, const int32_t *ids, const double *xyz, const double *headers_host) {
     if (!be || !counts || !ids || !xyz || !headers_host) return VIO_ERR_ARG;
     VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
-    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));          // pinned header staging is reused
-    memcpy(be->h_headers_pinned, headers_host, be->s.B * sizeof(double));
-    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_headers, be->h_headers_pinned, be->s.B * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    // pageable source: the runtime stages the bytes before returning, so the caller's buffer may be reused immediately
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_headers, headers_host, be->s.B * sizeof(double), cudaMemcpyHostToDevice, be->stream));
     return run_process_image(be, counts, ids, xyz, be->d_headers);
 }
 
@@ -343,11 +343,28 @@ extern "C" int vio_backend_get_prior(vio_backend *be, int s, double *H, double *
     return valid ? VIO_OK : VIO_ERR_STATE;
 }
 
+// whole-batch packed state [batch][W+1][16] -> caller memory (host or device), stream-ordered; host copies synchronise
+extern "C" int vio_backend_copy_state(vio_backend *be, double *dst, int dst_is_device) {
+    if (!be || !dst) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    const size_t n = (size_t)be->s.B * be->s.NF * 16 * sizeof(double);
+    VIO_CUDA_TRY(cudaMemcpyAsync(dst, be->s.state_out, n, dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, be->stream));
+    if (!dst_is_device) VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    return VIO_OK;
+}
 extern "C" int64_t vio_backend_launch_count(const vio_backend *be) { return be ? be->launches : 0; }
 extern "C" int vio_backend_sync(vio_backend *be) {
     if (!be) return VIO_ERR_ARG;
     VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
     VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    return VIO_OK;
+}
+extern "C" int vio_backend_profile(vio_backend *be, int enable, char *out, int cap) {
+    if (!be) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    const std::string r = be->timer.drain();
+    if (out && cap > 0) { strncpy(out, r.c_str(), cap - 1); out[cap - 1] = 0; }
+    be->timer.on = enable != 0;
     return VIO_OK;
 }
 // run the back end on another stream (e.g. the front end's) so that device-to-device hand-over needs no host sync

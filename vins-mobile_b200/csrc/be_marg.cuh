@@ -134,7 +134,6 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     // ---- which canonical dofs are marginalised / kept --------------------------------------------------------
     // new "present" set = blocks touched by any factor of this marginalisation
     __shared__ int touched[2 * (VIO_MAX_WIN + 1) + 1];
-    __shared__ int lm_m[1];                                             // unused placeholder to keep layout explicit
     for (int i = tid; i < 2 * NF + 1; i += MARG_T) touched[i] = prior_valid ? pres[i] : 0;
     __syncthreads();
     int *lm_work = (int *)(s.scratch + (size_t)b * s.scratch_stride);    // [LCAP] work index of landmark l (or -1)

@@ -47,3 +47,37 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// ---- optional per-kernel timing with CUDA events on the launching stream (bench.py roofline leg) -----------------
+#include <vector>
+#include <string>
+#include <map>
+struct KernelTimer {
+    bool on = false;
+    struct Rec { const char *name; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    void begin(const char *name, cudaStream_t st) {
+        if (!on) return;
+        Rec r; r.name = name;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, st);
+        recs.push_back(r);
+    }
+    void end(cudaStream_t st) { if (on && !recs.empty()) cudaEventRecord(recs.back().b, st); }
+    // drains: returns "name:count:total_ms;..." ; caller must have synchronised the stream
+    std::string drain() {
+        std::map<std::string, std::pair<int, double>> acc;
+        for (auto &r : recs) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            auto &e = acc[r.name]; e.first++; e.second += ms;
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        }
+        recs.clear();
+        std::string out;
+        char buf[160];
+        for (auto &kv : acc) { snprintf(buf, sizeof(buf), "%s:%d:%.6f;", kv.first.c_str(), kv.second.first, kv.second.second); out += buf; }
+        return out;
+    }
+};
+#define VIO_LAUNCH(timer, stream, name, ...) do { (timer).begin(name, stream); __VA_ARGS__; (timer).end(stream); } while (0)

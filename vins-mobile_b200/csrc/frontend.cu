@@ -20,6 +20,8 @@ struct vio_frontend {
     TrackArrays A;
     int img_cnt;
     cudaStream_t stream;
+    bool own_stream;
+    KernelTimer timer;
     int64_t launches;
     int *err_flag_dev;
     std::vector<void *> allocs;
@@ -58,7 +60,7 @@ extern "C" int vio_frontend_create(const vio_config *cfg, vio_frontend **out) {
     vio_frontend *fe = new (std::nothrow) vio_frontend();
     if (!fe) return VIO_ERR_ARG;
     fe->cfg = *cfg; fe->B = cfg->batch; fe->maxp = cfg->max_cnt;
-    fe->cur = 0; fe->has_cur = false; fe->img_cnt = 0; fe->launches = 0;
+    fe->cur = 0; fe->has_cur = false; fe->img_cnt = 0; fe->launches = 0; fe->own_stream = true;
     VIO_CUDA_TRY(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking));
     int r = cfg->rows, c = cfg->cols;
     for (int l = 0; l < 4; l++) {
@@ -106,7 +108,7 @@ extern "C" void vio_frontend_destroy(vio_frontend *fe) {
     cudaSetDevice(fe->cfg.device);
     cudaStreamSynchronize(fe->stream);
     for (void *p : fe->allocs) cudaFree(p);
-    cudaStreamDestroy(fe->stream);
+    if (fe->own_stream) cudaStreamDestroy(fe->stream);
     delete fe;
 }
 
@@ -122,26 +124,26 @@ static int run_frame(vio_frontend *fe, int *published) {
     cudaStream_t s = fe->stream;
     for (int l = 0; l < 3; l++) {                                           // K1
         dim3 blk(32, 8), grd((fe->lc[l + 1] + 127) / 128, (fe->lr[l + 1] + 7) / 8, B);
-        pyr_down_kernel<<<grd, blk, 0, s>>>(fe->pyr[forw][l], fe->pyr[forw][l + 1], fe->lr[l], fe->lc[l], fe->lr[l + 1], fe->lc[l + 1],
-                                            fe->lsz[l], fe->lsz[l + 1]);
+        VIO_LAUNCH(fe->timer, s, "pyr_down_kernel", (pyr_down_kernel<<<grd, blk, 0, s>>>(fe->pyr[forw][l], fe->pyr[forw][l + 1], fe->lr[l], fe->lc[l],
+                   fe->lr[l + 1], fe->lc[l + 1], fe->lsz[l], fe->lsz[l + 1])));
         fe->launches++;
     }
     const int detect = fe->img_cnt == 0;
     if (fe->has_cur) {                                                      // K4
         dim3 grd((fe->maxp + LK_WARPS - 1) / LK_WARPS, B);
-        lk_kernel<<<grd, LK_WARPS * 32, 0, s>>>(levels_of(fe, fe->cur), levels_of(fe, forw), fe->A.cur_pts, fe->A.forw_pts, fe->A.status,
-                                                fe->A.n, fe->maxp);
+        VIO_LAUNCH(fe->timer, s, "lk_kernel", (lk_kernel<<<grd, LK_WARPS * 32, 0, s>>>(levels_of(fe, fe->cur), levels_of(fe, forw), fe->A.cur_pts,
+                   fe->A.forw_pts, fe->A.status, fe->A.n, fe->maxp)));
         fe->launches++;
     }
-    post_track_kernel<<<B, 256, sizeof(TrackSmem), s>>>(fe->A, fe->maxp, fe->cfg.rows, fe->cfg.cols, fe->cfg.min_dist, fe->cfg.f_threshold,
-                                                       detect, fe->has_cur ? 1 : 0);
+    VIO_LAUNCH(fe->timer, s, "post_track_kernel", (post_track_kernel<<<B, 256, sizeof(TrackSmem), s>>>(fe->A, fe->maxp, fe->cfg.rows, fe->cfg.cols,
+               fe->cfg.min_dist, fe->cfg.f_threshold, detect, fe->has_cur ? 1 : 0)));
     fe->launches++;
     if (detect) {
         dim3 grd((fe->cfg.cols + ET - 1) / ET, (fe->cfg.rows + ET - 1) / ET, B);
-        eig_candidates_kernel<<<grd, 256, 0, s>>>(fe->pyr[forw][0], fe->lsz[0], fe->cfg.rows, fe->cfg.cols, fe->A.kept, fe->A.n_kept, fe->maxp,
-                                                  fe->cfg.min_dist, fe->A.max_bits, fe->A.cand, fe->A.cand_cnt);
-        select_kernel<<<B, 256, sizeof(SelectSmem), s>>>(fe->A, fe->maxp, fe->cfg.rows, fe->cfg.cols, fe->cfg.max_cnt, fe->cfg.min_dist,
-                                                         fe->cfg.fx, fe->cfg.fy, fe->cfg.cx, fe->cfg.cy);
+        VIO_LAUNCH(fe->timer, s, "eig_candidates_kernel", (eig_candidates_kernel<<<grd, 256, 0, s>>>(fe->pyr[forw][0], fe->lsz[0], fe->cfg.rows,
+                   fe->cfg.cols, fe->A.kept, fe->A.n_kept, fe->maxp, fe->cfg.min_dist, fe->A.max_bits, fe->A.cand, fe->A.cand_cnt)));
+        VIO_LAUNCH(fe->timer, s, "select_kernel", (select_kernel<<<B, 256, sizeof(SelectSmem), s>>>(fe->A, fe->maxp, fe->cfg.rows, fe->cfg.cols,
+                   fe->cfg.max_cnt, fe->cfg.min_dist, fe->cfg.fx, fe->cfg.fy, fe->cfg.cx, fe->cfg.cy)));
         fe->launches += 2;
     }
     VIO_CUDA_TRY(cudaGetLastError());
@@ -234,6 +236,21 @@ extern "C" int64_t vio_frontend_launch_count(const vio_frontend *fe) { return fe
 
 // cudaStream handle for callers that chain the back end on the same stream (C-ABI keeps it opaque)
 extern "C" void *vio_frontend_stream(vio_frontend *fe) { return fe ? (void *)fe->stream : nullptr; }
+extern "C" int vio_frontend_use_stream(vio_frontend *fe, void *cuda_stream) {
+    if (!fe) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaStreamSynchronize(fe->stream));
+    if (fe->own_stream) cudaStreamDestroy(fe->stream);
+    fe->stream = (cudaStream_t)cuda_stream; fe->own_stream = false;
+    return VIO_OK;
+}
+extern "C" int vio_frontend_profile(vio_frontend *fe, int enable, char *out, int cap) {
+    if (!fe) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaStreamSynchronize(fe->stream));
+    const std::string r = fe->timer.drain();
+    if (out && cap > 0) { strncpy(out, r.c_str(), cap - 1); out[cap - 1] = 0; }
+    fe->timer.on = enable != 0;
+    return VIO_OK;
+}
 extern "C" int vio_frontend_sync(vio_frontend *fe) {
     if (!fe) return VIO_ERR_ARG;
     VIO_CUDA_TRY(cudaSetDevice(fe->cfg.device));

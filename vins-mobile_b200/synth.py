@@ -230,3 +230,64 @@ def make_stream(stream_id: int, n_frames: int, cam: Camera | None = None, fps: f
     else:
         images = torch.zeros((0, cam.rows, cam.cols), dtype=torch.uint8)
     return Stream(images, ft, it, acc, gyr, P, R, V, cam)
+
+
+def make_tracks(stream_id: int, n_kf: int, max_cnt: int = 150, cam: Camera | None = None, kf_dt: float = 0.1,
+                imu_hz: float = 200.0, px_noise: float = 0.1, speed: float = 1.0,
+                gyr_noise: float = 0.002, acc_noise: float = 0.05):
+    """Feature tracks without rendering (for back-end tests): landmarks on the Surface are projected into every keyframe,
+    leave when they exit the image (1-px border, like inBorder) and are replaced by fresh ids, exactly the id discipline of
+    FeatureTracker (monotone ids, kept points first).  Returns dict with per-keyframe (ids int32, xyz float64 (n,3)),
+    the IMU samples between keyframes, and ground truth P/R/V at the keyframes."""
+    cam = cam or Camera()
+    traj = Trajectory(stream_id, speed)
+    surf_z0, surf_k = -3.2, 0.10
+    rng = np.random.default_rng(4000 + stream_id)
+    ric = np.array(cam.ric).reshape(3, 3)
+    tic = np.array(cam.tic)
+    t_kf = np.arange(n_kf) * kf_dt
+    P = traj.pos(t_kf); V = traj.pos(t_kf, 1); R = traj.R(t_kf)
+    per = int(round(kf_dt * imu_hz))
+    it = (np.arange((n_kf - 1) * per) + 1) / imu_hz
+    Ri = traj.R(it)
+    a_w = traj.pos(it, 2) + np.array([0.0, 0.0, GRAVITY])
+    acc = np.einsum("nji,nj->ni", Ri, a_w) + rng.normal(0, acc_noise, (len(it), 3))
+    gyr = traj.omega_body(it) + rng.normal(0, gyr_noise, (len(it), 3))
+
+    def raycast(c, d):
+        A = surf_k * (d[..., 0] ** 2 + d[..., 1] ** 2)
+        B = 2 * surf_k * (c[0] * d[..., 0] + c[1] * d[..., 1]) - d[..., 2]
+        C = surf_k * (c[0] ** 2 + c[1] ** 2) + surf_z0 - c[2]
+        s = -2 * C / (B + np.sqrt(np.maximum(B * B - 4 * A * C, 0)))
+        return c + s[..., None] * d
+
+    ids_live = np.zeros(0, np.int64)
+    X_live = np.zeros((0, 3))
+    next_id = 0
+    frames = []
+    for k in range(n_kf):
+        R_wc = R[k] @ ric
+        c_w = P[k] + R[k] @ tic
+        if len(X_live):
+            pc = (X_live - c_w) @ R_wc
+            u = cam.fx * pc[:, 0] / pc[:, 2] + cam.cx
+            v = cam.fy * pc[:, 1] / pc[:, 2] + cam.cy
+            ok = (pc[:, 2] > 0.1) & (np.rint(u) >= 1) & (np.rint(u) < cam.cols - 1) & (np.rint(v) >= 1) & (np.rint(v) < cam.rows - 1)
+            ids_live, X_live, u, v = ids_live[ok], X_live[ok], u[ok], v[ok]
+        else:
+            u = v = np.zeros(0)
+        n_new = max_cnt - len(ids_live)
+        if n_new > 0:
+            un = rng.uniform(2, cam.cols - 3, n_new)
+            vn = rng.uniform(2, cam.rows - 3, n_new)
+            d = np.stack([(un - cam.cx) / cam.fx, (vn - cam.cy) / cam.fy, np.ones(n_new)], -1) @ R_wc.T
+            Xn = raycast(c_w, d)
+            ids_live = np.concatenate([ids_live, next_id + np.arange(n_new)])
+            next_id += n_new
+            X_live = np.concatenate([X_live, Xn])
+            u = np.concatenate([u, un]); v = np.concatenate([v, vn])
+        un_ = u + rng.normal(0, px_noise, len(u))
+        vn_ = v + rng.normal(0, px_noise, len(v))
+        xyz = np.stack([(un_ - cam.cx) / cam.fx, (vn_ - cam.cy) / cam.fy, np.ones(len(u))], -1)
+        frames.append((ids_live.astype(np.int32).copy(), xyz))
+    return dict(frames=frames, t_kf=t_kf, imu_t=it, acc=acc, gyr=gyr, per=per, P=P, R=R, V=V, cam=cam)
