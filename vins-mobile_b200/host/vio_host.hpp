@@ -1,0 +1,165 @@
+// vio_host.hpp -- host-side C++ mirror of the reference call surface over the C-ABI (include/vio_b200.h).
+//
+// The reference owns the hot path through two global objects, `FeatureTracker featuretracker; VINS vins;`
+// (/root/reference/VINS_ios/ViewController.mm:107,109).  These two classes keep the member names, argument order and the public
+// fields a caller reads (feature_tracker.hpp:52-90, VINS.hpp:51-172) so that the estimator loop of ViewController.mm:364-494 and
+// :701-882 compiles against them with the OpenCV / Eigen types swapped for the plain structs below.  One object = one stream
+// (batch 1); batched use goes through the C-ABI directly.  Everything numerical happens in libvio_b200.so on the GPU.
+#pragma once
+#include <array>
+#include <cmath>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/vio_b200.h"
+
+namespace vio {
+
+struct Point2f { float x, y; };
+struct Vector3d { double x, y, z; double &operator()(int i) { return (&x)[i]; } };
+struct Matrix3d { double m[9]; };                          // row-major
+struct Mat { const uint8_t *data; int rows, cols; bool empty() const { return data == nullptr; } };   // CV_8UC1, stride == cols
+
+inline void check(int rc, const char *what) {
+    if (rc != VIO_OK) throw std::runtime_error(std::string(what) + " failed with code " + std::to_string(rc));
+}
+
+// feature_tracker.hpp:52-90
+class FeatureTracker {
+  public:
+    explicit FeatureTracker(const vio_config &cfg) : cfg_(cfg), img_cnt(0), update_finished(false), use_pnp(false) {
+        cfg_.batch = 1;
+        check(vio_frontend_create(&cfg_, &h_), "vio_frontend_create");
+        ids.reserve(cfg_.max_cnt);
+    }
+    ~FeatureTracker() { vio_frontend_destroy(h_); }
+    FeatureTracker(const FeatureTracker &) = delete;
+
+    // void readImage(const cv::Mat &_img, cv::Mat &result, int _frame_cnt, vector<Point2f> &good_pts, vector<double> &track_len,
+    //                double header, Vector3d &P, Matrix3d &R, bool vins_normal)               feature_tracker.hpp:59
+    // P / R are outputs of the motion-only PnP tracker (solveVinsPnP), which is out of scope (use_pnp defaults to false,
+    // ViewController.mm:144): they are left untouched.
+    void readImage(const Mat &_img, Mat &result, int _frame_cnt, std::vector<Point2f> &good_pts, std::vector<double> &track_len, double header,
+                   Vector3d &P, Matrix3d &R, bool vins_normal) {
+        (void)_frame_cnt; (void)header; (void)P; (void)R; (void)vins_normal;
+        if (_img.rows != cfg_.rows || _img.cols != cfg_.cols) throw std::invalid_argument("readImage: image size differs from vio_config");
+        result = _img;
+        int published = 0;
+        check(vio_frontend_read_images(h_, _img.data, &published), "vio_frontend_read_images");
+        const int cap = cfg_.max_cnt;
+        int n = 0;
+        std::vector<float> g(2 * cap);
+        std::vector<double> tl(cap);
+        check(vio_frontend_get_ui(h_, 0, &n, g.data(), tl.data()), "vio_frontend_get_ui");
+        for (int i = 0; i < n; i++) { good_pts.push_back(Point2f{g[2 * i], g[2 * i + 1]}); track_len.push_back(tl[i]); }
+        std::vector<int32_t> id(cap), cnt(cap);
+        std::vector<float> pts(2 * cap);
+        std::vector<double> xyz(3 * cap);
+        check(vio_frontend_get_stream(h_, 0, &n, id.data(), pts.data(), cnt.data(), xyz.data()), "vio_frontend_get_stream");
+        ids.assign(id.begin(), id.begin() + n);
+        track_cnt.assign(cnt.begin(), cnt.begin() + n);
+        cur_pts.resize(n);
+        for (int i = 0; i < n; i++) cur_pts[i] = Point2f{pts[2 * i], pts[2 * i + 1]};
+        if (published) {                                                    // feature_tracker.cpp:287-307
+            image_msg.clear();
+            for (int i = 0; i < n; i++) image_msg[ids[i]] = Vector3d{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        }
+        update_finished = true;
+        img_cnt = (img_cnt + 1) % cfg_.freq;                                // the caller does this at ViewController.mm:494
+    }
+
+    std::vector<Point2f> cur_pts;
+    std::vector<int> ids, track_cnt;
+    int img_cnt;
+    std::map<int, Vector3d> image_msg;
+    bool update_finished;
+    bool use_pnp;
+    vio_frontend *handle() { return h_; }
+
+  private:
+    vio_config cfg_;
+    vio_frontend *h_ = nullptr;
+};
+
+// VINS.hpp:51-172
+class VINS {
+  public:
+    enum SolverFlag { INITIAL, NON_LINEAR };
+    enum MarginalizationFlag { MARGIN_OLD = 0, MARGIN_SECOND_NEW = 1 };
+
+    explicit VINS(const vio_config &cfg) : cfg_(cfg), frame_count(0), solver_flag(INITIAL), marginalization_flag(MARGIN_OLD), failure_occur(false),
+                                           final_cost(0), feature_num(0) {
+        cfg_.batch = 1;
+        const int n = cfg_.window_size + 1;
+        Ps.resize(n); Vs.resize(n); Bas.resize(n); Bgs.resize(n); Qs.resize(n); Headers.resize(n);
+        check(vio_backend_create(&cfg_, &h_), "vio_backend_create");
+    }
+    ~VINS() { vio_backend_destroy(h_); }
+    VINS(const VINS &) = delete;
+
+    void setIMUModel() {}                      // ProjectionFactor::sqrt_info = fx/1.5 is derived from vio_config (VINS.cpp:29-32)
+    void setExtrinsic() {}                     // tic/ric come from vio_config (VINS.cpp:82-88)
+    void clearState() { check(vio_backend_clear(h_), "vio_backend_clear"); refresh(); }
+
+    // void processIMU(double dt, const Vector3d &linear_acceleration, const Vector3d &angular_velocity)        VINS.hpp:164
+    void processIMU(double dt, const Vector3d &acc, const Vector3d &gyr) {
+        check(vio_backend_process_imu(h_, 1, &dt, &acc.x, &gyr.x), "vio_backend_process_imu");
+    }
+
+    // caller-supplied result of solveInitial() (VINS.cpp:833-1102, out of scope): P,Q(xyzw),V for frames 0..WINDOW_SIZE
+    void setInitialWindow(const double *P, const double *Q, const double *V, const double Ba[3], const double Bg[3]) {
+        check(vio_backend_set_init_window(h_, P, Q, V, Ba, Bg), "vio_backend_set_init_window");
+    }
+
+    // void processImage(map<int, Vector3d> &image_msg, double header, int buf_num)                             VINS.hpp:163
+    // buf_num only scaled the wall-time cap of ceres::Solve (VINS.cpp:648-653); the cap is removed (it made the reference
+    // timing-dependent), so buf_num is accepted and ignored.  solve_ceres() runs inside, on the device.
+    void processImage(std::map<int, Vector3d> &image_msg, double header, int buf_num) {
+        (void)buf_num;
+        const int cap = cfg_.max_cnt;
+        std::vector<int32_t> ids(cap, 0);
+        std::vector<double> xyz(3 * cap, 1.0);
+        int32_t n = 0;
+        for (auto &kv : image_msg) {
+            if (n >= cap) throw std::length_error("processImage: more than max_cnt features");
+            ids[n] = kv.first; xyz[3 * n] = kv.second.x; xyz[3 * n + 1] = kv.second.y; xyz[3 * n + 2] = kv.second.z; n++;
+        }
+        check(vio_backend_process_image(h_, &n, ids.data(), xyz.data(), &header), "vio_backend_process_image");
+        refresh();
+    }
+    void solve_ceres(int buf_num) { (void)buf_num; }      // VINS.hpp:153: fused into processImage on the device
+
+    int frame_count;
+    SolverFlag solver_flag;
+    MarginalizationFlag marginalization_flag;
+    std::vector<Vector3d> Ps, Vs, Bas, Bgs;
+    std::vector<std::array<double, 4>> Qs;                 // Rs as quaternions (x,y,z,w)
+    std::vector<double> Headers;
+    bool failure_occur;
+    double final_cost;
+    int feature_num;
+    vio_backend *handle() { return h_; }
+
+  private:
+    void refresh() {
+        const int n = cfg_.window_size + 1;
+        std::vector<double> P(3 * n), Q(4 * n), V(3 * n), Ba(3 * n), Bg(3 * n);
+        check(vio_backend_get_state(h_, 0, P.data(), Q.data(), V.data(), Ba.data(), Bg.data(), Headers.data()), "vio_backend_get_state");
+        for (int i = 0; i < n; i++) {
+            Ps[i] = Vector3d{P[3 * i], P[3 * i + 1], P[3 * i + 2]}; Vs[i] = Vector3d{V[3 * i], V[3 * i + 1], V[3 * i + 2]};
+            Bas[i] = Vector3d{Ba[3 * i], Ba[3 * i + 1], Ba[3 * i + 2]}; Bgs[i] = Vector3d{Bg[3 * i], Bg[3 * i + 1], Bg[3 * i + 2]};
+            Qs[i] = {Q[4 * i], Q[4 * i + 1], Q[4 * i + 2], Q[4 * i + 3]};
+        }
+        int32_t info[8]; double dinfo[4];
+        check(vio_backend_get_info(h_, 0, info, dinfo), "vio_backend_get_info");
+        solver_flag = info[0] ? NON_LINEAR : INITIAL;
+        marginalization_flag = info[1] ? MARGIN_SECOND_NEW : MARGIN_OLD;
+        frame_count = info[2]; failure_occur = info[3] != 0; feature_num = info[4]; final_cost = dinfo[1];
+    }
+    vio_config cfg_;
+    vio_backend *h_ = nullptr;
+};
+
+}  // namespace vio
