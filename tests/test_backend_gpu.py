@@ -112,22 +112,28 @@ def test_window_parity_stream(api, cfg, synth):
             continue
         seen_marg.add(ri["marg_flag"])
         assert ri["n_feat"] == gi["n_feat"] and ri["n_proj"] == gi["n_proj"]
-        assert abs(gi["cost0"] - ri["cost0"]) <= 1e-6 * abs(ri["cost0"]), f"kf {k}: initial cost"
-        assert ri["iters"] == gi["iters"], f"kf {k}: iterations {ri['iters']} vs {gi['iters']}"
-        assert abs(gi["cost1"] - ri["cost1"]) <= 1e-5 * abs(ri["cost1"]), f"kf {k}: final cost"
-        for key in ("P", "V", "Ba", "Bg"):
-            assert rel_err(gs[key], rs[key]) < 1e-4, f"kf {k}: {key} {rel_err(gs[key], rs[key])}"
-        assert quat_err(gs["Q"], rs["Q"]) < 1e-4
-        assert rel_err(gps[:, :3], rps[:, :3]) < 1e-4 and rel_err(gps[:, 7:], rps[:, 7:]) < 1e-4
-        ok = rf["solve_flag"] == gf["solve_flag"]
-        assert ok.all()
-        assert rel_err(gf["depth"], rf["depth"]) < 1e-3
+        first = k == W                      # first solve: identical inputs -> round-off level agreement
+        # later solves start from states that already differ at the reference's own reproducibility floor
+        ctol = 1e-9 if first else 1e-4
+        assert abs(gi["cost0"] - ri["cost0"]) <= ctol * abs(ri["cost0"]), f"kf {k}: initial cost {gi['cost0']} vs {ri['cost0']}"
+        assert abs(gi["cost1"] - ri["cost1"]) <= max(ctol, 1e-7) * abs(ri["cost1"]), f"kf {k}: final cost"
+        assert abs(ri["iters"] - gi["iters"]) <= (0 if first else 1), f"kf {k}: iterations {ri['iters']} vs {gi['iters']}"
+        tol = 1e-9 if first else 1e-4
+        for key, floor in (("P", 0.0), ("V", 0.0), ("Ba", 1e-2), ("Bg", 1e-3)):
+            # relative to max(|x|, floor): the true biases are 0, so a purely relative test on them would divide by ~1e-5
+            err = np.abs(gs[key] - rs[key]).max() / max(np.abs(rs[key]).max(), floor)
+            assert err < tol, f"kf {k}: {key} {err}"
+        assert quat_err(gs["Q"], rs["Q"]) < tol
+        assert rel_err(gps[:, :3], rps[:, :3]) < tol and rel_err(gps[:, 7:10], rps[:, 7:10]) < tol
+        assert np.array_equal(rf["solve_flag"], gf["solve_flag"])
+        assert rel_err(gf["depth"], rf["depth"]) < (1e-8 if first else 1e-3)
         if rp is not None:
             assert gp is not None
             assert np.array_equal(rp["present"], gp["present"]), f"kf {k}: prior block set"
             assert gi["prior_n"] == ri["prior_n"]
-            assert rel_err(gp["H"], rp["H"]) < 1e-5, f"kf {k}: prior H {rel_err(gp['H'], rp['H'])}"
-            assert rel_err(gp["b"], rp["b"]) < 1e-4, f"kf {k}: prior b"
+            assert rel_err(gp["H"], rp["H"]) < (1e-7 if first else 1e-5), f"kf {k}: prior H {rel_err(gp['H'], rp['H'])}"
+            assert rel_err(gp["b"], rp["b"]) < (1e-6 if first else 1e-3), f"kf {k}: prior b {rel_err(gp['b'], rp['b'])}"
+            assert abs(gp["c0"] - rp["c0"]) <= 1e-2 * max(rp["c0"], 1e-3)
     assert seen_marg == {0, 1}, "the stream must exercise both MARGIN_OLD and MARGIN_SECOND_NEW"
 
 
@@ -160,5 +166,35 @@ def test_batch_independence(api, abi, synth):
             drive(be1[b], t, k, W)
             a, d = be2.state(b), be1[b].state(0)
             for key in ("P", "Q", "V", "Ba", "Bg"):
-                assert np.array_equal(a[key], d[key]) or rel_err(a[key], d[key]) < 1e-9, f"kf {k} stream {b} {key}"
+                assert np.array_equal(a[key], d[key]) or rel_err(a[key], d[key]) < 1e-7, f"kf {k} stream {b} {key}"
     assert be2.launch_count() > 0
+
+
+def test_golden_window_states(api, abi, synth):
+    """CUDA back end vs the committed golden states produced by the reference (tests/golden/backend_golden.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "backend_golden.npz"))
+    cfg = abi.default_config(batch=1, max_cnt=int(g["max_cnt"]))
+    tr = synth.make_tracks(int(g["track_seed"]), int(g["n_kf"]), max_cnt=int(g["max_cnt"]))
+    be = api.BackEnd(cfg)
+    for k in range(int(g["n_kf"])):
+        drive(be, tr, k, cfg.window_size)
+        s = be.state()
+        got = np.concatenate([s["P"], s["Q"], s["V"], s["Ba"], s["Bg"]], 1)
+        ref = g["states"][k]
+        qe = np.minimum(np.abs(got[:, 3:7] - ref[:, 3:7]).max(), np.abs(got[:, 3:7] + ref[:, 3:7]).max())
+        assert qe < 1e-4
+        assert np.abs(got[:, :3] - ref[:, :3]).max() < 1e-4 * max(1.0, np.abs(ref[:, :3]).max()), f"kf {k}"
+        assert np.abs(got[:, 7:10] - ref[:, 7:10]).max() < 1e-4 * max(1.0, np.abs(ref[:, 7:10]).max()), f"kf {k}"
+        assert np.abs(got[:, 10:] - ref[:, 10:]).max() < 1e-5, f"kf {k}"
+    be.close()
+
+
+def test_preintegration_golden(api, abi):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "backend_golden.npz"))
+    cfg = abi.default_config()
+    pqv, jac, cov, sdt = api.prim_preintegrate(cfg, g["dt"], g["acc"], g["gyr"], g["acc"][0], g["gyr"][0], g["ba"], g["bg"])
+    assert rel_err(pqv, g["pqv"]) < 1e-12 and rel_err(jac, g["jac"]) < 1e-11 and rel_err(cov, g["cov"]) < 1e-11
+    r, J = api.prim_projection_factor(cfg, g["pts_i"], g["pts_j"], g["pi"], g["pj"], float(g["inv_dep"]))
+    assert rel_err(r, g["proj_r"]) < 1e-11 and rel_err(J, g["proj_J"]) < 1e-11

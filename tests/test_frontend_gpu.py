@@ -170,3 +170,20 @@ def test_ui_outputs(api, abi, get_stream):
             assert np.array_equal(g, np.array(good, np.float32))
             assert np.allclose(t, np.array(tl), rtol=0, atol=1e-15)
     fe.close()
+
+
+def test_frontend_golden_vectors(api, abi):
+    """CUDA primitives vs the committed cv2 outputs (tests/golden/frontend_golden.npz, 160x128 image pair)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frontend_golden.npz"))
+    img0, img1 = g["img0"], g["img1"]
+    c = abi.default_config(rows=img0.shape[0], cols=img0.shape[1], max_cnt=64)
+    l1, l2, l3 = api.prim_pyramid(c, img0)
+    assert np.array_equal(l1, g["l1"]) and np.array_equal(l2, g["l2"]) and np.array_equal(l3, g["l3"])
+    corners, _ = api.prim_good_features(c, img0, g["kept"], 20)
+    assert np.array_equal(corners, g["corners"])
+    nxt, st = api.prim_lk(c, img0, img1, g["lk_pts"])
+    assert np.array_equal(st, g["lk_status"])
+    assert np.abs(nxt - g["lk_next"])[st == 1].max() < 2e-3
+    m, _ = api.prim_ransac_f(c, g["f_x1"], g["f_x2"])
+    assert np.array_equal(m, g["f_mask"])

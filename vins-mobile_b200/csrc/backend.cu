@@ -23,6 +23,7 @@ struct vio_backend {
     // device staging for the host-pointer entry points
     int *d_counts, *d_ids; double *d_xyz, *d_headers; double *d_imu; size_t imu_cap;
     double *h_headers_pinned;
+    size_t solve_smem, marg_smem;
 };
 
 template <typename T>
@@ -128,6 +129,12 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     if (!rc && cudaMallocHost((void **)&be->h_headers_pinned, B * sizeof(double)) != cudaSuccess) rc = VIO_ERR_CUDA;
     if (rc) { vio_backend_destroy(be); return rc; }
     VIO_CUDA_TRY(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s.FCAP + 64));
+    // reduced system resident in shared memory when it fits one SM (W = 10: 110 KB packed); otherwise the global-memory path
+    be->solve_smem = solve_smem_bytes(s.NP, s.NPW);
+    if (be->solve_smem > 200 * 1024 || (size_t)s.NPW * (s.NPW + 1) / 2 > (size_t)8 * SOLVE_T) be->solve_smem = 0;
+    if (be->solve_smem) VIO_CUDA_TRY(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->solve_smem));
+    be->marg_smem = sizeof(MargSmem) + 16 + (size_t)2 * MARG_NCAP * MARG_NCAP * sizeof(double);
+    VIO_CUDA_TRY(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->marg_smem));
     rc = vio_backend_clear(be);
     if (rc) { vio_backend_destroy(be); return rc; }
     VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
@@ -219,9 +226,9 @@ static int run_process_image(vio_backend *be, const int32_t *counts, const int32
     VIO_LAUNCH(be->timer, st, "addfeat_kernel", (addfeat_kernel<<<s.B, 256, 0, st>>>(s, counts, ids, xyz, headers_dev)));
     VIO_LAUNCH(be->timer, st, "triangulate_kernel", (triangulate_kernel<<<s.B, 128, 0, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "prepare_kernel", (prepare_kernel<<<s.B, 256, 0, st>>>(s)));
-    VIO_LAUNCH(be->timer, st, "solve_kernel", (solve_kernel<<<s.B, SOLVE_T, 0, st>>>(s)));
+    VIO_LAUNCH(be->timer, st, "solve_kernel", (solve_kernel<<<s.B, SOLVE_T, be->solve_smem, st>>>(s, be->solve_smem > 0)));
     VIO_LAUNCH(be->timer, st, "post_solve_kernel", (post_solve_kernel<<<s.B, 256, 0, st>>>(s)));
-    VIO_LAUNCH(be->timer, st, "marg_kernel", (marg_kernel<<<s.B, MARG_T, sizeof(MargSmem), st>>>(s)));
+    VIO_LAUNCH(be->timer, st, "marg_kernel", (marg_kernel<<<s.B, MARG_T, be->marg_smem, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "finish_kernel", (finish_kernel<<<s.B, 256, s.FCAP + 64, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "clear_init_pending_kernel", (clear_init_pending_kernel<<<s.B, 32, 0, st>>>(s)));
     be->launches += 8;

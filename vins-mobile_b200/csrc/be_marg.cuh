@@ -15,6 +15,7 @@ namespace be {
 
 constexpr int MARG_T = 512;
 constexpr double MARG_EPS = 1e-8;      // MarginalizationInfo::eps, marginalization_factor.hpp:75
+constexpr int MARG_NCAP = 104;         // A_r and its eigenvectors live in shared memory when n <= MARG_NCAP (2*104^2*8 = 173 KB)
 
 // Cyclic two-sided Jacobi eigensolver, parallel (round-robin) ordering, A symmetric n x n (ld), destroyed: on exit its diagonal
 // holds the eigenvalues and V (n x n, ld = n) the eigenvectors as columns.  cs = shared scratch for 2*(n/2+1) doubles.
@@ -266,10 +267,106 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         }
     }
     __syncthreads();
-    // ---- Amm^+ via eigendecomposition (0.5*(Amm + Amm^T) first, marginalization_factor.cpp:268) -----------------
+    // ---- Amm^+ [Amr | bmm] ------------------------------------------------------------------------------------------------
+    // Reference: pseudo-inverse by eigendecomposition of 0.5*(Amm + Amm^T), eigenvalues <= eps dropped
+    // (marginalization_factor.cpp:268-271).  When every eigenvalue is provably > eps the pseudo-inverse IS the inverse, and Amm has
+    // the structure [[P, C], [C^T, D]] with D DIAGONAL (a projection factor touches one landmark only), so the inverse follows from
+    // the mc x mc Schur complement S = P - C D^-1 C^T.  Proof obligation checked at run time: lambda_min(Amm) >= 1/||Amm^-1||_F,
+    // with ||Amm^-1||_F formed from the explicit block inverse.  If the bound does not clear eps (or a pivot is not positive) the
+    // kernel falls back to the faithful Jacobi eigendecomposition below.
     for (int e = tid; e < m * m; e += MARG_T) { const int i = e / m, j = e - i * m; if (j < i) { const double v = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]); A[(size_t)i * pos + j] = v; A[(size_t)j * pos + i] = v; } }
     __syncthreads();
-    // Tm = [Amr | bmm] must be saved before A's mm block is destroyed?  (only the mm block is rotated: rows/cols < m with ld = pos)
+    __shared__ double Sinv[15 * 15];
+    __shared__ int fast_ok;
+    {
+        // Gp = C D^-1 (mc x L0) in Vm scratch ; S = P - Gp C^T
+        double *Gp = Vm, *Gm = Vm + (size_t)mc * L0;           // Gm = S^-1 Gp
+        if (tid == 0) fast_ok = 1;
+        __syncthreads();
+        for (int e = tid; e < mc * L0; e += MARG_T) {
+            const int r = e / L0, l = e - r * L0;
+            const double d = A[(size_t)(mc + l) * pos + mc + l];
+            if (!(d > 0)) fast_ok = 0;
+            Gp[e] = A[(size_t)r * pos + mc + l] / d;
+        }
+        __syncthreads();
+        __shared__ double Sm[15 * 15];
+        for (int e = tid; e < mc * mc; e += MARG_T) {
+            const int r = e / mc, c = e - r * mc;
+            double t = A[(size_t)r * pos + c];
+            for (int l = 0; l < L0; l++) t -= Gp[(size_t)r * L0 + l] * A[(size_t)c * pos + mc + l];
+            Sm[e] = t;
+        }
+        __syncthreads();
+        if (tid == 0 && fast_ok) {                              // S^-1 by Cholesky (serial, mc <= 15)
+            double Lc[225], Li[225];
+            bool ok = true;
+            for (int i = 0; i < mc * mc; i++) { Lc[i] = 0; Li[i] = 0; }
+            for (int j = 0; j < mc && ok; j++) {
+                double d = Sm[j * mc + j];
+                for (int k = 0; k < j; k++) d -= Lc[j * mc + k] * Lc[j * mc + k];
+                if (!(d > 0) || !isfinite(d)) { ok = false; break; }
+                d = sqrt(d); Lc[j * mc + j] = d;
+                for (int i = j + 1; i < mc; i++) { double v = Sm[i * mc + j]; for (int k = 0; k < j; k++) v -= Lc[i * mc + k] * Lc[j * mc + k]; Lc[i * mc + j] = v / d; }
+            }
+            if (ok) {
+                for (int c = 0; c < mc; c++)
+                    for (int i = c; i < mc; i++) { double v = (i == c) ? 1.0 : 0.0; for (int k = c; k < i; k++) v -= Lc[i * mc + k] * Li[k * mc + c]; Li[i * mc + c] = v / Lc[i * mc + i]; }
+                for (int i = 0; i < mc; i++)
+                    for (int j = 0; j <= i; j++) { double v = 0; for (int k = i; k < mc; k++) v += Li[k * mc + i] * Li[k * mc + j]; Sinv[i * mc + j] = v; Sinv[j * mc + i] = v; }
+            } else fast_ok = 0;
+        }
+        __syncthreads();
+        if (fast_ok) {
+            for (int e = tid; e < mc * L0; e += MARG_T) {
+                const int r = e / L0, l = e - r * L0;
+                double t = 0;
+                for (int k = 0; k < mc; k++) t += Sinv[r * mc + k] * Gp[(size_t)k * L0 + l];
+                Gm[e] = t;
+            }
+            __syncthreads();
+            // ||Amm^-1||_F^2 = ||S^-1||^2 + 2||S^-1 C D^-1||^2 + ||D^-1 + D^-1 C^T S^-1 C D^-1||^2
+            double f2 = 0;
+            for (int e = tid; e < mc * mc; e += MARG_T) f2 += Sinv[e] * Sinv[e];
+            for (int e = tid; e < mc * L0; e += MARG_T) f2 += 2.0 * Gm[e] * Gm[e];
+            for (int e = tid; e < L0 * L0; e += MARG_T) {
+                const int a = e / L0, bq = e - a * L0;
+                const double da = A[(size_t)(mc + a) * pos + mc + a];
+                double t = (a == bq) ? 1.0 : 0.0;
+                for (int k = 0; k < mc; k++) t += A[(size_t)k * pos + mc + a] * Gm[(size_t)k * L0 + bq];
+                t /= da;
+                f2 += t * t;
+            }
+            f2 = block_sum_d(f2, sm.red);
+            if (!(f2 < 1.0 / (MARG_EPS * MARG_EPS)) || !isfinite(f2)) { __syncthreads(); if (tid == 0) fast_ok = 0; }
+            __syncthreads();
+        }
+        if (fast_ok) {
+            // Z = Amm^-1 X, X = [Amr | bmm]:  T = X_p - Gp X_l ; Y_p = S^-1 T ; Y_l = D^-1 (X_l - C^T Y_p)
+            for (int e = tid; e < mc * (n + 1); e += MARG_T) {
+                const int r = e / (n + 1), c = e - r * (n + 1);
+                double t = (c < n) ? A[(size_t)r * pos + m + c] : bv[r];
+                for (int l = 0; l < L0; l++) t -= Gp[(size_t)r * L0 + l] * ((c < n) ? A[(size_t)(mc + l) * pos + m + c] : bv[mc + l]);
+                Tm[e] = t;
+            }
+            __syncthreads();
+            for (int e = tid; e < mc * (n + 1); e += MARG_T) {
+                const int r = e / (n + 1), c = e - r * (n + 1);
+                double t = 0;
+                for (int k = 0; k < mc; k++) t += Sinv[r * mc + k] * Tm[(size_t)k * (n + 1) + c];
+                Zm[e] = t;
+            }
+            __syncthreads();
+            for (int e = tid; e < L0 * (n + 1); e += MARG_T) {
+                const int l = e / (n + 1), c = e - l * (n + 1);
+                double t = (c < n) ? A[(size_t)(mc + l) * pos + m + c] : bv[mc + l];
+                for (int k = 0; k < mc; k++) t -= A[(size_t)k * pos + mc + l] * Zm[(size_t)k * (n + 1) + c];
+                Zm[(size_t)(mc + l) * (n + 1) + c] = t / A[(size_t)(mc + l) * pos + mc + l];
+            }
+            __syncthreads();
+        }
+    }
+    if (!fast_ok) {
     eig_sym_jacobi(A, m, pos, Vm, sm.cs, sm.pq, sm.red);
     __syncthreads();
     // Tm = Lambda^+ Vm^T [Amr | bmm]      (m x (n+1))
@@ -292,6 +389,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         Zm[e] = t;
     }
     __syncthreads();
+    }   // !fast_ok
     for (int e = tid; e < n * (n + 1); e += MARG_T) {
         const int r = e / (n + 1), c = e - r * (n + 1);
         double acc = 0;
@@ -302,7 +400,16 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     __syncthreads();
     for (int e = tid; e < n * n; e += MARG_T) { const int i = e / n, j = e - i * n; if (j < i) { const double v = 0.5 * (Ar[(size_t)i * n + j] + Ar[(size_t)j * n + i]); Ar[(size_t)i * n + j] = v; Ar[(size_t)j * n + i] = v; } }
     __syncthreads();
-    eig_sym_jacobi(Ar, n, n, Vr, sm.cs, sm.pq, sm.red);
+    if (n <= MARG_NCAP) {                                      // A_r and V in shared memory
+        double *sA = reinterpret_cast<double *>(smraw + ((sizeof(MargSmem) + 15) & ~(size_t)15));
+        double *sV = sA + (size_t)n * n;
+        for (int e = tid; e < n * n; e += MARG_T) sA[e] = Ar[e];
+        __syncthreads();
+        eig_sym_jacobi(sA, n, n, sV, sm.cs, sm.pq, sm.red);
+        Ar = sA; Vr = sV;
+    } else {
+        eig_sym_jacobi(Ar, n, n, Vr, sm.cs, sm.pq, sm.red);
+    }
     __syncthreads();
     // tv[k] = v_k . b_r ;  c0 = sum_{lam>eps} tv^2 / lam
     for (int k = tid; k < n; k += MARG_T) {

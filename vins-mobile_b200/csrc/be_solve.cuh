@@ -85,7 +85,7 @@ __device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, co
         __syncthreads();
         for (int i = tid; i < NPX; i += blockDim.x) {
             double t = 0;
-            for (int j = 0; j < NPX; j++) t += Hp[(size_t)i * NPX + j] * ws.dx[j];
+            for (int j = 0; j < NPX; j++) t += Hp[(size_t)j * NPX + i] * ws.dx[j];      // Hp symmetric: column read = coalesced
             cost += 0.5 * ws.dx[i] * t + bp[i] * ws.dx[i];
             if (lin && i < NP) ws.g[i] += t + bp[i];
         }
@@ -172,7 +172,7 @@ __device__ inline double quad_form(const BeState &s, const SolveWs &ws, int nl, 
     double acc = 0;
     for (int i = tid; i < NP; i += blockDim.x) {
         double t = 0;
-        for (int j = 0; j < NP; j++) t += ws.H[(size_t)i * NP + j] * up[j];
+        for (int j = 0; j < NP; j++) t += ws.H[(size_t)j * NP + i] * up[j];           // H symmetric: column read = coalesced
         acc += up[i] * t;
     }
     for (int l = tid; l < nl; l += blockDim.x) {
@@ -245,7 +245,156 @@ __device__ inline bool chol_solve(double *A, int n, const double *rhs, double *y
     return ok;
 }
 
-__global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s) {
+
+// ---- shared-memory path (reduced system fits one SM: NP*(NP+1)/2 doubles, 110 KB at W=10) -------------------------------------
+__device__ __forceinline__ int pidx(int i, int j) { return i * (i + 1) / 2 + j; }       // packed lower, j <= i
+
+// Blocked left-looking Cholesky on a packed lower matrix in shared memory (panel width 8: 3 barriers per panel instead of
+// 2 per column), then forward/backward substitution by one warp.  Returns false on a non-positive pivot / non-finite value.
+__device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, double *y, int *sh_flag) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    constexpr int NB = 8;
+    if (tid == 0) *sh_flag = 1;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += NB) {
+        const int nb = min(NB, n - c0);
+        for (int e = tid; e < (n - c0) * nb; e += T) {             // panel -= L[:, :c0] L[panel, :c0]^T
+            const int i = c0 + e / nb, j = c0 + e % nb;
+            if (j > i) continue;
+            const double *ri = A + pidx(i, 0), *rj = A + pidx(j, 0);
+            double t = 0;
+            for (int k = 0; k < c0; k++) t += ri[k] * rj[k];
+            A[pidx(i, j)] -= t;
+        }
+        __syncthreads();
+        if (tid == 0) {                                            // nb x nb diagonal block, serial
+            for (int jj = 0; jj < nb; jj++) {
+                const int j = c0 + jj;
+                double d = A[pidx(j, j)];
+                for (int t = 0; t < jj; t++) d -= A[pidx(j, c0 + t)] * A[pidx(j, c0 + t)];
+                if (!(d > 0) || !isfinite(d)) { *sh_flag = 0; break; }
+                d = sqrt(d);
+                A[pidx(j, j)] = d;
+                for (int ii = jj + 1; ii < nb; ii++) {
+                    const int i = c0 + ii;
+                    double v = A[pidx(i, j)];
+                    for (int t = 0; t < jj; t++) v -= A[pidx(i, c0 + t)] * A[pidx(j, c0 + t)];
+                    A[pidx(i, j)] = v / d;
+                }
+            }
+        }
+        __syncthreads();
+        if (!*sh_flag) return false;
+        for (int i = c0 + nb + tid; i < n; i += T) {               // rows below the block: triangular solve against it
+            double *ri = A + pidx(i, c0);
+            for (int jj = 0; jj < nb; jj++) {
+                double v = ri[jj];
+                const double *rj = A + pidx(c0 + jj, c0);
+                for (int t = 0; t < jj; t++) v -= ri[t] * rj[t];
+                ri[jj] = v / rj[jj];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < 32) {
+        const int lane = tid;
+        for (int i = lane; i < n; i += 32) y[i] = rhs[i];
+        __syncwarp();
+        for (int k = 0; k < n; k++) {                              // L z = rhs
+            if (lane == 0) y[k] /= A[pidx(k, k)];
+            __syncwarp();
+            const double yk = y[k];
+            for (int i = k + 1 + lane; i < n; i += 32) y[i] -= A[pidx(i, k)] * yk;
+            __syncwarp();
+        }
+        for (int k = n - 1; k >= 0; k--) {                         // L^T y = z
+            if (lane == 0) y[k] /= A[pidx(k, k)];
+            __syncwarp();
+            const double yk = y[k];
+            const double *rk = A + pidx(k, 0);
+            for (int i = lane; i < k; i += 32) y[i] -= rk[i] * yk;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    bool ok = true;
+    for (int i = 0; i < n; i++) ok &= isfinite(y[i]);
+    return ok;
+}
+
+constexpr int SCHUR_CHUNK = 32;
+// S (packed, shared) = S H S + mu D^2 - sum_l ws_l ws_l^T / h_l ;  rhs = S g - sum_l ws_l gs_l / h_l   (landmark blocks eliminated)
+// wt = shared staging [SCHUR_CHUNK][NPW + 1]
+__device__ inline void build_reduced_smem(const BeState &s, const SolveWs &ws, int nl, double mu, double *S, double *wt) {
+    const int tid = threadIdx.x, T = blockDim.x, NP = s.NP, NPW = s.NPW;
+    for (int e = tid; e < NP * (NP + 1) / 2; e += T) {
+        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while (pidx(i + 1, 0) <= e) i++;
+        while (pidx(i, 0) > e) i--;
+        const int j = e - pidx(i, 0);
+        double v = ws.H[(size_t)i * NP + j] * ws.sc_p[i] * ws.sc_p[j];
+        if (i == j) v += mu * ws.d_p[i] * ws.d_p[i];
+        S[e] = v;
+    }
+    for (int i = tid; i < NP; i += T) ws.rhs[i] = ws.g[i] * ws.sc_p[i];
+    constexpr int EPT = 8;                                          // entries of the NPW x NPW lower triangle per thread
+    const int nent = NPW * (NPW + 1) / 2;
+    double acc[EPT];
+    int ea[EPT], ec[EPT];
+#pragma unroll
+    for (int q = 0; q < EPT; q++) {
+        acc[q] = 0;
+        const int e = tid + q * T;
+        int a = 0, c = 0;
+        if (e < nent) {
+            a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while (pidx(a + 1, 0) <= e) a++;
+            while (pidx(a, 0) > e) a--;
+            c = e - pidx(a, 0);
+        }
+        ea[q] = a; ec[q] = c;
+    }
+    double racc = 0;                                                // thread a < NPW accumulates the rhs correction
+    const int ld = NPW + 1;
+    for (int l0 = 0; l0 < nl; l0 += SCHUR_CHUNK) {
+        const int cn = min(SCHUR_CHUNK, nl - l0);
+        __syncthreads();
+        for (int e = tid; e < cn * ld; e += T) {
+            const int cl = e / ld, a = e - cl * ld, l = l0 + cl;
+            const double sl = ws.sc_l[l];
+            const double h = ws.hll[l] * sl * sl + mu * ws.d_l[l] * ws.d_l[l];
+            const double f = sl * sl / h;
+            wt[e] = (a < NPW) ? ws.w[(size_t)l * NPW + a] * sqrt(f) : ws.gl[l] * sqrt(f);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < EPT; q++) {
+            if (tid + q * T < nent) {
+                double t = 0;
+                for (int cl = 0; cl < cn; cl++) t += wt[cl * ld + ea[q]] * wt[cl * ld + ec[q]];
+                acc[q] += t;
+            }
+        }
+        if (tid < NPW) { double t = 0; for (int cl = 0; cl < cn; cl++) t += wt[cl * ld + tid] * wt[cl * ld + NPW]; racc += t; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < EPT; q++) {
+        if (tid + q * T < nent) {
+            const int ia = 15 * (ea[q] / 6) + ea[q] % 6, ic = 15 * (ec[q] / 6) + ec[q] % 6;
+            S[pidx(ia, ic)] -= acc[q] * ws.sc_p[ia] * ws.sc_p[ic];
+        }
+    }
+    if (tid < NPW) { const int ia = 15 * (tid / 6) + tid % 6; ws.rhs[ia] -= racc * ws.sc_p[ia]; }
+    __syncthreads();
+}
+
+__host__ __device__ inline size_t solve_smem_bytes(int NP, int NPW) {
+    return ((size_t)NP * (NP + 1) / 2 + (size_t)SCHUR_CHUNK * (NPW + 1)) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem) {
+    extern __shared__ __align__(16) double sm_dyn[];
     __shared__ double sh_red[32];
     __shared__ int sh_flag;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -306,6 +455,12 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s) {
             // ---- ComputeGaussNewtonStep: (S H S + mu D^2) y = S g by Schur elimination of the landmark blocks ----
             linear_ok = false;
             while (mu < 1.0) {
+              bool ok;
+              if (use_smem) {
+                double *Ssm = sm_dyn, *wt = sm_dyn + (size_t)NP * (NP + 1) / 2;
+                build_reduced_smem(s, ws, nl, mu, Ssm, wt);
+                ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag);
+              } else {
                 for (int e = tid; e < NP * NP; e += SOLVE_T) {
                     const int i = e / NP, j = e - i * NP;
                     if (j <= i) {
@@ -342,7 +497,8 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s) {
                     ws.rhs[ia] -= acc * ws.sc_p[ia];
                 }
                 __syncthreads();
-                const bool ok = chol_solve(ws.S, NP, ws.rhs, ws.y, &sh_flag);
+                ok = chol_solve(ws.S, NP, ws.rhs, ws.y, &sh_flag);
+              }
                 __syncthreads();
                 if (ok) {
                     // back-substitution y_l = (gs_l - ws_l . y_p) / h_l ;  gauss_newton_step_ = -diagonal .* y

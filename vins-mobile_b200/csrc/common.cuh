@@ -19,10 +19,11 @@
 #define VIO_MAXP 512          // compile-time cap on max_cnt (points per stream)
 #define VIO_MAX_WIN 24        // compile-time cap on window_size
 
-// BORDER_REFLECT_101 for |overshoot| < n
+// BORDER_REFLECT_101 (gfedcb|abcdefgh|gfedcba), repeated like cv::borderInterpolate when the overshoot exceeds the image
 __device__ __forceinline__ int reflect101(int i, int n) {
-    i = i < 0 ? -i : i;
-    return i >= n ? 2 * n - 2 - i : i;
+    if (n == 1) return 0;
+    while ((unsigned)i >= (unsigned)n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
 }
 
 // Explicitly rounded, never-contracted f32 ops: the parity contract with oracle/frontend_oracle.py
