@@ -114,11 +114,11 @@ def test_window_parity_stream(api, cfg, synth):
         assert ri["n_feat"] == gi["n_feat"] and ri["n_proj"] == gi["n_proj"]
         first = k == W                      # first solve: identical inputs -> round-off level agreement
         # later solves start from states that already differ at the reference's own reproducibility floor
-        ctol = 1e-9 if first else 1e-4
+        ctol = 1e-8 if first else 1e-4
         assert abs(gi["cost0"] - ri["cost0"]) <= ctol * abs(ri["cost0"]), f"kf {k}: initial cost {gi['cost0']} vs {ri['cost0']}"
         assert abs(gi["cost1"] - ri["cost1"]) <= max(ctol, 1e-7) * abs(ri["cost1"]), f"kf {k}: final cost"
         assert abs(ri["iters"] - gi["iters"]) <= (0 if first else 1), f"kf {k}: iterations {ri['iters']} vs {gi['iters']}"
-        tol = 1e-9 if first else 1e-4
+        tol = 1e-7 if first else 1e-4
         for key, floor in (("P", 0.0), ("V", 0.0), ("Ba", 1e-2), ("Bg", 1e-3)):
             # relative to max(|x|, floor): the true biases are 0, so a purely relative test on them would divide by ~1e-5
             err = np.abs(gs[key] - rs[key]).max() / max(np.abs(rs[key]).max(), floor)

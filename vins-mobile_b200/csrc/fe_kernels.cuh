@@ -88,22 +88,24 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
                                                            float2 *__restrict__ next_pts, uint8_t *__restrict__ status,
                                                            const int *__restrict__ n_pts, int maxp) {
     __shared__ uint8_t sI[LK_WARPS][24 * 24];
-    __shared__ uint8_t sJ[LK_WARPS][22 * 24];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int f = blockIdx.x * LK_WARPS + warp;
     if (f >= n_pts[b]) return;
     const float2 pt = prev_pts[(size_t)b * maxp + f];
     uint8_t *pI = sI[warp];
-    uint8_t *pJ = sJ[warp];
     const float half = 10.f;
     float nx = 0.f, ny = 0.f;          // nextPts[ptidx] (level coordinates, window centre)
     bool ok = true;                    // status[ptidx]
+    // this lane's 14 window pixels: p = lane + 32k -> (y, x) in the 21x21 window (level independent)
+    unsigned char wy[LK_PIX], wx[LK_PIX];
+#pragma unroll
+    for (int k = 0; k < LK_PIX; k++) { const int p = lane + 32 * k; wy[k] = (unsigned char)(p / LK_WIN); wx[k] = (unsigned char)(p - (p / LK_WIN) * LK_WIN); }
 
     for (int level = LK_LEVELS; level >= 0; level--) {
         const int rows = I.rows[level], cols = I.cols[level];
-        const uint8_t *imI = I.p[level] + (size_t)b * I.stride[level];
-        const uint8_t *imJ = J.p[level] + (size_t)b * J.stride[level];
+        const uint8_t *__restrict__ imI = I.p[level] + (size_t)b * I.stride[level];
+        const uint8_t *__restrict__ imJ = J.p[level] + (size_t)b * J.stride[level];
         const float scale = 1.f / (float)(1 << level);
         float px = fmul(pt.x, scale), py = fmul(pt.y, scale);
         if (level == LK_LEVELS) { nx = px; ny = py; }
@@ -114,11 +116,25 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
             if (level == 0) ok = false;
             continue;
         }
-        // stage the 24x24 template neighbourhood, rows ipy-1 .. ipy+22, cols ipx-1 .. ipx+22
+        // stage the 24x24 template neighbourhood, rows ipy-1 .. ipy+22, cols ipx-1 .. ipx+22: all 18 loads of a lane are issued
+        // before the first store so that they overlap
         __syncwarp();
-        for (int i = lane; i < 24 * 24; i += 32) {
-            const int r = i / 24, c = i - r * 24;
-            pI[i] = imI[(size_t)reflect101(ipy - 1 + r, rows) * cols + reflect101(ipx - 1 + c, cols)];
+        {
+            uint8_t v[18];
+            const bool inner = ipx >= 1 && ipx + 23 <= cols && ipy >= 1 && ipy + 23 <= rows;
+            if (inner) {
+                const uint8_t *base = imI + (size_t)(ipy - 1) * cols + (ipx - 1);
+#pragma unroll
+                for (int t = 0; t < 18; t++) { const int i = lane + 32 * t; const int r = i / 24, c = i - r * 24; v[t] = base[r * cols + c]; }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 18; t++) {
+                    const int i = lane + 32 * t; const int r = i / 24, c = i - r * 24;
+                    v[t] = imI[(size_t)reflect101(ipy - 1 + r, rows) * cols + reflect101(ipx - 1 + c, cols)];
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 18; t++) pI[lane + 32 * t] = v[t];
         }
         __syncwarp();
         int w00, w01, w10, w11;
@@ -130,7 +146,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
             const int p = lane + 32 * k;
             Iw[k] = gx[k] = gy[k] = 0;
             if (p < LK_WIN * LK_WIN) {
-                const int y = p / LK_WIN, x = p - y * LK_WIN;
+                const int y = wy[k], x = wx[k];
                 int iv = 0, dxv = 0, dyv = 0;
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
@@ -173,25 +189,35 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
                 if (level == 0) ok = false;
                 break;
             }
-            __syncwarp();
-            for (int i = lane; i < 22 * 22; i += 32) {
-                const int r = i / 22, c = i - r * 22;
-                pJ[r * 24 + c] = imJ[(size_t)reflect101(jy + r, rows) * cols + reflect101(jx + c, cols)];
-            }
-            __syncwarp();
             int v00, v01, v10, v11;
             lk_weights(fsub(cx, (float)jx), fsub(cy, (float)jy), v00, v01, v10, v11);
             int b1 = 0, b2 = 0;
+            // the 22x22 window of J is read straight through L1 (4 independent byte loads per pixel, coalesced across lanes);
+            // REFLECT_101 indexing only when the window leaves the image
+            if (jx >= 0 && jx + 22 <= cols && jy >= 0 && jy + 22 <= rows) {
+                const uint8_t *base = imJ + (size_t)jy * cols + jx;
 #pragma unroll
-            for (int k = 0; k < LK_PIX; k++) {
-                const int p = lane + 32 * k;
-                if (p < LK_WIN * LK_WIN) {
-                    const int y = p / LK_WIN, x = p - y * LK_WIN;
-                    const uint8_t *q = pJ + y * 24 + x;
-                    const int jv = (q[0] * v00 + q[1] * v01 + q[24] * v10 + q[25] * v11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                    const int diff = jv - Iw[k];
-                    b1 += diff * gx[k];
-                    b2 += diff * gy[k];
+                for (int k = 0; k < LK_PIX; k++) {
+                    if (lane + 32 * k < LK_WIN * LK_WIN) {
+                        const uint8_t *q = base + wy[k] * cols + wx[k];
+                        const int jv = (q[0] * v00 + q[1] * v01 + q[cols] * v10 + q[cols + 1] * v11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                        const int diff = jv - Iw[k];
+                        b1 += diff * gx[k];
+                        b2 += diff * gy[k];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < LK_PIX; k++) {
+                    if (lane + 32 * k < LK_WIN * LK_WIN) {
+                        const int y0 = reflect101(jy + wy[k], rows), y1 = reflect101(jy + wy[k] + 1, rows);
+                        const int x0 = reflect101(jx + wx[k], cols), x1 = reflect101(jx + wx[k] + 1, cols);
+                        const int jv = (imJ[(size_t)y0 * cols + x0] * v00 + imJ[(size_t)y0 * cols + x1] * v01 + imJ[(size_t)y1 * cols + x0] * v10 +
+                                        imJ[(size_t)y1 * cols + x1] * v11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                        const int diff = jv - Iw[k];
+                        b1 += diff * gx[k];
+                        b2 += diff * gy[k];
+                    }
                 }
             }
             const float B1 = fmul(__ll2float_rn(warp_sum_ll(b1)), FLT_SCALE);
@@ -237,7 +263,8 @@ __global__ void __launch_bounds__(256) eig_candidates_kernel(const uint8_t *__re
     __shared__ float sp[(ET + 6) * (ET + 6)];        // pixels as f32, origin (ty0-3, tx0-3)
     __shared__ float sdx[(ET + 4) * (ET + 4)];       // origin (ty0-2, tx0-2)
     __shared__ float sdy[(ET + 4) * (ET + 4)];
-    __shared__ float se[(ET + 2) * (ET + 2)];        // eig, origin (ty0-1, tx0-1)
+    __shared__ double srs[3][(ET + 4) * (ET + 2)];   // f64 ROW sums of dx*dx, dx*dy, dy*dy: rows origin ty0-2, cols origin tx0-1
+    float *se = sp;                                  // eig, origin (ty0-1, tx0-1): aliases sp (dead once dx/dy exist)
     __shared__ int2 sk[64];
     __shared__ int nk;
     const int b = blockIdx.z;
@@ -261,7 +288,7 @@ __global__ void __launch_bounds__(256) eig_candidates_kernel(const uint8_t *__re
     for (int i = tid; i < PW * PW; i += 256) {
         const int r = i / PW, c = i - r * PW;
         const int y = reflect101(ty0 - 3 + r, rows), x = reflect101(tx0 - 3 + c, cols);
-        sp[i] = (y >= 0 && y < rows && x >= 0 && x < cols) ? (float)im[(size_t)y * cols + x] : 0.f;
+        sp[i] = (float)im[(size_t)y * cols + x];
     }
     __syncthreads();
     const float a = (float)(1.0 / 3060.0);
@@ -278,31 +305,32 @@ __global__ void __launch_bounds__(256) eig_candidates_kernel(const uint8_t *__re
         sdy[i] = fsub(spv, sm);
     }
     __syncthreads();
+    // separable 3x3 box filter, exactly cv2's order: row sums (c0+c1)+c2 in f64 first, then column sums (r0+r1)+r2
+    for (int i = tid; i < DW * EW; i += 256) {
+        const int r = i / EW, c = i - r * EW;
+        const int gy = ty0 - 2 + r, gx = tx0 - 1 + c;
+        if (gy < 0 || gy >= rows || gx < 0 || gx >= cols) continue;
+        double pa[3], pb[3], pc[3];
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+            const int xx = reflect101(gx + dx, cols) - (tx0 - 2);
+            const float vx = sdx[r * DW + xx], vy = sdy[r * DW + xx];
+            pa[dx + 1] = (double)fmul(vx, vx); pb[dx + 1] = (double)fmul(vx, vy); pc[dx + 1] = (double)fmul(vy, vy);
+        }
+        srs[0][i] = __dadd_rn(__dadd_rn(pa[0], pa[1]), pa[2]);
+        srs[1][i] = __dadd_rn(__dadd_rn(pb[0], pb[1]), pb[2]);
+        srs[2][i] = __dadd_rn(__dadd_rn(pc[0], pc[1]), pc[2]);
+    }
+    __syncthreads();
     for (int i = tid; i < EW * EW; i += 256) {
         const int r = i / EW, c = i - r * EW;
         const int gy = ty0 - 1 + r, gx = tx0 - 1 + c;
         float e = -1.f;
         if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
-            double A[3], Bc[3], Cc[3];
-#pragma unroll
-            for (int dy = -1; dy <= 1; dy++) {
-                const int yy = reflect101(gy + dy, rows) - (ty0 - 2);
-                double ra[3], rb[3], rc[3];
-#pragma unroll
-                for (int dx = -1; dx <= 1; dx++) {
-                    const int xx = reflect101(gx + dx, cols) - (tx0 - 2);
-                    const float vx = sdx[yy * DW + xx], vy = sdy[yy * DW + xx];
-                    ra[dx + 1] = (double)fmul(vx, vx);
-                    rb[dx + 1] = (double)fmul(vx, vy);
-                    rc[dx + 1] = (double)fmul(vy, vy);
-                }
-                A[dy + 1] = __dadd_rn(__dadd_rn(ra[0], ra[1]), ra[2]);
-                Bc[dy + 1] = __dadd_rn(__dadd_rn(rb[0], rb[1]), rb[2]);
-                Cc[dy + 1] = __dadd_rn(__dadd_rn(rc[0], rc[1]), rc[2]);
-            }
-            const float fa = (float)__dadd_rn(__dadd_rn(A[0], A[1]), A[2]);
-            const float fb = (float)__dadd_rn(__dadd_rn(Bc[0], Bc[1]), Bc[2]);
-            const float fc = (float)__dadd_rn(__dadd_rn(Cc[0], Cc[1]), Cc[2]);
+            const int y0 = reflect101(gy - 1, rows) - (ty0 - 2), y1 = gy - (ty0 - 2), y2 = reflect101(gy + 1, rows) - (ty0 - 2);
+            const float fa = (float)__dadd_rn(__dadd_rn(srs[0][y0 * EW + c], srs[0][y1 * EW + c]), srs[0][y2 * EW + c]);
+            const float fb = (float)__dadd_rn(__dadd_rn(srs[1][y0 * EW + c], srs[1][y1 * EW + c]), srs[1][y2 * EW + c]);
+            const float fc = (float)__dadd_rn(__dadd_rn(srs[2][y0 * EW + c], srs[2][y1 * EW + c]), srs[2][y2 * EW + c]);
             const float ha = fmul(fa, 0.5f), hc = fmul(fc, 0.5f);
             const float t = fsub(ha, hc);
             e = fsub(fadd(ha, hc), __fsqrt_rn(fadd(fmul(t, t), fmul(fb, fb))));
