@@ -96,13 +96,12 @@ class Pipeline:
     """One FeatureTracker + VINS pair per stream, batched, both on one CUDA stream (front end hands image_msg to the back end
     in device memory)."""
 
-    def __init__(self, api, cfg, stream_handle, gt, host_inputs):
+    def __init__(self, api, cfg, fe_stream, be_stream, gt, host_inputs):
         self.api, self.cfg, self.W, self.B = api, cfg, cfg.window_size, cfg.batch
         self.fe = api.FrontEnd(cfg)
         self.be = api.BackEnd(cfg)
-        self.fe.use_stream(stream_handle)
-        self.be.use_stream(stream_handle)
-        self.msg = self.fe.image_msg_dev()
+        self.fe.use_stream(fe_stream)          # tracker of frames k+1.. overlaps the solve of keyframe k (event-ordered hand-over)
+        self.be.use_stream(be_stream)
         self.gt, self.host = gt, host_inputs
         self.kf = 0
         self.frame = 0
@@ -124,7 +123,7 @@ class Pipeline:
                 P = np.stack([g[0][:self.W + 1] for g in self.gt]); Q = np.stack([g[1][:self.W + 1] for g in self.gt])
                 V = np.stack([g[2][:self.W + 1] for g in self.gt])
                 self.be.set_init_window(P, Q, V, np.zeros((self.B, 3)), np.zeros((self.B, 3)))
-            self.be.process_image_dev(self.msg[0], self.msg[1], self.msg[2], np.full(self.B, self.frame / 30.0))
+            self.be.process_image_from_frontend(self.fe, np.full(self.B, self.frame / 30.0))
             if self.host:
                 self.state_host = self.be.state_all()          # device -> host read of the step's result
             self.kf += 1
@@ -156,8 +155,8 @@ def run_ours(args):
     frames, dt, acc, gyr, gt, cam = make_data(synth, B, n_frames, rank * B, dev)
     t_data = time.time() - t0
     dt_d, acc_d, gyr_d = (torch.as_tensor(x, device=dev).contiguous() for x in (dt, acc, gyr))
-    stream = torch.cuda.Stream(device=dev)
-    sh = stream.cuda_stream
+    stream = torch.cuda.Stream(device=dev)          # front end
+    stream_b = torch.cuda.Stream(device=dev) if not args.no_overlap else stream      # back end
 
     def imu_dev(k):
         return dt_d[k].data_ptr(), acc_d[k].data_ptr(), gyr_d[k].data_ptr()
@@ -177,14 +176,15 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed_run(host_inputs):
-        pipe = Pipeline(api, cfg, sh, gt, host_inputs)
+        pipe = Pipeline(api, cfg, stream.cuda_stream, stream_b.cuda_stream, gt, host_inputs)
         src = frames.cpu().pin_memory().numpy() if host_inputs else None
         with torch.cuda.stream(stream):
             def one(i):
                 pub = pipe.step(src[i] if host_inputs else frames[i].data_ptr(), imu_host if host_inputs else imu_dev)
                 if pub and world > 1:
-                    pipe.be.copy_state(send_buf.data_ptr(), True)
-                    dist.all_gather_into_tensor(gather_buf.view(world * B, W + 1, 16), send_buf)
+                    with torch.cuda.stream(stream_b):
+                        pipe.be.copy_state(send_buf.data_ptr(), True)
+                        dist.all_gather_into_tensor(gather_buf.view(world * B, W + 1, 16), send_buf)
             for i in range(prologue + args.warmup):
                 one(i)
             barrier()
@@ -194,8 +194,10 @@ def run_ours(args):
                 clocks.start()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
+            stream_b.wait_stream(stream)
             for i in range(prologue + args.warmup, prologue + args.warmup + args.steps):
                 one(i)
+            stream.wait_stream(stream_b)
             e1.record(stream)
             barrier()
             clocks.stop_flag = True
@@ -248,7 +250,8 @@ def run_ours(args):
         "config": {"workload": f"batch {B} independent streams per GPU, 640x480@30fps + 200 Hz IMU, 150 feats, 10-KF window, FREQ=3 "
                                "(BASELINE.json configs[2]; configs[3] at 8 GPUs)", "batch_per_gpu": B, "streams": B * world, "freq": FREQ,
                    "keyframe_steps_timed": n_kf_steps, "l2": "inputs change every step and the working set exceeds L2; no explicit flush",
-                   "prologue_frames_untimed": prologue, "data_gen_s": round(t_data, 1)},
+                   "prologue_frames_untimed": prologue, "data_gen_s": round(t_data, 1),
+                   "streams_overlap": "front end and back end on two CUDA streams, event-ordered hand-over" if not args.no_overlap else "single stream"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * cam.rows * cam.cols + B * IMU_PER_KF * 7 * 8 / FREQ),
                 "d2h_bytes_per_step": int(B * (W + 1) * 16 * 8 / FREQ), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
@@ -357,6 +360,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-overlap", action="store_true", help="front end and back end on ONE CUDA stream (no overlap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -138,6 +138,10 @@ int vio_backend_process_image(vio_backend *be, const int32_t *counts, const int3
 int vio_backend_process_image_dev(vio_backend *be, const int32_t *counts, const int32_t *ids, const double *norm_xyz,
                                   const double *headers_host);
 
+/* processImage fed from a front end's device-resident image_msg; event-ordered hand-over when the two handles use different
+ * CUDA streams (front end of the next frames overlaps the solve). */
+int vio_backend_process_image_from_frontend(vio_backend *be, vio_frontend *fe, const double *headers_host);
+
 /* Window state of stream s (VINS::Ps/Rs/Vs/Bas/Bgs/Headers, VINS.hpp:73-77,107):
  * P[(W+1)*3], Q[(W+1)*4] x,y,z,w, V[(W+1)*3], Ba[(W+1)*3], Bg[(W+1)*3], headers[W+1]. NULL = skip */
 int vio_backend_get_state(vio_backend *be, int s, double *P, double *Q, double *V, double *Ba, double *Bg, double *headers);
@@ -165,6 +169,7 @@ int vio_backend_sync(vio_backend *be);
 int vio_backend_use_stream(vio_backend *be, void *cuda_stream);
 int vio_frontend_use_stream(vio_frontend *fe, void *cuda_stream);
 int vio_frontend_sync(vio_frontend *fe);
+void *vio_frontend_stream(vio_frontend *fe);
 /* Per-kernel CUDA-event timing: returns "name:launches:total_ms;..." accumulated since the previous call and switches the
  * timer on/off for subsequent launches. */
 int vio_frontend_profile(vio_frontend *fe, int enable, char *out, int cap);

@@ -50,6 +50,8 @@ def lib():
         L.vio_frontend_launch_count.argtypes = [vp]
         L.vio_frontend_launch_count.restype = C.c_int64
         L.vio_frontend_sync.argtypes = [vp]
+        L.vio_frontend_stream.argtypes = [vp]
+        L.vio_frontend_stream.restype = vp
         L.vio_frontend_use_stream.argtypes = [vp, vp]
         L.vio_frontend_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
         L.vio_prim_pyramid.argtypes = [cfgp, UP, UP, UP, UP]
@@ -65,6 +67,7 @@ def lib():
             L.vio_backend_set_init_window.argtypes = [vp, DP, DP, DP, DP, DP]
             L.vio_backend_process_image.argtypes = [vp, IP, IP, DP, DP]
             L.vio_backend_process_image_dev.argtypes = [vp, vp, vp, vp, DP]
+            L.vio_backend_process_image_from_frontend.argtypes = [vp, vp, DP]
             L.vio_backend_get_state.argtypes = [vp, C.c_int, DP, DP, DP, DP, DP, DP]
             L.vio_backend_state_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64)]
             L.vio_backend_get_info.argtypes = [vp, C.c_int, IP, DP]
@@ -273,6 +276,10 @@ class BackEnd:
     def process_image_dev(self, counts_ptr, ids_ptr, xyz_ptr, headers):
         headers = np.ascontiguousarray(headers, np.float64).reshape(self.B)
         _check(lib().vio_backend_process_image_dev(self.h, counts_ptr, ids_ptr, xyz_ptr, ptr(headers, C.c_double)), "vio_backend_process_image_dev")
+
+    def process_image_from_frontend(self, fe, headers):
+        headers = np.ascontiguousarray(headers, np.float64).reshape(self.B)
+        _check(lib().vio_backend_process_image_from_frontend(self.h, fe.h, ptr(headers, C.c_double)), "vio_backend_process_image_from_frontend")
 
     def process_image_single(self, ids, xyz, header):
         """convenience for batch 1: variable-length ids/xyz"""

@@ -24,6 +24,8 @@ struct vio_backend {
     int *d_counts, *d_ids; double *d_xyz, *d_headers; double *d_imu; size_t imu_cap;
     double *h_headers_pinned;
     size_t solve_smem, marg_smem;
+    cudaEvent_t evt_ready, evt_consumed;
+    bool consumed_valid, record_consumed;
 };
 
 template <typename T>
@@ -69,7 +71,9 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     VIO_CUDA_TRY(cudaSetDevice(cfg->device));
     vio_backend *be = new (std::nothrow) vio_backend();
     if (!be) return VIO_ERR_ARG;
-    be->cfg = *cfg; be->launches = 0; be->own_stream = true;
+    be->cfg = *cfg; be->launches = 0; be->own_stream = true; be->consumed_valid = false; be->record_consumed = false;
+    VIO_CUDA_TRY(cudaEventCreateWithFlags(&be->evt_ready, cudaEventDisableTiming));
+    VIO_CUDA_TRY(cudaEventCreateWithFlags(&be->evt_consumed, cudaEventDisableTiming));
     VIO_CUDA_TRY(cudaStreamCreateWithFlags(&be->stream, cudaStreamNonBlocking));
     BeState &s = be->s;
     memset(&s, 0, sizeof(s));
@@ -147,6 +151,7 @@ extern "C" void vio_backend_destroy(vio_backend *be) {
     cudaSetDevice(be->cfg.device);
     cudaStreamSynchronize(be->stream);
     for (void *p : be->allocs) cudaFree(p);
+    cudaEventDestroy(be->evt_ready); cudaEventDestroy(be->evt_consumed);
     if (be->h_headers_pinned) cudaFreeHost(be->h_headers_pinned);
     if (be->own_stream) cudaStreamDestroy(be->stream);
     delete be;
@@ -224,6 +229,7 @@ static int run_process_image(vio_backend *be, const int32_t *counts, const int32
     BeState &s = be->s;
     cudaStream_t st = be->stream;
     VIO_LAUNCH(be->timer, st, "addfeat_kernel", (addfeat_kernel<<<s.B, 256, 0, st>>>(s, counts, ids, xyz, headers_dev)));
+    if (be->record_consumed) { cudaEventRecord(be->evt_consumed, st); be->consumed_valid = true; be->record_consumed = false; }   // image_msg fully read
     VIO_LAUNCH(be->timer, st, "triangulate_kernel", (triangulate_kernel<<<s.B, 128, 0, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "prepare_kernel", (prepare_kernel<<<s.B, 256, 0, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "solve_kernel", (solve_kernel<<<s.B, SOLVE_T, be->solve_smem, st>>>(s, be->solve_smem > 0)));
@@ -252,6 +258,29 @@ extern "C" int vio_backend_process_image(vio_backend *be, const int32_t *counts,
     VIO_CUDA_TRY(cudaMemcpyAsync(be->d_ids, ids, B * P * sizeof(int), cudaMemcpyHostToDevice, be->stream));
     VIO_CUDA_TRY(cudaMemcpyAsync(be->d_xyz, xyz, B * P * 3 * sizeof(double), cudaMemcpyHostToDevice, be->stream));
     VIO_CUDA_TRY(cudaMemcpyAsync(be->d_headers, headers, B * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    return run_process_image(be, be->d_counts, be->d_ids, be->d_xyz, be->d_headers);
+}
+
+extern "C" void *vio_frontend_stream(vio_frontend *fe);
+// VINS::processImage fed straight from a front end's device-resident image_msg.  If the two handles run on different CUDA streams
+// the hand-over is event-ordered (no host synchronisation): the front end may already track the next frames while the solve runs.
+extern "C" int vio_backend_process_image_from_frontend(vio_backend *be, vio_frontend *fe, const double *headers_host) {
+    if (!be || !fe || !headers_host) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    const int32_t *cnt, *ids; const double *xyz;
+    int rc = vio_frontend_image_msg_dev(fe, &cnt, &ids, &xyz);
+    if (rc) return rc;
+    cudaStream_t fs = (cudaStream_t)vio_frontend_stream(fe);
+    if (fs == be->stream) return vio_backend_process_image_dev(be, cnt, ids, xyz, headers_host);
+    const size_t B = be->s.B, P = be->cfg.max_cnt;
+    if (be->consumed_valid) VIO_CUDA_TRY(cudaStreamWaitEvent(fs, be->evt_consumed, 0));     // previous image_msg copy has been read
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_counts, cnt, B * sizeof(int), cudaMemcpyDeviceToDevice, fs));
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_ids, ids, B * P * sizeof(int), cudaMemcpyDeviceToDevice, fs));
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_xyz, xyz, B * P * 3 * sizeof(double), cudaMemcpyDeviceToDevice, fs));
+    VIO_CUDA_TRY(cudaEventRecord(be->evt_ready, fs));
+    VIO_CUDA_TRY(cudaStreamWaitEvent(be->stream, be->evt_ready, 0));
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_headers, headers_host, B * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    be->record_consumed = true;
     return run_process_image(be, be->d_counts, be->d_ids, be->d_xyz, be->d_headers);
 }
 

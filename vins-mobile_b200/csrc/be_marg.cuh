@@ -18,7 +18,9 @@ constexpr double MARG_EPS = 1e-8;      // MarginalizationInfo::eps, marginalizat
 constexpr int MARG_NCAP = 104;         // A_r and its eigenvectors live in shared memory when n <= MARG_NCAP (2*104^2*8 = 173 KB)
 
 // Cyclic two-sided Jacobi eigensolver, parallel (round-robin) ordering, A symmetric n x n (ld), destroyed: on exit its diagonal
-// holds the eigenvalues and V (n x n, ld = n) the eigenvectors as columns.  cs = shared scratch for 2*(n/2+1) doubles.
+// holds the eigenvalues and V (n x n, ld = n) the eigenvectors as columns.  Per round the n/2 disjoint rotations are computed
+// (phase 1) and then every 2x2 block (pair a, pair b) of A' = J^T A J is updated by ONE thread (phase 2, together with V' = V J):
+// two barriers per round.  cs/pq: shared scratch for 2*(n/2+1) doubles / ints.
 __device__ inline void eig_sym_jacobi(double *A, int n, int ld, double *V, double *cs, int *pq, double *sh_red) {
     const int tid = threadIdx.x, T = blockDim.x;
     for (int e = tid; e < n * n; e += T) { const int i = e / n, j = e - i * n; V[e] = (i == j) ? 1.0 : 0.0; }
@@ -44,30 +46,35 @@ __device__ inline void eig_sym_jacobi(double *A, int n, int ld, double *V, doubl
                         const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                         c = 1.0 / sqrt(1.0 + t * t); sn = c * t;
                     }
-                } else { p = -1; }
+                } else q = -1;                                         // odd n: p is the bye of this round
                 pq[2 * k] = p; pq[2 * k + 1] = q; cs[2 * k] = c; cs[2 * k + 1] = sn;
             }
             __syncthreads();
-            // rows:  B = J^T A
-            for (int e = tid; e < np * n; e += T) {
-                const int k = e / n, j = e - k * n;
-                const int p = pq[2 * k], q = pq[2 * k + 1];
-                if (p < 0) continue;
-                const double c = cs[2 * k], sn = cs[2 * k + 1];
-                const double x = A[(size_t)p * ld + j], y = A[(size_t)q * ld + j];
-                A[(size_t)p * ld + j] = c * x - sn * y; A[(size_t)q * ld + j] = sn * x + c * y;
-            }
-            __syncthreads();
-            // columns:  A' = B J ,  V' = V J
-            for (int e = tid; e < np * n; e += T) {
-                const int i = e / np, k = e - i * np;
-                const int p = pq[2 * k], q = pq[2 * k + 1];
-                if (p < 0) continue;
-                const double c = cs[2 * k], sn = cs[2 * k + 1];
-                double x = A[(size_t)i * ld + p], y = A[(size_t)i * ld + q];
-                A[(size_t)i * ld + p] = c * x - sn * y; A[(size_t)i * ld + q] = sn * x + c * y;
-                x = V[(size_t)i * n + p]; y = V[(size_t)i * n + q];
-                V[(size_t)i * n + p] = c * x - sn * y; V[(size_t)i * n + q] = sn * x + c * y;
+            const int nblk = np * np;
+            for (int e = tid; e < nblk + n * np; e += T) {
+                if (e < nblk) {                                         // A block (pair a rows) x (pair b cols)
+                    const int a = e / np, b = e - a * np;
+                    const int pa = pq[2 * a], qa = pq[2 * a + 1], pb = pq[2 * b], qb = pq[2 * b + 1];
+                    const double ca = cs[2 * a], sa = cs[2 * a + 1], cb = cs[2 * b], sb = cs[2 * b + 1];
+                    const double x00 = A[(size_t)pa * ld + pb];
+                    const double x01 = qb >= 0 ? A[(size_t)pa * ld + qb] : 0.0;
+                    const double x10 = qa >= 0 ? A[(size_t)qa * ld + pb] : 0.0;
+                    const double x11 = (qa >= 0 && qb >= 0) ? A[(size_t)qa * ld + qb] : 0.0;
+                    const double r00 = ca * x00 - sa * x10, r01 = ca * x01 - sa * x11;
+                    const double r10 = sa * x00 + ca * x10, r11 = sa * x01 + ca * x11;
+                    A[(size_t)pa * ld + pb] = cb * r00 - sb * r01;
+                    if (qb >= 0) A[(size_t)pa * ld + qb] = sb * r00 + cb * r01;
+                    if (qa >= 0) A[(size_t)qa * ld + pb] = cb * r10 - sb * r11;
+                    if (qa >= 0 && qb >= 0) A[(size_t)qa * ld + qb] = sb * r10 + cb * r11;
+                } else {                                                // V columns of pair b, row i
+                    const int f = e - nblk;
+                    const int i = f / np, b = f - i * np;
+                    const int pb = pq[2 * b], qb = pq[2 * b + 1];
+                    if (qb < 0) continue;
+                    const double cb = cs[2 * b], sb = cs[2 * b + 1];
+                    const double x = V[(size_t)i * n + pb], y = V[(size_t)i * n + qb];
+                    V[(size_t)i * n + pb] = cb * x - sb * y; V[(size_t)i * n + qb] = sb * x + cb * y;
+                }
             }
             __syncthreads();
         }

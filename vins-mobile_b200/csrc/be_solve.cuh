@@ -249,77 +249,102 @@ __device__ inline bool chol_solve(double *A, int n, const double *rhs, double *y
 // ---- shared-memory path (reduced system fits one SM: NP*(NP+1)/2 doubles, 110 KB at W=10) -------------------------------------
 __device__ __forceinline__ int pidx(int i, int j) { return i * (i + 1) / 2 + j; }       // packed lower, j <= i
 
-// Blocked left-looking Cholesky on a packed lower matrix in shared memory (panel width 8: 3 barriers per panel instead of
-// 2 per column), then forward/backward substitution by one warp.  Returns false on a non-positive pivot / non-finite value.
-__device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, double *y, int *sh_flag) {
+// Blocked left-looking Cholesky on a packed lower matrix in shared memory, BORDERED by the right-hand side: row n of the packed
+// array holds rhs, so the forward substitution z = L^-1 rhs falls out of the row-solve phase of the factorisation itself.
+// Panel width 8; the 8x8 diagonal block is factored by one thread entirely in registers; 3 barriers per panel.  The backward
+// substitution L^T y = z is blocked the same way (2 barriers per panel).  A must have room for (n+1)(n+2)/2 doubles.
+// Returns false (in all threads) on a non-positive pivot / non-finite value (Eigen LLT info() != Success).
+__device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, double *y, int *sh_flag, double *sh_inv /*>= 8*/) {
     const int tid = threadIdx.x, T = blockDim.x;
     constexpr int NB = 8;
     if (tid == 0) *sh_flag = 1;
+    for (int j = tid; j < n; j += T) A[pidx(n, j)] = rhs[j];
     __syncthreads();
     for (int c0 = 0; c0 < n; c0 += NB) {
         const int nb = min(NB, n - c0);
-        for (int e = tid; e < (n - c0) * nb; e += T) {             // panel -= L[:, :c0] L[panel, :c0]^T
+        for (int e = tid; e < (n + 1 - c0) * nb; e += T) {          // panel (incl. the rhs row) -= L[:, :c0] L[panel, :c0]^T
             const int i = c0 + e / nb, j = c0 + e % nb;
             if (j > i) continue;
             const double *ri = A + pidx(i, 0), *rj = A + pidx(j, 0);
-            double t = 0;
-            for (int k = 0; k < c0; k++) t += ri[k] * rj[k];
-            A[pidx(i, j)] -= t;
+            double t0 = 0, t1 = 0;
+            int k = 0;
+            for (; k + 1 < c0; k += 2) { t0 += ri[k] * rj[k]; t1 += ri[k + 1] * rj[k + 1]; }
+            if (k < c0) t0 += ri[k] * rj[k];
+            A[pidx(i, j)] -= t0 + t1;
         }
         __syncthreads();
-        if (tid == 0) {                                            // nb x nb diagonal block, serial
-            for (int jj = 0; jj < nb; jj++) {
-                const int j = c0 + jj;
-                double d = A[pidx(j, j)];
-                for (int t = 0; t < jj; t++) d -= A[pidx(j, c0 + t)] * A[pidx(j, c0 + t)];
-                if (!(d > 0) || !isfinite(d)) { *sh_flag = 0; break; }
-                d = sqrt(d);
-                A[pidx(j, j)] = d;
-                for (int ii = jj + 1; ii < nb; ii++) {
-                    const int i = c0 + ii;
-                    double v = A[pidx(i, j)];
-                    for (int t = 0; t < jj; t++) v -= A[pidx(i, c0 + t)] * A[pidx(j, c0 + t)];
-                    A[pidx(i, j)] = v / d;
+        if (tid == 0) {                                              // nb x nb diagonal block in registers
+            double d[NB][NB];
+#pragma unroll
+            for (int i = 0; i < NB; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) d[i][j] = (i < nb) ? A[pidx(c0 + i, c0 + j)] : (i == j ? 1.0 : 0.0);
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                double v = d[j][j];
+#pragma unroll
+                for (int t = 0; t < j; t++) v -= d[j][t] * d[j][t];
+                ok &= (v > 0) && isfinite(v);
+                const double l = sqrt(v), il = 1.0 / l;
+                d[j][j] = l;
+                if (j < nb) sh_inv[j] = il;
+#pragma unroll
+                for (int i = j + 1; i < NB; i++) {
+                    double w = d[i][j];
+#pragma unroll
+                    for (int t = 0; t < j; t++) w -= d[i][t] * d[j][t];
+                    d[i][j] = w * il;
+                }
+            }
+            if (!ok) *sh_flag = 0;
+#pragma unroll
+            for (int i = 0; i < NB; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) if (i < nb) A[pidx(c0 + i, c0 + j)] = d[i][j];
+        }
+        __syncthreads();
+        if (!*sh_flag) return false;
+        for (int i = c0 + nb + tid; i <= n; i += T) {                // rows below the block (and the rhs row): triangular solve
+            double *ri = A + pidx(i, c0);
+            double v[NB];
+#pragma unroll
+            for (int jj = 0; jj < NB; jj++) {
+                if (jj < nb) {
+                    double w = ri[jj];
+                    const double *rj = A + pidx(c0 + jj, c0);
+#pragma unroll
+                    for (int t = 0; t < jj; t++) w -= v[t] * rj[t];
+                    v[jj] = w * sh_inv[jj];
+                    ri[jj] = v[jj];
                 }
             }
         }
         __syncthreads();
-        if (!*sh_flag) return false;
-        for (int i = c0 + nb + tid; i < n; i += T) {               // rows below the block: triangular solve against it
-            double *ri = A + pidx(i, c0);
-            for (int jj = 0; jj < nb; jj++) {
-                double v = ri[jj];
-                const double *rj = A + pidx(c0 + jj, c0);
-                for (int t = 0; t < jj; t++) v -= ri[t] * rj[t];
-                ri[jj] = v / rj[jj];
+    }
+    // backward: L^T y = z, z = row n of A
+    for (int j = tid; j < n; j += T) y[j] = A[pidx(n, j)];
+    __syncthreads();
+    for (int c0 = ((n - 1) / NB) * NB; c0 >= 0; c0 -= NB) {
+        const int nb = min(NB, n - c0);
+        if (tid == 0) {
+            for (int j = nb - 1; j >= 0; j--) {
+                double v = y[c0 + j];
+                for (int t = j + 1; t < nb; t++) v -= A[pidx(c0 + t, c0 + j)] * y[c0 + t];
+                y[c0 + j] = v / A[pidx(c0 + j, c0 + j)];
             }
         }
         __syncthreads();
-    }
-    if (tid < 32) {
-        const int lane = tid;
-        for (int i = lane; i < n; i += 32) y[i] = rhs[i];
-        __syncwarp();
-        for (int k = 0; k < n; k++) {                              // L z = rhs
-            if (lane == 0) y[k] /= A[pidx(k, k)];
-            __syncwarp();
-            const double yk = y[k];
-            for (int i = k + 1 + lane; i < n; i += 32) y[i] -= A[pidx(i, k)] * yk;
-            __syncwarp();
+        for (int i = tid; i < c0; i += T) {
+            double v = y[i];
+            for (int t = 0; t < nb; t++) v -= A[pidx(c0 + t, i)] * y[c0 + t];
+            y[i] = v;
         }
-        for (int k = n - 1; k >= 0; k--) {                         // L^T y = z
-            if (lane == 0) y[k] /= A[pidx(k, k)];
-            __syncwarp();
-            const double yk = y[k];
-            const double *rk = A + pidx(k, 0);
-            for (int i = lane; i < k; i += 32) y[i] -= rk[i] * yk;
-            __syncwarp();
-        }
+        __syncthreads();
     }
-    __syncthreads();
     bool ok = true;
-    for (int i = 0; i < n; i++) ok &= isfinite(y[i]);
-    return ok;
+    for (int i = tid; i < n; i += T) ok &= isfinite(y[i]);
+    return __syncthreads_and(ok) != 0;
 }
 
 constexpr int SCHUR_CHUNK = 32;
@@ -390,7 +415,7 @@ __device__ inline void build_reduced_smem(const BeState &s, const SolveWs &ws, i
 }
 
 __host__ __device__ inline size_t solve_smem_bytes(int NP, int NPW) {
-    return ((size_t)NP * (NP + 1) / 2 + (size_t)SCHUR_CHUNK * (NPW + 1)) * sizeof(double);
+    return ((size_t)(NP + 1) * (NP + 2) / 2 + 8 + (size_t)SCHUR_CHUNK * (NPW + 1)) * sizeof(double);
 }
 
 __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem) {
@@ -457,9 +482,9 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
             while (mu < 1.0) {
               bool ok;
               if (use_smem) {
-                double *Ssm = sm_dyn, *wt = sm_dyn + (size_t)NP * (NP + 1) / 2;
+                double *Ssm = sm_dyn, *wt = sm_dyn + (size_t)(NP + 1) * (NP + 2) / 2 + 8;
                 build_reduced_smem(s, ws, nl, mu, Ssm, wt);
-                ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag);
+                ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag, sh_red);
               } else {
                 for (int e = tid; e < NP * NP; e += SOLVE_T) {
                     const int i = e / NP, j = e - i * NP;

@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict
 //     registers (14 pixels per lane).  The 2x2 normal equations and the mismatch vector are reduced EXACTLY in
 //     integers with warp shuffles and converted to f32 once.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int LK_WARPS = 4;
-constexpr int LK_PIX = (LK_WIN * LK_WIN + 31) / 32;     // 14 pixels per lane
+constexpr int LK_WARPS = 8;
+constexpr int LK_NPIX = LK_WIN * LK_WIN;                 // 441
+constexpr int LK_PIX = (LK_NPIX + 31) / 32;              // 14 pixels per lane
 
 __device__ __forceinline__ void lk_weights(float fx, float fy, int &w00, int &w01, int &w10, int &w11) {
     const float s = (float)(1 << W_BITS);
@@ -84,23 +85,49 @@ __device__ __forceinline__ void lk_weights(float fx, float fy, int &w00, int &w0
     w11 = (1 << W_BITS) - w00 - w01 - w10;
 }
 
+// stage an (nr x nc) u8 window whose top-left is (y0, x0) into dst (row stride 24), 4 loads in flight per lane
+__device__ __forceinline__ void lk_stage(uint8_t *dst, const uint8_t *__restrict__ im, int rows, int cols, int y0, int x0, int nr, int nc,
+                                         int lane) {
+    const int total = nr * nc;
+    const bool inner = x0 >= 0 && x0 + nc <= cols && y0 >= 0 && y0 + nr <= rows;
+    const uint8_t *base = im + (ptrdiff_t)y0 * cols + x0;
+    for (int i0 = lane; i0 < total; i0 += 128) {
+        uint8_t v[4];
+        int d[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int i = i0 + 32 * t;
+            const int r = i / nc, c = i - r * nc;
+            d[t] = r * 24 + c;
+            if (i < total)
+                v[t] = inner ? base[r * cols + c] : im[(size_t)reflect101(y0 + r, rows) * cols + reflect101(x0 + c, cols)];
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            if (i0 + 32 * t < total) dst[d[t]] = v[t];
+    }
+}
+
 __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevels J, const float2 *__restrict__ prev_pts,
                                                            float2 *__restrict__ next_pts, uint8_t *__restrict__ status,
                                                            const int *__restrict__ n_pts, int maxp) {
+    // per warp: 24x24 template neighbourhood of I, 22x22 (stride 24) window of J, and the bilinear template (Iw, gx, gy) as int16.
+    // Everything is shared-memory resident so that the per-pixel loops stay rolled (small code, few registers, 8 warps per CTA).
     __shared__ uint8_t sI[LK_WARPS][24 * 24];
+    __shared__ uint8_t sJ[LK_WARPS][22 * 24];
+    __shared__ short sT[LK_WARPS][3 * LK_NPIX + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int f = blockIdx.x * LK_WARPS + warp;
     if (f >= n_pts[b]) return;
     const float2 pt = prev_pts[(size_t)b * maxp + f];
     uint8_t *pI = sI[warp];
+    uint8_t *pJ = sJ[warp];
+    short *tI = sT[warp], *tX = tI + LK_NPIX, *tY = tX + LK_NPIX;
     const float half = 10.f;
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
     float nx = 0.f, ny = 0.f;          // nextPts[ptidx] (level coordinates, window centre)
     bool ok = true;                    // status[ptidx]
-    // this lane's 14 window pixels: p = lane + 32k -> (y, x) in the 21x21 window (level independent)
-    unsigned char wy[LK_PIX], wx[LK_PIX];
-#pragma unroll
-    for (int k = 0; k < LK_PIX; k++) { const int p = lane + 32 * k; wy[k] = (unsigned char)(p / LK_WIN); wx[k] = (unsigned char)(p - (p / LK_WIN) * LK_WIN); }
 
     for (int level = LK_LEVELS; level >= 0; level--) {
         const int rows = I.rows[level], cols = I.cols[level];
@@ -116,59 +143,35 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
             if (level == 0) ok = false;
             continue;
         }
-        // stage the 24x24 template neighbourhood, rows ipy-1 .. ipy+22, cols ipx-1 .. ipx+22: all 18 loads of a lane are issued
-        // before the first store so that they overlap
         __syncwarp();
-        {
-            uint8_t v[18];
-            const bool inner = ipx >= 1 && ipx + 23 <= cols && ipy >= 1 && ipy + 23 <= rows;
-            if (inner) {
-                const uint8_t *base = imI + (size_t)(ipy - 1) * cols + (ipx - 1);
-#pragma unroll
-                for (int t = 0; t < 18; t++) { const int i = lane + 32 * t; const int r = i / 24, c = i - r * 24; v[t] = base[r * cols + c]; }
-            } else {
-#pragma unroll
-                for (int t = 0; t < 18; t++) {
-                    const int i = lane + 32 * t; const int r = i / 24, c = i - r * 24;
-                    v[t] = imI[(size_t)reflect101(ipy - 1 + r, rows) * cols + reflect101(ipx - 1 + c, cols)];
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < 18; t++) pI[lane + 32 * t] = v[t];
-        }
+        lk_stage(pI, imI, rows, cols, ipy - 1, ipx - 1, 24, 24, lane);      // rows ipy-1 .. ipy+22, cols ipx-1 .. ipx+22
         __syncwarp();
         int w00, w01, w10, w11;
         lk_weights(fsub(px, (float)ipx), fsub(py, (float)ipy), w00, w01, w10, w11);
-        short Iw[LK_PIX], gx[LK_PIX], gy[LK_PIX];
         int a11 = 0, a12 = 0, a22 = 0;
+#pragma unroll 1
+        for (int p = lane; p < LK_NPIX; p += 32) {
+            const int y = p / LK_WIN, x = p - y * LK_WIN;
+            int iv = 0, dxv = 0, dyv = 0;
 #pragma unroll
-        for (int k = 0; k < LK_PIX; k++) {
-            const int p = lane + 32 * k;
-            Iw[k] = gx[k] = gy[k] = 0;
-            if (p < LK_WIN * LK_WIN) {
-                const int y = wy[k], x = wx[k];
-                int iv = 0, dxv = 0, dyv = 0;
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int yy = y + (t >> 1), xx = x + (t & 1);       // window pixel (yy,xx) in 0..21
-                    const int wgt = t == 0 ? w00 : t == 1 ? w01 : t == 2 ? w10 : w11;
-                    const uint8_t *q = pI + (yy + 1) * 24 + (xx + 1);
-                    iv += wgt * q[0];
-                    const int gyi = ipy + yy, gxi = ipx + xx;
-                    if (gyi >= 0 && gyi < rows && gxi >= 0 && gxi < cols) {
-                        const int tl = q[-25], tc = q[-24], tr = q[-23], ml = q[-1], mr = q[1], bl = q[23], bc = q[24], br = q[25];
-                        dxv += wgt * (3 * (tr - tl) + 10 * (mr - ml) + 3 * (br - bl));
-                        dyv += wgt * (3 * (bl - tl) + 10 * (bc - tc) + 3 * (br - tr));
-                    }
+            for (int t = 0; t < 4; t++) {
+                const int yy = y + (t >> 1), xx = x + (t & 1);           // window pixel (yy,xx) in 0..21
+                const int wgt = t == 0 ? w00 : t == 1 ? w01 : t == 2 ? w10 : w11;
+                const uint8_t *q = pI + (yy + 1) * 24 + (xx + 1);
+                iv += wgt * q[0];
+                const int gyi = ipy + yy, gxi = ipx + xx;
+                if (gyi >= 0 && gyi < rows && gxi >= 0 && gxi < cols) {
+                    const int tl = q[-25], tc = q[-24], tr = q[-23], ml = q[-1], mr = q[1], bl = q[23], bc = q[24], br = q[25];
+                    dxv += wgt * (3 * (tr - tl) + 10 * (mr - ml) + 3 * (br - bl));
+                    dyv += wgt * (3 * (bl - tl) + 10 * (bc - tc) + 3 * (br - tr));
                 }
-                const int ivs = (iv + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                const int gxs = (dxv + (1 << (W_BITS - 1))) >> W_BITS;
-                const int gys = (dyv + (1 << (W_BITS - 1))) >> W_BITS;
-                Iw[k] = (short)ivs; gx[k] = (short)gxs; gy[k] = (short)gys;
-                a11 += gxs * gxs; a12 += gxs * gys; a22 += gys * gys;
             }
+            const int ivs = (iv + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+            const int gxs = (dxv + (1 << (W_BITS - 1))) >> W_BITS;
+            const int gys = (dyv + (1 << (W_BITS - 1))) >> W_BITS;
+            tI[p] = (short)ivs; tX[p] = (short)gxs; tY[p] = (short)gys;
+            a11 += gxs * gxs; a12 += gxs * gys; a22 += gys * gys;
         }
-        const float FLT_SCALE = 1.f / (float)(1 << 20);
         const float A11 = fmul(__ll2float_rn(warp_sum_ll(a11)), FLT_SCALE);
         const float A12 = fmul(__ll2float_rn(warp_sum_ll(a12)), FLT_SCALE);
         const float A22 = fmul(__ll2float_rn(warp_sum_ll(a22)), FLT_SCALE);
@@ -183,42 +186,27 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
         const float Dinv = __fdiv_rn(1.f, D);
         float cx = fsub(nx, half), cy = fsub(ny, half);       // nextPt (window top-left, float)
         float pdx = 0.f, pdy = 0.f;
+#pragma unroll 1
         for (int j = 0; j < LK_MAX_ITERS; j++) {
             const int jx = (int)floorf(cx), jy = (int)floorf(cy);
             if (jx < -LK_WIN || jx >= cols || jy < -LK_WIN || jy >= rows) {
                 if (level == 0) ok = false;
                 break;
             }
+            __syncwarp();
+            lk_stage(pJ, imJ, rows, cols, jy, jx, 22, 22, lane);
+            __syncwarp();
             int v00, v01, v10, v11;
             lk_weights(fsub(cx, (float)jx), fsub(cy, (float)jy), v00, v01, v10, v11);
             int b1 = 0, b2 = 0;
-            // the 22x22 window of J is read straight through L1 (4 independent byte loads per pixel, coalesced across lanes);
-            // REFLECT_101 indexing only when the window leaves the image
-            if (jx >= 0 && jx + 22 <= cols && jy >= 0 && jy + 22 <= rows) {
-                const uint8_t *base = imJ + (size_t)jy * cols + jx;
-#pragma unroll
-                for (int k = 0; k < LK_PIX; k++) {
-                    if (lane + 32 * k < LK_WIN * LK_WIN) {
-                        const uint8_t *q = base + wy[k] * cols + wx[k];
-                        const int jv = (q[0] * v00 + q[1] * v01 + q[cols] * v10 + q[cols + 1] * v11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                        const int diff = jv - Iw[k];
-                        b1 += diff * gx[k];
-                        b2 += diff * gy[k];
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < LK_PIX; k++) {
-                    if (lane + 32 * k < LK_WIN * LK_WIN) {
-                        const int y0 = reflect101(jy + wy[k], rows), y1 = reflect101(jy + wy[k] + 1, rows);
-                        const int x0 = reflect101(jx + wx[k], cols), x1 = reflect101(jx + wx[k] + 1, cols);
-                        const int jv = (imJ[(size_t)y0 * cols + x0] * v00 + imJ[(size_t)y0 * cols + x1] * v01 + imJ[(size_t)y1 * cols + x0] * v10 +
-                                        imJ[(size_t)y1 * cols + x1] * v11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                        const int diff = jv - Iw[k];
-                        b1 += diff * gx[k];
-                        b2 += diff * gy[k];
-                    }
-                }
+#pragma unroll 2
+            for (int p = lane; p < LK_NPIX; p += 32) {
+                const int y = p / LK_WIN, x = p - y * LK_WIN;
+                const uint8_t *q = pJ + y * 24 + x;
+                const int jv = (q[0] * v00 + q[1] * v01 + q[24] * v10 + q[25] * v11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                const int diff = jv - tI[p];
+                b1 += diff * tX[p];
+                b2 += diff * tY[p];
             }
             const float B1 = fmul(__ll2float_rn(warp_sum_ll(b1)), FLT_SCALE);
             const float B2 = fmul(__ll2float_rn(warp_sum_ll(b2)), FLT_SCALE);
@@ -345,7 +333,17 @@ __global__ void __launch_bounds__(256) eig_candidates_kernel(const uint8_t *__re
         const int r = i / ET, c = i - r * ET;
         const int gy = ty0 + r, gx = tx0 + c;
         if (gy >= rows || gx >= cols) continue;
-        const float e = se[(r + 1) * EW + (c + 1)];
+        const float *q = se + (r + 1) * EW + (c + 1);
+        const float e = q[0];
+        // the (analytic) mask only matters for a pixel that would raise the running maximum or that is an interior local maximum,
+        // so it is evaluated lazily
+        bool is_cand = false;
+        if (e > 0.f && gy >= 1 && gy < rows - 1 && gx >= 1 && gx < cols - 1) {
+            const float m = fmaxf(fmaxf(fmaxf(q[-EW - 1], q[-EW]), fmaxf(q[-EW + 1], q[-1])),
+                                  fmaxf(fmaxf(q[1], q[EW - 1]), fmaxf(q[EW], q[EW + 1])));
+            is_cand = e >= m;
+        }
+        if (!is_cand && !(e > local_max)) continue;
         bool masked = false;
         for (int k = 0; k < nkk; k++) {
             const int ddx = gx - sk[k].x, ddy = gy - sk[k].y;
@@ -353,11 +351,7 @@ __global__ void __launch_bounds__(256) eig_candidates_kernel(const uint8_t *__re
         }
         if (masked) continue;
         local_max = fmaxf(local_max, e);
-        if (gy < 1 || gy >= rows - 1 || gx < 1 || gx >= cols - 1 || !(e > 0.f)) continue;
-        const float *q = se + (r + 1) * EW + (c + 1);
-        const float m = fmaxf(fmaxf(fmaxf(q[-EW - 1], q[-EW]), fmaxf(q[-EW + 1], q[-1])),
-                              fmaxf(fmaxf(q[1], q[EW - 1]), fmaxf(q[EW], q[EW + 1])));
-        if (e >= m) {
+        if (is_cand) {
             const int s = atomicAdd(&cand_cnt[b], 1);
             if (s < CAND_CAP)
                 cand[(size_t)b * CAND_CAP + s] = ((unsigned long long)__float_as_uint(e) << 32) | (unsigned)(gy * cols + gx);
