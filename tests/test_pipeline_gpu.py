@@ -1,0 +1,60 @@
+"""End-to-end GPU parity: images -> FeatureTracker::readImage -> VINS::processIMU/processImage, CUDA path vs the oracles
+(restated tracker + reference factors/Ceres), including the device-to-device image_msg hand-over across CUDA streams."""
+import numpy as np
+import pytest
+
+import backend_oracle as bo
+import frontend_oracle as fo
+from be_common import Quiet, quat_err, rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not bo.available(), reason="oracle/_ref/libvins_ref.so not built")]
+
+FREQ, PER = 3, 20
+
+
+def test_images_to_window_state(api, abi, synth, get_stream):
+    n_frames = 42                                   # 14 keyframes: fill (11) + 3 more solves
+    s = get_stream(0, n_frames)
+    cfg = abi.default_config(batch=1, max_cnt=150)
+    W = cfg.window_size
+    fe, be = api.FrontEnd(cfg), api.BackEnd(cfg)     # two handles, two CUDA streams -> event-ordered hand-over
+    fe2, be2 = api.FrontEnd(cfg), api.BackEnd(cfg)   # same kernels, image_msg through the host
+    tr = fo.FeatureTrackerOracle(max_cnt=150, backend="restated")
+    ref = bo.RefEstimator(cfg)
+    gtQ = synth.rot_to_quat_xyzw(s.R[::FREQ])
+    kf = 0
+    for i in range(n_frames):
+        im = s.images[i].numpy()
+        pub = fe.read_images(im[None])
+        fe2.read_images(im[None])
+        tr.read_image(im)
+        if not pub:
+            continue
+        if kf > 0:
+            sl = slice((kf - 1) * PER, kf * PER)
+            dts = np.full(PER, 1.0 / 200.0)
+            be.process_imu(dts[:, None], s.acc[sl][:, None], s.gyr[sl][:, None])
+            be2.process_imu(dts[:, None], s.acc[sl][:, None], s.gyr[sl][:, None])
+            for j in range(PER):
+                ref.process_imu(dts[j], s.acc[sl][j], s.gyr[sl][j])
+        if kf == W:
+            P, Q, V = s.P[::FREQ][:W + 1], gtQ[:W + 1], s.V[::FREQ][:W + 1]
+            for h in (be, be2):
+                h.set_init_window(P[None], Q[None], V[None], np.zeros((1, 3)), np.zeros((1, 3)))
+            ref.set_init_window(P, Q, V, np.zeros(3), np.zeros(3))
+        be.process_image_from_frontend(fe, [i / 30.0])
+        g = fe2.stream(0)
+        be2.process_image_single(g["ids"], g["norm_xyz"], i / 30.0)
+        ids = np.array(sorted(tr.image_msg.keys()), np.int32)
+        with Quiet():
+            ref.process_image(ids, np.array([tr.image_msg[k] for k in ids]), i / 30.0)
+        a, b, r = be.state(0), be2.state(0), ref.state()
+        for key in ("P", "Q", "V", "Ba", "Bg"):
+            assert np.array_equal(a[key], b[key]), f"kf {kf}: device hand-over differs from the host path ({key})"
+        assert {int(x) for x in g["ids"]} == set(tr.image_msg.keys()), f"kf {kf}: front-end ids differ from the oracle"
+        tol = 1e-9 if kf < W else 1e-4
+        assert rel_err(a["P"], r["P"]) < tol and rel_err(a["V"], r["V"]) < tol and quat_err(a["Q"], r["Q"]) < tol, f"kf {kf}"
+        kf += 1
+    assert be.info(0)["solver_flag"] == 1 and ref.info()["solver_flag"] == 1
+    for h in (fe, be, fe2, be2):
+        h.close()
