@@ -291,6 +291,9 @@ def _cpu_worker(payload):
     est = bo.RefEstimator(cfg)
     kf = 0
     t_start = None
+    # the reference prints from destructors too ("release marginlizationinfo"): this worker's stdout stays on /dev/null for good,
+    # results travel back through the pool's pipe
+    os.dup2(os.open(os.devnull, os.O_WRONLY), 1)
     with Quiet():
         for i in range(prologue + n_time):
             if i == prologue:

@@ -50,7 +50,8 @@ def test_images_to_window_state(api, abi, synth, get_stream):
             ref.process_image(ids, np.array([tr.image_msg[k] for k in ids]), i / 30.0)
         a, b, r = be.state(0), be2.state(0), ref.state()
         for key in ("P", "Q", "V", "Ba", "Bg"):
-            assert np.array_equal(a[key], b[key]), f"kf {kf}: device hand-over differs from the host path ({key})"
+            # same kernels, same inputs; H is accumulated with floating-point atomics, so the two runs agree to round-off, not bitwise
+            assert np.abs(a[key] - b[key]).max() < 1e-7, f"kf {kf}: device hand-over differs from the host path ({key})"
         assert {int(x) for x in g["ids"]} == set(tr.image_msg.keys()), f"kf {kf}: front-end ids differ from the oracle"
         tol = 1e-9 if kf < W else 1e-4
         assert rel_err(a["P"], r["P"]) < tol and rel_err(a["V"], r["V"]) < tol and quat_err(a["Q"], r["Q"]) < tol, f"kf {kf}"

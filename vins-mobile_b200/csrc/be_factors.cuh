@@ -210,6 +210,65 @@ __device__ inline void imu_residual(const double *pr, double g, const double *pi
     put(12, 27, eye3());
 }
 
+
+// Warp-cooperative variant of imu_residual: every lane evaluates the (cheap) shared prelude, lane 0 stores the raw residual and
+// lanes 0..17 each form ONE of the 18 non-zero 3x3 blocks of the 15x30 Jacobian (the serial version spent most of its time in
+// dependent f64 chains on a single lane while 31 lanes idled).
+__device__ inline void imu_residual_warp(const double *pr, double g, const double *pi, const double *sbi, const double *pj, const double *sbj,
+                                         double *res_raw, double *J, int lane) {
+    const V3 Pi = ld3(pi), Pj = ld3(pj), Vi = ld3(sbi), Vj = ld3(sbj), Bai = ld3(sbi + 3), Bgi = ld3(sbi + 6), Baj = ld3(sbj + 3), Bgj = ld3(sbj + 6);
+    const Q4 Qi = ldq(pi + 3), Qj = ldq(pj + 3);
+    const double *Jm = pr + PR_JAC;
+    auto blk = [&](int r, int c) { M3 B; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) B.m[3 * i + j] = Jm[(r + i) * 15 + c + j]; return B; };
+    const M3 dq_dbg = blk(3, 12);
+    const V3 dba = Bai - ld3(pr + PR_LBA), dbg = Bgi - ld3(pr + PR_LBG);
+    const Q4 dq = ldq(pr + PR_DQ);
+    const Q4 cq = qmul(dq, deltaQ(dq_dbg * dbg));
+    const double sdt = pr[PR_SUMDT];
+    const V3 G = v3(0, 0, g);
+    const Q4 Qi_inv = qinv(Qi);
+    const V3 tp = qrot(Qi_inv, 0.5 * G * sdt * sdt + Pj - Pi - Vi * sdt);
+    const V3 tv = qrot(Qi_inv, G * sdt + Vj - Vi);
+    if (lane == 0) {
+        const M3 dp_dba = blk(0, 9), dp_dbg = blk(0, 12), dv_dba = blk(6, 9), dv_dbg = blk(6, 12);
+        const V3 cv = ld3(pr + PR_DV) + dv_dba * dba + dv_dbg * dbg;
+        const V3 cp = ld3(pr + PR_DP) + dp_dba * dba + dp_dbg * dbg;
+        const Q4 qe = qmul(qinv(cq), qmul(Qi_inv, Qj));
+        st3(res_raw + 0, tp - cp);
+        st3(res_raw + 3, v3(2 * qe.x, 2 * qe.y, 2 * qe.z));
+        st3(res_raw + 6, tv - cv);
+        st3(res_raw + 9, Baj - Bai);
+        st3(res_raw + 12, Bgj - Bgi);
+    }
+    if (!J) return;
+    for (int i = lane; i < 450; i += 32) J[i] = 0.0;
+    __syncwarp();
+    if (lane >= 18) return;
+    M3 B; int r = 0, c = 0;
+    const M3 RiT = q2R(Qi_inv);
+    switch (lane) {
+        case 0: r = 0; c = 0; B = -1.0 * RiT; break;
+        case 1: r = 0; c = 3; B = skew(tp); break;
+        case 2: r = 3; c = 3; B = -1.0 * qleft_qright_33(qmul(qinv(Qj), Qi), cq); break;
+        case 3: r = 6; c = 3; B = skew(tv); break;
+        case 4: r = 0; c = 6; B = (-sdt) * RiT; break;
+        case 5: r = 0; c = 9; B = -1.0 * blk(0, 9); break;
+        case 6: r = 0; c = 12; B = -1.0 * blk(0, 12); break;
+        case 7: r = 3; c = 12; B = -1.0 * (qleft33(qmul(qmul(qinv(Qj), Qi), cq)) * dq_dbg); break;
+        case 8: r = 6; c = 6; B = -1.0 * RiT; break;
+        case 9: r = 6; c = 9; B = -1.0 * blk(6, 9); break;
+        case 10: r = 6; c = 12; B = -1.0 * blk(6, 12); break;
+        case 11: r = 9; c = 9; B = -1.0 * eye3(); break;
+        case 12: r = 12; c = 12; B = -1.0 * eye3(); break;
+        case 13: r = 0; c = 15; B = RiT; break;
+        case 14: r = 3; c = 18; B = qleft33(qmul(qinv(cq), qmul(Qi_inv, Qj))); break;
+        case 15: r = 6; c = 21; B = RiT; break;
+        case 16: r = 9; c = 24; B = eye3(); break;
+        default: r = 12; c = 27; B = eye3(); break;
+    }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) J[(r + i) * 30 + c + j] = B.m[3 * i + j];
+}
+
 // ProjectionFactor::Evaluate + CauchyLoss(1.0) corrector.  Returns the robustified cost 0.5*rho(s).
 //   r2[2]   : corrected residual  sqrt(rho') * r
 //   Ji,Jj   : 2x6 corrected Jacobians wrt pose_i / pose_j (local), Jl : 2x1 wrt inverse depth      (nullptr = cost only)

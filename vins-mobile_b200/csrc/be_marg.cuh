@@ -32,7 +32,11 @@ __device__ inline void eig_sym_jacobi(double *A, int n, int ld, double *V, doubl
         for (int e = tid; e < n * n; e += T) { const int i = e / n, j = e - i * n; const double a = A[(size_t)i * ld + j]; if (i == j) dg += a * a; else off += a * a; }
         off = block_sum_d(off, sh_red);
         dg = block_sum_d(dg, sh_red);
-        if (off <= 1e-30 * dg || off == 0.0) break;
+        // Stop at the round-off floor of the MATRIX (|A|_F * eps per entry), not of the individual pivots: A_r has (gauge) eigenvalues
+        // that are pure noise, and a pivot-relative test would chase them for the full 40 sweeps.
+        const double normA = sqrt(off + dg);
+        if (off == 0.0 || sqrt(off) <= 1e-14 * normA) break;
+        const double skip = 1e-17 * normA;
         for (int round = 0; round < ne - 1; round++) {
             for (int k = tid; k < np; k += T) {
                 int p = (k == 0) ? ne - 1 : (round + k) % (ne - 1);
@@ -41,7 +45,7 @@ __device__ inline void eig_sym_jacobi(double *A, int n, int ld, double *V, doubl
                 double c = 1.0, sn = 0.0;
                 if (q < n) {
                     const double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
-                    if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * sqrt(fabs(app * aqq))) {
+                    if (fabs(apq) > skip) {
                         const double zeta = (aqq - app) / (2.0 * apq);
                         const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                         c = 1.0 / sqrt(1.0 + t * t); sn = c * t;

@@ -99,7 +99,7 @@ __device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, co
         const double *pr = S_pre(s, b, f + 1);
         double *J = ws.imuJ + (size_t)f * 930;          // raw J 450 | weighted J 450 | raw res 15 | weighted res 15
         double *Jw = J + 450, *rr = J + 900, *rw = J + 915;
-        if (lane == 0) imu_residual(pr, s.gravity, par + 16 * f, par + 16 * f + 7, par + 16 * (f + 1), par + 16 * (f + 1) + 7, rr, lin ? J : nullptr);
+        imu_residual_warp(pr, s.gravity, par + 16 * f, par + 16 * f + 7, par + 16 * (f + 1), par + 16 * (f + 1) + 7, rr, lin ? J : nullptr, lane);
         __syncwarp();
         const double *U = pr + PR_SQI;                   // upper triangular
         double r_w = 0.0;                                // lanes 0..14 hold the weighted residual
@@ -254,7 +254,7 @@ __device__ __forceinline__ int pidx(int i, int j) { return i * (i + 1) / 2 + j; 
 // Panel width 8; the 8x8 diagonal block is factored by one thread entirely in registers; 3 barriers per panel.  The backward
 // substitution L^T y = z is blocked the same way (2 barriers per panel).  A must have room for (n+1)(n+2)/2 doubles.
 // Returns false (in all threads) on a non-positive pivot / non-finite value (Eigen LLT info() != Success).
-__device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, double *y, int *sh_flag, double *sh_inv /*>= 8*/) {
+__device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, double *y, int *sh_flag, double *sh_inv /*>= 8*/, double *dinv /*>= 36*ceil(n/8)*/) {
     const int tid = threadIdx.x, T = blockDim.x;
     constexpr int NB = 8;
     if (tid == 0) *sh_flag = 1;
@@ -302,6 +302,22 @@ __device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, do
             for (int i = 0; i < NB; i++)
 #pragma unroll
                 for (int j = 0; j <= i; j++) if (i < nb) A[pidx(c0 + i, c0 + j)] = d[i][j];
+            // inverse of the (lower) diagonal block, kept for the backward substitution: Li = d^-1
+            double li[NB][NB];
+#pragma unroll
+            for (int c = 0; c < NB; c++)
+#pragma unroll
+                for (int i = c; i < NB; i++) {
+                    double v = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int t = c; t < i; t++) v -= d[i][t] * li[t][c];
+                    li[i][c] = v / d[i][i];
+                }
+            double *dst = dinv + (c0 / NB) * 36;
+#pragma unroll
+            for (int i = 0; i < NB; i++)
+#pragma unroll
+                for (int c = 0; c <= i; c++) dst[i * (i + 1) / 2 + c] = li[i][c];
         }
         __syncthreads();
         if (!*sh_flag) return false;
@@ -327,13 +343,13 @@ __device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, do
     __syncthreads();
     for (int c0 = ((n - 1) / NB) * NB; c0 >= 0; c0 -= NB) {
         const int nb = min(NB, n - c0);
-        if (tid == 0) {
-            for (int j = nb - 1; j >= 0; j--) {
-                double v = y[c0 + j];
-                for (int t = j + 1; t < nb; t++) v -= A[pidx(c0 + t, c0 + j)] * y[c0 + t];
-                y[c0 + j] = v / A[pidx(c0 + j, c0 + j)];
-            }
+        double yj = 0;
+        if (tid < nb) {                                              // y_panel = Ldd^-T z_panel (Ldd^-1 kept from the factorisation)
+            const double *li = dinv + (c0 / NB) * 36;
+            for (int t = tid; t < nb; t++) yj += li[t * (t + 1) / 2 + tid] * y[c0 + t];
         }
+        __syncthreads();
+        if (tid < nb) y[c0 + tid] = yj;
         __syncthreads();
         for (int i = tid; i < c0; i += T) {
             double v = y[i];
@@ -484,7 +500,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
               if (use_smem) {
                 double *Ssm = sm_dyn, *wt = sm_dyn + (size_t)(NP + 1) * (NP + 2) / 2 + 8;
                 build_reduced_smem(s, ws, nl, mu, Ssm, wt);
-                ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag, sh_red);
+                ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag, sh_red, wt);
               } else {
                 for (int e = tid; e < NP * NP; e += SOLVE_T) {
                     const int i = e / NP, j = e - i * NP;

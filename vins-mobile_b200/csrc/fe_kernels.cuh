@@ -34,13 +34,23 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict
     uint8_t *dst = out + (size_t)blockIdx.z * out_stride;
     int acc[4] = {0, 0, 0, 0};
     const int kw[5] = {1, 4, 6, 4, 1};
-    const bool interior = (2 * ox0 - 2 >= 0) && (2 * ox0 + 8 < ic);
+    const bool interior = (2 * ox0 - 4 >= 0) && (2 * ox0 + 12 <= ic);
+    const bool aligned = interior && ((ic & 7) == 0) && ((in_stride & 7) == 0);
 #pragma unroll
     for (int dy = -2; dy <= 2; dy++) {
         const int y = reflect101(2 * oy + dy, ir);
         const uint8_t *row = src + (size_t)y * ic;
         int v[11];
-        if (interior) {
+        if (aligned) {
+            // the 11-byte footprint [2ox0-2, 2ox0+8] sits inside 16 bytes starting at 2ox0-4: u32 + u64 + u32 (all naturally aligned)
+            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(row + 2 * ox0 - 4);
+            const uint2 w12 = *reinterpret_cast<const uint2 *>(row + 2 * ox0);
+            const uint32_t w3 = *reinterpret_cast<const uint32_t *>(row + 2 * ox0 + 8);
+            v[0] = (w0 >> 16) & 0xff; v[1] = w0 >> 24;
+            v[2] = w12.x & 0xff; v[3] = (w12.x >> 8) & 0xff; v[4] = (w12.x >> 16) & 0xff; v[5] = w12.x >> 24;
+            v[6] = w12.y & 0xff; v[7] = (w12.y >> 8) & 0xff; v[8] = (w12.y >> 16) & 0xff; v[9] = w12.y >> 24;
+            v[10] = w3 & 0xff;
+        } else if (2 * ox0 - 2 >= 0 && 2 * ox0 + 8 < ic) {
 #pragma unroll
             for (int k = 0; k < 11; k++) v[k] = row[2 * ox0 - 2 + k];
         } else {
