@@ -210,7 +210,7 @@ def run_ours(args):
                 one(i)
             prof = {}
             prof.update(pipe.fe.profile(False)); prof.update(pipe.be.profile(False))
-            info = [pipe.be.info(b) for b in range(min(B, 4))]
+            info = [pipe.be.info(b) for b in range(B)]
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -256,6 +256,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(B * (W + 1) * 16 * 8 / FREQ), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
         "solve_info_stream0": info[0] if info else None,
+        "solve_info_batch": {k: [min(i[k] for i in info), max(i[k] for i in info)] for k in ("iters", "n_feat", "n_proj", "prior_n", "marg_fast", "marg_sweeps", "marg_m", "chol_retry", "err")} if info else None,
     }
     print(json.dumps(line))
 

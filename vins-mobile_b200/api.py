@@ -309,7 +309,8 @@ class BackEnd:
         i = np.zeros(8, np.int32); d = np.zeros(4)
         _check(lib().vio_backend_get_info(self.h, s, ptr(i, C.c_int32), ptr(d, C.c_double)), "vio_backend_get_info")
         return dict(solver_flag=int(i[0]), marg_flag=int(i[1]), frame_count=int(i[2]), failure=int(i[3]), n_feat=int(i[4]), n_proj=int(i[5]),
-                    iters=int(i[6]), last_track_num=int(i[7]), cost0=float(d[0]), cost1=float(d[1]), prior_n=int(d[2]), err=int(d[3]))
+                    iters=int(i[6]), last_track_num=int(i[7]), cost0=float(d[0]), cost1=float(d[1]), prior_n=int(d[2]), err=int(d[3]) & 15,
+                    marg_fast=(int(d[3]) >> 4) & 1, marg_sweeps=(int(d[3]) >> 5) & 127, marg_m=(int(d[3]) >> 12) & 1023, chol_retry=int(d[3]) >> 22)
 
     def features(self, s=0, cap=8192):
         n = C.c_int(0)

@@ -340,7 +340,8 @@ extern "C" int vio_backend_get_info(vio_backend *be, int s, int32_t info[8], dou
     VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
     if (info) { info[0] = iv[IV_SOLVER_FLAG]; info[1] = iv[IV_MARG_FLAG]; info[2] = iv[IV_FRAME_COUNT]; info[3] = iv[IV_FAILURE];
                 info[4] = iv[IV_N_LM]; info[5] = iv[IV_N_FAC]; info[6] = iv[IV_ITERS]; info[7] = iv[IV_LAST_TRACK]; }
-    if (dinfo) { dinfo[0] = dv[DV_COST0]; dinfo[1] = dv[DV_COST1]; dinfo[2] = iv[IV_PRIOR_VALID] ? iv[IV_PRIOR_N] : 0; dinfo[3] = iv[IV_ERR]; }
+    if (dinfo) { dinfo[0] = dv[DV_COST0]; dinfo[1] = dv[DV_COST1]; dinfo[2] = iv[IV_PRIOR_VALID] ? iv[IV_PRIOR_N] : 0;
+                 dinfo[3] = iv[IV_ERR] + 16.0 * iv[IV_MARG_FAST] + 32.0 * iv[IV_MARG_SWEEPS] + 4096.0 * iv[IV_MARG_M] + 4194304.0 * iv[IV_CHOL_RETRY]; }
     return VIO_OK;
 }
 

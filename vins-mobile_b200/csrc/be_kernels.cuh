@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) addfeat_kernel(BeState s, const int *__re
         if (iv[IV_SOLVER_FLAG] == 0) act = (fc == s.W) ? (iv[IV_INIT_PENDING] ? ACT_INIT_SOLVE : ACT_SLIDE_ONLY) : ACT_ACCUMULATE;
         else act = ACT_NL_SOLVE;
         iv[IV_ACTION] = act;
-        iv[IV_N_LM] = 0; iv[IV_N_FAC] = 0; iv[IV_ITERS] = 0;
+        iv[IV_N_LM] = 0; iv[IV_N_FAC] = 0; iv[IV_ITERS] = 0; iv[IV_CHOL_RETRY] = 0; iv[IV_MARG_SWEEPS] = 0; iv[IV_MARG_FAST] = 0;
     }
 }
 

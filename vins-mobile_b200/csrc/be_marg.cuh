@@ -21,13 +21,14 @@ constexpr int MARG_NCAP = 104;         // A_r and its eigenvectors live in share
 // holds the eigenvalues and V (n x n, ld = n) the eigenvectors as columns.  Per round the n/2 disjoint rotations are computed
 // (phase 1) and then every 2x2 block (pair a, pair b) of A' = J^T A J is updated by ONE thread (phase 2, together with V' = V J):
 // two barriers per round.  cs/pq: shared scratch for 2*(n/2+1) doubles / ints.
-__device__ inline void eig_sym_jacobi(double *A, int n, int ld, double *V, double *cs, int *pq, double *sh_red) {
+__device__ inline int eig_sym_jacobi(double *A, int n, int ld, double *V, double *cs, int *pq, double *sh_red) {
     const int tid = threadIdx.x, T = blockDim.x;
     for (int e = tid; e < n * n; e += T) { const int i = e / n, j = e - i * n; V[e] = (i == j) ? 1.0 : 0.0; }
     __syncthreads();
-    if (n < 2) return;
+    if (n < 2) return 0;
     const int ne = (n + 1) & ~1, np = ne / 2;
-    for (int sweep = 0; sweep < 40; sweep++) {
+    int sweep = 0;
+    for (; sweep < 40; sweep++) {
         double off = 0, dg = 0;
         for (int e = tid; e < n * n; e += T) { const int i = e / n, j = e - i * n; const double a = A[(size_t)i * ld + j]; if (i == j) dg += a * a; else off += a * a; }
         off = block_sum_d(off, sh_red);
@@ -83,6 +84,7 @@ __device__ inline void eig_sym_jacobi(double *A, int n, int ld, double *V, doubl
             __syncthreads();
         }
     }
+    return sweep;
 }
 
 // ProjectionFactor Jacobian wrt para_Ex_Pose (projection_facor.cpp:73-84), corrected by sqrt(rho'): 2x6
@@ -411,16 +413,18 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     __syncthreads();
     for (int e = tid; e < n * n; e += MARG_T) { const int i = e / n, j = e - i * n; if (j < i) { const double v = 0.5 * (Ar[(size_t)i * n + j] + Ar[(size_t)j * n + i]); Ar[(size_t)i * n + j] = v; Ar[(size_t)j * n + i] = v; } }
     __syncthreads();
+    int sweeps = 0;
     if (n <= MARG_NCAP) {                                      // A_r and V in shared memory
         double *sA = reinterpret_cast<double *>(smraw + ((sizeof(MargSmem) + 15) & ~(size_t)15));
         double *sV = sA + (size_t)n * n;
         for (int e = tid; e < n * n; e += MARG_T) sA[e] = Ar[e];
         __syncthreads();
-        eig_sym_jacobi(sA, n, n, sV, sm.cs, sm.pq, sm.red);
+        sweeps = eig_sym_jacobi(sA, n, n, sV, sm.cs, sm.pq, sm.red);
         Ar = sA; Vr = sV;
     } else {
-        eig_sym_jacobi(Ar, n, n, Vr, sm.cs, sm.pq, sm.red);
+        sweeps = eig_sym_jacobi(Ar, n, n, Vr, sm.cs, sm.pq, sm.red);
     }
+    if (tid == 0) { iv[IV_MARG_FAST] = fast_ok; iv[IV_MARG_SWEEPS] = sweeps; iv[IV_MARG_M] = m; }
     __syncthreads();
     // tv[k] = v_k . b_r ;  c0 = sum_{lam>eps} tv^2 / lam
     for (int k = tid; k < n; k += MARG_T) {

@@ -70,15 +70,20 @@ __device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, co
     const int *iv = S_iv(s, b);
     const int NP = s.NP, NPW = s.NPW, nl = iv[IV_N_LM], nfac = iv[IV_N_FAC];
     double cost = 0.0;
+    const int has_prior = iv[IV_PRIOR_VALID];
     if (lin) {
-        for (int i = tid; i < NP * NP; i += blockDim.x) ws.H[i] = 0.0;
+        // H starts as the prior's J0^T J0 (pose / speed-bias rows and columns of the canonical layout), or zero
+        if (has_prior) {
+            const double *Hp = s.Hp + (size_t)b * s.NPX * s.NPX;
+            for (int e = tid; e < NP * NP; e += blockDim.x) { const int i = e / NP, j = e - i * NP; ws.H[e] = Hp[(size_t)i * s.NPX + j]; }
+        } else
+            for (int i = tid; i < NP * NP; i += blockDim.x) ws.H[i] = 0.0;
         for (int i = tid; i < NP; i += blockDim.x) ws.g[i] = 0.0;
         for (int i = tid; i < nl; i += blockDim.x) { ws.hll[i] = 0.0; ws.gl[i] = 0.0; }
         for (int i = tid; i < nl * NPW; i += blockDim.x) ws.w[i] = 0.0;
     }
-    __syncthreads();
     // ---- prior ------------------------------------------------------------------------------------------
-    if (iv[IV_PRIOR_VALID]) {
+    if (has_prior) {
         const int NPX = s.NPX;
         const double *Hp = s.Hp + (size_t)b * NPX * NPX, *bp = s.bp + (size_t)b * NPX;
         prior_dx(s, b, par, ws.dx);
@@ -90,10 +95,8 @@ __device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, co
             if (lin && i < NP) ws.g[i] += t + bp[i];
         }
         if (tid == 0) cost += 0.5 * S_dv(s, b)[DV_PRIOR_C0];
-        if (lin)
-            for (int e = tid; e < NP * NP; e += blockDim.x) { const int i = e / NP, j = e - i * NP; ws.H[e] += Hp[(size_t)i * NPX + j]; }
-        __syncthreads();
     }
+    __syncthreads();
     // ---- IMU factors: one warp per factor ---------------------------------------------------------------
     for (int f = warp; f < s.W; f += nwarp) {
         const double *pr = S_pre(s, b, f + 1);
@@ -116,6 +119,7 @@ __device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, co
             const int off = 15 * f;
             for (int e = lane; e < 900; e += 32) {
                 const int r = e / 30, c = e - r * 30;
+                if (c > r) continue;                      // lower triangle only; the upper one is mirrored after the accumulation
                 double t = 0;
                 for (int k = 0; k < 15; k++) t += Jw[k * 30 + r] * Jw[k * 30 + c];
                 atomic_add(&ws.H[(size_t)(off + r) * NP + off + c], t);
@@ -144,14 +148,12 @@ __device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, co
             cost += proj_eval(K, pi, pj, par + 16 * i, par + 16 * j, par[16 * s.NF + l], r2, Ji, Jj, Jl);
             const int oi = 15 * i, oj = 15 * j;
             for (int a = 0; a < 6; a++) {
-                for (int c = 0; c < 6; c++) {
-                    const double hii = Ji[a] * Ji[c] + Ji[6 + a] * Ji[6 + c];
-                    const double hjj = Jj[a] * Jj[c] + Jj[6 + a] * Jj[6 + c];
-                    const double hij = Ji[a] * Jj[c] + Ji[6 + a] * Jj[6 + c];
-                    atomic_add(&ws.H[(size_t)(oi + a) * NP + oi + c], hii);
-                    atomic_add(&ws.H[(size_t)(oj + a) * NP + oj + c], hjj);
-                    atomic_add(&ws.H[(size_t)(oi + a) * NP + oj + c], hij);
-                    atomic_add(&ws.H[(size_t)(oj + c) * NP + oi + a], hij);
+                for (int c = 0; c < 6; c++) {             // lower triangle only (i < j always): blocks (i,i), (j,j) lower halves and (j,i)
+                    if (c <= a) {
+                        atomic_add(&ws.H[(size_t)(oi + a) * NP + oi + c], Ji[a] * Ji[c] + Ji[6 + a] * Ji[6 + c]);
+                        atomic_add(&ws.H[(size_t)(oj + a) * NP + oj + c], Jj[a] * Jj[c] + Jj[6 + a] * Jj[6 + c]);
+                    }
+                    atomic_add(&ws.H[(size_t)(oj + a) * NP + oi + c], Jj[a] * Ji[c] + Jj[6 + a] * Ji[6 + c]);
                 }
                 atomic_add(&ws.g[oi + a], Ji[a] * r2[0] + Ji[6 + a] * r2[1]);
                 atomic_add(&ws.g[oj + a], Jj[a] * r2[0] + Jj[6 + a] * r2[1]);
@@ -163,7 +165,12 @@ __device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, co
         }
     }
     __syncthreads();
-    return block_sum_d(cost, sh_red);
+    if (lin) {                                            // mirror the lower triangle (the prior part is already symmetric)
+        for (int e = tid; e < NP * NP; e += blockDim.x) { const int i = e / NP, j = e - i * NP; if (j > i) ws.H[e] = ws.H[(size_t)j * NP + i]; }
+    }
+    const double total = block_sum_d(cost, sh_red);
+    __syncthreads();
+    return total;
 }
 
 // u^T H u over the full (pose/speed-bias + landmark) system
@@ -559,6 +566,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
                     break;
                 }
                 mu *= 10.0;
+                if (tid == 0) iv[IV_CHOL_RETRY] += 1;
             }
         }
         bool valid = false;

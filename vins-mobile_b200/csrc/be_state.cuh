@@ -8,7 +8,7 @@ namespace be {
 
 // per-stream integer scalars (BeState::iv)
 enum { IV_FRAME_COUNT = 0, IV_FIRST_IMU, IV_SOLVER_FLAG, IV_MARG_FLAG, IV_FAILURE, IV_NFEAT, IV_LAST_TRACK, IV_ACTION, IV_INIT_PENDING,
-       IV_PRIOR_VALID, IV_N_LM, IV_N_FAC, IV_ITERS, IV_PRIOR_N, IV_ERR, IV_COUNT = 16 };
+       IV_PRIOR_VALID, IV_N_LM, IV_N_FAC, IV_ITERS, IV_PRIOR_N, IV_ERR, IV_MARG_FAST, IV_MARG_SWEEPS, IV_MARG_M, IV_CHOL_RETRY, IV_COUNT = 20 };
 // per-stream double scalars (BeState::dv)
 enum { DV_ACC0 = 0, DV_GYR0 = 3, DV_LAST_P = 6, DV_LAST_P_OLD = 9, DV_BACK_P0 = 12, DV_LAST_R = 15, DV_LAST_R_OLD = 24, DV_BACK_R0 = 33,
        DV_COST0 = 42, DV_COST1 = 43, DV_PRIOR_C0 = 44, DV_TIC = 45, DV_RIC = 48, DV_COUNT = 64 };
