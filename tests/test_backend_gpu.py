@@ -198,3 +198,51 @@ def test_preintegration_golden(api, abi):
     assert rel_err(pqv, g["pqv"]) < 1e-12 and rel_err(jac, g["jac"]) < 1e-11 and rel_err(cov, g["cov"]) < 1e-11
     r, J = api.prim_projection_factor(cfg, g["pts_i"], g["pts_j"], g["pi"], g["pj"], float(g["inv_dep"]))
     assert rel_err(r, g["proj_r"]) < 1e-11 and rel_err(J, g["proj_J"]) < 1e-11
+
+
+def test_config_c4_window20(api, abi, synth):
+    """BASELINE.json configs[4] shape for the back end: 20-keyframe window (reduced system 315x315: global-memory Cholesky path,
+    prior up to 156 dofs), 300 features."""
+    cam = synth.Camera().scaled(720, 1280)
+    cfg = abi.default_config(batch=1, max_cnt=300, window_size=20, rows=720, cols=1280)
+    W = cfg.window_size
+    tr = synth.make_tracks(11, W + 4, max_cnt=300, cam=cam)
+    ref = bo.RefEstimator(cfg)
+    gpu = api.BackEnd(cfg)
+    for k in range(W + 4):
+        with Quiet():
+            drive(ref, tr, k, W)
+        drive(gpu, tr, k, W)
+        if k >= W:
+            rs, gs, ri, gi = ref.state(), gpu.state(), ref.info(), gpu.info()
+            assert gi["err"] == 0
+            assert ri["n_feat"] == gi["n_feat"] and ri["n_proj"] == gi["n_proj"] and ri["marg_flag"] == gi["marg_flag"]
+            tol = 1e-7 if k == W else 1e-4
+            assert rel_err(gs["P"], rs["P"]) < tol and rel_err(gs["V"], rs["V"]) < tol and quat_err(gs["Q"], rs["Q"]) < tol, f"kf {k}"
+            assert gi["prior_n"] == ri["prior_n"]
+    ref.close(); gpu.close()
+
+
+@pytest.mark.parametrize("eig,slow", [("ql", "0"), ("jacobi", "0"), ("ql", "1"), ("jacobi", "1")])
+def test_marginalisation_eigen_paths(api, cfg, synth, monkeypatch, eig, slow):
+    """K13 has two eigensolvers (Householder+QL default, parallel Jacobi) and two routes to Amm^+ (structured inverse guarded by an
+    eigenvalue bound, or the reference's eigendecomposition): all four combinations must reproduce the reference prior."""
+    monkeypatch.setenv("VIO_EIG", eig)
+    monkeypatch.setenv("VIO_MARG_SLOW", slow)
+    tr = synth.make_tracks(2, 15, max_cnt=cfg.max_cnt)
+    ref = bo.RefEstimator(cfg)
+    gpu = api.BackEnd(cfg)
+    W = cfg.window_size
+    for k in range(15):
+        with Quiet():
+            drive(ref, tr, k, W)
+        drive(gpu, tr, k, W)
+        if k >= W:
+            rp, gp, gi = ref.prior(), gpu.prior(), gpu.info()
+            assert gi["err"] == 0 and gi["marg_fast"] == (0 if slow == "1" else 1)
+            assert rp is not None and gp is not None
+            assert np.array_equal(rp["present"], gp["present"])
+            tol = 1e-7 if k == W else 1e-5
+            assert rel_err(gp["H"], rp["H"]) < tol, f"kf {k}: prior H {rel_err(gp['H'], rp['H'])}"
+            assert rel_err(gs := gpu.state()["P"], ref.state()["P"]) < (1e-7 if k == W else 1e-4)
+    ref.close(); gpu.close()

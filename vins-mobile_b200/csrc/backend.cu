@@ -9,6 +9,7 @@
 #include <new>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 
 using namespace be;
 
@@ -88,6 +89,8 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     s.noise[0] = s.noise[2] = cfg->acc_n * cfg->acc_n; s.noise[1] = s.noise[3] = cfg->gyr_n * cfg->gyr_n;
     s.noise[4] = cfg->acc_w * cfg->acc_w; s.noise[5] = cfg->gyr_w * cfg->gyr_w;
     s.max_iters = cfg->max_iters;
+    { const char *e = getenv("VIO_EIG"); s.eig_mode = (e && !strcmp(e, "jacobi")) ? 0 : 1; }
+    { const char *e = getenv("VIO_MARG_SLOW"); s.force_slow_marg = (e && e[0] == '1') ? 1 : 0; }
     const size_t B = s.B, NF = s.NF;
     int rc = VIO_OK;
     if (!rc) rc = dalloc(be, &s.Ps, B * NF * 3);

@@ -87,6 +87,143 @@ __device__ inline int eig_sym_jacobi(double *A, int n, int ld, double *V, double
     return sweep;
 }
 
+
+// Symmetric eigensolver by Householder tridiagonalisation + implicit-shift QL (the EISPACK tred2/tql2 pair; Eigen's
+// SelfAdjointEigenSolver, which the reference calls at marginalization_factor.cpp:270,290, is the same two-stage scheme).
+// Same contract as eig_sym_jacobi: A symmetric n x n (ld); on exit diag(A) = eigenvalues, V (ld n) = eigenvectors as columns.
+// Parallelisation: every O(n^2) inner loop of tred2 is spread over the CTA; in tql2 one thread runs the scalar rotation
+// recurrence of a QL step, then every thread applies the whole rotation sequence to the rows of V it owns.
+// de: shared scratch for 2n doubles (d, e); rot: shared scratch for 2n doubles.  Returns the number of QL steps.
+__device__ inline int eig_sym_ql(double *A, int n, int ld, double *V, double *de, double *rot, double *sh_red, int *sh_i) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    double *d = de, *e = de + n;
+    for (int x = tid; x < n * n; x += T) { const int i = x / n, j = x - i * n; V[x] = A[(size_t)i * ld + j]; }
+    __syncthreads();
+    double *a = V;                                          // a[i][k] = a[i * n + k]
+    // ---- tred2 ------------------------------------------------------------------------------------------------------------
+    for (int i = n - 1; i >= 1; i--) {
+        const int l = i - 1;
+        double h = 0.0;
+        if (l > 0) {
+            double sc = 0;
+            for (int k = tid; k <= l; k += T) sc += fabs(a[i * n + k]);
+            const double scale = block_sum_d(sc, sh_red);
+            __syncthreads();
+            if (scale == 0.0) {
+                if (tid == 0) e[i] = a[i * n + l];
+            } else {
+                double hp = 0;
+                for (int k = tid; k <= l; k += T) { const double v = a[i * n + k] / scale; a[i * n + k] = v; hp += v * v; }
+                h = block_sum_d(hp, sh_red);
+                __syncthreads();
+                const double f0 = a[i * n + l];
+                const double g0 = f0 >= 0 ? -sqrt(h) : sqrt(h);
+                h -= f0 * g0;
+                __syncthreads();
+                if (tid == 0) { e[i] = scale * g0; a[i * n + l] = f0 - g0; }
+                __syncthreads();
+                // e[j] = (A u)_j / h ,  a[j][i] = u_j / h
+                double fp = 0;
+                for (int j = tid; j <= l; j += T) {
+                    a[j * n + i] = a[i * n + j] / h;
+                    double g = 0;
+                    for (int k = 0; k <= j; k++) g += a[j * n + k] * a[i * n + k];
+                    for (int k = j + 1; k <= l; k++) g += a[k * n + j] * a[i * n + k];
+                    e[j] = g / h;
+                    fp += (g / h) * a[i * n + j];
+                }
+                const double f = block_sum_d(fp, sh_red);
+                __syncthreads();
+                const double hh = f / (h + h);
+                for (int j = tid; j <= l; j += T) e[j] -= hh * a[i * n + j];
+                __syncthreads();
+                for (int x = tid; x < (l + 1) * (l + 1); x += T) {
+                    const int j = x / (l + 1), k = x - j * (l + 1);
+                    if (k <= j) a[j * n + k] -= a[i * n + j] * e[k] + e[j] * a[i * n + k];
+                }
+            }
+        } else if (tid == 0) e[i] = a[i * n + l];
+        __syncthreads();
+        if (tid == 0) d[i] = h;
+        __syncthreads();
+    }
+    if (tid == 0) { d[0] = 0.0; e[0] = 0.0; }
+    __syncthreads();
+    for (int i = 0; i < n; i++) {                           // accumulate the transformation
+        const int l = i - 1;
+        if (d[i] != 0.0 && l >= 0) {
+            for (int j = tid; j <= l; j += T) {
+                double g = 0;
+                for (int k = 0; k <= l; k++) g += a[i * n + k] * a[k * n + j];
+                rot[j] = g;
+            }
+            __syncthreads();
+            for (int x = tid; x < (l + 1) * (l + 1); x += T) {
+                const int k = x / (l + 1), j = x - k * (l + 1);
+                a[k * n + j] -= rot[j] * a[k * n + i];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { d[i] = a[i * n + i]; a[i * n + i] = 1.0; }
+        for (int j = tid; j <= l; j += T) { a[j * n + i] = 0.0; a[i * n + j] = 0.0; }
+        __syncthreads();
+    }
+    // ---- tql2 -------------------------------------------------------------------------------------------------------------
+    if (tid == 0) { for (int i = 1; i < n; i++) e[i - 1] = e[i]; e[n - 1] = 0.0; }
+    __syncthreads();
+    int steps = 0;
+    for (int l = 0; l < n; l++) {
+        for (int iter = 0; iter < 60; iter++) {
+            if (tid == 0) {
+                int m = l;
+                for (; m < n - 1; m++) { const double dd = fabs(d[m]) + fabs(d[m + 1]); if (fabs(e[m]) + dd == dd) break; }
+                sh_i[0] = m; sh_i[1] = l;                   // rotations i = m-1 .. first (inclusive); first = l unless the sweep aborts early
+                if (m != l) {
+                    double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                    double r = hypot(g, 1.0);
+                    g = d[m] - d[l] + e[l] / (g + (g >= 0 ? fabs(r) : -fabs(r)));
+                    double sn = 1.0, c = 1.0, p = 0.0;
+                    int i = m - 1;
+                    bool brk = false;
+                    for (; i >= l; i--) {
+                        double f = sn * e[i];
+                        const double bb = c * e[i];
+                        r = hypot(f, g);
+                        e[i + 1] = r;
+                        if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; brk = true; break; }
+                        sn = f / r; c = g / r;
+                        g = d[i + 1] - p;
+                        r = (d[i] - g) * sn + 2.0 * c * bb;
+                        p = sn * r;
+                        d[i + 1] = g + p;
+                        g = c * r - bb;
+                        rot[2 * i] = c; rot[2 * i + 1] = sn;
+                    }
+                    sh_i[1] = brk ? i + 1 : l;
+                    if (!brk) { d[l] -= p; e[l] = g; e[m] = 0.0; }
+                }
+            }
+            __syncthreads();
+            const int m = sh_i[0], first = sh_i[1];
+            if (m == l) break;
+            steps++;
+            for (int k = tid; k < n; k += T) {              // apply the rotation sequence to row k of V
+                double *zr = a + (size_t)k * n;
+                for (int i = m - 1; i >= first; i--) {
+                    const double c = rot[2 * i], sn = rot[2 * i + 1];
+                    const double f = zr[i + 1];
+                    zr[i + 1] = sn * zr[i] + c * f;
+                    zr[i] = c * zr[i] - sn * f;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += T) A[(size_t)i * ld + i] = d[i];
+    __syncthreads();
+    return steps;
+}
+
 // ProjectionFactor Jacobian wrt para_Ex_Pose (projection_facor.cpp:73-84), corrected by sqrt(rho'): 2x6
 __device__ inline void proj_jac_ex(const ProjConst &K, V3 pts_i, const double *pi, const double *pj, double inv_dep, double *Jex) {
     const V3 Pi = ld3(pi), Pj = ld3(pj);
@@ -117,6 +254,9 @@ struct MargSmem {
     int kept[VIO_MAX_WIN * 15 + 15 + 6 + 8];     // kept work position -> canonical dof
     int pq[2 * 256];
     double cs[2 * 256];
+    double de[2 * 400];
+    double rot[2 * 400];
+    int ql_i[4];
     double red[32];
     int scan[33];
     int n_eff, m, L0, mc;
@@ -294,7 +434,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     {
         // Gp = C D^-1 (mc x L0) in Vm scratch ; S = P - Gp C^T
         double *Gp = Vm, *Gm = Vm + (size_t)mc * L0;           // Gm = S^-1 Gp
-        if (tid == 0) fast_ok = 1;
+        if (tid == 0) fast_ok = s.force_slow_marg ? 0 : 1;
         __syncthreads();
         for (int e = tid; e < mc * L0; e += MARG_T) {
             const int r = e / L0, l = e - r * L0;
@@ -380,7 +520,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         }
     }
     if (!fast_ok) {
-    eig_sym_jacobi(A, m, pos, Vm, sm.cs, sm.pq, sm.red);
+    if (s.eig_mode) eig_sym_ql(A, m, pos, Vm, sm.de, sm.rot, sm.red, sm.ql_i); else eig_sym_jacobi(A, m, pos, Vm, sm.cs, sm.pq, sm.red);
     __syncthreads();
     // Tm = Lambda^+ Vm^T [Amr | bmm]      (m x (n+1))
     for (int e = tid; e < m * (n + 1); e += MARG_T) {
@@ -419,10 +559,10 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         double *sV = sA + (size_t)n * n;
         for (int e = tid; e < n * n; e += MARG_T) sA[e] = Ar[e];
         __syncthreads();
-        sweeps = eig_sym_jacobi(sA, n, n, sV, sm.cs, sm.pq, sm.red);
+        sweeps = s.eig_mode ? eig_sym_ql(sA, n, n, sV, sm.de, sm.rot, sm.red, sm.ql_i) : eig_sym_jacobi(sA, n, n, sV, sm.cs, sm.pq, sm.red);
         Ar = sA; Vr = sV;
     } else {
-        sweeps = eig_sym_jacobi(Ar, n, n, Vr, sm.cs, sm.pq, sm.red);
+        sweeps = s.eig_mode ? eig_sym_ql(Ar, n, n, Vr, sm.de, sm.rot, sm.red, sm.ql_i) : eig_sym_jacobi(Ar, n, n, Vr, sm.cs, sm.pq, sm.red);
     }
     if (tid == 0) { iv[IV_MARG_FAST] = fast_ok; iv[IV_MARG_SWEEPS] = sweeps; iv[IV_MARG_M] = m; }
     __syncthreads();

@@ -24,6 +24,8 @@ struct BeState {
     double gravity, min_parallax, init_depth, sqrt_info;
     double noise[6];         // acc_n^2, gyr_n^2, acc_n^2, gyr_n^2, acc_w^2, gyr_w^2   (integration_base.h:37-43)
     int max_iters;
+    int eig_mode;            // 0 = parallel Jacobi, 1 = Householder tridiagonalisation + implicit QL (default)
+    int force_slow_marg;     // test hook: always take the eigendecomposition path for Amm^+
     // window state
     double *Ps, *Rs, *Vs, *Bas, *Bgs, *Headers;       // [B][NF][3|9|3|3|3|1]
     double *pre;                                      // [B][NF][PR_STRIDE]

@@ -10,7 +10,7 @@ constexpr int LK_WIN = 21;
 constexpr int LK_LEVELS = 3;          // maxLevel (4 pyramid levels)
 constexpr int LK_MAX_ITERS = 30;
 constexpr int W_BITS = 14;
-constexpr int CAND_CAP = 16384;       // raw local maxima per stream
+constexpr int CAND_CAP = 65536;       // raw local maxima per stream
 constexpr int SORT_CAP = 8192;        // candidates above the quality threshold per stream
 
 struct PyrLevels {

@@ -179,11 +179,13 @@ __global__ void __launch_bounds__(256) post_track_kernel(TrackArrays A, int maxp
 }
 
 // goodFeaturesToTrack tail + addPoints + updateID + image_msg (feature_tracker.cpp:257-307,311-321)
+constexpr int SEL_BINS = 8192;          // histogram of (f32 bits >> 13) above the quality threshold: a x100 value range spans < 7 * 1024 bins
 struct SelectSmem {
     unsigned long long key[SORT_CAP];
     int cell_cnt[2048];
     short cell_pt[2048][4][2];
-    int n_sorted, n_new;
+    int hist[SEL_BINS];
+    int n_sorted, n_new, taken, band_lo, band_hi, band_err;
     short newxy[VIO_MAXP][2];
 };
 
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(256) select_kernel(TrackArrays A, int maxp, in
     const int n_kept = A.n[b];
     const int n_max = max_cnt - n_kept;
     int *st = A.stats + b * 8;
-    if (tid == 0) { s.n_sorted = 0; s.n_new = 0; }
+    if (tid == 0) { s.n_sorted = 0; s.n_new = 0; s.taken = 0; s.band_err = 0; }
     const int gw = (cols + min_dist - 1) / min_dist, gh = (rows + min_dist - 1) / min_dist;
     for (int i = tid; i < gw * gh; i += 256) s.cell_cnt[i] = 0;
     __syncthreads();
@@ -206,60 +208,87 @@ __global__ void __launch_bounds__(256) select_kernel(TrackArrays A, int maxp, in
         // threshold(eig, maxVal*qualityLevel, TOZERO): thr is the f32 cast of the f64 product
         const float maxv = __uint_as_float(A.max_bits[b]);
         const float thr = (float)((double)maxv * 0.01);
+        const unsigned thr_bin = __float_as_uint(thr) >> 13;
         const unsigned long long *cand = A.cand + (size_t)b * CAND_CAP;
+        // Candidates are consumed in DESCENDING value order, in bands of at most SORT_CAP keys (one band in the common case; several when
+        // a high-resolution frame yields tens of thousands of corners): histogram of the value bits -> band boundaries.
+        for (int i = tid; i < SEL_BINS; i += 256) s.hist[i] = 0;
+        __syncthreads();
         for (int i = tid; i < nc; i += 256) {
-            const unsigned long long k = cand[i];
-            if (__uint_as_float((unsigned)(k >> 32)) > thr) {
-                const int d = atomicAdd(&s.n_sorted, 1);
-                if (d < SORT_CAP) s.key[d] = k;
-            }
+            const unsigned vb = (unsigned)(cand[i] >> 32);
+            if (__uint_as_float(vb) > thr) atomicAdd(&s.hist[min((vb >> 13) - thr_bin, (unsigned)SEL_BINS - 1)], 1);
         }
         __syncthreads();
-        int ns = s.n_sorted;
-        if (ns > SORT_CAP) { if (tid == 0) atomicExch(A.err_flag, VIO_ERR_CAPACITY); ns = SORT_CAP; }
-        int np2 = 1;
-        while (np2 < ns) np2 <<= 1;
-        for (int i = ns + tid; i < np2; i += 256) s.key[i] = 0ull;
+        if (tid == 0) s.band_hi = SEL_BINS;                        // exclusive upper bin of the next band
         __syncthreads();
-        // bitonic sort, DESCENDING on (value bits, address): value desc then address desc == cv greaterThanPtr
-        for (int k = 2; k <= np2; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < np2; i += 256) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const unsigned long long a = s.key[i], c = s.key[l];
-                        const bool desc = (i & k) == 0;
-                        if (desc ? (a < c) : (a > c)) { s.key[i] = c; s.key[l] = a; }
-                    }
-                }
-                __syncthreads();
+        const int md2 = min_dist * min_dist;
+        while (true) {
+            if (tid == 0) {
+                int lo = s.band_hi, cnt = 0;
+                while (lo > 0 && (cnt + s.hist[lo - 1] <= SORT_CAP || lo == s.band_hi)) { cnt += s.hist[lo - 1]; lo--; }
+                if (cnt > SORT_CAP) { s.band_err = 1; cnt = 0; lo = 0; }      // > SORT_CAP keys inside one 2^-10-relative value bin
+                s.band_lo = lo; s.n_sorted = 0;
             }
-        // greedy min-distance selection over the 3x3 cell neighbourhood (cell = rint(minDistance))
-        if (tid == 0) {
-            int taken = 0;
-            const int md2 = min_dist * min_dist;
-            for (int i = 0; i < ns && taken < n_max; i++) {
-                const unsigned lin = (unsigned)s.key[i];
-                const int y = lin / cols, x = lin - y * cols;
-                const int xc = x / min_dist, yc = y / min_dist;
-                const int x1 = max(0, xc - 1), y1 = max(0, yc - 1), x2 = min(gw - 1, xc + 1), y2 = min(gh - 1, yc + 1);
-                bool good = true;
-                for (int yy = y1; yy <= y2 && good; yy++)
-                    for (int xx = x1; xx <= x2 && good; xx++) {
-                        const int c = yy * gw + xx;
-                        for (int q = 0; q < s.cell_cnt[c]; q++) {
-                            const int dx = x - s.cell_pt[c][q][0], dy = y - s.cell_pt[c][q][1];
-                            if (dx * dx + dy * dy < md2) { good = false; break; }
+            __syncthreads();
+            if (s.band_err) { if (tid == 0) atomicExch(A.err_flag, VIO_ERR_CAPACITY); break; }
+            const int blo = s.band_lo, bhi = s.band_hi;
+            for (int i = tid; i < nc; i += 256) {
+                const unsigned long long k = cand[i];
+                const unsigned vb = (unsigned)(k >> 32);
+                if (__uint_as_float(vb) > thr) {
+                    const int bin = (int)min((vb >> 13) - thr_bin, (unsigned)SEL_BINS - 1);
+                    if (bin >= blo && bin < bhi) { const int d = atomicAdd(&s.n_sorted, 1); if (d < SORT_CAP) s.key[d] = k; }
+                }
+            }
+            __syncthreads();
+            const int ns = min(s.n_sorted, SORT_CAP);
+            int np2 = 1;
+            while (np2 < ns) np2 <<= 1;
+            for (int i = ns + tid; i < np2; i += 256) s.key[i] = 0ull;
+            __syncthreads();
+            // bitonic sort, DESCENDING on (value bits, address): value desc then address desc == cv greaterThanPtr
+            for (int k = 2; k <= np2; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < np2; i += 256) {
+                        const int l = i ^ j;
+                        if (l > i) {
+                            const unsigned long long a = s.key[i], c = s.key[l];
+                            const bool desc = (i & k) == 0;
+                            if (desc ? (a < c) : (a > c)) { s.key[i] = c; s.key[l] = a; }
                         }
                     }
-                if (!good) continue;
-                const int c = yc * gw + xc;
-                if (s.cell_cnt[c] < 4) { s.cell_pt[c][s.cell_cnt[c]][0] = (short)x; s.cell_pt[c][s.cell_cnt[c]][1] = (short)y; s.cell_cnt[c]++; }
-                s.newxy[taken][0] = (short)x; s.newxy[taken][1] = (short)y;
-                taken++;
+                    __syncthreads();
+                }
+            // greedy min-distance selection over the 3x3 cell neighbourhood (cell = rint(minDistance))
+            if (tid == 0) {
+                int taken = s.taken;
+                for (int i = 0; i < ns && taken < n_max; i++) {
+                    const unsigned lin = (unsigned)s.key[i];
+                    const int y = lin / cols, x = lin - y * cols;
+                    const int xc = x / min_dist, yc = y / min_dist;
+                    const int x1 = max(0, xc - 1), y1 = max(0, yc - 1), x2 = min(gw - 1, xc + 1), y2 = min(gh - 1, yc + 1);
+                    bool good = true;
+                    for (int yy = y1; yy <= y2 && good; yy++)
+                        for (int xx = x1; xx <= x2 && good; xx++) {
+                            const int c = yy * gw + xx;
+                            for (int q = 0; q < s.cell_cnt[c]; q++) {
+                                const int dx = x - s.cell_pt[c][q][0], dy = y - s.cell_pt[c][q][1];
+                                if (dx * dx + dy * dy < md2) { good = false; break; }
+                            }
+                        }
+                    if (!good) continue;
+                    const int c = yc * gw + xc;
+                    if (s.cell_cnt[c] < 4) { s.cell_pt[c][s.cell_cnt[c]][0] = (short)x; s.cell_pt[c][s.cell_cnt[c]][1] = (short)y; s.cell_cnt[c]++; }
+                    s.newxy[taken][0] = (short)x; s.newxy[taken][1] = (short)y;
+                    taken++;
+                }
+                s.taken = taken;
+                s.band_hi = s.band_lo;
             }
-            s.n_new = taken;
+            __syncthreads();
+            if (s.taken >= n_max || s.band_hi <= 0) break;
         }
+        if (tid == 0) s.n_new = s.taken;
         __syncthreads();
     }
     const int n_new = s.n_new;
