@@ -204,18 +204,23 @@ def run_ours(args):
             ms = e0.elapsed_time(e1)
             launches = pipe.fe.launch_count() + pipe.be.launch_count() - l0
             # per-kernel CUDA-event pass (separate, untimed): 2 more keyframe periods
-            pipe.fe.profile(True); pipe.be.profile(True)
+            pipe.fe.profile(True); pipe.be.profile(True); pipe.be.phase_cycles(True)
             base = prologue + args.warmup + args.steps
             for i in range(base, base + FREQ):
                 one(i)
             prof = {}
             prof.update(pipe.fe.profile(False)); prof.update(pipe.be.profile(False))
             info = [pipe.be.info(b) for b in range(B)]
+            ph = pipe.be.phase_cycles(True).astype(float)
+            names = ["solve.linearize", "solve.scale_cauchy", "solve.schur", "solve.cholesky", "solve.dogleg_model", "solve.cost_eval", "solve.accept", "",
+                     "marg.setup", "marg.accumulate", "marg.amm_inverse", "marg.schur", "marg.eig", "marg.recompose"]
+            phase_us = {nm: round(float(ph[:, i].max()) / 1.9e3, 1) for i, nm in enumerate(names) if nm}
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         pipe.close()
+        prof["_phases"] = phase_us
         return ms, launches, prof, info, clocks.summary() if rank == 0 else None
 
     ms, launches, prof, info, clk = timed_run(False)
@@ -229,6 +234,7 @@ def run_ours(args):
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm = peaks.get("hbm_gbs", 6650.0)
     # roofline of the dominant HBM-bound kernel of the front end (per launch = one batch of B images)
+    phases = prof.pop("_phases", None)
     kern = {k: {"launches": c, "ms_per_launch": t / c} for k, (c, t) in prof.items() if c}
     cand = {"pyr_down_kernel": ALGO_BYTES_PYR / 3.0, "eig_candidates_kernel": ALGO_BYTES_DETECT, "lk_kernel": ALGO_BYTES_KLT}
     dom = max((k for k in cand if k in kern), key=lambda k: kern[k]["ms_per_launch"] * (3 if k == "pyr_down_kernel" else 1), default=None)
@@ -255,6 +261,7 @@ def run_ours(args):
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * cam.rows * cam.cols + B * IMU_PER_KF * 7 * 8 / FREQ),
                 "d2h_bytes_per_step": int(B * (W + 1) * 16 * 8 / FREQ), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
+        "backend_phase_us_max_over_streams_at_1p9GHz": phases,
         "solve_info_stream0": info[0] if info else None,
         "solve_info_batch": {k: [min(i[k] for i in info), max(i[k] for i in info)] for k in ("iters", "n_feat", "n_proj", "prior_n", "marg_fast", "marg_sweeps", "marg_m", "chol_retry", "err")} if info else None,
     }

@@ -173,6 +173,8 @@ void *vio_frontend_stream(vio_frontend *fe);
 /* Per-kernel CUDA-event timing: returns "name:launches:total_ms;..." accumulated since the previous call and switches the
  * timer on/off for subsequent launches. */
 int vio_frontend_profile(vio_frontend *fe, int enable, char *out, int cap);
+/* Per-stream clock64 cycle counters of the solve (slots 0-7) and marginalisation (8-15) phases: out[batch*32]. */
+int vio_backend_phase_cycles(vio_backend *be, long long *out, int reset);
 int vio_backend_profile(vio_backend *be, int enable, char *out, int cap);
 
 /* Factor-level primitives for parity tests (host in/out, one factor each). */

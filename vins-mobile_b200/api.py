@@ -80,6 +80,7 @@ def lib():
             L.vio_backend_use_stream.argtypes = [vp, vp]
             L.vio_backend_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
             L.vio_backend_copy_state.argtypes = [vp, vp, C.c_int]
+            L.vio_backend_phase_cycles.argtypes = [vp, C.POINTER(C.c_longlong), C.c_int]
             L.vio_prim_preintegrate.argtypes = [cfgp, C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
             L.vio_prim_imu_factor.argtypes = [cfgp, DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP]
             L.vio_prim_projection_factor.argtypes = [cfgp, DP, DP, DP, DP, C.c_double, DP, DP]
@@ -336,6 +337,11 @@ class BackEnd:
         buf = C.create_string_buffer(4096)
         _check(lib().vio_backend_profile(self.h, int(enable), buf, 4096), "vio_backend_profile")
         return _parse_profile(buf.value.decode())
+
+    def phase_cycles(self, reset=True):
+        out = np.zeros((self.B, 32), np.int64)
+        _check(lib().vio_backend_phase_cycles(self.h, out.ctypes.data_as(C.POINTER(C.c_longlong)), int(reset)), "vio_backend_phase_cycles")
+        return out
 
     def copy_state(self, dst_ptr: int, is_device: bool):
         _check(lib().vio_backend_copy_state(self.h, dst_ptr, int(is_device)), "vio_backend_copy_state")

@@ -25,6 +25,7 @@ struct vio_backend {
     int *d_counts, *d_ids; double *d_xyz, *d_headers; double *d_imu; size_t imu_cap;
     double *h_headers_pinned;
     size_t solve_smem, marg_smem;
+    int be_threads;
     cudaEvent_t evt_ready, evt_consumed;
     bool consumed_valid, record_consumed;
 };
@@ -90,6 +91,7 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     s.noise[4] = cfg->acc_w * cfg->acc_w; s.noise[5] = cfg->gyr_w * cfg->gyr_w;
     s.max_iters = cfg->max_iters;
     { const char *e = getenv("VIO_EIG"); s.eig_mode = (e && !strcmp(e, "jacobi")) ? 0 : 1; }
+    { const char *e = getenv("VIO_BE_THREADS"); be->be_threads = (e && atoi(e) == 256) ? 256 : 512; }
     { const char *e = getenv("VIO_MARG_SLOW"); s.force_slow_marg = (e && e[0] == '1') ? 1 : 0; }
     const size_t B = s.B, NF = s.NF;
     int rc = VIO_OK;
@@ -122,6 +124,7 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     if (!rc) rc = dalloc(be, &s.fac_j, B * s.PCAP);
     if (!rc) rc = dalloc(be, &s.post_solve, B * NF * 16);
     if (!rc) rc = dalloc(be, &s.state_out, B * NF * 16);
+    if (!rc) rc = dalloc(be, &s.prof, B * 32);
     size_t sc = solve_scratch_doubles(s.NP, s.NPX, s.NPW, s.LCAP, s.W);
     sc = std::max(sc, marg_scratch_doubles(s.NPX, s.LCAP, cfg->max_cnt));
     sc = std::max(sc, (size_t)s.FCAP * (5 + 2 * NF));
@@ -138,7 +141,7 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     VIO_CUDA_TRY(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s.FCAP + 64));
     // reduced system resident in shared memory when it fits one SM (W = 10: 110 KB packed); otherwise the global-memory path
     be->solve_smem = solve_smem_bytes(s.NP, s.NPW);
-    if (be->solve_smem > 200 * 1024 || (size_t)s.NPW * (s.NPW + 1) / 2 > (size_t)8 * SOLVE_T) be->solve_smem = 0;
+    if (be->solve_smem > 200 * 1024 || (size_t)s.NPW * (s.NPW + 1) / 2 > (size_t)10 * 256) be->solve_smem = 0;
     if (be->solve_smem) VIO_CUDA_TRY(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->solve_smem));
     be->marg_smem = sizeof(MargSmem) + 16 + (size_t)2 * MARG_NCAP * MARG_NCAP * sizeof(double);
     VIO_CUDA_TRY(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->marg_smem));
@@ -235,9 +238,9 @@ static int run_process_image(vio_backend *be, const int32_t *counts, const int32
     if (be->record_consumed) { cudaEventRecord(be->evt_consumed, st); be->consumed_valid = true; be->record_consumed = false; }   // image_msg fully read
     VIO_LAUNCH(be->timer, st, "triangulate_kernel", (triangulate_kernel<<<s.B, 128, 0, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "prepare_kernel", (prepare_kernel<<<s.B, 256, 0, st>>>(s)));
-    VIO_LAUNCH(be->timer, st, "solve_kernel", (solve_kernel<<<s.B, SOLVE_T, be->solve_smem, st>>>(s, be->solve_smem > 0)));
+    VIO_LAUNCH(be->timer, st, "solve_kernel", (solve_kernel<<<s.B, be->be_threads, be->solve_smem, st>>>(s, be->solve_smem > 0)));
     VIO_LAUNCH(be->timer, st, "post_solve_kernel", (post_solve_kernel<<<s.B, 256, 0, st>>>(s)));
-    VIO_LAUNCH(be->timer, st, "marg_kernel", (marg_kernel<<<s.B, MARG_T, be->marg_smem, st>>>(s)));
+    VIO_LAUNCH(be->timer, st, "marg_kernel", (marg_kernel<<<s.B, be->be_threads, be->marg_smem, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "finish_kernel", (finish_kernel<<<s.B, 256, s.FCAP + 64, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "clear_init_pending_kernel", (clear_init_pending_kernel<<<s.B, 32, 0, st>>>(s)));
     be->launches += 8;
@@ -390,6 +393,15 @@ extern "C" int vio_backend_copy_state(vio_backend *be, double *dst, int dst_is_d
     const size_t n = (size_t)be->s.B * be->s.NF * 16 * sizeof(double);
     VIO_CUDA_TRY(cudaMemcpyAsync(dst, be->s.state_out, n, dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, be->stream));
     if (!dst_is_device) VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    return VIO_OK;
+}
+// diagnostics: per-stream clock64 cycle counters of the solve / marginalisation phases, [batch][32]; reset = 1 zeroes them
+extern "C" int vio_backend_phase_cycles(vio_backend *be, long long *out, int reset) {
+    if (!be) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    if (out) VIO_CUDA_TRY(cudaMemcpyAsync(out, be->s.prof, (size_t)be->s.B * 32 * sizeof(long long), cudaMemcpyDeviceToHost, be->stream));
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    if (reset) VIO_CUDA_TRY(cudaMemsetAsync(be->s.prof, 0, (size_t)be->s.B * 32 * sizeof(long long), be->stream));
     return VIO_OK;
 }
 extern "C" int64_t vio_backend_launch_count(const vio_backend *be) { return be ? be->launches : 0; }

@@ -265,7 +265,7 @@ struct MargSmem {
 __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     extern __shared__ __align__(16) unsigned char smraw[];
     MargSmem &sm = *reinterpret_cast<MargSmem *>(smraw);
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     int *iv = S_iv(s, b);
     const int act = iv[IV_ACTION];
     if (act != ACT_INIT_SOLVE && act != ACT_NL_SOLVE) return;
@@ -278,17 +278,18 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     double *par = s.par + (size_t)b * (NF * 16 + s.LCAP);
     const size_t fo = (size_t)b * s.FCAP;
     const int nl = iv[IV_N_LM], nfac = iv[IV_N_FAC];
+    BE_PROF_INIT;
     // old2new() after new2old(): repack the (re-anchored) state; inverse depths come back from the feature table
-    for (int i = tid; i < NF; i += MARG_T) {
+    for (int i = tid; i < NF; i += T) {
         double *p = par + 16 * i;
         st3(p, ld3(S_Ps(s, b, i))); stq(p + 3, R2q(ldm(S_Rs(s, b, i))));
         st3(p + 7, ld3(S_Vs(s, b, i))); st3(p + 10, ld3(S_Bas(s, b, i))); st3(p + 13, ld3(S_Bgs(s, b, i)));
     }
-    for (int l = tid; l < nl; l += MARG_T) par[16 * NF + l] = 1.0 / s.f_depth[fo + s.lm_slot[(size_t)b * s.LCAP + l]];
+    for (int l = tid; l < nl; l += T) par[16 * NF + l] = 1.0 / s.f_depth[fo + s.lm_slot[(size_t)b * s.LCAP + l]];
     // ---- which canonical dofs are marginalised / kept --------------------------------------------------------
     // new "present" set = blocks touched by any factor of this marginalisation
     __shared__ int touched[2 * (VIO_MAX_WIN + 1) + 1];
-    for (int i = tid; i < 2 * NF + 1; i += MARG_T) touched[i] = prior_valid ? pres[i] : 0;
+    for (int i = tid; i < 2 * NF + 1; i += T) touched[i] = prior_valid ? pres[i] : 0;
     __syncthreads();
     int *lm_work = (int *)(s.scratch + (size_t)b * s.scratch_stride);    // [LCAP] work index of landmark l (or -1)
     double *base = s.scratch + (size_t)b * s.scratch_stride + ((s.LCAP + 7) / 2);
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         __syncthreads();
         // landmarks that start in frame 0, in list order
         int lbase = 0;
-        for (int c0 = 0; c0 < nl; c0 += MARG_T) {
+        for (int c0 = 0; c0 < nl; c0 += T) {
             const int l = c0 + tid;
             int is = 0;
             if (l < nl) is = s.f_start[fo + s.lm_slot[(size_t)b * s.LCAP + l]] == 0;
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
             lbase += tot;
         }
         if (tid == 0) { sm.L0 = lbase; sm.mc = 15; }
-        for (int f = tid; f < nfac; f += MARG_T) {
+        for (int f = tid; f < nfac; f += T) {
             const int l = s.fac_lm[(size_t)b * s.PCAP + f];
             if (s.f_start[fo + s.lm_slot[(size_t)b * s.LCAP + l]] == 0) { touched[2 * s.fac_j[(size_t)b * s.PCAP + f]] = 1; touched[2 * NF] = 1; }
         }
@@ -343,20 +344,21 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     double *Vr = br + n;
     double *dx = Vr + (size_t)n * n;
     double *tv = dx + NPX;
-    for (size_t e = tid; e < (size_t)pos * pos + pos; e += MARG_T) A[e] = 0.0;      // A and b are contiguous
+    for (size_t e = tid; e < (size_t)pos * pos + pos; e += T) A[e] = 0.0;      // A and b are contiguous
     __syncthreads();
+    BE_PROF(8);
     // ---- accumulate A, b ---------------------------------------------------------------------------------------
     if (prior_valid) {                                      // MarginalizationFactor of the previous prior, evaluated at the current point
         const double *Hp = s.Hp + (size_t)b * NPX * NPX, *bp = s.bp + (size_t)b * NPX;
         prior_dx(s, b, par, dx);
         __syncthreads();
-        for (int i = tid; i < NPX; i += MARG_T) {
+        for (int i = tid; i < NPX; i += T) {
             double t = 0;
             for (int j = 0; j < NPX; j++) t += Hp[(size_t)i * NPX + j] * dx[j];
             const int wi = sm.c2w[i];
             if (wi >= 0) bv[wi] += t + bp[i];
         }
-        for (int e = tid; e < NPX * NPX; e += MARG_T) {
+        for (int e = tid; e < NPX * NPX; e += T) {
             const int i = e / NPX, j = e - i * NPX;
             const int wi = sm.c2w[i], wj = sm.c2w[j];
             if (wi >= 0 && wj >= 0) A[(size_t)wi * pos + wj] += Hp[e];
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         }
         // ProjectionFactors of the landmarks that start in frame 0: blocks {Pose0, Pose_j, Ex_Pose, Feature}
         ProjConst K; K.ric = ldm(dvs + DV_RIC); K.tic = ld3(dvs + DV_TIC); K.sqrt_info = s.sqrt_info;
-        for (int f = tid; f < nfac; f += MARG_T) {
+        for (int f = tid; f < nfac; f += T) {
             const int l = s.fac_lm[(size_t)b * s.PCAP + f], j = s.fac_j[(size_t)b * s.PCAP + f];
             const int lw = lm_work[l];
             if (lw < 0) continue;
@@ -420,6 +422,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         }
     }
     __syncthreads();
+    BE_PROF(9);
     // ---- Amm^+ [Amr | bmm] ------------------------------------------------------------------------------------------------
     // Reference: pseudo-inverse by eigendecomposition of 0.5*(Amm + Amm^T), eigenvalues <= eps dropped
     // (marginalization_factor.cpp:268-271).  When every eigenvalue is provably > eps the pseudo-inverse IS the inverse, and Amm has
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     // the mc x mc Schur complement S = P - C D^-1 C^T.  Proof obligation checked at run time: lambda_min(Amm) >= 1/||Amm^-1||_F,
     // with ||Amm^-1||_F formed from the explicit block inverse.  If the bound does not clear eps (or a pivot is not positive) the
     // kernel falls back to the faithful Jacobi eigendecomposition below.
-    for (int e = tid; e < m * m; e += MARG_T) { const int i = e / m, j = e - i * m; if (j < i) { const double v = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]); A[(size_t)i * pos + j] = v; A[(size_t)j * pos + i] = v; } }
+    for (int e = tid; e < m * m; e += T) { const int i = e / m, j = e - i * m; if (j < i) { const double v = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]); A[(size_t)i * pos + j] = v; A[(size_t)j * pos + i] = v; } }
     __syncthreads();
     __shared__ double Sinv[15 * 15];
     __shared__ int fast_ok;
@@ -436,7 +439,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         double *Gp = Vm, *Gm = Vm + (size_t)mc * L0;           // Gm = S^-1 Gp
         if (tid == 0) fast_ok = s.force_slow_marg ? 0 : 1;
         __syncthreads();
-        for (int e = tid; e < mc * L0; e += MARG_T) {
+        for (int e = tid; e < mc * L0; e += T) {
             const int r = e / L0, l = e - r * L0;
             const double d = A[(size_t)(mc + l) * pos + mc + l];
             if (!(d > 0)) fast_ok = 0;
@@ -444,7 +447,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         }
         __syncthreads();
         __shared__ double Sm[15 * 15];
-        for (int e = tid; e < mc * mc; e += MARG_T) {
+        for (int e = tid; e < mc * mc; e += T) {
             const int r = e / mc, c = e - r * mc;
             double t = A[(size_t)r * pos + c];
             for (int l = 0; l < L0; l++) t -= Gp[(size_t)r * L0 + l] * A[(size_t)c * pos + mc + l];
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         }
         __syncthreads();
         if (fast_ok) {
-            for (int e = tid; e < mc * L0; e += MARG_T) {
+            for (int e = tid; e < mc * L0; e += T) {
                 const int r = e / L0, l = e - r * L0;
                 double t = 0;
                 for (int k = 0; k < mc; k++) t += Sinv[r * mc + k] * Gp[(size_t)k * L0 + l];
@@ -480,9 +483,9 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
             __syncthreads();
             // ||Amm^-1||_F^2 = ||S^-1||^2 + 2||S^-1 C D^-1||^2 + ||D^-1 + D^-1 C^T S^-1 C D^-1||^2
             double f2 = 0;
-            for (int e = tid; e < mc * mc; e += MARG_T) f2 += Sinv[e] * Sinv[e];
-            for (int e = tid; e < mc * L0; e += MARG_T) f2 += 2.0 * Gm[e] * Gm[e];
-            for (int e = tid; e < L0 * L0; e += MARG_T) {
+            for (int e = tid; e < mc * mc; e += T) f2 += Sinv[e] * Sinv[e];
+            for (int e = tid; e < mc * L0; e += T) f2 += 2.0 * Gm[e] * Gm[e];
+            for (int e = tid; e < L0 * L0; e += T) {
                 const int a = e / L0, bq = e - a * L0;
                 const double da = A[(size_t)(mc + a) * pos + mc + a];
                 double t = (a == bq) ? 1.0 : 0.0;
@@ -496,21 +499,21 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         }
         if (fast_ok) {
             // Z = Amm^-1 X, X = [Amr | bmm]:  T = X_p - Gp X_l ; Y_p = S^-1 T ; Y_l = D^-1 (X_l - C^T Y_p)
-            for (int e = tid; e < mc * (n + 1); e += MARG_T) {
+            for (int e = tid; e < mc * (n + 1); e += T) {
                 const int r = e / (n + 1), c = e - r * (n + 1);
                 double t = (c < n) ? A[(size_t)r * pos + m + c] : bv[r];
                 for (int l = 0; l < L0; l++) t -= Gp[(size_t)r * L0 + l] * ((c < n) ? A[(size_t)(mc + l) * pos + m + c] : bv[mc + l]);
                 Tm[e] = t;
             }
             __syncthreads();
-            for (int e = tid; e < mc * (n + 1); e += MARG_T) {
+            for (int e = tid; e < mc * (n + 1); e += T) {
                 const int r = e / (n + 1), c = e - r * (n + 1);
                 double t = 0;
                 for (int k = 0; k < mc; k++) t += Sinv[r * mc + k] * Tm[(size_t)k * (n + 1) + c];
                 Zm[e] = t;
             }
             __syncthreads();
-            for (int e = tid; e < L0 * (n + 1); e += MARG_T) {
+            for (int e = tid; e < L0 * (n + 1); e += T) {
                 const int l = e / (n + 1), c = e - l * (n + 1);
                 double t = (c < n) ? A[(size_t)(mc + l) * pos + m + c] : bv[mc + l];
                 for (int k = 0; k < mc; k++) t -= A[(size_t)k * pos + mc + l] * Zm[(size_t)k * (n + 1) + c];
@@ -523,7 +526,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     if (s.eig_mode) eig_sym_ql(A, m, pos, Vm, sm.de, sm.rot, sm.red, sm.ql_i); else eig_sym_jacobi(A, m, pos, Vm, sm.cs, sm.pq, sm.red);
     __syncthreads();
     // Tm = Lambda^+ Vm^T [Amr | bmm]      (m x (n+1))
-    for (int e = tid; e < m * (n + 1); e += MARG_T) {
+    for (int e = tid; e < m * (n + 1); e += T) {
         const int k = e / (n + 1), c = e - k * (n + 1);
         const double lam = A[(size_t)k * pos + k];
         double t = 0;
@@ -534,8 +537,9 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         Tm[e] = t;
     }
     __syncthreads();
+    BE_PROF(10);
     // Z = Vm Tm = Amm^+ [Amr | bmm]   (m x (n+1)) ;  A_r = Arr - Amr^T Z ,  b_r = brr - Amr^T z_b
-    for (int e = tid; e < m * (n + 1); e += MARG_T) {
+    for (int e = tid; e < m * (n + 1); e += T) {
         const int i = e / (n + 1), c = e - i * (n + 1);
         double t = 0;
         for (int k = 0; k < m; k++) t += Vm[(size_t)i * m + k] * Tm[(size_t)k * (n + 1) + c];
@@ -543,7 +547,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     }
     __syncthreads();
     }   // !fast_ok
-    for (int e = tid; e < n * (n + 1); e += MARG_T) {
+    for (int e = tid; e < n * (n + 1); e += T) {
         const int r = e / (n + 1), c = e - r * (n + 1);
         double acc = 0;
         for (int i = 0; i < m; i++) acc += A[(size_t)i * pos + m + r] * Zm[(size_t)i * (n + 1) + c];
@@ -551,13 +555,14 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         else br[r] = bv[m + r] - acc;
     }
     __syncthreads();
-    for (int e = tid; e < n * n; e += MARG_T) { const int i = e / n, j = e - i * n; if (j < i) { const double v = 0.5 * (Ar[(size_t)i * n + j] + Ar[(size_t)j * n + i]); Ar[(size_t)i * n + j] = v; Ar[(size_t)j * n + i] = v; } }
+    for (int e = tid; e < n * n; e += T) { const int i = e / n, j = e - i * n; if (j < i) { const double v = 0.5 * (Ar[(size_t)i * n + j] + Ar[(size_t)j * n + i]); Ar[(size_t)i * n + j] = v; Ar[(size_t)j * n + i] = v; } }
     __syncthreads();
+    BE_PROF(11);
     int sweeps = 0;
     if (n <= MARG_NCAP) {                                      // A_r and V in shared memory
         double *sA = reinterpret_cast<double *>(smraw + ((sizeof(MargSmem) + 15) & ~(size_t)15));
         double *sV = sA + (size_t)n * n;
-        for (int e = tid; e < n * n; e += MARG_T) sA[e] = Ar[e];
+        for (int e = tid; e < n * n; e += T) sA[e] = Ar[e];
         __syncthreads();
         sweeps = s.eig_mode ? eig_sym_ql(sA, n, n, sV, sm.de, sm.rot, sm.red, sm.ql_i) : eig_sym_jacobi(sA, n, n, sV, sm.cs, sm.pq, sm.red);
         Ar = sA; Vr = sV;
@@ -566,33 +571,34 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     }
     if (tid == 0) { iv[IV_MARG_FAST] = fast_ok; iv[IV_MARG_SWEEPS] = sweeps; iv[IV_MARG_M] = m; }
     __syncthreads();
+    BE_PROF(12);
     // tv[k] = v_k . b_r ;  c0 = sum_{lam>eps} tv^2 / lam
-    for (int k = tid; k < n; k += MARG_T) {
+    for (int k = tid; k < n; k += T) {
         double t = 0;
         for (int i = 0; i < n; i++) t += Vr[(size_t)i * n + k] * br[i];
         tv[k] = t;
     }
     __syncthreads();
     double c0p = 0;
-    for (int k = tid; k < n; k += MARG_T) { const double lam = Ar[(size_t)k * n + k]; if (lam > MARG_EPS) c0p += tv[k] * tv[k] / lam; }
+    for (int k = tid; k < n; k += T) { const double lam = Ar[(size_t)k * n + k]; if (lam > MARG_EPS) c0p += tv[k] * tv[k] / lam; }
     const double c0 = block_sum_d(c0p, sm.red);
     // ---- write the new prior in canonical layout, shifted like addr_shift (VINS.cpp:759-774 / 806-829) ---------------
     double *Hp = s.Hp + (size_t)b * NPX * NPX, *bp = s.bp + (size_t)b * NPX;
-    for (int e = tid; e < NPX * NPX; e += MARG_T) Hp[e] = 0.0;
-    for (int e = tid; e < NPX; e += MARG_T) bp[e] = 0.0;
+    for (int e = tid; e < NPX * NPX; e += T) Hp[e] = 0.0;
+    for (int e = tid; e < NPX; e += T) bp[e] = 0.0;
     __syncthreads();
     auto shift = [&](int c) {
         if (c >= NP) return c;                                            // para_Ex_Pose stays
         if (marg == 0) return c - 15;                                     // frame i -> i-1
         return c >= 15 * W ? c - 15 : c;                                  // frame W -> W-1
     };
-    for (int e = tid; e < n * n; e += MARG_T) {
+    for (int e = tid; e < n * n; e += T) {
         const int i = e / n, j = e - i * n;
         double t = 0;
         for (int k = 0; k < n; k++) { const double lam = Ar[(size_t)k * n + k]; if (lam > MARG_EPS) t += Vr[(size_t)i * n + k] * lam * Vr[(size_t)j * n + k]; }
         Hp[(size_t)shift(sm.kept[i]) * NPX + shift(sm.kept[j])] = t;
     }
-    for (int i = tid; i < n; i += MARG_T) {
+    for (int i = tid; i < n; i += T) {
         double t = 0;
         for (int k = 0; k < n; k++) { const double lam = Ar[(size_t)k * n + k]; if (lam > MARG_EPS) t += Vr[(size_t)i * n + k] * tv[k]; }
         bp[shift(sm.kept[i])] = t;
@@ -621,6 +627,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         }
         for (int i = 0; i < 2 * NF + 1; i++) pres[i] = np[i];
         iv[IV_PRIOR_VALID] = 1; iv[IV_PRIOR_N] = n;
+        { const long long _t = clock64(); _pp[13] += _t - _pt0; }
         dvs[DV_PRIOR_C0] = c0;
     }
 }

@@ -385,7 +385,7 @@ __device__ inline void build_reduced_smem(const BeState &s, const SolveWs &ws, i
         S[e] = v;
     }
     for (int i = tid; i < NP; i += T) ws.rhs[i] = ws.g[i] * ws.sc_p[i];
-    constexpr int EPT = 8;                                          // entries of the NPW x NPW lower triangle per thread
+    constexpr int EPT = 10;                                         // entries of the NPW x NPW lower triangle per thread (2211 / 256 threads)
     const int nent = NPW * (NPW + 1) / 2;
     double acc[EPT];
     int ea[EPT], ec[EPT];
@@ -443,6 +443,7 @@ __host__ __device__ inline size_t solve_smem_bytes(int NP, int NPW) {
 
 __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem) {
     extern __shared__ __align__(16) double sm_dyn[];
+    const int T = blockDim.x;                              // 256 or 512 (VIO_BE_THREADS)
     __shared__ double sh_red[32];
     __shared__ int sh_flag;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -455,11 +456,13 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
     double *par = s.par + (size_t)b * (NF * 16 + s.LCAP);
     double *cand = s.cand + (size_t)b * (NF * 16 + s.LCAP);
 
+    BE_PROF_INIT;
     double x_cost = evaluate(s, b, ws, par, 1, sh_red);
+    BE_PROF(0);
     if (tid == 0) dvs[DV_COST0] = x_cost;
     // Jacobi scaling, frozen at iteration 0 (trust_region_minimizer.cc:239-254)
-    for (int i = tid; i < NP; i += SOLVE_T) ws.sc_p[i] = 1.0 / (1.0 + sqrt(ws.H[(size_t)i * NP + i]));
-    for (int l = tid; l < nl; l += SOLVE_T) ws.sc_l[l] = 1.0 / (1.0 + sqrt(ws.hll[l]));
+    for (int i = tid; i < NP; i += T) ws.sc_p[i] = 1.0 / (1.0 + sqrt(ws.H[(size_t)i * NP + i]));
+    for (int l = tid; l < nl; l += T) ws.sc_l[l] = 1.0 / (1.0 + sqrt(ws.hll[l]));
     __syncthreads();
 
     double radius = 1e4, mu = 1e-8, alpha = 0.0, dogleg_norm = 0.0, x_norm = -1.0;
@@ -471,8 +474,8 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
         if (iter >= s.max_iters) break;
         if (step_ok) {
             double gm = 0;                                 // gradient_max_norm ~ max |g|
-            for (int i = tid; i < NP; i += SOLVE_T) gm = fmax(gm, fabs(ws.g[i]));
-            for (int l = tid; l < nl; l += SOLVE_T) gm = fmax(gm, fabs(ws.gl[l]));
+            for (int i = tid; i < NP; i += T) gm = fmax(gm, fabs(ws.g[i]));
+            for (int l = tid; l < nl; l += T) gm = fmax(gm, fabs(ws.gl[l]));
             const double m = block_max_d(gm, sh_red);
             if (m <= 1e-10) break;
         }
@@ -482,14 +485,14 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
         bool linear_ok = true;
         if (!reuse) {
             reuse = true;
-            for (int i = tid; i < NP; i += SOLVE_T) {
+            for (int i = tid; i < NP; i += T) {
                 const double sc = ws.sc_p[i];
                 const double d = sqrt(fmin(fmax(ws.H[(size_t)i * NP + i] * sc * sc, 1e-6), 1e32));
                 ws.d_p[i] = d;
                 ws.gr_p[i] = ws.g[i] * sc / d;                       // gradient_ = (JS)^T r ./ diagonal
                 ws.u_p[i] = sc * (ws.g[i] * sc / (d * d));           // S * (gradient_ ./ diagonal)
             }
-            for (int l = tid; l < nl; l += SOLVE_T) {
+            for (int l = tid; l < nl; l += T) {
                 const double sc = ws.sc_l[l];
                 const double d = sqrt(fmin(fmax(ws.hll[l] * sc * sc, 1e-6), 1e32));
                 ws.d_l[l] = d;
@@ -500,6 +503,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
             const double g2 = dot2(ws.gr_p, ws.gr_l, ws.gr_p, ws.gr_l, NP, nl, sh_red);
             const double jg2 = quad_form(s, ws, nl, ws.u_p, ws.u_l, sh_red);
             alpha = g2 / jg2;                                         // ComputeCauchyPoint
+            BE_PROF(1);
             // ---- ComputeGaussNewtonStep: (S H S + mu D^2) y = S g by Schur elimination of the landmark blocks ----
             linear_ok = false;
             while (mu < 1.0) {
@@ -507,9 +511,11 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
               if (use_smem) {
                 double *Ssm = sm_dyn, *wt = sm_dyn + (size_t)(NP + 1) * (NP + 2) / 2 + 8;
                 build_reduced_smem(s, ws, nl, mu, Ssm, wt);
+                BE_PROF(2);
                 ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag, sh_red, wt);
+                BE_PROF(3);
               } else {
-                for (int e = tid; e < NP * NP; e += SOLVE_T) {
+                for (int e = tid; e < NP * NP; e += T) {
                     const int i = e / NP, j = e - i * NP;
                     if (j <= i) {
                         double v = ws.H[e] * ws.sc_p[i] * ws.sc_p[j];
@@ -517,10 +523,10 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
                         ws.S[e] = v;
                     }
                 }
-                for (int i = tid; i < NP; i += SOLVE_T) ws.rhs[i] = ws.g[i] * ws.sc_p[i];
+                for (int i = tid; i < NP; i += T) ws.rhs[i] = ws.g[i] * ws.sc_p[i];
                 __syncthreads();
                 // S -= sum_l ws_l ws_l^T / h_l on the pose (6-dof) rows/cols; rhs -= ws_l gs_l / h_l
-                for (int e = tid; e < NPW * NPW; e += SOLVE_T) {
+                for (int e = tid; e < NPW * NPW; e += T) {
                     const int a = e / NPW, c = e - a * NPW;
                     if (c > a) continue;
                     const int ia = 15 * (a / 6) + a % 6, ic = 15 * (c / 6) + c % 6;
@@ -534,7 +540,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
                     }
                     ws.S[(size_t)ia * NP + ic] -= acc * ws.sc_p[ia] * ws.sc_p[ic];
                 }
-                for (int a = tid; a < NPW; a += SOLVE_T) {
+                for (int a = tid; a < NPW; a += T) {
                     const int ia = 15 * (a / 6) + a % 6;
                     double acc = 0;
                     for (int l = 0; l < nl; l++) {
@@ -550,7 +556,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
                 __syncthreads();
                 if (ok) {
                     // back-substitution y_l = (gs_l - ws_l . y_p) / h_l ;  gauss_newton_step_ = -diagonal .* y
-                    for (int l = tid; l < nl; l += SOLVE_T) {
+                    for (int l = tid; l < nl; l += T) {
                         const double sl = ws.sc_l[l];
                         const double h = ws.hll[l] * sl * sl + mu * ws.d_l[l] * ws.d_l[l];
                         double t = 0;
@@ -560,7 +566,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
                         const double yl = (ws.gl[l] * sl - sl * t) / h;
                         ws.gn_l[l] = -ws.d_l[l] * yl;
                     }
-                    for (int i = tid; i < NP; i += SOLVE_T) ws.gn_p[i] = -ws.d_p[i] * ws.y[i];
+                    for (int i = tid; i < NP; i += T) ws.gn_p[i] = -ws.d_p[i] * ws.y[i];
                     __syncthreads();
                     linear_ok = true;
                     break;
@@ -588,19 +594,20 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
                 ca = -alpha * (1.0 - beta); cb = beta;
                 dogleg_norm = -1.0;
             }
-            for (int i = tid; i < NP; i += SOLVE_T) ws.st_p[i] = ca * ws.gr_p[i] + cb * ws.gn_p[i];
-            for (int l = tid; l < nl; l += SOLVE_T) ws.st_l[l] = ca * ws.gr_l[l] + cb * ws.gn_l[l];
+            for (int i = tid; i < NP; i += T) ws.st_p[i] = ca * ws.gr_p[i] + cb * ws.gn_p[i];
+            for (int l = tid; l < nl; l += T) ws.st_l[l] = ca * ws.gr_l[l] + cb * ws.gn_l[l];
             __syncthreads();
             if (dogleg_norm < 0) dogleg_norm = sqrt(dot2(ws.st_p, ws.st_l, ws.st_p, ws.st_l, NP, nl, sh_red));
             // trust_region_step_ = dogleg ./ diagonal ;  delta = trust_region_step_ .* jacobian_scaling_
-            for (int i = tid; i < NP; i += SOLVE_T) ws.u_p[i] = ws.st_p[i] / ws.d_p[i] * ws.sc_p[i];
-            for (int l = tid; l < nl; l += SOLVE_T) ws.u_l[l] = ws.st_l[l] / ws.d_l[l] * ws.sc_l[l];
+            for (int i = tid; i < NP; i += T) ws.u_p[i] = ws.st_p[i] / ws.d_p[i] * ws.sc_p[i];
+            for (int l = tid; l < nl; l += T) ws.u_l[l] = ws.st_l[l] / ws.d_l[l] * ws.sc_l[l];
             __syncthreads();
             // model_cost_change = -(J d)^T (r + J d / 2) = -(d^T g + d^T H d / 2)
             const double dg = dot2(ws.u_p, ws.u_l, ws.g, ws.gl, NP, nl, sh_red);
             const double dHd = quad_form(s, ws, nl, ws.u_p, ws.u_l, sh_red);
             model_change = -(dg + 0.5 * dHd);
             valid = model_change > 0.0;
+            BE_PROF(4);
         }
         if (!valid) {                                                 // HandleInvalidStep()
             if (++invalid_run >= 5) break;
@@ -609,27 +616,30 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
         }
         invalid_run = 0;
         // ---- candidate = Plus(x, delta), cost-only evaluation ---------------------------------------------
-        for (int i = tid; i < NF; i += SOLVE_T) {
+        for (int i = tid; i < NF; i += T) {
             pose_plus(par + 16 * i, ws.u_p + 15 * i, cand + 16 * i);
             for (int k = 0; k < 9; k++) cand[16 * i + 7 + k] = par[16 * i + 7 + k] + ws.u_p[15 * i + 6 + k];
         }
-        for (int l = tid; l < nl; l += SOLVE_T) cand[16 * NF + l] = par[16 * NF + l] + ws.u_l[l];
+        for (int l = tid; l < nl; l += T) cand[16 * NF + l] = par[16 * NF + l] + ws.u_l[l];
         __syncthreads();
         const double cand_cost = evaluate(s, b, ws, cand, 0, sh_red);
+        BE_PROF(5);
         // ParameterToleranceReached / FunctionToleranceReached (trust_region_minimizer.cc:662-705)
         double sn = 0;
-        for (int i = tid; i < 16 * NF + nl; i += SOLVE_T) { const double d = par[i] - cand[i]; sn += d * d; }
+        for (int i = tid; i < 16 * NF + nl; i += T) { const double d = par[i] - cand[i]; sn += d * d; }
         const double step_norm = sqrt(block_sum_d(sn, sh_red));
         if (step_norm <= 1e-8 * (x_norm + 1e-8)) break;
         if (fabs(x_cost - cand_cost) <= 1e-6 * x_cost) break;
         const double quality = (x_cost - cand_cost) / model_change;   // StepQuality with max_consecutive_nonmonotonic_steps = 0
         if (quality > 1e-3) {                                         // HandleSuccessfulStep()
-            for (int i = tid; i < 16 * NF + nl; i += SOLVE_T) par[i] = cand[i];
+            for (int i = tid; i < 16 * NF + nl; i += T) par[i] = cand[i];
             __syncthreads();
             double xn = 0;
-            for (int i = tid; i < 16 * NF + nl; i += SOLVE_T) xn += par[i] * par[i];
+            for (int i = tid; i < 16 * NF + nl; i += T) xn += par[i] * par[i];
             x_norm = sqrt(block_sum_d(xn, sh_red));
+            BE_PROF(6);
             x_cost = evaluate(s, b, ws, par, 1, sh_red);
+            BE_PROF(0);
             step_ok = true;
             if (quality < 0.25) radius *= 0.5;                        // DoglegStrategy::StepAccepted
             if (quality > 0.75) radius = fmax(radius, 3.0 * dogleg_norm);

@@ -43,6 +43,7 @@ struct BeState {
     double *scratch; size_t scratch_stride;           // [B][scratch_stride] doubles
     double *post_solve;                               // [B][NF][16]
     double *state_out;                                // [B][NF][16] packed P,Q,V,Ba,Bg after the step
+    long long *prof;                                  // [B][32] clock64 cycles per kernel phase (diagnostics)
 };
 
 __device__ __forceinline__ double *S_Ps(const BeState &s, int b, int i) { return s.Ps + ((size_t)b * s.NF + i) * 3; }
@@ -57,6 +58,10 @@ __device__ __forceinline__ double *S_dv(const BeState &s, int b) { return s.dv +
 __device__ __forceinline__ double *S_obs(const BeState &s, int b, int slot) { return s.f_obs + ((size_t)b * s.FCAP + slot) * s.NF * 2; }
 __device__ __forceinline__ double *S_par_pose(const BeState &s, double *par, int i) { return par + 16 * i; }
 __device__ __forceinline__ double *S_par_sb(const BeState &s, double *par, int i) { return par + 16 * i + 7; }
+
+// phase timer: thread 0 accumulates the cycles since the previous mark into prof[b][slot]
+#define BE_PROF_INIT long long _pt0 = clock64(); long long *_pp = s.prof + (size_t)blockIdx.x * 32
+#define BE_PROF(slot) do { if (threadIdx.x == 0) { const long long _t = clock64(); _pp[slot] += _t - _pt0; _pt0 = _t; } } while (0)
 
 // the predicate repeated throughout the reference: used_num >= 2 && start_frame < WINDOW_SIZE - 2
 __device__ __forceinline__ bool in_solve(const BeState &s, int nobs, int start) { return nobs >= 2 && start < s.W - 2; }
