@@ -94,7 +94,8 @@ __device__ inline int eig_sym_jacobi(double *A, int n, int ld, double *V, double
 // Parallelisation: every O(n^2) inner loop of tred2 is spread over the CTA; in tql2 one thread runs the scalar rotation
 // recurrence of a QL step, then every thread applies the whole rotation sequence to the rows of V it owns.
 // de: shared scratch for 2n doubles (d, e); rot: shared scratch for 2n doubles.  Returns the number of QL steps.
-__device__ inline int eig_sym_ql(double *A, int n, int ld, double *V, double *de, double *rot, double *sh_red, int *sh_i) {
+__device__ inline int eig_sym_ql(double *A, int n, int ld, double *V, double *de, double *rot, double *sh_red, int *sh_i, long long *pp) {
+    BE_PROF2_INIT;
     const int tid = threadIdx.x, T = blockDim.x;
     double *d = de, *e = de + n;
     for (int x = tid; x < n * n; x += T) { const int i = x / n, j = x - i * n; V[x] = A[(size_t)i * ld + j]; }
@@ -149,6 +150,7 @@ __device__ inline int eig_sym_ql(double *A, int n, int ld, double *V, double *de
     }
     if (tid == 0) { d[0] = 0.0; e[0] = 0.0; }
     __syncthreads();
+    BE_PROF2(pp, 24);
     for (int i = 0; i < n; i++) {                           // accumulate the transformation
         const int l = i - 1;
         if (d[i] != 0.0 && l >= 0) {
@@ -168,6 +170,7 @@ __device__ inline int eig_sym_ql(double *A, int n, int ld, double *V, double *de
         for (int j = tid; j <= l; j += T) { a[j * n + i] = 0.0; a[i * n + j] = 0.0; }
         __syncthreads();
     }
+    BE_PROF2(pp, 25);
     // ---- tql2 -------------------------------------------------------------------------------------------------------------
     if (tid == 0) { for (int i = 1; i < n; i++) e[i - 1] = e[i]; e[n - 1] = 0.0; }
     __syncthreads();
@@ -185,19 +188,23 @@ __device__ inline int eig_sym_ql(double *A, int n, int ld, double *V, double *de
                     double sn = 1.0, c = 1.0, p = 0.0;
                     int i = m - 1;
                     bool brk = false;
+                    double ei = e[i], di = d[i], dip1 = d[i + 1];          // software-pipelined operands of rotation i
                     for (; i >= l; i--) {
-                        double f = sn * e[i];
-                        const double bb = c * e[i];
-                        r = hypot(f, g);
+                        const double en = i > l ? e[i - 1] : 0.0, dn = i > l ? d[i - 1] : 0.0;
+                        const double f = sn * ei;
+                        const double bb = c * ei;
+                        r = sqrt(f * f + g * g);                           // |f|,|g| are O(|A|): no overflow concern at this scale
                         e[i + 1] = r;
-                        if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; brk = true; break; }
-                        sn = f / r; c = g / r;
-                        g = d[i + 1] - p;
-                        r = (d[i] - g) * sn + 2.0 * c * bb;
+                        if (r == 0.0) { d[i + 1] = dip1 - p; e[m] = 0.0; brk = true; break; }
+                        const double ir = 1.0 / r;
+                        sn = f * ir; c = g * ir;
+                        g = dip1 - p;
+                        r = (di - g) * sn + 2.0 * c * bb;
                         p = sn * r;
                         d[i + 1] = g + p;
                         g = c * r - bb;
                         rot[2 * i] = c; rot[2 * i + 1] = sn;
+                        dip1 = di; di = dn; ei = en;
                     }
                     sh_i[1] = brk ? i + 1 : l;
                     if (!brk) { d[l] -= p; e[l] = g; e[m] = 0.0; }
@@ -221,6 +228,7 @@ __device__ inline int eig_sym_ql(double *A, int n, int ld, double *V, double *de
     }
     for (int i = tid; i < n; i += T) A[(size_t)i * ld + i] = d[i];
     __syncthreads();
+    BE_PROF2(pp, 26);
     return steps;
 }
 
@@ -416,11 +424,15 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
                 J[r][18] = Jl[r];
             }
             for (int a = 0; a < 19; a++) {
-                for (int c = 0; c < 19; c++) atomic_add(&A[(size_t)idx[a] * pos + idx[c]], J[0][a] * J[0][c] + J[1][a] * J[1][c]);
+                // one triangle only (row index >= column index in work order); mirrored after the accumulation
+                for (int c = 0; c < 19; c++)
+                    if (idx[a] > idx[c] || (idx[a] == idx[c] && a >= c)) atomic_add(&A[(size_t)idx[a] * pos + idx[c]], J[0][a] * J[0][c] + J[1][a] * J[1][c]);
                 atomic_add(&bv[idx[a]], J[0][a] * r2[0] + J[1][a] * r2[1]);
             }
         }
     }
+    __syncthreads();
+    for (int e = tid; e < pos * pos; e += T) { const int i = e / pos, j = e - i * pos; if (j > i) A[e] = A[(size_t)j * pos + i]; }     // mirror
     __syncthreads();
     BE_PROF(9);
     // ---- Amm^+ [Amr | bmm] ------------------------------------------------------------------------------------------------
@@ -523,7 +535,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         }
     }
     if (!fast_ok) {
-    if (s.eig_mode) eig_sym_ql(A, m, pos, Vm, sm.de, sm.rot, sm.red, sm.ql_i); else eig_sym_jacobi(A, m, pos, Vm, sm.cs, sm.pq, sm.red);
+    if (s.eig_mode) eig_sym_ql(A, m, pos, Vm, sm.de, sm.rot, sm.red, sm.ql_i, s.prof + (size_t)blockIdx.x * 32); else eig_sym_jacobi(A, m, pos, Vm, sm.cs, sm.pq, sm.red);
     __syncthreads();
     // Tm = Lambda^+ Vm^T [Amr | bmm]      (m x (n+1))
     for (int e = tid; e < m * (n + 1); e += T) {
@@ -564,10 +576,10 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         double *sV = sA + (size_t)n * n;
         for (int e = tid; e < n * n; e += T) sA[e] = Ar[e];
         __syncthreads();
-        sweeps = s.eig_mode ? eig_sym_ql(sA, n, n, sV, sm.de, sm.rot, sm.red, sm.ql_i) : eig_sym_jacobi(sA, n, n, sV, sm.cs, sm.pq, sm.red);
+        sweeps = s.eig_mode ? eig_sym_ql(sA, n, n, sV, sm.de, sm.rot, sm.red, sm.ql_i, s.prof + (size_t)blockIdx.x * 32) : eig_sym_jacobi(sA, n, n, sV, sm.cs, sm.pq, sm.red);
         Ar = sA; Vr = sV;
     } else {
-        sweeps = s.eig_mode ? eig_sym_ql(Ar, n, n, Vr, sm.de, sm.rot, sm.red, sm.ql_i) : eig_sym_jacobi(Ar, n, n, Vr, sm.cs, sm.pq, sm.red);
+        sweeps = s.eig_mode ? eig_sym_ql(Ar, n, n, Vr, sm.de, sm.rot, sm.red, sm.ql_i, s.prof + (size_t)blockIdx.x * 32) : eig_sym_jacobi(Ar, n, n, Vr, sm.cs, sm.pq, sm.red);
     }
     if (tid == 0) { iv[IV_MARG_FAST] = fast_ok; iv[IV_MARG_SWEEPS] = sweeps; iv[IV_MARG_M] = m; }
     __syncthreads();

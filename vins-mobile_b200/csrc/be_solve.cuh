@@ -66,6 +66,7 @@ __device__ inline void prior_dx(const BeState &s, int b, const double *par, doub
 
 // cost (and, when lin != 0, H / g / landmark terms) at parameter vector `par`.  Returns the total cost in every thread.
 __device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, const double *par, int lin, double *sh_red) {
+    long long *pp = s.prof + (size_t)b * 32; BE_PROF2_INIT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int *iv = S_iv(s, b);
     const int NP = s.NP, NPW = s.NPW, nl = iv[IV_N_LM], nfac = iv[IV_N_FAC];
@@ -97,6 +98,7 @@ __device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, co
         if (tid == 0) cost += 0.5 * S_dv(s, b)[DV_PRIOR_C0];
     }
     __syncthreads();
+    if (lin) BE_PROF2(pp, 16);
     // ---- IMU factors: one warp per factor ---------------------------------------------------------------
     for (int f = warp; f < s.W; f += nwarp) {
         const double *pr = S_pre(s, b, f + 1);
@@ -131,6 +133,8 @@ __device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, co
             }
         }
     }
+    __syncthreads();
+    if (lin) BE_PROF2(pp, 17);
     // ---- projection factors: one thread per factor ------------------------------------------------------
     {
         const double *dv = S_dv(s, b);
@@ -165,11 +169,13 @@ __device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, co
         }
     }
     __syncthreads();
+    if (lin) BE_PROF2(pp, 18);
     if (lin) {                                            // mirror the lower triangle (the prior part is already symmetric)
         for (int e = tid; e < NP * NP; e += blockDim.x) { const int i = e / NP, j = e - i * NP; if (j > i) ws.H[e] = ws.H[(size_t)j * NP + i]; }
     }
     const double total = block_sum_d(cost, sh_red);
     __syncthreads();
+    if (lin) BE_PROF2(pp, 19);
     return total;
 }
 
@@ -261,7 +267,8 @@ __device__ __forceinline__ int pidx(int i, int j) { return i * (i + 1) / 2 + j; 
 // Panel width 8; the 8x8 diagonal block is factored by one thread entirely in registers; 3 barriers per panel.  The backward
 // substitution L^T y = z is blocked the same way (2 barriers per panel).  A must have room for (n+1)(n+2)/2 doubles.
 // Returns false (in all threads) on a non-positive pivot / non-finite value (Eigen LLT info() != Success).
-__device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, double *y, int *sh_flag, double *sh_inv /*>= 8*/, double *dinv /*>= 36*ceil(n/8)*/) {
+__device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, double *y, int *sh_flag, double *sh_inv /*>= 8*/, double *dinv /*>= 36*ceil(n/8)*/, long long *pp) {
+    BE_PROF2_INIT;
     const int tid = threadIdx.x, T = blockDim.x;
     constexpr int NB = 8;
     if (tid == 0) *sh_flag = 1;
@@ -269,64 +276,67 @@ __device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, do
     __syncthreads();
     for (int c0 = 0; c0 < n; c0 += NB) {
         const int nb = min(NB, n - c0);
-        for (int e = tid; e < (n + 1 - c0) * nb; e += T) {          // panel (incl. the rhs row) -= L[:, :c0] L[panel, :c0]^T
-            const int i = c0 + e / nb, j = c0 + e % nb;
-            if (j > i) continue;
-            const double *ri = A + pidx(i, 0), *rj = A + pidx(j, 0);
-            double t0 = 0, t1 = 0;
-            int k = 0;
-            for (; k + 1 < c0; k += 2) { t0 += ri[k] * rj[k]; t1 += ri[k + 1] * rj[k + 1]; }
-            if (k < c0) t0 += ri[k] * rj[k];
-            A[pidx(i, j)] -= t0 + t1;
+        // panel (incl. the rhs row) -= L[:, :c0] L[panel, :c0]^T : one thread per row i, 8 accumulators; the 8 panel rows are
+        // read at the same address by every thread (shared-memory broadcast), so a k step costs 1 private + 8 broadcast loads
+        for (int i = c0 + tid; i <= n; i += T) {
+            const double *ri = A + pidx(i, 0);
+            double acc[NB];
+#pragma unroll
+            for (int jj = 0; jj < NB; jj++) acc[jj] = 0.0;
+            for (int k = 0; k < c0; k++) {
+                const double li = ri[k];
+#pragma unroll
+                for (int jj = 0; jj < NB; jj++) if (jj < nb) acc[jj] += li * A[pidx(c0 + jj, 0) + k];
+            }
+#pragma unroll
+            for (int jj = 0; jj < NB; jj++) if (jj < nb && c0 + jj <= i) A[pidx(i, c0 + jj)] -= acc[jj];
         }
         __syncthreads();
-        if (tid == 0) {                                              // nb x nb diagonal block in registers
-            double d[NB][NB];
+        BE_PROF2(pp, 20);
+        if (tid < 32) {                                              // nb x nb diagonal block: lane r owns row r (registers + shuffles)
+            const int lane = tid;
+            const int r = lane < NB ? lane : 0;
+            double row[NB];
 #pragma unroll
-            for (int i = 0; i < NB; i++)
-#pragma unroll
-                for (int j = 0; j <= i; j++) d[i][j] = (i < nb) ? A[pidx(c0 + i, c0 + j)] : (i == j ? 1.0 : 0.0);
+            for (int j = 0; j < NB; j++) row[j] = (lane < nb && j <= r && j < nb) ? A[pidx(c0 + r, c0 + j)] : ((lane < NB && j == r) ? 1.0 : 0.0);
             bool ok = true;
 #pragma unroll
-            for (int j = 0; j < NB; j++) {
-                double v = d[j][j];
+            for (int k = 0; k < NB; k++) {
+                // pivot of column k lives in lane k
+                const double piv = __shfl_sync(0xffffffffu, row[k], k);
+                ok &= (piv > 0) && isfinite(piv);
+                const double l = sqrt(piv), il = 1.0 / l;
+                if (lane == k) row[k] = l; else if (lane > k && lane < NB) row[k] *= il;      // column k of L
+                if (lane == 0 && k < nb) sh_inv[k] = il;
 #pragma unroll
-                for (int t = 0; t < j; t++) v -= d[j][t] * d[j][t];
-                ok &= (v > 0) && isfinite(v);
-                const double l = sqrt(v), il = 1.0 / l;
-                d[j][j] = l;
-                if (j < nb) sh_inv[j] = il;
-#pragma unroll
-                for (int i = j + 1; i < NB; i++) {
-                    double w = d[i][j];
-#pragma unroll
-                    for (int t = 0; t < j; t++) w -= d[i][t] * d[j][t];
-                    d[i][j] = w * il;
+                for (int j = k + 1; j < NB; j++) {
+                    const double ljk = __shfl_sync(0xffffffffu, row[k], j);                    // L[j][k]
+                    if (lane >= j && lane < NB) row[j] -= row[k] * ljk;
                 }
             }
-            if (!ok) *sh_flag = 0;
+            if (!ok && lane == 0) *sh_flag = 0;
 #pragma unroll
-            for (int i = 0; i < NB; i++)
+            for (int j = 0; j < NB; j++) if (lane < nb && j <= lane) A[pidx(c0 + lane, c0 + j)] = row[j];
+            // inverse of the lower block for the backward substitution: lane c solves column c of L^-1 by forward substitution
+            __syncwarp();
+            if (lane < NB) {
+                const int c = lane;
+                double x[NB];
 #pragma unroll
-                for (int j = 0; j <= i; j++) if (i < nb) A[pidx(c0 + i, c0 + j)] = d[i][j];
-            // inverse of the (lower) diagonal block, kept for the backward substitution: Li = d^-1
-            double li[NB][NB];
-#pragma unroll
-            for (int c = 0; c < NB; c++)
-#pragma unroll
-                for (int i = c; i < NB; i++) {
+                for (int i = 0; i < NB; i++) {
                     double v = (i == c) ? 1.0 : 0.0;
 #pragma unroll
-                    for (int t = c; t < i; t++) v -= d[i][t] * li[t][c];
-                    li[i][c] = v / d[i][i];
+                    for (int t = 0; t < NB; t++) if (t < i && t >= c) v -= ((i < nb && t < nb) ? A[pidx(c0 + i, c0 + t)] : 0.0) * x[t];
+                    const double dii = (i < nb) ? A[pidx(c0 + i, c0 + i)] : 1.0;
+                    x[i] = (i >= c) ? v / dii : 0.0;
                 }
-            double *dst = dinv + (c0 / NB) * 36;
+                double *dst = dinv + (c0 / NB) * 36;
 #pragma unroll
-            for (int i = 0; i < NB; i++)
-#pragma unroll
-                for (int c = 0; c <= i; c++) dst[i * (i + 1) / 2 + c] = li[i][c];
+                for (int i = 0; i < NB; i++) if (i >= c) dst[i * (i + 1) / 2 + c] = x[i];
+            }
         }
         __syncthreads();
+        BE_PROF2(pp, 21);
         if (!*sh_flag) return false;
         for (int i = c0 + nb + tid; i <= n; i += T) {                // rows below the block (and the rhs row): triangular solve
             double *ri = A + pidx(i, c0);
@@ -345,6 +355,7 @@ __device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, do
         }
         __syncthreads();
     }
+    BE_PROF2(pp, 22);
     // backward: L^T y = z, z = row n of A
     for (int j = tid; j < n; j += T) y[j] = A[pidx(n, j)];
     __syncthreads();
@@ -367,6 +378,7 @@ __device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, do
     }
     bool ok = true;
     for (int i = tid; i < n; i += T) ok &= isfinite(y[i]);
+    BE_PROF2(pp, 23);
     return __syncthreads_and(ok) != 0;
 }
 
@@ -402,6 +414,10 @@ __device__ inline void build_reduced_smem(const BeState &s, const SolveWs &ws, i
         }
         ea[q] = a; ec[q] = c;
     }
+    for (int l = tid; l < nl; l += T) {                             // per-landmark weight sqrt(s_l^2 / h_l) (u_l is free scratch here)
+        const double sl = ws.sc_l[l];
+        ws.u_l[l] = sqrt(sl * sl / (ws.hll[l] * sl * sl + mu * ws.d_l[l] * ws.d_l[l]));
+    }
     double racc = 0;                                                // thread a < NPW accumulates the rhs correction
     const int ld = NPW + 1;
     for (int l0 = 0; l0 < nl; l0 += SCHUR_CHUNK) {
@@ -409,10 +425,7 @@ __device__ inline void build_reduced_smem(const BeState &s, const SolveWs &ws, i
         __syncthreads();
         for (int e = tid; e < cn * ld; e += T) {
             const int cl = e / ld, a = e - cl * ld, l = l0 + cl;
-            const double sl = ws.sc_l[l];
-            const double h = ws.hll[l] * sl * sl + mu * ws.d_l[l] * ws.d_l[l];
-            const double f = sl * sl / h;
-            wt[e] = (a < NPW) ? ws.w[(size_t)l * NPW + a] * sqrt(f) : ws.gl[l] * sqrt(f);
+            wt[e] = ((a < NPW) ? ws.w[(size_t)l * NPW + a] : ws.gl[l]) * ws.u_l[l];      // u_l holds sqrt(s_l^2 / h_l), set below
         }
         __syncthreads();
 #pragma unroll
@@ -512,7 +525,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
                 double *Ssm = sm_dyn, *wt = sm_dyn + (size_t)(NP + 1) * (NP + 2) / 2 + 8;
                 build_reduced_smem(s, ws, nl, mu, Ssm, wt);
                 BE_PROF(2);
-                ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag, sh_red, wt);
+                ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag, sh_red, wt, s.prof + (size_t)b * 32);
                 BE_PROF(3);
               } else {
                 for (int e = tid; e < NP * NP; e += T) {

@@ -61,6 +61,8 @@ __device__ __forceinline__ double *S_par_sb(const BeState &s, double *par, int i
 
 // phase timer: thread 0 accumulates the cycles since the previous mark into prof[b][slot]
 #define BE_PROF_INIT long long _pt0 = clock64(); long long *_pp = s.prof + (size_t)blockIdx.x * 32
+#define BE_PROF2_INIT long long _qt0 = clock64()
+#define BE_PROF2(pp, slot) do { if (threadIdx.x == 0) { const long long _t = clock64(); (pp)[slot] += _t - _qt0; _qt0 = _t; } } while (0)
 #define BE_PROF(slot) do { if (threadIdx.x == 0) { const long long _t = clock64(); _pp[slot] += _t - _pt0; _pt0 = _t; } } while (0)
 
 // the predicate repeated throughout the reference: used_num >= 2 && start_frame < WINDOW_SIZE - 2

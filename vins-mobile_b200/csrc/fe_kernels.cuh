@@ -125,15 +125,18 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
     // Everything is shared-memory resident so that the per-pixel loops stay rolled (small code, few registers, 8 warps per CTA).
     __shared__ uint8_t sI[LK_WARPS][24 * 24];
     __shared__ uint8_t sJ[LK_WARPS][22 * 24];
-    __shared__ short sT[LK_WARPS][3 * LK_NPIX + 1];
+    __shared__ short4 sT[LK_WARPS][LK_NPIX];            // (Iw, gx, gy, -) per window pixel: one 8-byte load per pixel per iteration
+    __shared__ unsigned short sOff[LK_NPIX];             // window pixel -> offset y*24 + x (shared by the 8 warps)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int f = blockIdx.x * LK_WARPS + warp;
+    for (int p = threadIdx.x; p < LK_NPIX; p += LK_WARPS * 32) sOff[p] = (unsigned short)((p / LK_WIN) * 24 + (p % LK_WIN));
+    __syncthreads();
     if (f >= n_pts[b]) return;
     const float2 pt = prev_pts[(size_t)b * maxp + f];
     uint8_t *pI = sI[warp];
     uint8_t *pJ = sJ[warp];
-    short *tI = sT[warp], *tX = tI + LK_NPIX, *tY = tX + LK_NPIX;
+    short4 *tT = sT[warp];
     const float half = 10.f;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
     float nx = 0.f, ny = 0.f;          // nextPts[ptidx] (level coordinates, window centre)
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
             const int ivs = (iv + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
             const int gxs = (dxv + (1 << (W_BITS - 1))) >> W_BITS;
             const int gys = (dyv + (1 << (W_BITS - 1))) >> W_BITS;
-            tI[p] = (short)ivs; tX[p] = (short)gxs; tY[p] = (short)gys;
+            tT[p] = make_short4((short)ivs, (short)gxs, (short)gys, 0);
             a11 += gxs * gxs; a12 += gxs * gys; a22 += gys * gys;
         }
         const float A11 = fmul(__ll2float_rn(warp_sum_ll(a11)), FLT_SCALE);
@@ -211,12 +214,12 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
             int b1 = 0, b2 = 0;
 #pragma unroll 2
             for (int p = lane; p < LK_NPIX; p += 32) {
-                const int y = p / LK_WIN, x = p - y * LK_WIN;
-                const uint8_t *q = pJ + y * 24 + x;
+                const uint8_t *q = pJ + sOff[p];
+                const short4 t = tT[p];
                 const int jv = (q[0] * v00 + q[1] * v01 + q[24] * v10 + q[25] * v11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                const int diff = jv - tI[p];
-                b1 += diff * tX[p];
-                b2 += diff * tY[p];
+                const int diff = jv - t.x;
+                b1 += diff * t.y;
+                b2 += diff * t.z;
             }
             const float B1 = fmul(__ll2float_rn(warp_sum_ll(b1)), FLT_SCALE);
             const float B2 = fmul(__ll2float_rn(warp_sum_ll(b2)), FLT_SCALE);
