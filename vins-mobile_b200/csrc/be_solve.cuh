@@ -65,7 +65,7 @@ __device__ inline void prior_dx(const BeState &s, int b, const double *par, doub
 }
 
 // cost (and, when lin != 0, H / g / landmark terms) at parameter vector `par`.  Returns the total cost in every thread.
-__device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, const double *par, int lin, double *sh_red) {
+__device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &ws, const double *par, int lin, double *sh_red) {
     long long *pp = s.prof + (size_t)b * 32; BE_PROF2_INIT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int *iv = S_iv(s, b);
@@ -142,30 +142,65 @@ __device__ inline double evaluate(const BeState &s, int b, const SolveWs &ws, co
         const int *fl = s.fac_lm + (size_t)b * s.PCAP, *fj = s.fac_j + (size_t)b * s.PCAP;
         const int *slot = s.lm_slot + (size_t)b * s.LCAP;
         const size_t fo = (size_t)b * s.FCAP;
-        for (int f = tid; f < nfac; f += blockDim.x) {
-            const int l = fl[f], j = fj[f], k = slot[l];
-            const int i = s.f_start[fo + k];
-            const double *o = S_obs(s, b, k);
-            const V3 pi = v3(o[0], o[1], 1.0), pj = v3(o[2 * (j - i)], o[2 * (j - i) + 1], 1.0);
-            double r2[2], Ji[12], Jj[12], Jl[2];
-            if (!lin) { cost += proj_eval(K, pi, pj, par + 16 * i, par + 16 * j, par[16 * s.NF + l], nullptr, nullptr, nullptr, nullptr); continue; }
-            cost += proj_eval(K, pi, pj, par + 16 * i, par + 16 * j, par[16 * s.NF + l], r2, Ji, Jj, Jl);
-            const int oi = 15 * i, oj = 15 * j;
-            for (int a = 0; a < 6; a++) {
-                for (int c = 0; c < 6; c++) {             // lower triangle only (i < j always): blocks (i,i), (j,j) lower halves and (j,i)
-                    if (c <= a) {
-                        atomic_add(&ws.H[(size_t)(oi + a) * NP + oi + c], Ji[a] * Ji[c] + Ji[6 + a] * Ji[6 + c]);
-                        atomic_add(&ws.H[(size_t)(oj + a) * NP + oj + c], Jj[a] * Jj[c] + Jj[6 + a] * Jj[6 + c]);
-                    }
-                    atomic_add(&ws.H[(size_t)(oj + a) * NP + oi + c], Jj[a] * Ji[c] + Jj[6 + a] * Ji[6 + c]);
-                }
-                atomic_add(&ws.g[oi + a], Ji[a] * r2[0] + Ji[6 + a] * r2[1]);
-                atomic_add(&ws.g[oj + a], Jj[a] * r2[0] + Jj[6 + a] * r2[1]);
-                atomic_add(&ws.w[(size_t)l * NPW + 6 * i + a], Ji[a] * Jl[0] + Ji[6 + a] * Jl[1]);
-                atomic_add(&ws.w[(size_t)l * NPW + 6 * j + a], Jj[a] * Jl[0] + Jj[6 + a] * Jl[1]);
+        if (!lin) {
+            for (int f = tid; f < nfac; f += blockDim.x) {           // cost only: one thread per factor
+                const int l = fl[f], j = fj[f], k = slot[l];
+                const int i = s.f_start[fo + k];
+                const double *o = S_obs(s, b, k);
+                const V3 pi = v3(o[0], o[1], 1.0), pj = v3(o[2 * (j - i)], o[2 * (j - i) + 1], 1.0);
+                cost += proj_eval(K, pi, pj, par + 16 * i, par + 16 * j, par[16 * s.NF + l], nullptr, nullptr, nullptr, nullptr);
             }
-            atomic_add(&ws.hll[l], Jl[0] * Jl[0] + Jl[1] * Jl[1]);
-            atomic_add(&ws.gl[l], Jl[0] * r2[0] + Jl[1] * r2[1]);
+        } else {
+            // linearisation: one thread per LANDMARK.  Everything that belongs to the landmark alone (h_ll, g_l, its coupling rows w_l)
+            // and the (i,i) block / g_i of its anchor frame are reduced in registers over the landmark's factors, so only the
+            // (j,j), (j,i) blocks and g_j of each factor go through atomics (63 instead of 104 per factor, and the hot anchor block
+            // receives one update per landmark instead of one per factor).
+            for (int l = tid; l < nl; l += blockDim.x) {
+                const int k = slot[l];
+                const int i = s.f_start[fo + k], no = s.f_nobs[fo + k];
+                const double *o = S_obs(s, b, k);
+                const V3 pi = v3(o[0], o[1], 1.0);
+                const double lam = par[16 * s.NF + l];
+                double Hii[21], gi[6], wi[6], hl = 0, gll = 0;
+#pragma unroll
+                for (int q = 0; q < 21; q++) Hii[q] = 0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) { gi[q] = 0; wi[q] = 0; }
+                const int oi = 15 * i;
+                for (int t = 1; t < no; t++) {
+                    const int j = i + t, oj = 15 * j;
+                    const V3 pj = v3(o[2 * t], o[2 * t + 1], 1.0);
+                    double r2[2], Ji[12], Jj[12], Jl[2];
+                    cost += proj_eval(K, pi, pj, par + 16 * i, par + 16 * j, lam, r2, Ji, Jj, Jl);
+                    int q = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; a++) {
+#pragma unroll
+                        for (int c = 0; c < 6; c++) {
+                            if (c <= a) {
+                                Hii[q++] += Ji[a] * Ji[c] + Ji[6 + a] * Ji[6 + c];
+                                atomic_add(&ws.H[(size_t)(oj + a) * NP + oj + c], Jj[a] * Jj[c] + Jj[6 + a] * Jj[6 + c]);
+                            }
+                            atomic_add(&ws.H[(size_t)(oj + a) * NP + oi + c], Jj[a] * Ji[c] + Jj[6 + a] * Ji[6 + c]);
+                        }
+                        gi[a] += Ji[a] * r2[0] + Ji[6 + a] * r2[1];
+                        wi[a] += Ji[a] * Jl[0] + Ji[6 + a] * Jl[1];
+                        atomic_add(&ws.g[oj + a], Jj[a] * r2[0] + Jj[6 + a] * r2[1]);
+                        ws.w[(size_t)l * NPW + 6 * j + a] = Jj[a] * Jl[0] + Jj[6 + a] * Jl[1];
+                    }
+                    hl += Jl[0] * Jl[0] + Jl[1] * Jl[1];
+                    gll += Jl[0] * r2[0] + Jl[1] * r2[1];
+                }
+                int q = 0;
+#pragma unroll
+                for (int a = 0; a < 6; a++) {
+#pragma unroll
+                    for (int c = 0; c <= a; c++) atomic_add(&ws.H[(size_t)(oi + a) * NP + oi + c], Hii[q++]);
+                    atomic_add(&ws.g[oi + a], gi[a]);
+                    ws.w[(size_t)l * NPW + 6 * i + a] = wi[a];
+                }
+                ws.hll[l] = hl; ws.gl[l] = gll;
+            }
         }
     }
     __syncthreads();
@@ -262,83 +297,48 @@ __device__ inline bool chol_solve(double *A, int n, const double *rhs, double *y
 // ---- shared-memory path (reduced system fits one SM: NP*(NP+1)/2 doubles, 110 KB at W=10) -------------------------------------
 __device__ __forceinline__ int pidx(int i, int j) { return i * (i + 1) / 2 + j; }       // packed lower, j <= i
 
-// Blocked left-looking Cholesky on a packed lower matrix in shared memory, BORDERED by the right-hand side: row n of the packed
-// array holds rhs, so the forward substitution z = L^-1 rhs falls out of the row-solve phase of the factorisation itself.
-// Panel width 8; the 8x8 diagonal block is factored by one thread entirely in registers; 3 barriers per panel.  The backward
-// substitution L^T y = z is blocked the same way (2 barriers per panel).  A must have room for (n+1)(n+2)/2 doubles.
+// Blocked RIGHT-looking Cholesky on a packed lower matrix in shared memory, BORDERED by the right-hand side (row n of the packed
+// array holds rhs, so the forward substitution z = L^-1 rhs is a by-product of the factorisation).  Per 8-column panel:
+//   (a) warp 0 factors the 8x8 diagonal block in place (shared memory, one __syncwarp-separated step per column);
+//   (b) one thread per row below the block solves its 8 entries against the block (block reads are warp broadcasts);
+//   (c) the trailing matrix gets the rank-8 update in 4x4 register tiles (0.5 shared loads per FMA), spread over the whole CTA.
+// Three barriers per panel.  Backward substitution L^T y = z is blocked the same way.  A must hold (n+1)(n+2)/2 doubles.
 // Returns false (in all threads) on a non-positive pivot / non-finite value (Eigen LLT info() != Success).
-__device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, double *y, int *sh_flag, double *sh_inv /*>= 8*/, double *dinv /*>= 36*ceil(n/8)*/, long long *pp) {
+__device__ __noinline__ bool chol_solve_packed(double *A, int n, const double *rhs, double *y, int *sh_flag, double *sh_inv /*>= 8*/, long long *pp) {
     BE_PROF2_INIT;
-    const int tid = threadIdx.x, T = blockDim.x;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
     constexpr int NB = 8;
     if (tid == 0) *sh_flag = 1;
     for (int j = tid; j < n; j += T) A[pidx(n, j)] = rhs[j];
     __syncthreads();
     for (int c0 = 0; c0 < n; c0 += NB) {
         const int nb = min(NB, n - c0);
-        // panel (incl. the rhs row) -= L[:, :c0] L[panel, :c0]^T : one thread per row i, 8 accumulators; the 8 panel rows are
-        // read at the same address by every thread (shared-memory broadcast), so a k step costs 1 private + 8 broadcast loads
-        for (int i = c0 + tid; i <= n; i += T) {
-            const double *ri = A + pidx(i, 0);
-            double acc[NB];
-#pragma unroll
-            for (int jj = 0; jj < NB; jj++) acc[jj] = 0.0;
-            for (int k = 0; k < c0; k++) {
-                const double li = ri[k];
-#pragma unroll
-                for (int jj = 0; jj < NB; jj++) if (jj < nb) acc[jj] += li * A[pidx(c0 + jj, 0) + k];
-            }
-#pragma unroll
-            for (int jj = 0; jj < NB; jj++) if (jj < nb && c0 + jj <= i) A[pidx(i, c0 + jj)] -= acc[jj];
-        }
-        __syncthreads();
-        BE_PROF2(pp, 20);
-        if (tid < 32) {                                              // nb x nb diagonal block: lane r owns row r (registers + shuffles)
-            const int lane = tid;
-            const int r = lane < NB ? lane : 0;
-            double row[NB];
-#pragma unroll
-            for (int j = 0; j < NB; j++) row[j] = (lane < nb && j <= r && j < nb) ? A[pidx(c0 + r, c0 + j)] : ((lane < NB && j == r) ? 1.0 : 0.0);
+        if (tid < 32) {                                              // (a) diagonal block, in place
             bool ok = true;
-#pragma unroll
-            for (int k = 0; k < NB; k++) {
-                // pivot of column k lives in lane k
-                const double piv = __shfl_sync(0xffffffffu, row[k], k);
+            for (int k = 0; k < nb; k++) {
+                const double piv = A[pidx(c0 + k, c0 + k)];
                 ok &= (piv > 0) && isfinite(piv);
                 const double l = sqrt(piv), il = 1.0 / l;
-                if (lane == k) row[k] = l; else if (lane > k && lane < NB) row[k] *= il;      // column k of L
-                if (lane == 0 && k < nb) sh_inv[k] = il;
-#pragma unroll
-                for (int j = k + 1; j < NB; j++) {
-                    const double ljk = __shfl_sync(0xffffffffu, row[k], j);                    // L[j][k]
-                    if (lane >= j && lane < NB) row[j] -= row[k] * ljk;
+                __syncwarp();
+                if (lane == 0) { A[pidx(c0 + k, c0 + k)] = l; sh_inv[k] = il; }
+                if (lane > k && lane < nb) A[pidx(c0 + lane, c0 + k)] *= il;
+                __syncwarp();
+                // rank-1 update of the remaining block: lanes 0..27 own the strictly-lower pairs, lanes 0..7 then the diagonal
+                if (lane < 28) {
+                    int i = 1, t = lane;                             // strict-lower pair index -> (i, j): i = 1..7, j = 0..i-1
+                    while (t >= i) { t -= i; i++; }
+                    const int j = t;
+                    if (j > k && i < nb) A[pidx(c0 + i, c0 + j)] -= A[pidx(c0 + i, c0 + k)] * A[pidx(c0 + j, c0 + k)];
                 }
+                if (lane > k && lane < nb) { const double v = A[pidx(c0 + lane, c0 + k)]; A[pidx(c0 + lane, c0 + lane)] -= v * v; }
+                __syncwarp();
             }
             if (!ok && lane == 0) *sh_flag = 0;
-#pragma unroll
-            for (int j = 0; j < NB; j++) if (lane < nb && j <= lane) A[pidx(c0 + lane, c0 + j)] = row[j];
-            // inverse of the lower block for the backward substitution: lane c solves column c of L^-1 by forward substitution
-            __syncwarp();
-            if (lane < NB) {
-                const int c = lane;
-                double x[NB];
-#pragma unroll
-                for (int i = 0; i < NB; i++) {
-                    double v = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-                    for (int t = 0; t < NB; t++) if (t < i && t >= c) v -= ((i < nb && t < nb) ? A[pidx(c0 + i, c0 + t)] : 0.0) * x[t];
-                    const double dii = (i < nb) ? A[pidx(c0 + i, c0 + i)] : 1.0;
-                    x[i] = (i >= c) ? v / dii : 0.0;
-                }
-                double *dst = dinv + (c0 / NB) * 36;
-#pragma unroll
-                for (int i = 0; i < NB; i++) if (i >= c) dst[i * (i + 1) / 2 + c] = x[i];
-            }
         }
         __syncthreads();
         BE_PROF2(pp, 21);
         if (!*sh_flag) return false;
-        for (int i = c0 + nb + tid; i <= n; i += T) {                // rows below the block (and the rhs row): triangular solve
+        for (int i = c0 + nb + tid; i <= n; i += T) {                // (b) rows below the block (and the rhs row)
             double *ri = A + pidx(i, c0);
             double v[NB];
 #pragma unroll
@@ -354,20 +354,62 @@ __device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, do
             }
         }
         __syncthreads();
+        BE_PROF2(pp, 22);
+        {                                                            // (c) trailing update, 4x4 register tiles
+            const int r0 = c0 + nb;                                  // first trailing row / column
+            const int R = n + 1 - r0;                                // rows r0 .. n (the rhs row included)
+            const int RT = (R + 3) >> 2;
+            const int ntile = RT * (RT + 1) / 2;
+            for (int e = tid; e < ntile; e += T) {
+                int ti = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+                while ((ti + 1) * (ti + 2) / 2 <= e) ti++;
+                while (ti * (ti + 1) / 2 > e) ti--;
+                const int tj = e - ti * (ti + 1) / 2;
+                const int I = r0 + 4 * ti, J = r0 + 4 * tj;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
+                const double *pi_[4], *pj_[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) { pi_[a] = A + pidx(min(I + a, n), c0); pj_[a] = A + pidx(min(J + a, n), c0); }
+#pragma unroll
+                for (int t = 0; t < NB; t++) {
+                    if (t < nb) {
+                        double li[4], lj[4];
+#pragma unroll
+                        for (int a = 0; a < 4; a++) { li[a] = pi_[a][t]; lj[a] = pj_[a][t]; }
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+#pragma unroll
+                            for (int c = 0; c < 4; c++) acc[a][c] += li[a] * lj[c];
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const int i = I + a, j = J + c;
+                        if (i <= n && j <= i && j < n) A[pidx(i, j)] -= acc[a][c];
+                    }
+            }
+        }
+        __syncthreads();
+        BE_PROF2(pp, 20);
     }
-    BE_PROF2(pp, 22);
     // backward: L^T y = z, z = row n of A
     for (int j = tid; j < n; j += T) y[j] = A[pidx(n, j)];
     __syncthreads();
     for (int c0 = ((n - 1) / NB) * NB; c0 >= 0; c0 -= NB) {
         const int nb = min(NB, n - c0);
-        double yj = 0;
-        if (tid < nb) {                                              // y_panel = Ldd^-T z_panel (Ldd^-1 kept from the factorisation)
-            const double *li = dinv + (c0 / NB) * 36;
-            for (int t = tid; t < nb; t++) yj += li[t * (t + 1) / 2 + tid] * y[c0 + t];
+        if (tid == 0) {
+            for (int j = nb - 1; j >= 0; j--) {
+                double v = y[c0 + j];
+                for (int t = j + 1; t < nb; t++) v -= A[pidx(c0 + t, c0 + j)] * y[c0 + t];
+                y[c0 + j] = v / A[pidx(c0 + j, c0 + j)];
+            }
         }
-        __syncthreads();
-        if (tid < nb) y[c0 + tid] = yj;
         __syncthreads();
         for (int i = tid; i < c0; i += T) {
             double v = y[i];
@@ -385,7 +427,7 @@ __device__ inline bool chol_solve_packed(double *A, int n, const double *rhs, do
 constexpr int SCHUR_CHUNK = 32;
 // S (packed, shared) = S H S + mu D^2 - sum_l ws_l ws_l^T / h_l ;  rhs = S g - sum_l ws_l gs_l / h_l   (landmark blocks eliminated)
 // wt = shared staging [SCHUR_CHUNK][NPW + 1]
-__device__ inline void build_reduced_smem(const BeState &s, const SolveWs &ws, int nl, double mu, double *S, double *wt) {
+__device__ __noinline__ void build_reduced_smem(const BeState &s, const SolveWs &ws, int nl, double mu, double *S, double *wt) {
     const int tid = threadIdx.x, T = blockDim.x, NP = s.NP, NPW = s.NPW;
     for (int e = tid; e < NP * (NP + 1) / 2; e += T) {
         int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
@@ -525,7 +567,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
                 double *Ssm = sm_dyn, *wt = sm_dyn + (size_t)(NP + 1) * (NP + 2) / 2 + 8;
                 build_reduced_smem(s, ws, nl, mu, Ssm, wt);
                 BE_PROF(2);
-                ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag, sh_red, wt, s.prof + (size_t)b * 32);
+                ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag, sh_red, s.prof + (size_t)b * 32);
                 BE_PROF(3);
               } else {
                 for (int e = tid; e < NP * NP; e += T) {
