@@ -25,6 +25,7 @@ struct vio_backend {
     int *d_counts, *d_ids; double *d_xyz, *d_headers; double *d_imu; size_t imu_cap;
     double *h_headers_pinned;
     size_t solve_smem, marg_smem;
+    int use_smem_solve;
     int be_threads;
     cudaEvent_t evt_ready, evt_consumed;
     bool consumed_valid, record_consumed;
@@ -122,6 +123,9 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     if (!rc) rc = dalloc(be, &s.lm_slot, B * s.LCAP);
     if (!rc) rc = dalloc(be, &s.fac_lm, B * s.PCAP);
     if (!rc) rc = dalloc(be, &s.fac_j, B * s.PCAP);
+    if (!rc) rc = dalloc(be, &s.fac_sorted, B * s.PCAP);
+    if (!rc) rc = dalloc(be, &s.pair_off, B * (NF * NF + 1));
+    if (!rc) rc = dalloc(be, &s.fac_obs, B * s.PCAP * 4);
     if (!rc) rc = dalloc(be, &s.post_solve, B * NF * 16);
     if (!rc) rc = dalloc(be, &s.state_out, B * NF * 16);
     if (!rc) rc = dalloc(be, &s.prof, B * 32);
@@ -141,8 +145,10 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     VIO_CUDA_TRY(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s.FCAP + 64));
     // reduced system resident in shared memory when it fits one SM (W = 10: 110 KB packed); otherwise the global-memory path
     be->solve_smem = solve_smem_bytes(s.NP, s.NPW);
-    if (be->solve_smem > 200 * 1024 || (size_t)s.NPW * (s.NPW + 1) / 2 > (size_t)10 * 256) be->solve_smem = 0;
-    if (be->solve_smem) VIO_CUDA_TRY(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->solve_smem));
+    if (be->solve_smem > 200 * 1024 || schur_ntile(s.NPW) > be->be_threads) be->solve_smem = 0;
+    be->use_smem_solve = be->solve_smem > 0;
+    be->solve_smem = std::max(be->solve_smem, eval_smem_bytes(s.W));
+    VIO_CUDA_TRY(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->solve_smem));
     be->marg_smem = sizeof(MargSmem) + 16 + (size_t)2 * MARG_NCAP * MARG_NCAP * sizeof(double);
     VIO_CUDA_TRY(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->marg_smem));
     rc = vio_backend_clear(be);
@@ -238,7 +244,7 @@ static int run_process_image(vio_backend *be, const int32_t *counts, const int32
     if (be->record_consumed) { cudaEventRecord(be->evt_consumed, st); be->consumed_valid = true; be->record_consumed = false; }   // image_msg fully read
     VIO_LAUNCH(be->timer, st, "triangulate_kernel", (triangulate_kernel<<<s.B, 128, 0, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "prepare_kernel", (prepare_kernel<<<s.B, 256, 0, st>>>(s)));
-    VIO_LAUNCH(be->timer, st, "solve_kernel", (solve_kernel<<<s.B, be->be_threads, be->solve_smem, st>>>(s, be->solve_smem > 0)));
+    VIO_LAUNCH(be->timer, st, "solve_kernel", (solve_kernel<<<s.B, be->be_threads, be->solve_smem, st>>>(s, be->use_smem_solve)));
     VIO_LAUNCH(be->timer, st, "post_solve_kernel", (post_solve_kernel<<<s.B, 256, 0, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "marg_kernel", (marg_kernel<<<s.B, be->be_threads, be->marg_smem, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "finish_kernel", (finish_kernel<<<s.B, 256, s.FCAP + 64, st>>>(s)));

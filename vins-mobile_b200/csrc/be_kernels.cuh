@@ -302,7 +302,47 @@ __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
         }
         lm_base += tl; fac_base += tf;
     }
-    if (tid == 0) { iv[IV_N_LM] = min(lm_base, s.LCAP); iv[IV_N_FAC] = min(fac_base, s.PCAP); }
+    const int nl = min(lm_base, s.LCAP), nfac_all = min(fac_base, s.PCAP);
+    if (tid == 0) { iv[IV_N_LM] = nl; iv[IV_N_FAC] = nfac_all; }
+    // the same factors ordered by (anchor frame i, observing frame j): a landmark contributes at most one factor to a pair, so
+    // "landmark order within the pair" is a deterministic order.  One thread per pair counts, then places.
+    __shared__ int sh_cnt[(VIO_MAX_WIN + 1) * (VIO_MAX_WIN + 1) + 1];
+    const int NF = s.NF, nkey = NF * NF;
+    const int *slot = s.lm_slot + (size_t)b * s.LCAP;
+    __syncthreads();
+    for (int key = tid; key < nkey; key += 256) {
+        const int i = key / NF, j = key - i * NF;
+        int c = 0;
+        if (j > i)
+            for (int l = 0; l < nl; l++) { const int k = slot[l]; c += (s.f_start[fo + k] == i && j < i + s.f_nobs[fo + k]); }
+        sh_cnt[key] = c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int key = 0; key < nkey; key++) { const int c = sh_cnt[key]; sh_cnt[key] = acc; acc += c; }
+        sh_cnt[nkey] = acc;
+    }
+    __syncthreads();
+    int *po = s.pair_off + (size_t)b * (nkey + 1);
+    for (int key = tid; key <= nkey; key += 256) po[key] = min(sh_cnt[key], nfac_all);
+    int *fs = s.fac_sorted + (size_t)b * s.PCAP;
+    double *fobs = s.fac_obs + (size_t)b * s.PCAP * 4;
+    for (int key = tid; key < nkey; key += 256) {
+        const int i = key / NF, j = key - i * NF;
+        if (j <= i) continue;
+        int pos = sh_cnt[key];
+        for (int l = 0; l < nl; l++) {
+            const int k = slot[l];
+            if (s.f_start[fo + k] == i && j < i + s.f_nobs[fo + k] && pos < s.PCAP) {
+                const double *o = S_obs(s, b, k);
+                fs[pos] = l | (i << 16) | (j << 24);
+                fobs[4 * (size_t)pos] = o[0]; fobs[4 * (size_t)pos + 1] = o[1];
+                fobs[4 * (size_t)pos + 2] = o[2 * (j - i)]; fobs[4 * (size_t)pos + 3] = o[2 * (j - i) + 1];
+                pos++;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -64,8 +64,40 @@ __device__ inline void prior_dx(const BeState &s, int b, const double *par, doub
     for (int k = tid; k < 6; k += blockDim.x) dx[s.NP + k] = 0.0;      // para_Ex_Pose is constant: x == x0
 }
 
+// D (8x8, f64) += A (8x4, row) * B (4x8, col): lane (g = lane >> 2, k = lane & 3) supplies A[g][k] and B[k][g] and holds
+// D[g][2k], D[g][2k+1]
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// adds a warp's accumulated pair blocks to H / g.  hacc[ps] = {cross c0,c1, jj c0,c1, ii c0,c1} fragments of pair (round*4+ps)*nwarp+warp.
+// The (j,i) block has a single owner (plain read-modify-write); the diagonal blocks and the gradient are shared between pairs.
+__device__ __forceinline__ void proj_flush(const SolveWs &ws, int NP, int NF, int npair, int nwarp, int warp, int lane, int round, const double (*hacc)[6]) {
+    const int g = lane >> 2, c = 2 * (lane & 3);
+#pragma unroll
+    for (int ps = 0; ps < 4; ps++) {
+        const int q = (round * 4 + ps) * nwarp + warp;
+        if (q >= npair || g >= 6) continue;
+        int i = 0, rem = q;
+        while (rem >= NF - 1 - i) { rem -= NF - 1 - i; i++; }
+        const int j = i + 1 + rem;
+        double *Hj = ws.H + (size_t)(15 * j + g) * NP, *Hi = ws.H + (size_t)(15 * i + g) * NP;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int cc = c + e;
+            if (cc < 6) {
+                Hj[15 * i + cc] += hacc[ps][e];
+                if (cc <= g) { atomic_add(&Hj[15 * j + cc], hacc[ps][2 + e]); atomic_add(&Hi[15 * i + cc], hacc[ps][4 + e]); }
+            } else if (cc == 6) {
+                atomic_add(&ws.g[15 * j + g], hacc[ps][e]);
+                atomic_add(&ws.g[15 * i + g], hacc[ps][4 + e]);
+            }
+        }
+    }
+}
+
 // cost (and, when lin != 0, H / g / landmark terms) at parameter vector `par`.  Returns the total cost in every thread.
-__device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &ws, const double *par, int lin, double *sh_red) {
+__device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &ws, const double *par, int lin, double *sh_red, double *smem_scratch) {
     long long *pp = s.prof + (size_t)b * 32; BE_PROF2_INIT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int *iv = S_iv(s, b);
@@ -76,9 +108,9 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
         // H starts as the prior's J0^T J0 (pose / speed-bias rows and columns of the canonical layout), or zero
         if (has_prior) {
             const double *Hp = s.Hp + (size_t)b * s.NPX * s.NPX;
-            for (int e = tid; e < NP * NP; e += blockDim.x) { const int i = e / NP, j = e - i * NP; ws.H[e] = Hp[(size_t)i * s.NPX + j]; }
+            for (int e = tid; e < NP * NP; e += blockDim.x) { const int i = e / NP, j = e - i * NP; if (j <= i) ws.H[e] = Hp[(size_t)i * s.NPX + j]; }
         } else
-            for (int i = tid; i < NP * NP; i += blockDim.x) ws.H[i] = 0.0;
+            for (int e = tid; e < NP * NP; e += blockDim.x) { const int i = e / NP, j = e - i * NP; if (j <= i) ws.H[e] = 0.0; }
         for (int i = tid; i < NP; i += blockDim.x) ws.g[i] = 0.0;
         for (int i = tid; i < nl; i += blockDim.x) { ws.hll[i] = 0.0; ws.gl[i] = 0.0; }
         for (int i = tid; i < nl * NPW; i += blockDim.x) ws.w[i] = 0.0;
@@ -102,7 +134,8 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
     // ---- IMU factors: one warp per factor ---------------------------------------------------------------
     for (int f = warp; f < s.W; f += nwarp) {
         const double *pr = S_pre(s, b, f + 1);
-        double *J = ws.imuJ + (size_t)f * 930;          // raw J 450 | weighted J 450 | raw res 15 | weighted res 15
+        // raw J 450 | weighted J 450 | raw res 15 | weighted res 15, in the shared scratch (free outside ComputeGaussNewtonStep)
+        double *J = smem_scratch + (size_t)f * 930;
         double *Jw = J + 450, *rr = J + 900, *rw = J + 915;
         imu_residual_warp(pr, s.gravity, par + 16 * f, par + 16 * f + 7, par + 16 * (f + 1), par + 16 * (f + 1) + 7, rr, lin ? J : nullptr, lane);
         __syncwarp();
@@ -135,95 +168,171 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
     }
     __syncthreads();
     if (lin) BE_PROF2(pp, 17);
-    // ---- projection factors: one thread per factor ------------------------------------------------------
+    // ---- projection factors ---------------------------------------------------------------------------------
+    // The factors are visited in (anchor frame i, observing frame j) order (prepare_kernel's fac_sorted / pair_off).  Everything
+    // that depends on the frame pair alone -- ric^T Rj^T Ri ric, the translation part, the rotation products of the Jacobians --
+    // is formed once per pair in shared memory, so a factor costs ~150 FMAs.  Linearisation runs in chunks of blockDim factors:
+    //   J-phase: one thread per factor writes its corrected Ji, Jj (2x6 each) and residual to shared memory (SoA) and adds the
+    //            landmark terms (w_l, h_ll, g_l) -- 8 atomics per factor;
+    //   H-phase: one thread per (pair, block part) sums Jj^T Ji, Jj^T Jj, Ji^T Ji, J^T r over the pair's factors in registers and
+    //            issues one atomic per output element and chunk (about 5k instead of 140k atomics per linearisation).
     {
         const double *dv = S_dv(s, b);
-        ProjConst K; K.ric = ldm(dv + DV_RIC); K.tic = ld3(dv + DV_TIC); K.sqrt_info = s.sqrt_info;
-        const int *fl = s.fac_lm + (size_t)b * s.PCAP, *fj = s.fac_j + (size_t)b * s.PCAP;
-        const int *slot = s.lm_slot + (size_t)b * s.LCAP;
-        const size_t fo = (size_t)b * s.FCAP;
-        if (!lin) {
-            for (int f = tid; f < nfac; f += blockDim.x) {           // cost only: one thread per factor
-                const int l = fl[f], j = fj[f], k = slot[l];
-                const int i = s.f_start[fo + k];
-                const double *o = S_obs(s, b, k);
-                const V3 pi = v3(o[0], o[1], 1.0), pj = v3(o[2 * (j - i)], o[2 * (j - i) + 1], 1.0);
-                cost += proj_eval(K, pi, pj, par + 16 * i, par + 16 * j, par[16 * s.NF + l], nullptr, nullptr, nullptr, nullptr);
-            }
-        } else {
-            // linearisation: one thread per LANDMARK.  Everything that belongs to the landmark alone (h_ll, g_l, its coupling rows w_l)
-            // and the (i,i) block / g_i of its anchor frame are reduced in registers over the landmark's factors, so only the
-            // (j,j), (j,i) blocks and g_j of each factor go through atomics (63 instead of 104 per factor, and the hot anchor block
-            // receives one update per landmark instead of one per factor).
-            for (int l = tid; l < nl; l += blockDim.x) {
-                const int k = slot[l];
-                const int i = s.f_start[fo + k], no = s.f_nobs[fo + k];
-                const double *o = S_obs(s, b, k);
-                const V3 pi = v3(o[0], o[1], 1.0);
-                const double lam = par[16 * s.NF + l];
-                double Hii[21], gi[6], wi[6], hl = 0, gll = 0;
+        const M3 ric = ldm(dv + DV_RIC), ricT = tr(ric);
+        const V3 tic = ld3(dv + DV_TIC);
+        const int T = blockDim.x, NF = s.NF, npair = NF * (NF - 1) / 2;
+        double *fr = smem_scratch, *prs = fr + 21 * NF, *Js = prs + 33 * npair + ((33 * npair + 21 * NF) & 1);
+        for (int f = tid; f < NF; f += T) {
+            const M3 R = q2R(ldq(par + 16 * f + 3));
+            stm(fr + 21 * f, R); st3(fr + 21 * f + 9, ld3(par + 16 * f)); stm(fr + 21 * f + 12, ricT * tr(R));
+        }
+        __syncthreads();
+        for (int q = tid; q < npair; q += T) {
+            int i = 0, rem = q;
+            while (rem >= NF - 1 - i) { rem -= NF - 1 - i; i++; }
+            const int j = i + 1 + rem;
+            const M3 Ri = ldm(fr + 21 * i), RjT = tr(ldm(fr + 21 * j));
+            const M3 RR = RjT * Ri;
+            const V3 d = RjT * (ld3(fr + 21 * i + 9) - ld3(fr + 21 * j + 9));
+            const M3 AR = ricT * RR;
+            double *o = prs + 33 * q;
+            stm(o, AR * ric); st3(o + 9, ricT * (RR * tic + d - tic)); stm(o + 12, AR); stm(o + 21, RR); st3(o + 30, d);
+        }
+        __syncthreads();
+        long long *pq2 = pp; long long _qt1 = clock64();
+        if (lin && tid == 0) { pq2[27] += _qt1 - _qt0; }
+        const int *fs = s.fac_sorted + (size_t)b * s.PCAP, *po = s.pair_off + (size_t)b * (NF * NF + 1);
+        const double *fobs = s.fac_obs + (size_t)b * s.PCAP * 4;
+        const double *lam_p = par + 16 * NF;
+        double hacc[4][6];
 #pragma unroll
-                for (int q = 0; q < 21; q++) Hii[q] = 0;
+        for (int ps = 0; ps < 4; ps++)
 #pragma unroll
-                for (int q = 0; q < 6; q++) { gi[q] = 0; wi[q] = 0; }
-                const int oi = 15 * i;
-                for (int t = 1; t < no; t++) {
-                    const int j = i + t, oj = 15 * j;
-                    const V3 pj = v3(o[2 * t], o[2 * t + 1], 1.0);
-                    double r2[2], Ji[12], Jj[12], Jl[2];
-                    cost += proj_eval(K, pi, pj, par + 16 * i, par + 16 * j, lam, r2, Ji, Jj, Jl);
-                    int q = 0;
+            for (int e = 0; e < 6; e++) hacc[ps][e] = 0.0;
+        const bool hold = npair <= 4 * nwarp;
+        for (int c0 = 0; c0 < nfac; c0 += T) {
+            const int pos = c0 + tid;
+            if (pos < nfac) {
+                const int rec = fs[pos], l = rec & 0xffff, i = (rec >> 16) & 0xff, j = (rec >> 24) & 0xff;
+                const double4 ob = *reinterpret_cast<const double4 *>(fobs + 4 * (size_t)pos);
+                const double lam = lam_p[l], inv = 1.0 / lam;
+                const double *pq = prs + 33 * (i * NF - i * (i + 1) / 2 + (j - i - 1));
+                const V3 pci = v3(ob.x * inv, ob.y * inv, inv);
+                const V3 pcj = ldm(pq) * pci + ld3(pq + 9);
+                const double dep = pcj.z;
+                const double rx = s.sqrt_info * (pcj.x / dep - ob.z), ry = s.sqrt_info * (pcj.y / dep - ob.w);
+                const double sq = rx * rx + ry * ry, sum = 1.0 + sq;
+                cost += 0.5 * log(sum);                                  // CauchyLoss(1.0): rho = log(1 + s)
+                if (lin) {
+                    const double sr = sqrt(fmax(2.2250738585072014e-308, 1.0 / sum));   // corrector.cc:113-118 (rho'' < 0: alpha = 0)
+                    const double r0 = s.sqrt_info / dep * sr, r2x = -s.sqrt_info * pcj.x / (dep * dep) * sr, r2y = -s.sqrt_info * pcj.y / (dep * dep) * sr;
+                    // corrected 2x3 "reduce" = sr * [r0 0 r2x; 0 r0 r2y]; red(X) = reduce * X for a 3x3 X
+                    const V3 p_i = ric * pci + tic;
+                    const V3 p_j = ldm(pq + 21) * p_i + ld3(pq + 30);
+                    const double *A = fr + 21 * j + 12, *AR = pq + 12;
+                    double Ji[12], Jj[12];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const double a0 = r0 * A[c] + r2x * A[6 + c], a1 = r0 * A[3 + c] + r2y * A[6 + c];
+                        Ji[c] = a0; Ji[6 + c] = a1; Jj[c] = -a0; Jj[6 + c] = -a1;
+                    }
+                    {   // Ji rotation part: -reduce * (AR * skew(p_i));  Jj rotation part: reduce * (ric^T * skew(p_j))
+                        double X[9], Y[9];
+#pragma unroll
+                        for (int r = 0; r < 3; r++) {
+                            X[3 * r + 0] = -(AR[3 * r + 1] * p_i.z - AR[3 * r + 2] * p_i.y);
+                            X[3 * r + 1] = -(AR[3 * r + 2] * p_i.x - AR[3 * r + 0] * p_i.z);
+                            X[3 * r + 2] = -(AR[3 * r + 0] * p_i.y - AR[3 * r + 1] * p_i.x);
+                            Y[3 * r + 0] = ricT.m[3 * r + 1] * p_j.z - ricT.m[3 * r + 2] * p_j.y;
+                            Y[3 * r + 1] = ricT.m[3 * r + 2] * p_j.x - ricT.m[3 * r + 0] * p_j.z;
+                            Y[3 * r + 2] = ricT.m[3 * r + 0] * p_j.y - ricT.m[3 * r + 1] * p_j.x;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            Ji[3 + c] = r0 * X[c] + r2x * X[6 + c]; Ji[9 + c] = r0 * X[3 + c] + r2y * X[6 + c];
+                            Jj[3 + c] = r0 * Y[c] + r2x * Y[6 + c]; Jj[9 + c] = r0 * Y[3 + c] + r2y * Y[6 + c];
+                        }
+                    }
+                    const V3 tl = ldm(pq) * v3(ob.x, ob.y, 1.0);
+                    const double kl = -1.0 / (lam * lam);
+                    const double Jl0 = kl * (r0 * tl.x + r2x * tl.z), Jl1 = kl * (r0 * tl.y + r2y * tl.z);
+                    const double c0r = sr * rx, c1r = sr * ry;
+#pragma unroll
+                    for (int c = 0; c < 12; c++) { Js[c * T + tid] = Ji[c]; Js[(12 + c) * T + tid] = Jj[c]; }
+                    Js[24 * T + tid] = c0r; Js[25 * T + tid] = c1r;
+                    double *wl = ws.w + (size_t)l * NPW;
 #pragma unroll
                     for (int a = 0; a < 6; a++) {
-#pragma unroll
-                        for (int c = 0; c < 6; c++) {
-                            if (c <= a) {
-                                Hii[q++] += Ji[a] * Ji[c] + Ji[6 + a] * Ji[6 + c];
-                                atomic_add(&ws.H[(size_t)(oj + a) * NP + oj + c], Jj[a] * Jj[c] + Jj[6 + a] * Jj[6 + c]);
-                            }
-                            atomic_add(&ws.H[(size_t)(oj + a) * NP + oi + c], Jj[a] * Ji[c] + Jj[6 + a] * Ji[6 + c]);
-                        }
-                        gi[a] += Ji[a] * r2[0] + Ji[6 + a] * r2[1];
-                        wi[a] += Ji[a] * Jl[0] + Ji[6 + a] * Jl[1];
-                        atomic_add(&ws.g[oj + a], Jj[a] * r2[0] + Jj[6 + a] * r2[1]);
-                        ws.w[(size_t)l * NPW + 6 * j + a] = Jj[a] * Jl[0] + Jj[6 + a] * Jl[1];
+                        wl[6 * j + a] = Jj[a] * Jl0 + Jj[6 + a] * Jl1;
+                        atomic_add(&wl[6 * i + a], Ji[a] * Jl0 + Ji[6 + a] * Jl1);
                     }
-                    hl += Jl[0] * Jl[0] + Jl[1] * Jl[1];
-                    gll += Jl[0] * r2[0] + Jl[1] * r2[1];
+                    atomic_add(&ws.hll[l], Jl0 * Jl0 + Jl1 * Jl1);
+                    atomic_add(&ws.gl[l], Jl0 * c0r + Jl1 * c1r);
                 }
-                int q = 0;
-#pragma unroll
-                for (int a = 0; a < 6; a++) {
-#pragma unroll
-                    for (int c = 0; c <= a; c++) atomic_add(&ws.H[(size_t)(oi + a) * NP + oi + c], Hii[q++]);
-                    atomic_add(&ws.g[oi + a], gi[a]);
-                    ws.w[(size_t)l * NPW + 6 * i + a] = wi[a];
-                }
-                ws.hll[l] = hl; ws.gl[l] = gll;
             }
+            if (!lin) continue;
+            __syncthreads();
+            if (tid == 0) { const long long t = clock64(); pq2[28] += t - _qt1; _qt1 = t; }
+            // H-phase on the FP64 tensor pipe: per frame pair, [Jj^T Ji | Jj^T r], Jj^T Jj and [Ji^T Ji | Ji^T r] are 8x8 (6x7 used)
+            // products with the pair's 2 m residual rows as the inner dimension -- one m8n8k4 DMMA per block and two factors.
+            // A fragment: lane (g = lane >> 2, k = lane & 3) holds element [dof g][row k]; the B fragment [row k][col g] is the
+            // same element, with column 6 = the residual.  Warp w owns pairs w, w + nwarp, ...; with <= 4 pairs per warp the
+            // accumulators stay in registers across the chunks and every output element is written once per linearisation.
+            for (int round = 0; round * 4 * nwarp < npair; round++) {
+#pragma unroll
+                for (int ps = 0; ps < 4; ps++) {
+                    const int q = (round * 4 + ps) * nwarp + warp;
+                    if (q >= npair) continue;
+                    int i = 0, rem = q;
+                    while (rem >= NF - 1 - i) { rem -= NF - 1 - i; i++; }
+                    const int j = i + 1 + rem, key = i * NF + j;
+                    const int lo = max(po[key], c0) - c0, hi = min(po[key + 1], c0 + T) - c0;
+                    const int g = lane >> 2, k = lane & 3, rr = k & 1;
+                    const double *pJi = Js + ((g < 6 ? 6 * rr + g : 24 + rr)) * T, *pJj = Js + (12 + 6 * rr + min(g, 5)) * T;
+                    for (int t0 = lo; t0 < hi; t0 += 2) {
+                        const int t = t0 + (k >> 1);
+                        const bool in = t < hi;
+                        const double bi = (in && g < 7) ? pJi[t] : 0.0;          // B: [Ji | r | 0]
+                        const double aj = (in && g < 6) ? pJj[t] : 0.0;          // A and B: Jj
+                        const double ai = (g < 6) ? bi : 0.0;                    // A: Ji
+                        dmma_m8n8k4(hacc[ps][0], hacc[ps][1], aj, bi);
+                        dmma_m8n8k4(hacc[ps][2], hacc[ps][3], aj, aj);
+                        dmma_m8n8k4(hacc[ps][4], hacc[ps][5], ai, bi);
+                    }
+                }
+                if (!hold) { proj_flush(ws, NP, NF, npair, nwarp, warp, lane, round, hacc); 
+#pragma unroll
+                    for (int ps = 0; ps < 4; ps++)
+#pragma unroll
+                        for (int e = 0; e < 6; e++) hacc[ps][e] = 0.0;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) { const long long t = clock64(); pq2[29] += t - _qt1; _qt1 = t; }
         }
+        if (lin && hold) proj_flush(ws, NP, NF, npair, nwarp, warp, lane, 0, hacc);
     }
     __syncthreads();
     if (lin) BE_PROF2(pp, 18);
-    if (lin) {                                            // mirror the lower triangle (the prior part is already symmetric)
-        for (int e = tid; e < NP * NP; e += blockDim.x) { const int i = e / NP, j = e - i * NP; if (j > i) ws.H[e] = ws.H[(size_t)j * NP + i]; }
-    }
     const double total = block_sum_d(cost, sh_red);
     __syncthreads();
     if (lin) BE_PROF2(pp, 19);
     return total;
 }
 
-// u^T H u over the full (pose/speed-bias + landmark) system
+// u^T H u over the full (pose/speed-bias + landmark) system.  Only the LOWER triangle of H is valid (the accumulation writes one
+// triangle); elements are visited in memory order, so the reads are coalesced.
 __device__ inline double quad_form(const BeState &s, const SolveWs &ws, int nl, const double *up, const double *ul, double *sh_red) {
-    const int tid = threadIdx.x, NP = s.NP, NPW = s.NPW, NF = s.NF;
+    const int tid = threadIdx.x, T = blockDim.x, NP = s.NP, NPW = s.NPW, NF = s.NF;
     double acc = 0;
-    for (int i = tid; i < NP; i += blockDim.x) {
-        double t = 0;
-        for (int j = 0; j < NP; j++) t += ws.H[(size_t)j * NP + i] * up[j];           // H symmetric: column read = coalesced
-        acc += up[i] * t;
+    int i = tid / NP, j = tid - i * NP;
+    for (int e = tid; e < NP * NP; e += T) {
+        if (j < i) acc += 2.0 * ws.H[e] * up[i] * up[j];
+        else if (j == i) acc += ws.H[e] * up[i] * up[i];
+        j += T;
+        while (j >= NP) { j -= NP; i++; }
     }
-    for (int l = tid; l < nl; l += blockDim.x) {
+    for (int l = tid; l < nl; l += T) {
         double t = 0;
         const double *w = ws.w + (size_t)l * NPW;
         for (int f = 0; f < NF; f++)
@@ -296,47 +405,78 @@ __device__ inline bool chol_solve(double *A, int n, const double *rhs, double *y
 
 // ---- shared-memory path (reduced system fits one SM: NP*(NP+1)/2 doubles, 110 KB at W=10) -------------------------------------
 __device__ __forceinline__ int pidx(int i, int j) { return i * (i + 1) / 2 + j; }       // packed lower, j <= i
+__device__ __forceinline__ int tri_row(int e) {             // largest i with i (i + 1) / 2 <= e
+    int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= e) i++;
+    while (i * (i + 1) / 2 > e) i--;
+    return i;
+}
+
+// 1 / sqrt(x) for a positive, finite, normal-range x: single-precision seed + three Newton steps (no MUFU.RSQ64H fix-up branches on
+// the critical path of the factorisation); relative error ~1e-16
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    if (!(x > 1e-30 && x < 1e30)) return rsqrt(x);
+    double y = (double)rsqrtf((float)x);
+    const double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    return y;
+}
+
+// In-register Cholesky of one diagonal block (at most 8 x 8, identity-padded) by a single thread: 8 pivots, 28 scalings, 84 FMAs.
+// Writes L over the block, 1 / L_kk to dinv; returns false on a non-positive / non-finite pivot.
+__device__ __forceinline__ bool chol_diag8(double *A, int c0, int nb, double *dinv) {
+    double a[36];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int c = 0; c <= r; c++) a[r * (r + 1) / 2 + c] = (r < nb) ? A[pidx(c0 + r, c0 + c)] : (r == c ? 1.0 : 0.0);
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const double piv = a[k * (k + 1) / 2 + k];
+        ok &= (piv > 0) && isfinite(piv);
+        const double il = fast_rsqrt(piv);
+        a[k * (k + 1) / 2 + k] = piv * il;
+        if (k < nb) dinv[c0 + k] = il;
+#pragma unroll
+        for (int r = k + 1; r < 8; r++) a[r * (r + 1) / 2 + k] *= il;
+#pragma unroll
+        for (int r = k + 1; r < 8; r++)
+#pragma unroll
+            for (int c = k + 1; c <= r; c++) a[r * (r + 1) / 2 + c] -= a[r * (r + 1) / 2 + k] * a[c * (c + 1) / 2 + k];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int c = 0; c <= r; c++) if (r < nb) A[pidx(c0 + r, c0 + c)] = a[r * (r + 1) / 2 + c];
+    return ok;
+}
 
 // Blocked RIGHT-looking Cholesky on a packed lower matrix in shared memory, BORDERED by the right-hand side (row n of the packed
 // array holds rhs, so the forward substitution z = L^-1 rhs is a by-product of the factorisation).  Per 8-column panel:
-//   (a) warp 0 factors the 8x8 diagonal block in place (shared memory, one __syncwarp-separated step per column);
-//   (b) one thread per row below the block solves its 8 entries against the block (block reads are warp broadcasts);
-//   (c) the trailing matrix gets the rank-8 update in 4x4 register tiles (0.5 shared loads per FMA), spread over the whole CTA.
-// Three barriers per panel.  Backward substitution L^T y = z is blocked the same way.  A must hold (n+1)(n+2)/2 doubles.
-// Returns false (in all threads) on a non-positive pivot / non-finite value (Eigen LLT info() != Success).
-__device__ __noinline__ bool chol_solve_packed(double *A, int n, const double *rhs, double *y, int *sh_flag, double *sh_inv /*>= 8*/, long long *pp) {
+//   (b) one thread per row below the diagonal block solves its 8 entries against the block (block reads are warp broadcasts);
+//   (c) the trailing matrix gets the rank-8 update in 4x4 register tiles (0.5 shared loads per FMA) from warps 1..; meanwhile
+//   (a) warp 0 LOOKS AHEAD: its lanes update the next diagonal block, then lane 0 factors it in registers (chol_diag8) -- the
+//       sequential pivot chain (8 x rsqrt + scaling + update) overlaps the trailing update instead of adding to it.
+// Two barriers per panel.  Backward substitution L^T y = z is blocked 16 wide: warp 0 back-solves a diagonal block with its columns
+// held in registers, then every thread folds the block's solution into the rows above.
+// A must hold (n+1)(n+2)/2 doubles, dinv n doubles (shared).  Returns false (in all threads) on a non-positive pivot / non-finite
+// value (Eigen LLT info() != Success).
+__device__ __noinline__ bool chol_solve_packed(double *A, int n, const double *rhs, double *y, int *sh_flag, double *dinv, long long *pp) {
     BE_PROF2_INIT;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
     constexpr int NB = 8;
+    constexpr unsigned FULL = 0xffffffffu;
     if (tid == 0) *sh_flag = 1;
     for (int j = tid; j < n; j += T) A[pidx(n, j)] = rhs[j];
     __syncthreads();
+    if (tid == 0 && !chol_diag8(A, 0, min(NB, n), dinv)) *sh_flag = 0;
+    __syncthreads();
+    BE_PROF2(pp, 21);
     for (int c0 = 0; c0 < n; c0 += NB) {
         const int nb = min(NB, n - c0);
-        if (tid < 32) {                                              // (a) diagonal block, in place
-            bool ok = true;
-            for (int k = 0; k < nb; k++) {
-                const double piv = A[pidx(c0 + k, c0 + k)];
-                ok &= (piv > 0) && isfinite(piv);
-                const double l = sqrt(piv), il = 1.0 / l;
-                __syncwarp();
-                if (lane == 0) { A[pidx(c0 + k, c0 + k)] = l; sh_inv[k] = il; }
-                if (lane > k && lane < nb) A[pidx(c0 + lane, c0 + k)] *= il;
-                __syncwarp();
-                // rank-1 update of the remaining block: lanes 0..27 own the strictly-lower pairs, lanes 0..7 then the diagonal
-                if (lane < 28) {
-                    int i = 1, t = lane;                             // strict-lower pair index -> (i, j): i = 1..7, j = 0..i-1
-                    while (t >= i) { t -= i; i++; }
-                    const int j = t;
-                    if (j > k && i < nb) A[pidx(c0 + i, c0 + j)] -= A[pidx(c0 + i, c0 + k)] * A[pidx(c0 + j, c0 + k)];
-                }
-                if (lane > k && lane < nb) { const double v = A[pidx(c0 + lane, c0 + k)]; A[pidx(c0 + lane, c0 + lane)] -= v * v; }
-                __syncwarp();
-            }
-            if (!ok && lane == 0) *sh_flag = 0;
-        }
-        __syncthreads();
-        BE_PROF2(pp, 21);
         if (!*sh_flag) return false;
         for (int i = c0 + nb + tid; i <= n; i += T) {                // (b) rows below the block (and the rhs row)
             double *ri = A + pidx(i, c0);
@@ -348,24 +488,39 @@ __device__ __noinline__ bool chol_solve_packed(double *A, int n, const double *r
                     const double *rj = A + pidx(c0 + jj, c0);
 #pragma unroll
                     for (int t = 0; t < jj; t++) w -= v[t] * rj[t];
-                    v[jj] = w * sh_inv[jj];
+                    v[jj] = w * dinv[c0 + jj];
                     ri[jj] = v[jj];
                 }
             }
         }
         __syncthreads();
         BE_PROF2(pp, 22);
-        {                                                            // (c) trailing update, 4x4 register tiles
-            const int r0 = c0 + nb;                                  // first trailing row / column
+        const int r0 = c0 + nb;                                      // first trailing row / column
+        const int nb2 = min(NB, n - r0);                             // size of the next diagonal block (<= 0: none)
+        if (tid < 32) {                                              // (a) look-ahead on the next diagonal block
+            if (nb2 > 0) {
+                for (int e = lane; e < 36; e += 32) {
+                    const int r = tri_row(e), c = e - r * (r + 1) / 2;
+                    if (r < nb2) {
+                        const double *pr_ = A + pidx(r0 + r, c0), *pc_ = A + pidx(r0 + c, c0);
+                        double acc = 0.0;
+#pragma unroll
+                        for (int t = 0; t < NB; t++) if (t < nb) acc += pr_[t] * pc_[t];
+                        A[pidx(r0 + r, r0 + c)] -= acc;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0 && !chol_diag8(A, r0, nb2, dinv)) *sh_flag = 0;
+            }
+        } else {                                                     // (c) trailing update, 4x4 register tiles
             const int R = n + 1 - r0;                                // rows r0 .. n (the rhs row included)
             const int RT = (R + 3) >> 2;
             const int ntile = RT * (RT + 1) / 2;
-            for (int e = tid; e < ntile; e += T) {
-                int ti = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-                while ((ti + 1) * (ti + 2) / 2 <= e) ti++;
-                while (ti * (ti + 1) / 2 > e) ti--;
-                const int tj = e - ti * (ti + 1) / 2;
+            const int skip = nb2 > 0 ? r0 + nb2 : r0;                // rows below `skip` belong to the look-ahead block
+            for (int e = tid - 32; e < ntile; e += T - 32) {
+                const int ti = tri_row(e), tj = e - ti * (ti + 1) / 2;
                 const int I = r0 + 4 * ti, J = r0 + 4 * tj;
+                if (I + 3 < skip) continue;
                 double acc[4][4];
 #pragma unroll
                 for (int a = 0; a < 4; a++)
@@ -391,109 +546,124 @@ __device__ __noinline__ bool chol_solve_packed(double *A, int n, const double *r
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         const int i = I + a, j = J + c;
-                        if (i <= n && j <= i && j < n) A[pidx(i, j)] -= acc[a][c];
+                        if (i <= n && i >= skip && j <= i && j < n) A[pidx(i, j)] -= acc[a][c];
                     }
             }
         }
         __syncthreads();
         BE_PROF2(pp, 20);
     }
-    // backward: L^T y = z, z = row n of A
-    for (int j = tid; j < n; j += T) y[j] = A[pidx(n, j)];
-    __syncthreads();
-    for (int c0 = ((n - 1) / NB) * NB; c0 >= 0; c0 -= NB) {
-        const int nb = min(NB, n - c0);
-        if (tid == 0) {
-            for (int j = nb - 1; j >= 0; j--) {
-                double v = y[c0 + j];
-                for (int t = j + 1; t < nb; t++) v -= A[pidx(c0 + t, c0 + j)] * y[c0 + t];
-                y[c0 + j] = v / A[pidx(c0 + j, c0 + j)];
+    // backward: L^T y = z, in place in row n of A
+    constexpr int BB = 16;
+    double *z = A + pidx(n, 0);
+    for (int c0 = ((n - 1) / BB) * BB; c0 >= 0; c0 -= BB) {
+        const int nb = min(BB, n - c0);
+        if (tid < 32) {
+            double col[BB];                                          // col[t] = L[c0 + t][c0 + lane], t > lane
+#pragma unroll
+            for (int t = 0; t < BB; t++) col[t] = (t > lane && t < nb) ? A[pidx(c0 + t, c0 + lane)] : 0.0;
+            double yv = (lane < nb) ? z[c0 + lane] : 0.0;
+            const double di = (lane < nb) ? dinv[c0 + lane] : 0.0;
+#pragma unroll
+            for (int j = BB - 1; j >= 0; j--) {
+                if (lane == j) yv *= di;
+                const double yj = __shfl_sync(FULL, yv, j);
+                if (lane < j) yv -= col[j] * yj;
             }
+            if (lane < nb) z[c0 + lane] = yv;
         }
         __syncthreads();
         for (int i = tid; i < c0; i += T) {
-            double v = y[i];
-            for (int t = 0; t < nb; t++) v -= A[pidx(c0 + t, i)] * y[c0 + t];
-            y[i] = v;
+            double v = z[i];
+#pragma unroll
+            for (int t = 0; t < BB; t++) if (t < nb) v -= A[pidx(c0 + t, i)] * z[c0 + t];
+            z[i] = v;
         }
         __syncthreads();
     }
     bool ok = true;
-    for (int i = tid; i < n; i += T) ok &= isfinite(y[i]);
+    for (int i = tid; i < n; i += T) { const double v = z[i]; y[i] = v; ok &= isfinite(v); }
     BE_PROF2(pp, 23);
     return __syncthreads_and(ok) != 0;
 }
 
-constexpr int SCHUR_CHUNK = 32;
 // S (packed, shared) = S H S + mu D^2 - sum_l ws_l ws_l^T / h_l ;  rhs = S g - sum_l ws_l gs_l / h_l   (landmark blocks eliminated)
-// wt = shared staging [SCHUR_CHUNK][NPW + 1]
+// The landmark sum is a SYRK over the (NPW+1)-vectors v_l = [w_l ; g_l] * sqrt(s_l^2 / h_l) (the border row yields the rhs
+// correction).  Chunks of SCHUR_CHUNK landmarks are staged in shared memory (wt = [SCHUR_CHUNK][SCHUR_LD]); a thread owns one 4x4
+// tile of the lower triangle (two 16-byte shared loads per operand per landmark, 0.25 loads per FMA) and the landmarks of a chunk
+// are split over G = blockDim / ntile thread groups whose partial tiles are applied one group after the other (fixed order).
+constexpr int SCHUR_CHUNK = 64;
+__host__ __device__ inline int schur_ld(int NPW) { return (NPW + 1 + 3) & ~3; }
+__host__ __device__ inline int schur_ntile(int NPW) { const int rt = schur_ld(NPW) / 4; return rt * (rt + 1) / 2; }
 __device__ __noinline__ void build_reduced_smem(const BeState &s, const SolveWs &ws, int nl, double mu, double *S, double *wt) {
     const int tid = threadIdx.x, T = blockDim.x, NP = s.NP, NPW = s.NPW;
     for (int e = tid; e < NP * (NP + 1) / 2; e += T) {
-        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-        while (pidx(i + 1, 0) <= e) i++;
-        while (pidx(i, 0) > e) i--;
-        const int j = e - pidx(i, 0);
+        const int i = tri_row(e), j = e - pidx(i, 0);
         double v = ws.H[(size_t)i * NP + j] * ws.sc_p[i] * ws.sc_p[j];
         if (i == j) v += mu * ws.d_p[i] * ws.d_p[i];
         S[e] = v;
     }
     for (int i = tid; i < NP; i += T) ws.rhs[i] = ws.g[i] * ws.sc_p[i];
-    constexpr int EPT = 10;                                         // entries of the NPW x NPW lower triangle per thread (2211 / 256 threads)
-    const int nent = NPW * (NPW + 1) / 2;
-    double acc[EPT];
-    int ea[EPT], ec[EPT];
-#pragma unroll
-    for (int q = 0; q < EPT; q++) {
-        acc[q] = 0;
-        const int e = tid + q * T;
-        int a = 0, c = 0;
-        if (e < nent) {
-            a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-            while (pidx(a + 1, 0) <= e) a++;
-            while (pidx(a, 0) > e) a--;
-            c = e - pidx(a, 0);
-        }
-        ea[q] = a; ec[q] = c;
-    }
     for (int l = tid; l < nl; l += T) {                             // per-landmark weight sqrt(s_l^2 / h_l) (u_l is free scratch here)
         const double sl = ws.sc_l[l];
         ws.u_l[l] = sqrt(sl * sl / (ws.hll[l] * sl * sl + mu * ws.d_l[l] * ws.d_l[l]));
     }
-    double racc = 0;                                                // thread a < NPW accumulates the rhs correction
-    const int ld = NPW + 1;
+    const int ld = schur_ld(NPW), ntile = schur_ntile(NPW), G = T / ntile;          // host guarantees G >= 1
+    const int grp = tid / ntile, tile = tid - grp * ntile;
+    const bool active = grp < G;
+    int I = 0, J = 0;
+    if (active) { const int ti = tri_row(tile); I = 4 * ti; J = 4 * (tile - ti * (ti + 1) / 2); }
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
     for (int l0 = 0; l0 < nl; l0 += SCHUR_CHUNK) {
         const int cn = min(SCHUR_CHUNK, nl - l0);
         __syncthreads();
         for (int e = tid; e < cn * ld; e += T) {
             const int cl = e / ld, a = e - cl * ld, l = l0 + cl;
-            wt[e] = ((a < NPW) ? ws.w[(size_t)l * NPW + a] : ws.gl[l]) * ws.u_l[l];      // u_l holds sqrt(s_l^2 / h_l), set below
+            wt[e] = (a < NPW) ? ws.w[(size_t)l * NPW + a] * ws.u_l[l] : (a == NPW ? ws.gl[l] * ws.u_l[l] : 0.0);
         }
         __syncthreads();
+        if (active)
+            for (int cl = grp; cl < cn; cl += G) {
+                const double *row = wt + cl * ld;
+                const double2 a01 = *reinterpret_cast<const double2 *>(row + I), a23 = *reinterpret_cast<const double2 *>(row + I + 2);
+                const double2 b01 = *reinterpret_cast<const double2 *>(row + J), b23 = *reinterpret_cast<const double2 *>(row + J + 2);
+                const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-        for (int q = 0; q < EPT; q++) {
-            if (tid + q * T < nent) {
-                double t = 0;
-                for (int cl = 0; cl < cn; cl++) t += wt[cl * ld + ea[q]] * wt[cl * ld + ec[q]];
-                acc[q] += t;
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[a][c] += av[a] * bv[c];
             }
-        }
-        if (tid < NPW) { double t = 0; for (int cl = 0; cl < cn; cl++) t += wt[cl * ld + tid] * wt[cl * ld + NPW]; racc += t; }
     }
-    __syncthreads();
+    for (int g = 0; g < G; g++) {
+        __syncthreads();
+        if (active && grp == g) {
 #pragma unroll
-    for (int q = 0; q < EPT; q++) {
-        if (tid + q * T < nent) {
-            const int ia = 15 * (ea[q] / 6) + ea[q] % 6, ic = 15 * (ec[q] / 6) + ec[q] % 6;
-            S[pidx(ia, ic)] -= acc[q] * ws.sc_p[ia] * ws.sc_p[ic];
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int ra = I + a, rc = J + c;
+                    if (rc > ra || ra > NPW || rc >= NPW) continue;
+                    const int ic = 15 * (rc / 6) + rc % 6;
+                    if (ra == NPW) ws.rhs[ic] -= acc[a][c] * ws.sc_p[ic];
+                    else { const int ia = 15 * (ra / 6) + ra % 6; S[pidx(ia, ic)] -= acc[a][c] * ws.sc_p[ia] * ws.sc_p[ic]; }
+                }
         }
     }
-    if (tid < NPW) { const int ia = 15 * (tid / 6) + tid % 6; ws.rhs[ia] -= racc * ws.sc_p[ia]; }
     __syncthreads();
 }
 
+// shared scratch evaluate() needs: IMU J buffers, then (aliased) frame / pair tables + the J store of one chunk of SOLVE_T factors
+__host__ __device__ inline size_t eval_smem_bytes(int W) {
+    const size_t NF = W + 1, npair = NF * (NF - 1) / 2;
+    const size_t a = (size_t)930 * W, c = 21 * NF + 33 * npair + 1 + (size_t)26 * SOLVE_T;
+    return (a > c ? a : c) * sizeof(double);
+}
 __host__ __device__ inline size_t solve_smem_bytes(int NP, int NPW) {
-    return ((size_t)(NP + 1) * (NP + 2) / 2 + 8 + (size_t)SCHUR_CHUNK * (NPW + 1)) * sizeof(double);
+    return ((size_t)(NP + 1) * (NP + 2) / 2 + 10 + (size_t)SCHUR_CHUNK * schur_ld(NPW)) * sizeof(double);
 }
 
 __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem) {
@@ -512,7 +682,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
     double *cand = s.cand + (size_t)b * (NF * 16 + s.LCAP);
 
     BE_PROF_INIT;
-    double x_cost = evaluate(s, b, ws, par, 1, sh_red);
+    double x_cost = evaluate(s, b, ws, par, 1, sh_red, sm_dyn);
     BE_PROF(0);
     if (tid == 0) dvs[DV_COST0] = x_cost;
     // Jacobi scaling, frozen at iteration 0 (trust_region_minimizer.cc:239-254)
@@ -564,10 +734,10 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
             while (mu < 1.0) {
               bool ok;
               if (use_smem) {
-                double *Ssm = sm_dyn, *wt = sm_dyn + (size_t)(NP + 1) * (NP + 2) / 2 + 8;
+                double *Ssm = sm_dyn, *wt = sm_dyn + ((((size_t)(NP + 1) * (NP + 2) / 2 + 8) + 1) & ~(size_t)1);   // 16-byte aligned
                 build_reduced_smem(s, ws, nl, mu, Ssm, wt);
                 BE_PROF(2);
-                ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag, sh_red, s.prof + (size_t)b * 32);
+                ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag, wt, s.prof + (size_t)b * 32);
                 BE_PROF(3);
               } else {
                 for (int e = tid; e < NP * NP; e += T) {
@@ -677,7 +847,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
         }
         for (int l = tid; l < nl; l += T) cand[16 * NF + l] = par[16 * NF + l] + ws.u_l[l];
         __syncthreads();
-        const double cand_cost = evaluate(s, b, ws, cand, 0, sh_red);
+        const double cand_cost = evaluate(s, b, ws, cand, 0, sh_red, sm_dyn);
         BE_PROF(5);
         // ParameterToleranceReached / FunctionToleranceReached (trust_region_minimizer.cc:662-705)
         double sn = 0;
@@ -693,7 +863,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
             for (int i = tid; i < 16 * NF + nl; i += T) xn += par[i] * par[i];
             x_norm = sqrt(block_sum_d(xn, sh_red));
             BE_PROF(6);
-            x_cost = evaluate(s, b, ws, par, 1, sh_red);
+            x_cost = evaluate(s, b, ws, par, 1, sh_red, sm_dyn);
             BE_PROF(0);
             step_ok = true;
             if (quality < 0.25) radius *= 0.5;                        // DoglegStrategy::StepAccepted

@@ -40,6 +40,7 @@ struct BeState {
     // solve workspace
     double *par, *cand;                               // [B][NF*16 + LCAP]   pose7 sb9 per frame, then inverse depths
     int *lm_slot, *fac_lm, *fac_j;                    // [B][LCAP], [B][PCAP], [B][PCAP]
+    int *fac_sorted, *pair_off; double *fac_obs;      // factors in (anchor i, frame j) order: [B][PCAP] l | i<<16 | j<<24, [B][NF*NF+1], [B][PCAP][4]
     double *scratch; size_t scratch_stride;           // [B][scratch_stride] doubles
     double *post_solve;                               // [B][NF][16]
     double *state_out;                                // [B][NF][16] packed P,Q,V,Ba,Bg after the step
