@@ -215,7 +215,7 @@ def run_ours(args):
             names = ["solve.linearize", "solve.scale_cauchy", "solve.schur", "solve.cholesky", "solve.dogleg_model", "solve.cost_eval", "solve.accept", "",
                      "marg.setup", "marg.accumulate", "marg.slow_amm", "marg.amm_inv+schur", "marg.eig", "marg.recompose", "", "",
                      "lin.prior", "lin.imu", "lin.projection", "lin.cost_sum", "chol.trailing_update", "chol.diag_block", "chol.row_solve",
-                     "chol.backward", "eig.tred2", "eig.accumulate", "eig.tql2", "proj.pair_tables", "proj.jacobians", "proj.block_sums"]
+                     "chol.backward", "eig.tred2", "eig.accumulate", "eig.tql2", "proj.pair_tables", "proj.jacobians", "proj.block_sums", "cost.prior", "cost.imu"]
             phase_us = {nm: round(float(ph[:, i].max()) / 1.9e3, 1) for i, nm in enumerate(names) if nm}
         if world > 1:
             t = torch.tensor([ms], device=dev)

@@ -223,12 +223,16 @@ def test_config_c4_window20(api, abi, synth):
     ref.close(); gpu.close()
 
 
-@pytest.mark.parametrize("eig,slow", [("ql", "0"), ("jacobi", "0"), ("ql", "1"), ("jacobi", "1")])
-def test_marginalisation_eigen_paths(api, cfg, synth, monkeypatch, eig, slow):
-    """K13 has two eigensolvers (Householder+QL default, parallel Jacobi) and two routes to Amm^+ (structured inverse guarded by an
-    eigenvalue bound, or the reference's eigendecomposition): all four combinations must reproduce the reference prior."""
+@pytest.mark.parametrize("eig,slow,exact", [("ql", "0", "0"), ("ql", "0", "1"), ("jacobi", "0", "1"), ("ql", "1", "1"), ("jacobi", "1", "1"),
+                                            ("ql", "1", "0")])
+def test_marginalisation_eigen_paths(api, cfg, synth, monkeypatch, eig, slow, exact):
+    """K13 forms the new prior either directly in information form (default: Hp = A_r, c0 from one Cholesky solve) or through the
+    reference's eigendecomposition of A_r (VIO_MARG_EXACT=1), with two eigensolvers (Householder+QL, parallel Jacobi) and two
+    routes to Amm^+ (structured inverse guarded by an eigenvalue bound, or the reference's eigendecomposition): every combination
+    must reproduce the reference prior (H, b and the constant c0 = |r0|^2)."""
     monkeypatch.setenv("VIO_EIG", eig)
     monkeypatch.setenv("VIO_MARG_SLOW", slow)
+    monkeypatch.setenv("VIO_MARG_EXACT", exact)
     tr = synth.make_tracks(2, 15, max_cnt=cfg.max_cnt)
     ref = bo.RefEstimator(cfg)
     gpu = api.BackEnd(cfg)
@@ -244,5 +248,8 @@ def test_marginalisation_eigen_paths(api, cfg, synth, monkeypatch, eig, slow):
             assert np.array_equal(rp["present"], gp["present"])
             tol = 1e-7 if k == W else 1e-5
             assert rel_err(gp["H"], rp["H"]) < tol, f"kf {k}: prior H {rel_err(gp['H'], rp['H'])}"
+            # b = H (x - x0) + ... amplifies the state differences of later windows (reference reproducibility floor)
+            assert rel_err(gp["b"], rp["b"]) < (1e-7 if k == W else 1e-3), f"kf {k}: prior b {rel_err(gp['b'], rp['b'])}"
+            assert abs(gp["c0"] - rp["c0"]) <= 1e-4 * max(1.0, abs(rp["c0"])), f"kf {k}: c0 {gp['c0']} vs {rp['c0']}"
             assert rel_err(gs := gpu.state()["P"], ref.state()["P"]) < (1e-7 if k == W else 1e-4)
     ref.close(); gpu.close()

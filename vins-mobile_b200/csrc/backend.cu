@@ -25,7 +25,7 @@ struct vio_backend {
     int *d_counts, *d_ids; double *d_xyz, *d_headers; double *d_imu; size_t imu_cap;
     double *h_headers_pinned;
     size_t solve_smem, marg_smem;
-    int use_smem_solve;
+    int use_smem_solve, solve_vec_off;
     int be_threads;
     cudaEvent_t evt_ready, evt_consumed;
     bool consumed_valid, record_consumed;
@@ -94,6 +94,7 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     { const char *e = getenv("VIO_EIG"); s.eig_mode = (e && !strcmp(e, "jacobi")) ? 0 : 1; }
     { const char *e = getenv("VIO_BE_THREADS"); be->be_threads = (e && atoi(e) == 256) ? 256 : 512; }
     { const char *e = getenv("VIO_MARG_SLOW"); s.force_slow_marg = (e && e[0] == '1') ? 1 : 0; }
+    { const char *e = getenv("VIO_MARG_EXACT"); s.marg_direct = (e && e[0] == '1') ? 0 : 1; }
     const size_t B = s.B, NF = s.NF;
     int rc = VIO_OK;
     if (!rc) rc = dalloc(be, &s.Ps, B * NF * 3);
@@ -123,13 +124,15 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     if (!rc) rc = dalloc(be, &s.lm_slot, B * s.LCAP);
     if (!rc) rc = dalloc(be, &s.fac_lm, B * s.PCAP);
     if (!rc) rc = dalloc(be, &s.fac_j, B * s.PCAP);
+    if (!rc) rc = dalloc(be, &s.lm_fac0, B * (s.LCAP + 1));
+    if (!rc) rc = dalloc(be, &s.lm_anchor, B * s.LCAP);
     if (!rc) rc = dalloc(be, &s.fac_sorted, B * s.PCAP);
     if (!rc) rc = dalloc(be, &s.pair_off, B * (NF * NF + 1));
     if (!rc) rc = dalloc(be, &s.fac_obs, B * s.PCAP * 4);
     if (!rc) rc = dalloc(be, &s.post_solve, B * NF * 16);
     if (!rc) rc = dalloc(be, &s.state_out, B * NF * 16);
     if (!rc) rc = dalloc(be, &s.prof, B * 32);
-    size_t sc = solve_scratch_doubles(s.NP, s.NPX, s.NPW, s.LCAP, s.W);
+    size_t sc = solve_scratch_doubles(s.NP, s.NPX, s.NPW, s.LCAP, s.PCAP);
     sc = std::max(sc, marg_scratch_doubles(s.NPX, s.LCAP, cfg->max_cnt));
     sc = std::max(sc, (size_t)s.FCAP * (5 + 2 * NF));
     s.scratch_stride = (sc + 15) & ~(size_t)15;
@@ -148,6 +151,8 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     if (be->solve_smem > 200 * 1024 || schur_ntile(s.NPW) > be->be_threads) be->solve_smem = 0;
     be->use_smem_solve = be->solve_smem > 0;
     be->solve_smem = std::max(be->solve_smem, eval_smem_bytes(s.W));
+    be->solve_vec_off = (int)((be->solve_smem / sizeof(double) + 3) & ~(size_t)3);
+    be->solve_smem = (be->solve_vec_off + solve_vec_doubles(s.NP, s.NPX)) * sizeof(double);
     VIO_CUDA_TRY(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->solve_smem));
     be->marg_smem = sizeof(MargSmem) + 16 + (size_t)2 * MARG_NCAP * MARG_NCAP * sizeof(double);
     VIO_CUDA_TRY(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->marg_smem));
@@ -244,7 +249,7 @@ static int run_process_image(vio_backend *be, const int32_t *counts, const int32
     if (be->record_consumed) { cudaEventRecord(be->evt_consumed, st); be->consumed_valid = true; be->record_consumed = false; }   // image_msg fully read
     VIO_LAUNCH(be->timer, st, "triangulate_kernel", (triangulate_kernel<<<s.B, 128, 0, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "prepare_kernel", (prepare_kernel<<<s.B, 256, 0, st>>>(s)));
-    VIO_LAUNCH(be->timer, st, "solve_kernel", (solve_kernel<<<s.B, be->be_threads, be->solve_smem, st>>>(s, be->use_smem_solve)));
+    VIO_LAUNCH(be->timer, st, "solve_kernel", (solve_kernel<<<s.B, be->be_threads, be->solve_smem, st>>>(s, be->use_smem_solve, be->solve_vec_off)));
     VIO_LAUNCH(be->timer, st, "post_solve_kernel", (post_solve_kernel<<<s.B, 256, 0, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "marg_kernel", (marg_kernel<<<s.B, be->be_threads, be->marg_smem, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "finish_kernel", (finish_kernel<<<s.B, 256, s.FCAP + 64, st>>>(s)));

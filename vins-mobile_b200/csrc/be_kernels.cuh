@@ -295,6 +295,8 @@ __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
         if (is) {
             if (li < s.LCAP && fi + nfac <= s.PCAP) {
                 s.lm_slot[(size_t)b * s.LCAP + li] = k;
+                s.lm_fac0[(size_t)b * (s.LCAP + 1) + li] = fi;
+                s.lm_anchor[(size_t)b * s.LCAP + li] = s.f_start[fo + k];
                 par[16 * s.NF + li] = 1.0 / s.f_depth[fo + k];
                 const int st = s.f_start[fo + k];
                 for (int j = 1; j <= nfac; j++) { s.fac_lm[(size_t)b * s.PCAP + fi + j - 1] = li; s.fac_j[(size_t)b * s.PCAP + fi + j - 1] = st + j; }
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
         lm_base += tl; fac_base += tf;
     }
     const int nl = min(lm_base, s.LCAP), nfac_all = min(fac_base, s.PCAP);
-    if (tid == 0) { iv[IV_N_LM] = nl; iv[IV_N_FAC] = nfac_all; }
+    if (tid == 0) { iv[IV_N_LM] = nl; iv[IV_N_FAC] = nfac_all; s.lm_fac0[(size_t)b * (s.LCAP + 1) + nl] = nfac_all; }
     // the same factors ordered by (anchor frame i, observing frame j): a landmark contributes at most one factor to a pair, so
     // "landmark order within the pair" is a deterministic order.  One thread per pair counts, then places.
     __shared__ int sh_cnt[(VIO_MAX_WIN + 1) * (VIO_MAX_WIN + 1) + 1];

@@ -268,6 +268,7 @@ struct MargSmem {
     double red[32];
     int scan[33];
     int n_eff, m, L0, mc;
+    long long prof_sink[32];
 };
 
 __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
@@ -570,7 +571,51 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     for (int e = tid; e < n * n; e += T) { const int i = e / n, j = e - i * n; if (j < i) { const double v = 0.5 * (Ar[(size_t)i * n + j] + Ar[(size_t)j * n + i]); Ar[(size_t)i * n + j] = v; Ar[(size_t)j * n + i] = v; } }
     __syncthreads();
     BE_PROF(11);
+    // ---- the new prior ---------------------------------------------------------------------------------------------------
+    // The reference factors A_r = V S V^T, drops eigenvalues <= 1e-8 and hands Ceres J0 = S^1/2 V^T, r0 = S^-1/2 V^T b_r
+    // (marginalization_factor.cpp:290-315).  In information form that is Hp = V S+ V^T, bp = V+ V+^T b_r, c0 = b_r^T A_r^+ b_r.
+    // DIRECT mode (default): the dropped directions are the gauge null space (|lambda| at the round-off level of A_r, b_r has no
+    // component along them), so Hp = A_r and bp = b_r up to that round-off, and c0 -- a constant of the cost -- comes from one
+    // Cholesky solve of the Jacobi-scaled, 1e-10-shifted A_r.  If that factorisation fails the exact eigen path below runs.
     int sweeps = 0;
+    bool direct_ok = false;
+    double c0 = 0.0;
+    if (s.marg_direct) {
+        // packed matrix in shared memory when it fits the kernel's dynamic allocation (2 MARG_NCAP^2 doubles), else in the (free) Vr scratch
+        double *sP = ((size_t)(n + 1) * (n + 2) / 2 <= (size_t)2 * MARG_NCAP * MARG_NCAP) ? reinterpret_cast<double *>(smraw + ((sizeof(MargSmem) + 15) & ~(size_t)15)) : Vr;
+        double *dinv = sm.de, *dsc = sm.de + 400, *rv = sm.rot, *yv = sm.rot + 400;        // n <= 400 (VIO_MAX_WIN = 24: NPX = 381)
+        for (int i = tid; i < n; i += T) { const double d = Ar[(size_t)i * n + i]; dsc[i] = d > 0 ? rsqrt(d) : 1.0; }
+        __syncthreads();
+        for (int i = tid >> 5; i < n; i += T >> 5)
+            for (int j = tid & 31; j <= i; j += 32) sP[pidx(i, j)] = Ar[(size_t)i * n + j] * dsc[i] * dsc[j] + (i == j ? 1e-10 : 0.0);
+        for (int i = tid; i < n; i += T) rv[i] = br[i] * dsc[i];
+        __syncthreads();
+        direct_ok = chol_solve_packed(sP, n, rv, yv, &sm.ql_i[0], dinv, sm.prof_sink);
+        if (direct_ok) {
+            // two steps of iterative refinement against the UNSHIFTED matrix: the component of the solution along an eigenvalue lambda of
+            // the scaled A_r converges like (1e-10 / lambda)^k, so c0 = b_r^T A_r^+ b_r is exact for every direction the reference keeps
+            double *ev = sP + pidx(n, 0);                              // the border row is free after the solve
+            for (int it = 0; it < 2; it++) {
+                for (int i = tid; i < n; i += T) {
+                    double t = 0;
+                    for (int j = 0; j < n; j++) t += Ar[(size_t)j * n + i] * (dsc[j] * yv[j]);      // A_r symmetric: column walk, coalesced
+                    ev[i] = rv[i] - dsc[i] * t;
+                }
+                __syncthreads();
+                chol_forward_packed(sP, n, ev, dinv);
+                chol_backward_packed(sP, n, ev, dinv);
+                for (int i = tid; i < n; i += T) yv[i] += ev[i];
+                __syncthreads();
+            }
+            double t = 0;
+            for (int i = tid; i < n; i += T) t += rv[i] * yv[i];
+            c0 = block_sum_d(t, sm.red);
+            direct_ok = isfinite(c0);
+        }
+        sweeps = direct_ok ? -1 : 0;
+        __syncthreads();
+    }
+    if (!direct_ok) {
     if (n <= MARG_NCAP) {                                      // A_r and V in shared memory
         double *sA = reinterpret_cast<double *>(smraw + ((sizeof(MargSmem) + 15) & ~(size_t)15));
         double *sV = sA + (size_t)n * n;
@@ -581,9 +626,11 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     } else {
         sweeps = s.eig_mode ? eig_sym_ql(Ar, n, n, Vr, sm.de, sm.rot, sm.red, sm.ql_i, s.prof + (size_t)blockIdx.x * 32) : eig_sym_jacobi(Ar, n, n, Vr, sm.cs, sm.pq, sm.red);
     }
+    }
     if (tid == 0) { iv[IV_MARG_FAST] = fast_ok; iv[IV_MARG_SWEEPS] = sweeps; iv[IV_MARG_M] = m; }
     __syncthreads();
     BE_PROF(12);
+    if (!direct_ok) {
     // tv[k] = v_k . b_r ;  c0 = sum_{lam>eps} tv^2 / lam
     for (int k = tid; k < n; k += T) {
         double t = 0;
@@ -593,7 +640,8 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     __syncthreads();
     double c0p = 0;
     for (int k = tid; k < n; k += T) { const double lam = Ar[(size_t)k * n + k]; if (lam > MARG_EPS) c0p += tv[k] * tv[k] / lam; }
-    const double c0 = block_sum_d(c0p, sm.red);
+    c0 = block_sum_d(c0p, sm.red);
+    }
     // ---- write the new prior in canonical layout, shifted like addr_shift (VINS.cpp:759-774 / 806-829) ---------------
     double *Hp = s.Hp + (size_t)b * NPX * NPX, *bp = s.bp + (size_t)b * NPX;
     for (int e = tid; e < NPX * NPX; e += T) Hp[e] = 0.0;
@@ -604,6 +652,13 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         if (marg == 0) return c - 15;                                     // frame i -> i-1
         return c >= 15 * W ? c - 15 : c;                                  // frame W -> W-1
     };
+    if (direct_ok) {
+        for (int e = tid; e < n * n; e += T) {
+            const int i = e / n, j = e - i * n;
+            Hp[(size_t)shift(sm.kept[i]) * NPX + shift(sm.kept[j])] = Ar[e];
+        }
+        for (int i = tid; i < n; i += T) bp[shift(sm.kept[i])] = br[i];
+    } else {
     for (int e = tid; e < n * n; e += T) {
         const int i = e / n, j = e - i * n;
         double t = 0;
@@ -614,6 +669,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         double t = 0;
         for (int k = 0; k < n; k++) { const double lam = Ar[(size_t)k * n + k]; if (lam > MARG_EPS) t += Vr[(size_t)i * n + k] * tv[k]; }
         bp[shift(sm.kept[i])] = t;
+    }
     }
     // linearisation point = current values of every kept block (preMarginalize memcpy), re-addressed
     double *x0 = s.x0 + (size_t)b * (NF * 16 + 7);

@@ -23,25 +23,36 @@ constexpr int SOLVE_T = 512;
 struct SolveWs {
     double *H, *S, *g, *hll, *gl, *w;
     double *sc_p, *sc_l, *d_p, *d_l, *gr_p, *gr_l, *gn_p, *gn_l, *st_p, *st_l, *u_p, *u_l, *rhs, *y;
-    double *dx, *imuJ;
+    double *dx, *lt;
 };
 
-__device__ inline SolveWs carve(const BeState &s, int b) {
+// The matrices (H, S, w, per-factor landmark terms) live in the stream's global scratch; the vectors every phase of the dogleg loop
+// touches live in shared memory (sv), the landmark-sized ones only when the problem has at most SOLVE_LV landmarks.
+constexpr int SOLVE_LV = 384;
+__host__ __device__ inline size_t solve_vec_doubles(int NP, int NPX) {
+    auto r = [](size_t n) { return (n + 3) & ~(size_t)3; };
+    return 9 * r(NP) + r(NPX) + 8 * r(SOLVE_LV);
+}
+__device__ inline SolveWs carve(const BeState &s, int b, double *sv, int nl) {
     SolveWs w;
     double *p = s.scratch + (size_t)b * s.scratch_stride;
     auto take = [&](size_t n) { double *r = p; p += (n + 3) & ~(size_t)3; return r; };
-    w.H = take((size_t)s.NP * s.NP); w.S = take((size_t)s.NP * s.NP); w.g = take(s.NP);
-    w.hll = take(s.LCAP); w.gl = take(s.LCAP); w.w = take((size_t)s.LCAP * s.NPW);
-    w.sc_p = take(s.NP); w.sc_l = take(s.LCAP); w.d_p = take(s.NP); w.d_l = take(s.LCAP);
-    w.gr_p = take(s.NP); w.gr_l = take(s.LCAP); w.gn_p = take(s.NP); w.gn_l = take(s.LCAP);
-    w.st_p = take(s.NP); w.st_l = take(s.LCAP); w.u_p = take(s.NP); w.u_l = take(s.LCAP);
-    w.rhs = take(s.NP); w.y = take(s.NP);
-    w.dx = take(s.NPX); w.imuJ = take((size_t)s.W * 930);
+    auto stake = [&](size_t n) { double *r = sv; sv += (n + 3) & ~(size_t)3; return r; };
+    w.H = take((size_t)s.NP * s.NP); w.S = take((size_t)s.NP * s.NP); w.w = take((size_t)s.LCAP * s.NPW); w.lt = take((size_t)s.PCAP * 8);
+    w.g = stake(s.NP); w.sc_p = stake(s.NP); w.d_p = stake(s.NP); w.gr_p = stake(s.NP); w.gn_p = stake(s.NP); w.st_p = stake(s.NP);
+    w.u_p = stake(s.NP); w.rhs = stake(s.NP); w.y = stake(s.NP); w.dx = stake(s.NPX);
+    if (nl <= SOLVE_LV) {
+        w.hll = stake(SOLVE_LV); w.gl = stake(SOLVE_LV); w.sc_l = stake(SOLVE_LV); w.d_l = stake(SOLVE_LV);
+        w.gr_l = stake(SOLVE_LV); w.gn_l = stake(SOLVE_LV); w.st_l = stake(SOLVE_LV); w.u_l = stake(SOLVE_LV);
+    } else {
+        w.hll = take(s.LCAP); w.gl = take(s.LCAP); w.sc_l = take(s.LCAP); w.d_l = take(s.LCAP);
+        w.gr_l = take(s.LCAP); w.gn_l = take(s.LCAP); w.st_l = take(s.LCAP); w.u_l = take(s.LCAP);
+    }
     return w;
 }
-__host__ __device__ inline size_t solve_scratch_doubles(int NP, int NPX, int NPW, int LCAP, int W) {
+__host__ __device__ inline size_t solve_scratch_doubles(int NP, int NPX, int NPW, int LCAP, int PCAP) {
     auto r = [](size_t n) { return (n + 3) & ~(size_t)3; };
-    return 2 * r((size_t)NP * NP) + 7 * r(NP) + 8 * r(LCAP) + r((size_t)LCAP * NPW) + r(NPX) + r((size_t)W * 930) + r(NP) * 2 + 64;
+    return 2 * r((size_t)NP * NP) + 7 * r(NP) + 8 * r(LCAP) + r((size_t)LCAP * NPW) + r(NPX) + r((size_t)PCAP * 8) + r(NP) * 2 + 64;
 }
 
 // prior dx over the canonical layout (MarginalizationFactor::Evaluate, marginalization_factor.cpp:340-366)
@@ -105,32 +116,60 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
     double cost = 0.0;
     const int has_prior = iv[IV_PRIOR_VALID];
     if (lin) {
-        // H starts as the prior's J0^T J0 (pose / speed-bias rows and columns of the canonical layout), or zero
-        if (has_prior) {
-            const double *Hp = s.Hp + (size_t)b * s.NPX * s.NPX;
-            for (int e = tid; e < NP * NP; e += blockDim.x) { const int i = e / NP, j = e - i * NP; if (j <= i) ws.H[e] = Hp[(size_t)i * s.NPX + j]; }
-        } else
-            for (int e = tid; e < NP * NP; e += blockDim.x) { const int i = e / NP, j = e - i * NP; if (j <= i) ws.H[e] = 0.0; }
+        // H (lower triangle; the upper one is never read) starts as the prior's J0^T J0 over the pose / speed-bias part of the
+        // canonical layout, or zero.  One warp per row: coalesced, no index arithmetic.
+        const double *Hp = s.Hp + (size_t)b * s.NPX * s.NPX;
+        for (int i = warp; i < NP; i += nwarp) {
+            double *row = ws.H + (size_t)i * NP;
+            const double *src = Hp + (size_t)i * s.NPX;
+            for (int j = lane; j <= i; j += 32) row[j] = has_prior ? src[j] : 0.0;
+        }
         for (int i = tid; i < NP; i += blockDim.x) ws.g[i] = 0.0;
-        for (int i = tid; i < nl; i += blockDim.x) { ws.hll[i] = 0.0; ws.gl[i] = 0.0; }
-        for (int i = tid; i < nl * NPW; i += blockDim.x) ws.w[i] = 0.0;
+        // w_l rows: the entries of observing frames are rewritten by every linearisation and the others stay zero for the whole solve
+        if (lin == 2) for (int i = tid; i < nl * NPW; i += blockDim.x) ws.w[i] = 0.0;
     }
     // ---- prior ------------------------------------------------------------------------------------------
     if (has_prior) {
-        const int NPX = s.NPX;
+        const int NPX = s.NPX, T = blockDim.x;
         const double *Hp = s.Hp + (size_t)b * NPX * NPX, *bp = s.bp + (size_t)b * NPX;
         prior_dx(s, b, par, ws.dx);
         __syncthreads();
-        for (int i = tid; i < NPX; i += blockDim.x) {
+        // t = Hp dx: the rows are split over P thread groups (Hp symmetric: thread i of a group walks column i, coalesced)
+        // dx is staged in shared memory (after the P partial-sum rows); the Hp loads of a thread are issued eight at a time so that
+        // the L2 latency is paid once per eight rows
+        const int P = max(1, T / NPX), part = tid / NPX;
+        const int rows = (NPX + P - 1) / P;
+        double *dxs = smem_scratch + P * NPX;
+        for (int j = tid; j < NPX; j += T) dxs[j] = ws.dx[j];
+        __syncthreads();
+        if (part < P) {
+            const int j0 = part * rows, j1 = min(NPX, (part + 1) * rows);
+            for (int i = tid - part * NPX; i < NPX; i += (P == 1 ? T : NPX)) {
+                double t = 0;
+                const double *col = Hp + i;
+                int j = j0;
+                for (; j + 8 <= j1; j += 8) {
+                    double h[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) h[q] = __ldg(col + (size_t)(j + q) * NPX);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) t += h[q] * dxs[j + q];
+                }
+                for (; j < j1; j++) t += __ldg(col + (size_t)j * NPX) * dxs[j];
+                smem_scratch[part * NPX + i] = t;
+            }
+        }
+        __syncthreads();
+        for (int i2 = tid; i2 < NPX; i2 += T) {
             double t = 0;
-            for (int j = 0; j < NPX; j++) t += Hp[(size_t)j * NPX + i] * ws.dx[j];      // Hp symmetric: column read = coalesced
-            cost += 0.5 * ws.dx[i] * t + bp[i] * ws.dx[i];
-            if (lin && i < NP) ws.g[i] += t + bp[i];
+            for (int q = 0; q < P; q++) t += smem_scratch[q * NPX + i2];
+            cost += 0.5 * dxs[i2] * t + bp[i2] * dxs[i2];
+            if (lin && i2 < NP) ws.g[i2] += t + bp[i2];
         }
         if (tid == 0) cost += 0.5 * S_dv(s, b)[DV_PRIOR_C0];
     }
     __syncthreads();
-    if (lin) BE_PROF2(pp, 16);
+    if (lin) BE_PROF2(pp, 16); else BE_PROF2(pp, 30);
     // ---- IMU factors: one warp per factor ---------------------------------------------------------------
     for (int f = warp; f < s.W; f += nwarp) {
         const double *pr = S_pre(s, b, f + 1);
@@ -167,7 +206,7 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
         }
     }
     __syncthreads();
-    if (lin) BE_PROF2(pp, 17);
+    if (lin) BE_PROF2(pp, 17); else BE_PROF2(pp, 31);
     // ---- projection factors ---------------------------------------------------------------------------------
     // The factors are visited in (anchor frame i, observing frame j) order (prepare_kernel's fac_sorted / pair_off).  Everything
     // that depends on the frame pair alone -- ric^T Rj^T Ri ric, the translation part, the rotation products of the Jacobians --
@@ -204,6 +243,7 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
         const int *fs = s.fac_sorted + (size_t)b * s.PCAP, *po = s.pair_off + (size_t)b * (NF * NF + 1);
         const double *fobs = s.fac_obs + (size_t)b * s.PCAP * 4;
         const double *lam_p = par + 16 * NF;
+        const int *lf0 = s.lm_fac0 + (size_t)b * (s.LCAP + 1);
         double hacc[4][6];
 #pragma unroll
         for (int ps = 0; ps < 4; ps++)
@@ -261,13 +301,17 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
                     for (int c = 0; c < 12; c++) { Js[c * T + tid] = Ji[c]; Js[(12 + c) * T + tid] = Jj[c]; }
                     Js[24 * T + tid] = c0r; Js[25 * T + tid] = c1r;
                     double *wl = ws.w + (size_t)l * NPW;
+                    double lt8[8];
 #pragma unroll
                     for (int a = 0; a < 6; a++) {
                         wl[6 * j + a] = Jj[a] * Jl0 + Jj[6 + a] * Jl1;
-                        atomic_add(&wl[6 * i + a], Ji[a] * Jl0 + Ji[6 + a] * Jl1);
+                        lt8[a] = Ji[a] * Jl0 + Ji[6 + a] * Jl1;
                     }
-                    atomic_add(&ws.hll[l], Jl0 * Jl0 + Jl1 * Jl1);
-                    atomic_add(&ws.gl[l], Jl0 * c0r + Jl1 * c1r);
+                    lt8[6] = Jl0 * Jl0 + Jl1 * Jl1; lt8[7] = Jl0 * c0r + Jl1 * c1r;
+                    // terms that are sums over the landmark's factors (w_l of the anchor frame, h_ll, g_l): stored per factor in
+                    // landmark order and summed by one thread per landmark after the last chunk -- no atomics
+                    double4 *dst = reinterpret_cast<double4 *>(ws.lt + 8 * (size_t)(lf0[l] + (j - i - 1)));
+                    dst[0] = make_double4(lt8[0], lt8[1], lt8[2], lt8[3]); dst[1] = make_double4(lt8[4], lt8[5], lt8[6], lt8[7]);
                 }
             }
             if (!lin) continue;
@@ -311,6 +355,23 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
             if (tid == 0) { const long long t = clock64(); pq2[29] += t - _qt1; _qt1 = t; }
         }
         if (lin && hold) proj_flush(ws, NP, NF, npair, nwarp, warp, lane, 0, hacc);
+        if (lin) {
+            const int *anchor = s.lm_anchor + (size_t)b * s.LCAP;
+            for (int l = tid; l < nl; l += T) {
+                double a8[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) a8[k] = 0.0;
+                const int f1 = lf0[l + 1];
+                for (int f = lf0[l]; f < f1; f++) {
+                    const double4 u = *reinterpret_cast<const double4 *>(ws.lt + 8 * (size_t)f), v = *reinterpret_cast<const double4 *>(ws.lt + 8 * (size_t)f + 4);
+                    a8[0] += u.x; a8[1] += u.y; a8[2] += u.z; a8[3] += u.w; a8[4] += v.x; a8[5] += v.y; a8[6] += v.z; a8[7] += v.w;
+                }
+                double *wl = ws.w + (size_t)l * NPW + 6 * anchor[l];
+#pragma unroll
+                for (int k = 0; k < 6; k++) wl[k] = a8[k];
+                ws.hll[l] = a8[6]; ws.gl[l] = a8[7];
+            }
+        }
     }
     __syncthreads();
     if (lin) BE_PROF2(pp, 18);
@@ -323,14 +384,15 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
 // u^T H u over the full (pose/speed-bias + landmark) system.  Only the LOWER triangle of H is valid (the accumulation writes one
 // triangle); elements are visited in memory order, so the reads are coalesced.
 __device__ inline double quad_form(const BeState &s, const SolveWs &ws, int nl, const double *up, const double *ul, double *sh_red) {
-    const int tid = threadIdx.x, T = blockDim.x, NP = s.NP, NPW = s.NPW, NF = s.NF;
+    const int tid = threadIdx.x, T = blockDim.x, NP = s.NP, NPW = s.NPW, NF = s.NF, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     double acc = 0;
-    int i = tid / NP, j = tid - i * NP;
-    for (int e = tid; e < NP * NP; e += T) {
-        if (j < i) acc += 2.0 * ws.H[e] * up[i] * up[j];
-        else if (j == i) acc += ws.H[e] * up[i] * up[i];
-        j += T;
-        while (j >= NP) { j -= NP; i++; }
+    for (int i = warp; i < NP; i += nwarp) {                         // one warp per row of the lower triangle
+        const double *row = ws.H + (size_t)i * NP;
+        double t = 0;
+#pragma unroll 2
+        for (int j = lane; j < i; j += 32) t += row[j] * up[j];
+        acc += 2.0 * up[i] * t;
+        if (lane == 0) acc += row[i] * up[i] * up[i];
     }
     for (int l = tid; l < nl; l += T) {
         double t = 0;
@@ -412,7 +474,7 @@ __device__ __forceinline__ int tri_row(int e) {             // largest i with i 
     return i;
 }
 
-// 1 / sqrt(x) for a positive, finite, normal-range x: single-precision seed + three Newton steps (no MUFU.RSQ64H fix-up branches on
+// 1 / sqrt(x) for a positive, finite, normal-range x: single-precision seed + two Newton steps + one to absorb the seed's rounding (no MUFU.RSQ64H fix-up branches on
 // the critical path of the factorisation); relative error ~1e-16
 __device__ __forceinline__ double fast_rsqrt(double x) {
     if (!(x > 1e-30 && x < 1e30)) return rsqrt(x);
@@ -454,6 +516,72 @@ __device__ __forceinline__ bool chol_diag8(double *A, int c0, int nb, double *di
     return ok;
 }
 
+// L^T y = z in place (z in shared memory), L packed lower in shared memory, dinv = 1 / diag(L).  Blocked 16 wide: warp 0 back-solves
+// a diagonal block with its columns held in registers, then every thread folds the block's solution into the rows above.
+__device__ inline void chol_backward_packed(const double *A, int n, double *z, const double *dinv) {
+    constexpr int BB = 16;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+    for (int c0 = ((n - 1) / BB) * BB; c0 >= 0; c0 -= BB) {
+        const int nb = min(BB, n - c0);
+        if (tid < 32) {
+            double col[BB];                                          // col[t] = L[c0 + t][c0 + lane], t > lane
+#pragma unroll
+            for (int t = 0; t < BB; t++) col[t] = (t > lane && t < nb) ? A[pidx(c0 + t, c0 + lane)] : 0.0;
+            double yv = (lane < nb) ? z[c0 + lane] : 0.0;
+            const double di = (lane < nb) ? dinv[c0 + lane] : 0.0;
+#pragma unroll
+            for (int j = BB - 1; j >= 0; j--) {
+                if (lane == j) yv *= di;
+                const double yj = __shfl_sync(FULL, yv, j);
+                if (lane < j) yv -= col[j] * yj;
+            }
+            if (lane < nb) z[c0 + lane] = yv;
+        }
+        __syncthreads();
+        for (int i = tid; i < c0; i += T) {
+            double v = z[i];
+#pragma unroll
+            for (int t = 0; t < BB; t++) if (t < nb) v -= A[pidx(c0 + t, i)] * z[c0 + t];
+            z[i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// L y = z in place, same conventions (used to re-solve with an existing factor)
+__device__ inline void chol_forward_packed(const double *A, int n, double *z, const double *dinv) {
+    constexpr int BB = 16;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+    for (int c0 = 0; c0 < n; c0 += BB) {
+        const int nb = min(BB, n - c0);
+        if (tid < 32) {
+            double row[BB];                                          // row[t] = L[c0 + lane][c0 + t], t < lane
+#pragma unroll
+            for (int t = 0; t < BB; t++) row[t] = (t < lane && lane < nb) ? A[pidx(c0 + lane, c0 + t)] : 0.0;
+            double yv = (lane < nb) ? z[c0 + lane] : 0.0;
+            const double di = (lane < nb) ? dinv[c0 + lane] : 0.0;
+#pragma unroll
+            for (int j = 0; j < BB; j++) {
+                if (lane == j) yv *= di;
+                const double yj = __shfl_sync(FULL, yv, j);
+                if (lane > j) yv -= row[j] * yj;
+            }
+            if (lane < nb) z[c0 + lane] = yv;
+        }
+        __syncthreads();
+        for (int i = c0 + nb + tid; i < n; i += T) {
+            double v = z[i];
+            const double *ri = A + pidx(i, c0);
+#pragma unroll
+            for (int t = 0; t < BB; t++) if (t < nb) v -= ri[t] * z[c0 + t];
+            z[i] = v;
+        }
+        __syncthreads();
+    }
+}
+
 // Blocked RIGHT-looking Cholesky on a packed lower matrix in shared memory, BORDERED by the right-hand side (row n of the packed
 // array holds rhs, so the forward substitution z = L^-1 rhs is a by-product of the factorisation).  Per 8-column panel:
 //   (b) one thread per row below the diagonal block solves its 8 entries against the block (block reads are warp broadcasts);
@@ -468,7 +596,6 @@ __device__ __noinline__ bool chol_solve_packed(double *A, int n, const double *r
     BE_PROF2_INIT;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
     constexpr int NB = 8;
-    constexpr unsigned FULL = 0xffffffffu;
     if (tid == 0) *sh_flag = 1;
     for (int j = tid; j < n; j += T) A[pidx(n, j)] = rhs[j];
     __syncthreads();
@@ -553,34 +680,8 @@ __device__ __noinline__ bool chol_solve_packed(double *A, int n, const double *r
         __syncthreads();
         BE_PROF2(pp, 20);
     }
-    // backward: L^T y = z, in place in row n of A
-    constexpr int BB = 16;
     double *z = A + pidx(n, 0);
-    for (int c0 = ((n - 1) / BB) * BB; c0 >= 0; c0 -= BB) {
-        const int nb = min(BB, n - c0);
-        if (tid < 32) {
-            double col[BB];                                          // col[t] = L[c0 + t][c0 + lane], t > lane
-#pragma unroll
-            for (int t = 0; t < BB; t++) col[t] = (t > lane && t < nb) ? A[pidx(c0 + t, c0 + lane)] : 0.0;
-            double yv = (lane < nb) ? z[c0 + lane] : 0.0;
-            const double di = (lane < nb) ? dinv[c0 + lane] : 0.0;
-#pragma unroll
-            for (int j = BB - 1; j >= 0; j--) {
-                if (lane == j) yv *= di;
-                const double yj = __shfl_sync(FULL, yv, j);
-                if (lane < j) yv -= col[j] * yj;
-            }
-            if (lane < nb) z[c0 + lane] = yv;
-        }
-        __syncthreads();
-        for (int i = tid; i < c0; i += T) {
-            double v = z[i];
-#pragma unroll
-            for (int t = 0; t < BB; t++) if (t < nb) v -= A[pidx(c0 + t, i)] * z[c0 + t];
-            z[i] = v;
-        }
-        __syncthreads();
-    }
+    chol_backward_packed(A, n, z, dinv);
     bool ok = true;
     for (int i = tid; i < n; i += T) { const double v = z[i]; y[i] = v; ok &= isfinite(v); }
     BE_PROF2(pp, 23);
@@ -666,7 +767,7 @@ __host__ __device__ inline size_t solve_smem_bytes(int NP, int NPW) {
     return ((size_t)(NP + 1) * (NP + 2) / 2 + 10 + (size_t)SCHUR_CHUNK * schur_ld(NPW)) * sizeof(double);
 }
 
-__global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem) {
+__global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem, int vec_off) {
     extern __shared__ __align__(16) double sm_dyn[];
     const int T = blockDim.x;                              // 256 or 512 (VIO_BE_THREADS)
     __shared__ double sh_red[32];
@@ -676,13 +777,13 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem)
     const int act = iv[IV_ACTION];
     if (act != ACT_INIT_SOLVE && act != ACT_NL_SOLVE) return;
     double *dvs = S_dv(s, b);
-    const SolveWs ws = carve(s, b);
     const int NP = s.NP, NPW = s.NPW, NF = s.NF, nl = iv[IV_N_LM];
+    const SolveWs ws = carve(s, b, sm_dyn + vec_off, nl);
     double *par = s.par + (size_t)b * (NF * 16 + s.LCAP);
     double *cand = s.cand + (size_t)b * (NF * 16 + s.LCAP);
 
     BE_PROF_INIT;
-    double x_cost = evaluate(s, b, ws, par, 1, sh_red, sm_dyn);
+    double x_cost = evaluate(s, b, ws, par, 2, sh_red, sm_dyn);
     BE_PROF(0);
     if (tid == 0) dvs[DV_COST0] = x_cost;
     // Jacobi scaling, frozen at iteration 0 (trust_region_minimizer.cc:239-254)

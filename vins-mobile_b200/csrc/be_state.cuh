@@ -26,6 +26,7 @@ struct BeState {
     int max_iters;
     int eig_mode;            // 0 = parallel Jacobi, 1 = Householder tridiagonalisation + implicit QL (default)
     int force_slow_marg;     // test hook: always take the eigendecomposition path for Amm^+
+    int marg_direct;         // 1 (default): new prior in information form straight from A_r; 0: the reference's eigendecomposition of A_r
     // window state
     double *Ps, *Rs, *Vs, *Bas, *Bgs, *Headers;       // [B][NF][3|9|3|3|3|1]
     double *pre;                                      // [B][NF][PR_STRIDE]
@@ -40,6 +41,7 @@ struct BeState {
     // solve workspace
     double *par, *cand;                               // [B][NF*16 + LCAP]   pose7 sb9 per frame, then inverse depths
     int *lm_slot, *fac_lm, *fac_j;                    // [B][LCAP], [B][PCAP], [B][PCAP]
+    int *lm_fac0, *lm_anchor;                         // [B][LCAP+1] first factor (landmark order) of each landmark, [B][LCAP] anchor frame
     int *fac_sorted, *pair_off; double *fac_obs;      // factors in (anchor i, frame j) order: [B][PCAP] l | i<<16 | j<<24, [B][NF*NF+1], [B][PCAP][4]
     double *scratch; size_t scratch_stride;           // [B][scratch_stride] doubles
     double *post_solve;                               // [B][NF][16]
