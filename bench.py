@@ -106,6 +106,11 @@ class Pipeline:
         self.kf = 0
         self.frame = 0
         self.state_host = None
+        self.be_stream = be_stream
+        if host_inputs:
+            import torch
+            self.state_pin = [torch.empty((self.B, self.W + 1, 16), dtype=torch.float64).pin_memory() for _ in range(2)]
+            self.state_evt = [None, None]
 
     def step(self, img, imu):
         """img: device pointer (device-resident run) or pinned host ndarray (e2e run).  imu(kf) -> (dt, acc, gyr) device pointers
@@ -125,7 +130,17 @@ class Pipeline:
                 self.be.set_init_window(P, Q, V, np.zeros((self.B, 3)), np.zeros((self.B, 3)))
             self.be.process_image_from_frontend(self.fe, np.full(self.B, self.frame / 30.0))
             if self.host:
-                self.state_host = self.be.state_all()          # device -> host read of the step's result
+                # device -> host read of the step's result: stream-ordered copy into pinned memory; the host consumes the result of
+                # the PREVIOUS keyframe (its event has long fired), so the tracker of the next frames is enqueued while this
+                # keyframe's solve runs
+                import torch
+                k2 = self.kf & 1
+                if self.state_evt[k2 ^ 1] is not None:
+                    self.state_evt[k2 ^ 1].synchronize()
+                    self.state_host = float(self.state_pin[k2 ^ 1][:, -1, :3].sum())
+                self.be.copy_state(self.state_pin[k2].data_ptr(), 2)
+                self.state_evt[k2] = torch.cuda.Event()
+                self.state_evt[k2].record(torch.cuda.ExternalStream(self.be_stream))
             self.kf += 1
         self.frame += 1
         return pub
@@ -161,8 +176,10 @@ def run_ours(args):
     def imu_dev(k):
         return dt_d[k].data_ptr(), acc_d[k].data_ptr(), gyr_d[k].data_ptr()
 
+    dt_p, acc_p, gyr_p = (torch.as_tensor(np.ascontiguousarray(x)).pin_memory().numpy() for x in (dt, acc, gyr))   # pinned host IMU
+
     def imu_host(k):
-        return dt[k], acc[k], gyr[k]
+        return dt_p[k], acc_p[k], gyr_p[k]
 
     gather_buf = None
     if world > 1:

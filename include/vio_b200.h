@@ -157,8 +157,9 @@ int vio_backend_get_features(vio_backend *be, int s, int cap, int *n_out, int32_
 /* Prior in information form over the canonical local layout [pose0(6) sb0(9) ... poseW sbW ex(6)],
  * n = 15*(W+1)+6:  H[n*n] = J0^T J0, b[n] = J0^T r0, present[2*(W+1)+1] block mask.  For parity tests. */
 int vio_backend_get_prior(vio_backend *be, int s, double *H, double *b, int32_t *present, double *c0);
-/* Packed state of the whole batch [batch][W+1][16] (P3,Q4 xyzw,V3,Ba3,Bg3) copied to caller memory (host: synchronous; device:
- * stream-ordered, e.g. the send buffer of an NCCL gather). */
+/* Packed state of the whole batch [batch][W+1][16] (P3,Q4 xyzw,V3,Ba3,Bg3) copied to caller memory.  dst_is_device = 0: host,
+ * synchronous; 1: device, stream-ordered (e.g. the send buffer of an NCCL gather); 2: PINNED host memory, stream-ordered -- the caller
+ * reads it after vio_backend_sync() or an event recorded on the back-end stream (keeps a pipelined caller from stalling on the solve). */
 int vio_backend_copy_state(vio_backend *be, double *dst, int dst_is_device);
 /* State right after new2old() of the last solve, before marginalisation / slideWindow: [W+1][16] of stream s (parity tests). */
 int vio_backend_get_post_solve(vio_backend *be, int s, double *out);

@@ -343,7 +343,8 @@ class BackEnd:
         _check(lib().vio_backend_phase_cycles(self.h, out.ctypes.data_as(C.POINTER(C.c_longlong)), int(reset)), "vio_backend_phase_cycles")
         return out
 
-    def copy_state(self, dst_ptr: int, is_device: bool):
+    def copy_state(self, dst_ptr: int, is_device):
+        """is_device: False/0 host (synchronous), True/1 device (stream-ordered), 2 pinned host (stream-ordered)."""
         _check(lib().vio_backend_copy_state(self.h, dst_ptr, int(is_device)), "vio_backend_copy_state")
 
     def state_all(self):

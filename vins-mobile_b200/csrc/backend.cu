@@ -402,8 +402,8 @@ extern "C" int vio_backend_copy_state(vio_backend *be, double *dst, int dst_is_d
     if (!be || !dst) return VIO_ERR_ARG;
     VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
     const size_t n = (size_t)be->s.B * be->s.NF * 16 * sizeof(double);
-    VIO_CUDA_TRY(cudaMemcpyAsync(dst, be->s.state_out, n, dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, be->stream));
-    if (!dst_is_device) VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(dst, be->s.state_out, n, dst_is_device == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, be->stream));
+    if (dst_is_device == 0) VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));      // 2: pinned host destination, caller synchronises
     return VIO_OK;
 }
 // diagnostics: per-stream clock64 cycle counters of the solve / marginalisation phases, [batch][32]; reset = 1 zeroes them

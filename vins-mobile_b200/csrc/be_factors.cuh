@@ -11,14 +11,15 @@
 namespace be {
 
 // ---- pre-integration record layout (doubles) ------------------------------------------------------------
-constexpr int PR_DP = 0, PR_DQ = 3, PR_DV = 7, PR_LBA = 10, PR_LBG = 13, PR_SUMDT = 16, PR_ACC0 = 17, PR_GYR0 = 20, PR_VALID = 23;
+constexpr int PR_DP = 0, PR_DQ = 3, PR_DV = 7, PR_LBA = 10, PR_LBG = 13, PR_SUMDT = 16, PR_ACC0 = 17, PR_GYR0 = 20, PR_VALID = 23,
+              PR_SQI_OK = 24;     // 1 when PR_SQI matches PR_COV (cleared by every propagation step, set by prepare_kernel)
 constexpr int PR_JAC = 32, PR_COV = PR_JAC + 225, PR_SQI = PR_COV + 225, PR_STRIDE = PR_SQI + 225 + 7;   // 714
 
 // IntegrationBase ctor (integration_base.h:26-44): called by one lane
 __device__ inline void pre_init(double *pr, V3 acc0, V3 gyr0, V3 ba, V3 bg) {
     st3(pr + PR_DP, v3(0, 0, 0)); stq(pr + PR_DQ, q4(0, 0, 0, 1)); st3(pr + PR_DV, v3(0, 0, 0));
     st3(pr + PR_LBA, ba); st3(pr + PR_LBG, bg); pr[PR_SUMDT] = 0;
-    st3(pr + PR_ACC0, acc0); st3(pr + PR_GYR0, gyr0); pr[PR_VALID] = 1;
+    st3(pr + PR_ACC0, acc0); st3(pr + PR_GYR0, gyr0); pr[PR_VALID] = 1; pr[PR_SQI_OK] = 0;
     for (int i = 0; i < 225; i++) { pr[PR_JAC + i] = (i % 16 == 0) ? 1.0 : 0.0; pr[PR_COV + i] = 0.0; }
 }
 
@@ -102,7 +103,7 @@ __device__ inline void pre_propagate_warp(double *pr, double dt, V3 a1, V3 g1, c
     if (lane == 0) {
         st3(pr + PR_DP, rp); st3(pr + PR_DV, rv);
         stq(pr + PR_DQ, qnormalized(rq));
-        pr[PR_SUMDT] += dt;
+        pr[PR_SUMDT] += dt; pr[PR_SQI_OK] = 0;
         st3(pr + PR_ACC0, a1); st3(pr + PR_GYR0, g1);
     }
     __syncwarp();
@@ -153,6 +154,57 @@ __device__ inline bool imu_sqrt_info(const double *cov, double *U) {
     }
     for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) U[i * 15 + j] = L[j * 15 + i];
     return true;
+}
+
+// Warp-cooperative variant (shared-memory work arrays of 225 doubles each): same result up to the summation order.
+//   chol15_warp: in-place right-looking Cholesky of the lower triangle of a 15x15 matrix
+__device__ inline bool chol15_warp(double *A, int lane) {
+    bool ok = true;
+    for (int j = 0; j < 15; j++) {
+        const double piv = A[j * 15 + j];
+        ok &= piv > 0;
+        const double d = sqrt(piv), id = 1.0 / d;
+        __syncwarp();
+        if (lane == 0) A[j * 15 + j] = d;
+        if (lane > j && lane < 15) A[lane * 15 + j] *= id;
+        __syncwarp();
+        const int m = 14 - j;                                        // trailing rows j+1..14: pairs (i >= k) of the lower triangle
+        for (int e = lane; e < m * (m + 1) / 2; e += 32) {
+            int r = 0, t = e;
+            while (t > r) { t -= r + 1; r++; }
+            const int i = j + 1 + r, k = j + 1 + t;
+            A[i * 15 + k] -= A[i * 15 + j] * A[k * 15 + j];
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+__device__ inline bool imu_sqrt_info_warp(const double *cov, double *U, double *L, double *Li, double *A, int lane) {
+    for (int e = lane; e < 225; e += 32) { L[e] = cov[e]; Li[e] = 0.0; }
+    __syncwarp();
+    bool ok = chol15_warp(L, lane);
+    if (lane < 15) {                                                 // Li = L^-1, one column per lane
+        const int c = lane;
+        for (int i = c; i < 15; i++) {
+            double sum = (i == c) ? 1.0 : 0.0;
+            for (int k = c; k < i; k++) sum -= L[i * 15 + k] * Li[k * 15 + c];
+            Li[i * 15 + c] = sum / L[i * 15 + i];
+        }
+    }
+    __syncwarp();
+    for (int e = lane; e < 120; e += 32) {                           // A = Li^T Li (lower)
+        int i = 0, t = e;
+        while (t > i) { t -= i + 1; i++; }
+        const int j = t;
+        double sum = 0;
+        for (int k = i; k < 15; k++) sum += Li[k * 15 + i] * Li[k * 15 + j];
+        A[i * 15 + j] = sum;
+    }
+    __syncwarp();
+    ok &= chol15_warp(A, lane);
+    for (int e = lane; e < 225; e += 32) { const int i = e / 15, j = e - 15 * i; U[e] = (j >= i) ? A[j * 15 + i] : 0.0; }
+    __syncwarp();
+    return ok;
 }
 
 // IntegrationBase::evaluate + IMUFactor::Evaluate.  Serial (one thread); res[15] is weighted by sqrt_info; when J != nullptr it

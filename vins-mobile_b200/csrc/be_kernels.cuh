@@ -277,9 +277,17 @@ __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
         stq(p + 3, R2q(ldm(S_Rs(s, b, i))));
         st3(p + 7, ld3(S_Vs(s, b, i))); st3(p + 10, ld3(S_Bas(s, b, i))); st3(p + 13, ld3(S_Bgs(s, b, i)));
     }
-    for (int i = tid; i < s.W; i += 256) {          // IMUFactor(pre_integrations[i+1])
-        double *pr = S_pre(s, b, i + 1);
-        if (!imu_sqrt_info(pr + PR_COV, pr + PR_SQI)) iv[IV_ERR] = VIO_ERR_STATE;
+    // IMUFactor(pre_integrations[i+1]): sqrt_info = LLT(cov^-1).matrixL()^T.  Cached while the covariance is unchanged (only the
+    // newest frames propagate between two solves); warps 0 and 1 factor the ones that need it.
+    __shared__ double sh_sqi[2][3][225];
+    if (tid < 64) {
+        const int w = tid >> 5, lane = tid & 31;
+        for (int i = w; i < s.W; i += 2) {
+            double *pr = S_pre(s, b, i + 1);
+            if (pr[PR_SQI_OK] != 0.0) continue;
+            if (!imu_sqrt_info_warp(pr + PR_COV, pr + PR_SQI, sh_sqi[w][0], sh_sqi[w][1], sh_sqi[w][2], lane) && lane == 0) iv[IV_ERR] = VIO_ERR_STATE;
+            if (lane == 0) pr[PR_SQI_OK] = 1.0;
+        }
     }
     // landmarks (in list order) and their factors
     int lm_base = 0, fac_base = 0;
@@ -311,12 +319,18 @@ __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
     __shared__ int sh_cnt[(VIO_MAX_WIN + 1) * (VIO_MAX_WIN + 1) + 1];
     const int NF = s.NF, nkey = NF * NF;
     const int *slot = s.lm_slot + (size_t)b * s.LCAP;
+    __shared__ unsigned short sh_lm[2048][2];                        // (anchor frame, observations) per landmark
+    const int nls = min(nl, 2048);
     __syncthreads();
+    for (int l = tid; l < nls; l += 256) { const int k = slot[l]; sh_lm[l][0] = (unsigned short)s.f_start[fo + k]; sh_lm[l][1] = (unsigned short)s.f_nobs[fo + k]; }
+    __syncthreads();
+    auto lm_start = [&](int l) { return l < 2048 ? (int)sh_lm[l][0] : s.f_start[fo + slot[l]]; };
+    auto lm_nobs = [&](int l) { return l < 2048 ? (int)sh_lm[l][1] : s.f_nobs[fo + slot[l]]; };
     for (int key = tid; key < nkey; key += 256) {
         const int i = key / NF, j = key - i * NF;
         int c = 0;
         if (j > i)
-            for (int l = 0; l < nl; l++) { const int k = slot[l]; c += (s.f_start[fo + k] == i && j < i + s.f_nobs[fo + k]); }
+            for (int l = 0; l < nl; l++) c += (lm_start(l) == i && j < i + lm_nobs(l));
         sh_cnt[key] = c;
     }
     __syncthreads();
@@ -335,9 +349,8 @@ __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
         if (j <= i) continue;
         int pos = sh_cnt[key];
         for (int l = 0; l < nl; l++) {
-            const int k = slot[l];
-            if (s.f_start[fo + k] == i && j < i + s.f_nobs[fo + k] && pos < s.PCAP) {
-                const double *o = S_obs(s, b, k);
+            if (lm_start(l) == i && j < i + lm_nobs(l) && pos < s.PCAP) {
+                const double *o = S_obs(s, b, slot[l]);
                 fs[pos] = l | (i << 16) | (j << 24);
                 fobs[4 * (size_t)pos] = o[0]; fobs[4 * (size_t)pos + 1] = o[1];
                 fobs[4 * (size_t)pos + 2] = o[2 * (j - i)]; fobs[4 * (size_t)pos + 3] = o[2 * (j - i) + 1];

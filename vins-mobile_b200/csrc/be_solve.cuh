@@ -381,10 +381,18 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
     return total;
 }
 
+// sum_{f,a} w_l[6f+a] * v[15f+a] with the 6*NF entries of the landmark's coupling row spread over the lanes of a warp (coalesced);
+// the result is valid in every lane
+__device__ __forceinline__ double w_dot_warp(const double *wl, const double *v, int NPW, int lane) {
+    double t = 0;
+    for (int e = lane; e < NPW; e += 32) { const int f = e / 6; t += wl[e] * v[e + 9 * f]; }
+    return warp_sum_d(t);
+}
+
 // u^T H u over the full (pose/speed-bias + landmark) system.  Only the LOWER triangle of H is valid (the accumulation writes one
 // triangle); elements are visited in memory order, so the reads are coalesced.
 __device__ inline double quad_form(const BeState &s, const SolveWs &ws, int nl, const double *up, const double *ul, double *sh_red) {
-    const int tid = threadIdx.x, T = blockDim.x, NP = s.NP, NPW = s.NPW, NF = s.NF, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    const int tid = threadIdx.x, T = blockDim.x, NP = s.NP, NPW = s.NPW, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     double acc = 0;
     for (int i = warp; i < NP; i += nwarp) {                         // one warp per row of the lower triangle
         const double *row = ws.H + (size_t)i * NP;
@@ -394,12 +402,9 @@ __device__ inline double quad_form(const BeState &s, const SolveWs &ws, int nl, 
         acc += 2.0 * up[i] * t;
         if (lane == 0) acc += row[i] * up[i] * up[i];
     }
-    for (int l = tid; l < nl; l += T) {
-        double t = 0;
-        const double *w = ws.w + (size_t)l * NPW;
-        for (int f = 0; f < NF; f++)
-            for (int a = 0; a < 6; a++) t += w[6 * f + a] * up[15 * f + a];
-        acc += 2.0 * ul[l] * t + ws.hll[l] * ul[l] * ul[l];
+    for (int l = warp; l < nl; l += nwarp) {                         // one warp per landmark row of the coupling block
+        const double t = w_dot_warp(ws.w + (size_t)l * NPW, up, NPW, lane);
+        if (lane == 0) acc += 2.0 * ul[l] * t + ws.hll[l] * ul[l] * ul[l];
     }
     return block_sum_d(acc, sh_red);
 }
@@ -791,7 +796,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem,
     for (int l = tid; l < nl; l += T) ws.sc_l[l] = 1.0 / (1.0 + sqrt(ws.hll[l]));
     __syncthreads();
 
-    double radius = 1e4, mu = 1e-8, alpha = 0.0, dogleg_norm = 0.0, x_norm = -1.0;
+    double radius = 1e4, mu = 1e-8, alpha = 0.0, dogleg_norm = 0.0, x_norm = -1.0, mu_gn = 0.0, g2_lin = 0.0, gHg_lin = 0.0;
     bool reuse = false;
     int iter = 0, invalid_run = 0;
     bool step_ok = true;                                   // iteration 0 counts as successful
@@ -829,6 +834,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem,
             const double g2 = dot2(ws.gr_p, ws.gr_l, ws.gr_p, ws.gr_l, NP, nl, sh_red);
             const double jg2 = quad_form(s, ws, nl, ws.u_p, ws.u_l, sh_red);
             alpha = g2 / jg2;                                         // ComputeCauchyPoint
+            g2_lin = g2; gHg_lin = jg2;
             BE_PROF(1);
             // ---- ComputeGaussNewtonStep: (S H S + mu D^2) y = S g by Schur elimination of the landmark blocks ----
             linear_ok = false;
@@ -882,18 +888,19 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem,
                 __syncthreads();
                 if (ok) {
                     // back-substitution y_l = (gs_l - ws_l . y_p) / h_l ;  gauss_newton_step_ = -diagonal .* y
-                    for (int l = tid; l < nl; l += T) {
-                        const double sl = ws.sc_l[l];
-                        const double h = ws.hll[l] * sl * sl + mu * ws.d_l[l] * ws.d_l[l];
-                        double t = 0;
-                        const double *w = ws.w + (size_t)l * NPW;
-                        for (int f = 0; f < NF; f++)
-                            for (int a = 0; a < 6; a++) t += w[6 * f + a] * ws.sc_p[15 * f + a] * ws.y[15 * f + a];
-                        const double yl = (ws.gl[l] * sl - sl * t) / h;
-                        ws.gn_l[l] = -ws.d_l[l] * yl;
-                    }
-                    for (int i = tid; i < NP; i += T) ws.gn_p[i] = -ws.d_p[i] * ws.y[i];
+                    for (int i = tid; i < NP; i += T) { ws.gn_p[i] = -ws.d_p[i] * ws.y[i]; ws.rhs[i] = ws.sc_p[i] * ws.y[i]; }   // rhs: free scratch
                     __syncthreads();
+                    for (int l = tid >> 5; l < nl; l += T >> 5) {
+                        const double t = w_dot_warp(ws.w + (size_t)l * NPW, ws.rhs, NPW, tid & 31);
+                        if ((tid & 31) == 0) {
+                            const double sl = ws.sc_l[l];
+                            const double h = ws.hll[l] * sl * sl + mu * ws.d_l[l] * ws.d_l[l];
+                            const double yl = (ws.gl[l] * sl - sl * t) / h;
+                            ws.gn_l[l] = -ws.d_l[l] * yl;
+                        }
+                    }
+                    __syncthreads();
+                    mu_gn = mu;
                     linear_ok = true;
                     break;
                 }
@@ -905,13 +912,17 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem,
         double model_change = 0.0;
         if (linear_ok) {
             // ---- ComputeTraditionalDoglegStep (dogleg_strategy.cc:199-255) ------------------------------------
-            const double g_norm = sqrt(dot2(ws.gr_p, ws.gr_l, ws.gr_p, ws.gr_l, NP, nl, sh_red));
-            const double gn_norm = sqrt(dot2(ws.gn_p, ws.gn_l, ws.gn_p, ws.gn_l, NP, nl, sh_red));
+            // In the dogleg coordinates (scaled by S and D): gradient g^ = gr, model Hessian M = D^-1 S H S D^-1, and the Gauss-Newton
+            // step satisfies (M + mu I) gn = -g^ exactly as solved above.
+            const double g_norm = sqrt(g2_lin);
+            const double gn2 = dot2(ws.gn_p, ws.gn_l, ws.gn_p, ws.gn_l, NP, nl, sh_red);
+            const double gngr = dot2(ws.gr_p, ws.gr_l, ws.gn_p, ws.gn_l, NP, nl, sh_red);
+            const double gn_norm = sqrt(gn2);
             double ca, cb;                                            // step = ca * gradient_ + cb * gauss_newton_step_
             if (gn_norm <= radius) { ca = 0; cb = 1; dogleg_norm = gn_norm; }
             else if (g_norm * alpha >= radius) { ca = -(radius / g_norm); cb = 0; dogleg_norm = radius; }
             else {
-                const double b_dot_a = -alpha * dot2(ws.gr_p, ws.gr_l, ws.gn_p, ws.gn_l, NP, nl, sh_red);
+                const double b_dot_a = -alpha * gngr;
                 const double a2 = (alpha * g_norm) * (alpha * g_norm);
                 const double bma2 = a2 - 2 * b_dot_a + gn_norm * gn_norm;
                 const double c = b_dot_a - a2;
@@ -920,18 +931,23 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem,
                 ca = -alpha * (1.0 - beta); cb = beta;
                 dogleg_norm = -1.0;
             }
-            for (int i = tid; i < NP; i += T) ws.st_p[i] = ca * ws.gr_p[i] + cb * ws.gn_p[i];
-            for (int l = tid; l < nl; l += T) ws.st_l[l] = ca * ws.gr_l[l] + cb * ws.gn_l[l];
+            for (int i = tid; i < NP; i += T) {
+                const double st = ca * ws.gr_p[i] + cb * ws.gn_p[i];
+                ws.st_p[i] = st;
+                ws.u_p[i] = st / ws.d_p[i] * ws.sc_p[i];              // trust_region_step_ = dogleg ./ diagonal ; delta = .* jacobian_scaling_
+            }
+            for (int l = tid; l < nl; l += T) {
+                const double st = ca * ws.gr_l[l] + cb * ws.gn_l[l];
+                ws.st_l[l] = st;
+                ws.u_l[l] = st / ws.d_l[l] * ws.sc_l[l];
+            }
             __syncthreads();
             if (dogleg_norm < 0) dogleg_norm = sqrt(dot2(ws.st_p, ws.st_l, ws.st_p, ws.st_l, NP, nl, sh_red));
-            // trust_region_step_ = dogleg ./ diagonal ;  delta = trust_region_step_ .* jacobian_scaling_
-            for (int i = tid; i < NP; i += T) ws.u_p[i] = ws.st_p[i] / ws.d_p[i] * ws.sc_p[i];
-            for (int l = tid; l < nl; l += T) ws.u_l[l] = ws.st_l[l] / ws.d_l[l] * ws.sc_l[l];
-            __syncthreads();
-            // model_cost_change = -(J d)^T (r + J d / 2) = -(d^T g + d^T H d / 2)
-            const double dg = dot2(ws.u_p, ws.u_l, ws.g, ws.gl, NP, nl, sh_red);
-            const double dHd = quad_form(s, ws, nl, ws.u_p, ws.u_l, sh_red);
-            model_change = -(dg + 0.5 * dHd);
+            // model_cost_change = -(J d)^T (r + J d / 2) = -(d^.g^ + d^^T M d^ / 2), with M gn = -g^ - mu gn and g^T M g^ from the
+            // Cauchy-point computation: no pass over H
+            const double dg = ca * g2_lin + cb * gngr;
+            const double dMd = ca * ca * gHg_lin + 2.0 * ca * cb * (-g2_lin - mu_gn * gngr) + cb * cb * (-gngr - mu_gn * gn2);
+            model_change = -(dg + 0.5 * dMd);
             valid = model_change > 0.0;
             BE_PROF(4);
         }

@@ -185,6 +185,7 @@ struct SelectSmem {
     int cell_cnt[2048];
     short cell_pt[2048][4][2];
     int hist[SEL_BINS];
+    int csum[SEL_BINS / 32];               // sums of 32 consecutive histogram bins (band search skips whole chunks)
     int n_sorted, n_new, taken, band_lo, band_hi, band_err;
     short newxy[VIO_MAXP][2];
 };
@@ -220,12 +221,16 @@ __global__ void __launch_bounds__(256) select_kernel(TrackArrays A, int maxp, in
         }
         __syncthreads();
         if (tid == 0) s.band_hi = SEL_BINS;                        // exclusive upper bin of the next band
+        { int c = 0; for (int q = 0; q < 32; q++) c += s.hist[tid * 32 + ((q + tid) & 31)]; s.csum[tid] = c; }       // 256 threads x 32 bins = SEL_BINS
         __syncthreads();
         const int md2 = min_dist * min_dist;
         while (true) {
             if (tid == 0) {
                 int lo = s.band_hi, cnt = 0;
-                while (lo > 0 && (cnt + s.hist[lo - 1] <= SORT_CAP || lo == s.band_hi)) { cnt += s.hist[lo - 1]; lo--; }
+                while (lo > 0) {
+                    if ((lo & 31) == 0 && cnt + s.csum[(lo >> 5) - 1] <= SORT_CAP) { cnt += s.csum[(lo >> 5) - 1]; lo -= 32; continue; }
+                    if (cnt + s.hist[lo - 1] <= SORT_CAP || lo == s.band_hi) { cnt += s.hist[lo - 1]; lo--; } else break;
+                }
                 if (cnt > SORT_CAP) { s.band_err = 1; cnt = 0; lo = 0; }      // > SORT_CAP keys inside one 2^-10-relative value bin
                 s.band_lo = lo; s.n_sorted = 0;
             }

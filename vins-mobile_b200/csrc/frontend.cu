@@ -25,6 +25,13 @@ struct vio_frontend {
     int64_t launches;
     int *err_flag_dev;
     std::vector<void *> allocs;
+    // host-image path: uploads go through a double-buffered staging area on their own stream so that the copy of frame k+1 overlaps
+    // the kernels of frame k (allocated on first use)
+    cudaStream_t up_stream;
+    uint8_t *stage[2];
+    cudaEvent_t ev_up[2], ev_free[2];
+    int up_idx;
+    bool stage_used[2];
 };
 
 template <typename T>
@@ -107,6 +114,11 @@ extern "C" void vio_frontend_destroy(vio_frontend *fe) {
     if (!fe) return;
     cudaSetDevice(fe->cfg.device);
     cudaStreamSynchronize(fe->stream);
+    if (fe->up_stream) {
+        cudaStreamSynchronize(fe->up_stream);
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(fe->ev_up[i]); cudaEventDestroy(fe->ev_free[i]); }
+        cudaStreamDestroy(fe->up_stream);
+    }
     for (void *p : fe->allocs) cudaFree(p);
     if (fe->own_stream) cudaStreamDestroy(fe->stream);
     delete fe;
@@ -159,7 +171,25 @@ extern "C" uint8_t *vio_frontend_next_image_buffer(vio_frontend *fe) { return fe
 extern "C" int vio_frontend_read_images(vio_frontend *fe, const uint8_t *images_host, int *published) {
     if (!fe || !images_host) return VIO_ERR_ARG;
     VIO_CUDA_TRY(cudaSetDevice(fe->cfg.device));
-    VIO_CUDA_TRY(cudaMemcpyAsync(fe->pyr[fe->cur ^ 1][0], images_host, (size_t)fe->B * fe->lsz[0], cudaMemcpyHostToDevice, fe->stream));
+    const size_t bytes = (size_t)fe->B * fe->lsz[0];
+    if (!fe->up_stream) {
+        VIO_CUDA_TRY(cudaStreamCreateWithFlags(&fe->up_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            VIO_CUDA_TRY(cudaMalloc((void **)&fe->stage[i], bytes));
+            fe->allocs.push_back(fe->stage[i]);
+            VIO_CUDA_TRY(cudaEventCreateWithFlags(&fe->ev_up[i], cudaEventDisableTiming));
+            VIO_CUDA_TRY(cudaEventCreateWithFlags(&fe->ev_free[i], cudaEventDisableTiming));
+        }
+    }
+    const int i = fe->up_idx;
+    fe->up_idx ^= 1;
+    if (fe->stage_used[i]) VIO_CUDA_TRY(cudaStreamWaitEvent(fe->up_stream, fe->ev_free[i], 0));
+    VIO_CUDA_TRY(cudaMemcpyAsync(fe->stage[i], images_host, bytes, cudaMemcpyHostToDevice, fe->up_stream));
+    VIO_CUDA_TRY(cudaEventRecord(fe->ev_up[i], fe->up_stream));
+    VIO_CUDA_TRY(cudaStreamWaitEvent(fe->stream, fe->ev_up[i], 0));
+    VIO_CUDA_TRY(cudaMemcpyAsync(fe->pyr[fe->cur ^ 1][0], fe->stage[i], bytes, cudaMemcpyDeviceToDevice, fe->stream));
+    VIO_CUDA_TRY(cudaEventRecord(fe->ev_free[i], fe->stream));
+    fe->stage_used[i] = true;
     return run_frame(fe, published);
 }
 
