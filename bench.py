@@ -207,18 +207,23 @@ def run_ours(args):
             barrier()
             l0 = pipe.fe.launch_count() + pipe.be.launch_count()
             clocks = Clocks(local)
-            if rank == 0:
+            if rank == 0 and not os.environ.get("VIO_BENCH_NO_CLOCKS"):
                 clocks.start()
+            trace = [] if os.environ.get("VIO_BENCH_TRACE") else None
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             stream_b.wait_stream(stream)
             for i in range(prologue + args.warmup, prologue + args.warmup + args.steps):
                 one(i)
+                if trace is not None:
+                    trace.append(time.perf_counter())
             stream.wait_stream(stream_b)
             e1.record(stream)
             barrier()
             clocks.stop_flag = True
             ms = e0.elapsed_time(e1)
+            if trace:
+                print("host ms per step (host_inputs=%s): " % host_inputs + " ".join(f"{(b - a) * 1e3:.2f}" for a, b in zip(trace, trace[1:])), file=sys.stderr)
             launches = pipe.fe.launch_count() + pipe.be.launch_count() - l0
             # per-kernel CUDA-event pass (separate, untimed): 2 more keyframe periods
             pipe.fe.profile(True); pipe.be.profile(True); pipe.be.phase_cycles(True)

@@ -93,7 +93,8 @@ uint8_t *vio_frontend_next_image_buffer(vio_frontend *fe);
  * Any output pointer may be NULL.  Arrays must hold max_cnt entries. */
 int vio_frontend_get_stream(vio_frontend *fe, int s, int *n_out, int32_t *ids, float *pts_xy,
                             int32_t *track_cnt, double *norm_xyz);
-/* readImage's UI outputs good_pts / track_len (feature_tracker.cpp:209-226,237-250,276-280). */
+/* readImage's UI outputs good_pts / track_len (feature_tracker.cpp:209-226,237-250,276-280).  On a detecting frame the
+ * reference lists every point tracked BEFORE setMask plus the new corners, so the arrays must hold 2 * max_cnt entries. */
 int vio_frontend_get_ui(vio_frontend *fe, int s, int *n_out, float *good_pts_xy, double *track_len);
 /* Stage counters of the last call for stream s: [0] lk_in [1] lk_ok [2] f1_ok [3] f2_ok [4] kept [5] new [6] n_candidates [7] ransac iters */
 int vio_frontend_get_stats(vio_frontend *fe, int s, int32_t stats[8]);

@@ -59,3 +59,69 @@ def test_images_to_window_state(api, abi, synth, get_stream):
     assert be.info(0)["solver_flag"] == 1 and ref.info()["solver_flag"] == 1
     for h in (fe, be, fe2, be2):
         h.close()
+
+
+def _run_batched(api, abi, synth, B, n_frames, host_inputs, two_streams, data):
+    """Drives bench.Pipeline (the code path bench.py times) and returns per-stream summaries."""
+    import bench
+    import torch
+    frames, dt, acc, gyr, gt, _ = data
+    cfg = abi.default_config(batch=B, max_cnt=150, window_size=10, device=0)
+    f = frames[:, :B].contiguous()
+    imu_np = tuple(np.ascontiguousarray(x) for x in (dt[:, :, :B], acc[:, :, :B], gyr[:, :, :B]))
+    imu_d = tuple(torch.as_tensor(x, device="cuda:0") for x in imu_np)
+    imu_p = tuple(torch.as_tensor(x).pin_memory().numpy() for x in imu_np)
+    src = f.cpu().pin_memory().numpy() if host_inputs else None
+    s_fe = torch.cuda.Stream()
+    s_be = torch.cuda.Stream() if two_streams else s_fe
+    pipe = bench.Pipeline(api, cfg, s_fe.cuda_stream, s_be.cuda_stream, gt[:B], host_inputs)
+    with torch.cuda.stream(s_fe):
+        for i in range(n_frames):
+            if host_inputs:
+                pipe.step(src[i], lambda k: tuple(x[k] for x in imu_p))
+            else:
+                pipe.step(f[i].data_ptr(), lambda k: tuple(x[k].data_ptr() for x in imu_d))
+        torch.cuda.synchronize()
+    out = []
+    for b in range(B):
+        g, info, feat = pipe.fe.stream(b), pipe.be.info(b), pipe.be.features(b)
+        out.append(dict(ids=g["ids"].copy(), pts=g["pts"].copy(), info=info, feat=feat, state=pipe.be.state(b)))
+    pipe.close()
+    return out
+
+
+def test_batch_invariance_and_repeatability(api, abi, synth):
+    """A stream's result must not depend on the batch it runs in, on the input path (device / pinned host), on how many CUDA streams
+    the pipeline uses, or on a previous pipeline having lived in the same process.  Regression test for three round-1 bugs: the UI
+    arrays overflowing into the next stream's slice, zero-fills racing the first kernels, a barrier missing in the QL eigen-solver."""
+    import bench
+    n_frames = 48                                     # window fill + 5 solves with marginalisation
+    data = bench.make_data(synth, 24, n_frames + 3, 0, "cuda:0")
+    ref = _run_batched(api, abi, synth, 2, n_frames, False, False, data)
+    for (B, host, two) in ((24, False, True), (24, True, True), (24, False, False), (2, True, True)):
+        got = _run_batched(api, abi, synth, B, n_frames, host, two, data)
+        for b in range(2):
+            tag = f"B={B} host={host} two_streams={two} stream {b}"
+            assert np.array_equal(got[b]["ids"], ref[b]["ids"]) and np.array_equal(got[b]["pts"].view(np.uint32), ref[b]["pts"].view(np.uint32)), tag
+            for k in ("ids", "start", "n_obs"):
+                assert np.array_equal(got[b]["feat"][k], ref[b]["feat"][k]), f"{tag}: feature table {k}"
+            gi, ri = got[b]["info"], ref[b]["info"]
+            assert gi["n_proj"] == ri["n_proj"] and gi["iters"] == ri["iters"] and gi["failure"] == 0, tag
+            assert np.isfinite(gi["cost0"]) and abs(gi["cost0"] - ri["cost0"]) <= 1e-6 * abs(ri["cost0"]), f"{tag}: cost {gi['cost0']} vs {ri['cost0']}"
+            for k in ("P", "V"):
+                assert rel_err(got[b]["state"][k], ref[b]["state"][k]) < 1e-6, f"{tag}: {k}"
+
+
+def test_no_out_of_bounds_device_writes():
+    """Debug library (guard bands around every device array, built by __graft_entry__.build()): the batched pipeline must not write
+    outside any of its arrays.  compute-sanitizer cannot see a write that lands inside a neighbouring allocation; the bands can."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "vins-mobile_b200", "libvio_b200_dbg.so")):
+        pytest.skip("debug library not built")
+    env = dict(os.environ, VIO_LIB_NAME="libvio_b200_dbg.so")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "guard_check.py"), "32", "45", "two"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "final: corrupted guard bands = 0" in r.stdout, (r.stdout + r.stderr)[-3000:]

@@ -12,7 +12,7 @@ from . import abi
 from .abi import DP, FP, IP, UP, VioConfig, ptr
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvio_b200.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("VIO_LIB_NAME", "libvio_b200.so"))      # VIO_LIB_NAME: debug builds (tools/)
 _lib = None
 
 
@@ -152,7 +152,7 @@ class FrontEnd:
 
     def ui(self, s: int):
         n = C.c_int(0)
-        g = np.zeros((self.maxp, 2), np.float32); t = np.zeros(self.maxp)
+        g = np.zeros((2 * self.maxp, 2), np.float32); t = np.zeros(2 * self.maxp)
         _check(lib().vio_frontend_get_ui(self.h, s, C.byref(n), ptr(g, C.c_float), ptr(t, C.c_double)), "vio_frontend_get_ui")
         return g[:n.value], t[:n.value]
 

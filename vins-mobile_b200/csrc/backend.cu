@@ -33,9 +33,7 @@ struct vio_backend {
 
 template <typename T>
 static int dalloc(vio_backend *be, T **p, size_t n) {
-    VIO_CUDA_TRY(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
-    VIO_CUDA_TRY(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
-    be->allocs.push_back(*p);
+    VIO_CUDA_TRY(vio_dev_alloc((void **)p, n * sizeof(T), be->allocs));
     return VIO_OK;
 }
 
@@ -60,8 +58,9 @@ extern "C" int vio_backend_clear(vio_backend *be) {
     double h[12];
     memcpy(h, be->cfg.tic, sizeof(double) * 3);
     memcpy(h + 3, be->cfg.ric, sizeof(double) * 9);
-    VIO_CUDA_TRY(cudaMemcpyAsync(be->d_xyz, h, sizeof(h), cudaMemcpyHostToDevice, be->stream));
-    init_state_kernel<<<be->s.B, 128, 0, be->stream>>>(be->s, be->d_xyz, be->d_xyz + 3);
+    double *ext = be->d_xyz + (size_t)be->s.B * be->cfg.max_cnt * 3;          // 16 spare doubles behind the image_msg copy
+    VIO_CUDA_TRY(cudaMemcpyAsync(ext, h, sizeof(h), cudaMemcpyHostToDevice, be->stream));
+    init_state_kernel<<<be->s.B, 128, 0, be->stream>>>(be->s, ext, ext + 3);
     be->launches++;
     VIO_CUDA_TRY(cudaGetLastError());
     return VIO_OK;
@@ -72,6 +71,7 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
         cfg->num_of_f < 1 || cfg->max_imu_per_frame < 1)
         return VIO_ERR_ARG;
     VIO_CUDA_TRY(cudaSetDevice(cfg->device));
+    vio_poison_load_mask();
     vio_backend *be = new (std::nothrow) vio_backend();
     if (!be) return VIO_ERR_ARG;
     be->cfg = *cfg; be->launches = 0; be->own_stream = true; be->consumed_valid = false; be->record_consumed = false;
@@ -156,6 +156,9 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     VIO_CUDA_TRY(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->solve_smem));
     be->marg_smem = sizeof(MargSmem) + 16 + (size_t)2 * MARG_NCAP * MARG_NCAP * sizeof(double);
     VIO_CUDA_TRY(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->marg_smem));
+    // dalloc() zero-fills with cudaMemset on the legacy default stream, which does not order against this handle's non-blocking
+    // stream (nor against a caller's non-blocking stream given to vio_backend_use_stream): finish the fills before any kernel
+    VIO_CUDA_TRY(cudaDeviceSynchronize());
     rc = vio_backend_clear(be);
     if (rc) { vio_backend_destroy(be); return rc; }
     VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));

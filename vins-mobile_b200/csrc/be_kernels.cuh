@@ -47,6 +47,7 @@ __device__ inline double block_sum_d(double v, double *smem /*>=32*/) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) imu_kernel(BeState s, int n_samples, const double *__restrict__ dts, const double *__restrict__ accs,
                                                   const double *__restrict__ gyrs) {
+    VIO_POISON(1u);
     __shared__ PreScratch scr[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + warp;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(128) imu_kernel(BeState s, int n_samples, cons
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) addfeat_kernel(BeState s, const int *__restrict__ counts, const int *__restrict__ ids,
                                                       const double *__restrict__ xyz, const double *__restrict__ headers) {
+    VIO_POISON(2u);
     __shared__ int sh_new[VIO_MAXP];
     __shared__ int sh_scan[33];
     __shared__ double sh_d[32];
@@ -203,6 +205,7 @@ __device__ inline void smallest_right_sv4(double *A, int rows, double out[4]) {
 }
 
 __global__ void __launch_bounds__(128) triangulate_kernel(BeState s) {
+    VIO_POISON(4u);
     const int b = blockIdx.x, tid = threadIdx.x;
     int *iv = S_iv(s, b);
     const int act = iv[IV_ACTION];
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__(128) triangulate_kernel(BeState s) {
 // ---------------------------------------------------------------------------------------------------------
 // old2new() + enumeration of landmarks / projection factors in f_manager order + per-interval sqrt_info
 __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
+    VIO_POISON(8u);
     __shared__ int sh_scan[33];
     const int b = blockIdx.x, tid = threadIdx.x;
     int *iv = S_iv(s, b);
@@ -363,6 +367,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
 // ---------------------------------------------------------------------------------------------------------
 // new2old(): unpack + yaw / P0 re-anchoring (VINS.cpp:131-171), setDepth() flags (feature_manager.cpp:331-349)
 __global__ void __launch_bounds__(256) post_solve_kernel(BeState s) {
+    VIO_POISON(16u);
     const int b = blockIdx.x, tid = threadIdx.x;
     int *iv = S_iv(s, b);
     const int act = iv[IV_ACTION];
@@ -444,6 +449,7 @@ __device__ inline void clear_state_cta(const BeState &s, int b) {      // VINS::
 }
 
 __global__ void __launch_bounds__(256) finish_kernel(BeState s) {
+    VIO_POISON(32u);
     __shared__ int sh_scan[33];
     __shared__ int sh_total, sh_fail;
     __shared__ PreScratch scr;

@@ -212,6 +212,7 @@ __device__ inline int eig_sym_ql(double *A, int n, int ld, double *V, double *de
             }
             __syncthreads();
             const int m = sh_i[0], first = sh_i[1];
+            __syncthreads();                                // every thread has read sh_i before thread 0 may overwrite it (next l / next step)
             if (m == l) break;
             steps++;
             for (int k = tid; k < n; k += T) {              // apply the rotation sequence to row k of V
@@ -272,6 +273,7 @@ struct MargSmem {
 };
 
 __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
+    VIO_POISON(64u);
     extern __shared__ __align__(16) unsigned char smraw[];
     MargSmem &sm = *reinterpret_cast<MargSmem *>(smraw);
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;

@@ -773,6 +773,7 @@ __host__ __device__ inline size_t solve_smem_bytes(int NP, int NPW) {
 }
 
 __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem, int vec_off) {
+    VIO_POISON(128u);
     extern __shared__ __align__(16) double sm_dyn[];
     const int T = blockDim.x;                              // 256 or 512 (VIO_BE_THREADS)
     __shared__ double sh_red[32];

@@ -16,6 +16,27 @@
         }                                                                                      \
     } while (0)
 
+// Debug build only (-DVIO_DEBUG_POISON, libvio_b200_dbg.so): fill the CTA's whole shared-memory window (static + dynamic) with a
+// NaN / -1 pattern at kernel entry so that a read of uninitialised shared memory shows up deterministically.  kernel_bit selects
+// the kernel in the VIO_POISON_MASK environment variable read at library load (tools/poison_check.py).
+#ifdef VIO_DEBUG_POISON
+static __device__ unsigned g_vio_poison_mask = 0;
+#include <stdlib.h>
+static inline void vio_poison_load_mask() { const char *e = getenv("VIO_POISON_MASK"); const unsigned m = e ? (unsigned)strtoul(e, nullptr, 0) : 0u; cudaMemcpyToSymbol(g_vio_poison_mask, &m, sizeof(m)); }
+__device__ __forceinline__ void vio_poison_smem(unsigned kernel_bit) {
+    if (!(g_vio_poison_mask & kernel_bit)) return;
+    unsigned n;
+    asm volatile("mov.u32 %0, %%total_smem_size;" : "=r"(n));
+    const unsigned nt = blockDim.x * blockDim.y * blockDim.z, t = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    for (unsigned i = t * 4; i + 4 <= n; i += nt * 4) asm volatile("st.shared.u32 [%0], %1;" :: "r"(i), "r"(0xFFFFFFFFu) : "memory");
+    __syncthreads();
+}
+#define VIO_POISON(bit) vio_poison_smem(bit)
+#else
+#define VIO_POISON(bit) do { } while (0)
+static inline void vio_poison_load_mask() {}
+#endif
+
 #define VIO_MAXP 512          // compile-time cap on max_cnt (points per stream)
 #define VIO_MAX_WIN 24        // compile-time cap on window_size
 
@@ -47,6 +68,30 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// ---- device allocation.  Debug build (-DVIO_DEBUG_POISON): every array gets a 256-byte guard band on both sides filled with 0xA5;
+// vio_debug_check_guards() (tools/guard_check.py) reports which array was written out of bounds, where and with what.
+#include <vector>
+struct VioAlloc { void *raw; void *user; size_t bytes; int idx; };
+#ifdef VIO_DEBUG_POISON
+constexpr size_t VIO_GUARD = 256;
+inline std::vector<VioAlloc> &vio_guard_registry() { static std::vector<VioAlloc> r; return r; }
+#else
+constexpr size_t VIO_GUARD = 0;
+#endif
+inline cudaError_t vio_dev_alloc(void **user, size_t bytes, std::vector<void *> &owner) {
+    bytes = bytes ? bytes : 1;
+    unsigned char *raw = nullptr;
+    cudaError_t e = cudaMalloc((void **)&raw, bytes + 2 * VIO_GUARD);
+    if (e != cudaSuccess) return e;
+    owner.push_back(raw);
+#ifdef VIO_DEBUG_POISON
+    cudaMemset(raw, 0xA5, bytes + 2 * VIO_GUARD);
+    vio_guard_registry().push_back({raw, raw + VIO_GUARD, bytes, (int)vio_guard_registry().size()});
+#endif
+    *user = raw + VIO_GUARD;
+    return cudaMemset(*user, 0, bytes);
 }
 
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench.py roofline leg) -----------------

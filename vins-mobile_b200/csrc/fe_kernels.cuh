@@ -121,6 +121,7 @@ __device__ __forceinline__ void lk_stage(uint8_t *dst, const uint8_t *__restrict
 __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevels J, const float2 *__restrict__ prev_pts,
                                                            float2 *__restrict__ next_pts, uint8_t *__restrict__ status,
                                                            const int *__restrict__ n_pts, int maxp) {
+    VIO_POISON(256u);
     // per warp: 24x24 template neighbourhood of I, 22x22 (stride 24) window of J, and the bilinear template (Iw, gx, gy) as int16.
     // Everything is shared-memory resident so that the per-pixel loops stay rolled (small code, few registers, 8 warps per CTA).
     __shared__ uint8_t sI[LK_WARPS][24 * 24];
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(256) eig_candidates_kernel(const uint8_t *__re
                                                              int cols, const int2 *__restrict__ kept, const int *__restrict__ n_kept,
                                                              int maxp, int min_dist, unsigned *__restrict__ max_bits,
                                                              unsigned long long *__restrict__ cand, int *__restrict__ cand_cnt) {
+    VIO_POISON(512u);
     __shared__ float sp[(ET + 6) * (ET + 6)];        // pixels as f32, origin (ty0-3, tx0-3)
     __shared__ float sdx[(ET + 4) * (ET + 4)];       // origin (ty0-2, tx0-2)
     __shared__ float sdy[(ET + 4) * (ET + 4)];

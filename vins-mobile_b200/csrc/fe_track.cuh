@@ -13,7 +13,7 @@ struct TrackArrays {
     int *ids, *track_cnt, *n;
     uint8_t *status;
     int2 *kept; int *n_kept;
-    float2 *good_pts; double *track_len; int *n_good;
+    float2 *good_pts; double *track_len; int *n_good;      // UI outputs, stride 2 * max_cnt per stream (tracked before setMask + new corners)
     int *stats;
     int *n_id;
     int *msg_cnt, *msg_ids; double *msg_xyz;
@@ -76,6 +76,7 @@ __device__ inline void parallax_update(TrackSmem &s, float2 *good, double *tl, d
 
 __global__ void __launch_bounds__(256) post_track_kernel(TrackArrays A, int maxp, int rows, int cols, int min_dist, double f_thresh,
                                                          int detect, int have_tracks) {
+    VIO_POISON(1024u);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TrackSmem &s = *reinterpret_cast<TrackSmem *>(smem_raw);
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256) post_track_kernel(TrackArrays A, int maxp
         }
         if (tid == 0) st[2] = s.n;
         if (!detect) {
-            parallax_update(s, A.good_pts + o, A.track_len + o, 30.0);
+            parallax_update(s, A.good_pts + 2 * o, A.track_len + 2 * o, 30.0);
             n_good = s.n;
         }
     }
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(256) post_track_kernel(TrackArrays A, int maxp
         }
         if (tid == 0) st[3] = s.n;
         __syncthreads();
-        parallax_update(s, A.good_pts + o, A.track_len + o, 50.0);
+        parallax_update(s, A.good_pts + 2 * o, A.track_len + 2 * o, 50.0);
         n_good = s.n;
         for (int i = tid; i < s.n; i += 256) s.cnt[i] += 1;   // for (auto &n : track_cnt) n++
         __syncthreads();
@@ -192,6 +193,7 @@ struct SelectSmem {
 
 __global__ void __launch_bounds__(256) select_kernel(TrackArrays A, int maxp, int rows, int cols, int max_cnt, int min_dist,
                                                      double fx, double fy, double cx, double cy) {
+    VIO_POISON(2048u);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SelectSmem &s = *reinterpret_cast<SelectSmem *>(smem_raw);
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(256) select_kernel(TrackArrays A, int maxp, in
         const float2 p = make_float2((float)s.newxy[i][0], (float)s.newxy[i][1]);
         const size_t d = o + n_kept + i;
         A.forw_pts[d] = p; A.pmin[d] = p; A.pmax[d] = p; A.track_cnt[d] = 1;
-        A.good_pts[o + A.n_good[b] + i] = p; A.track_len[o + A.n_good[b] + i] = 0.0;
+        A.good_pts[2 * o + A.n_good[b] + i] = p; A.track_len[2 * o + A.n_good[b] + i] = 0.0;   // n_good <= max_cnt, n_new <= max_cnt
     }
     __syncthreads();
     const int n = n_kept + n_new;

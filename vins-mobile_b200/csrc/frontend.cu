@@ -36,11 +36,33 @@ struct vio_frontend {
 
 template <typename T>
 static int dev_alloc(vio_frontend *fe, T **p, size_t n) {
-    VIO_CUDA_TRY(cudaMalloc((void **)p, n * sizeof(T)));
-    VIO_CUDA_TRY(cudaMemset(*p, 0, n * sizeof(T)));
-    fe->allocs.push_back(*p);
+    VIO_CUDA_TRY(vio_dev_alloc((void **)p, n * sizeof(T), fe->allocs));
     return VIO_OK;
 }
+
+#ifdef VIO_DEBUG_POISON
+// debug library only: scan the guard bands of every live device array; prints and returns the number of corrupted bands
+extern "C" int vio_debug_check_guards() {
+    cudaDeviceSynchronize();
+    int bad = 0;
+    std::vector<unsigned char> h(VIO_GUARD);
+    for (const VioAlloc &a : vio_guard_registry())
+        for (int side = 0; side < 2; side++) {
+            const unsigned char *g = side ? (unsigned char *)a.user + a.bytes : (unsigned char *)a.raw;
+            if (cudaMemcpy(h.data(), g, VIO_GUARD, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); continue; }   // freed
+            for (size_t i = 0; i < VIO_GUARD; i++)
+                if (h[i] != 0xA5) {
+                    bad++;
+                    fprintf(stderr, "[guard] alloc #%d (%zu bytes) %s band: first bad byte at offset %zd, bytes:", a.idx, a.bytes, side ? "upper" : "lower",
+                            side ? (ssize_t)i : (ssize_t)i - (ssize_t)VIO_GUARD);
+                    for (size_t j = i; j < i + 16 && j < VIO_GUARD; j++) fprintf(stderr, " %02x", h[j]);
+                    fprintf(stderr, "\n");
+                    break;
+                }
+        }
+    return bad;
+}
+#endif
 
 extern "C" void vio_config_default(vio_config *c) {
     memset(c, 0, sizeof(*c));
@@ -64,6 +86,7 @@ extern "C" int vio_frontend_create(const vio_config *cfg, vio_frontend **out) {
     const int gw = (cfg->cols + cfg->min_dist - 1) / cfg->min_dist, gh = (cfg->rows + cfg->min_dist - 1) / cfg->min_dist;
     if (gw * gh > 2048) return VIO_ERR_ARG;
     VIO_CUDA_TRY(cudaSetDevice(cfg->device));
+    vio_poison_load_mask();
     vio_frontend *fe = new (std::nothrow) vio_frontend();
     if (!fe) return VIO_ERR_ARG;
     fe->cfg = *cfg; fe->B = cfg->batch; fe->maxp = cfg->max_cnt;
@@ -90,8 +113,8 @@ extern "C" int vio_frontend_create(const vio_config *cfg, vio_frontend **out) {
     if (!rc) rc = dev_alloc(fe, &A.status, B * P);
     if (!rc) rc = dev_alloc(fe, &A.kept, B * P);
     if (!rc) rc = dev_alloc(fe, &A.n_kept, B);
-    if (!rc) rc = dev_alloc(fe, &A.good_pts, B * P);
-    if (!rc) rc = dev_alloc(fe, &A.track_len, B * P);
+    if (!rc) rc = dev_alloc(fe, &A.good_pts, 2 * B * P);
+    if (!rc) rc = dev_alloc(fe, &A.track_len, 2 * B * P);
     if (!rc) rc = dev_alloc(fe, &A.n_good, B);
     if (!rc) rc = dev_alloc(fe, &A.stats, B * 8);
     if (!rc) rc = dev_alloc(fe, &A.n_id, B);
@@ -104,6 +127,7 @@ extern "C" int vio_frontend_create(const vio_config *cfg, vio_frontend **out) {
     if (!rc) rc = dev_alloc(fe, &fe->err_flag_dev, 1);
     A.err_flag = fe->err_flag_dev;
     if (rc) { vio_frontend_destroy(fe); return rc; }
+    VIO_CUDA_TRY(cudaDeviceSynchronize());       // dev_alloc() zero-fills on the legacy default stream; fe->stream is non-blocking
     VIO_CUDA_TRY(cudaFuncSetAttribute(post_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrackSmem)));
     VIO_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectSmem)));
     *out = fe;
@@ -238,7 +262,7 @@ extern "C" int vio_frontend_get_ui(vio_frontend *fe, int s, int *n_out, float *g
     int n = 0;
     VIO_CUDA_TRY(cudaMemcpyAsync(&n, fe->A.n_good + s, sizeof(int), cudaMemcpyDeviceToHost, fe->stream));
     VIO_CUDA_TRY(cudaStreamSynchronize(fe->stream));
-    const size_t o = (size_t)s * fe->maxp;
+    const size_t o = (size_t)s * 2 * fe->maxp;
     int rc = d2h(fe, (float2 *)good_pts_xy, fe->A.good_pts + o, n);
     if (!rc) rc = d2h(fe, track_len, fe->A.track_len + o, n);
     if (rc) return rc;

@@ -50,8 +50,8 @@ class FeatureTracker {
         check(vio_frontend_read_images(h_, _img.data, &published), "vio_frontend_read_images");
         const int cap = cfg_.max_cnt;
         int n = 0;
-        std::vector<float> g(2 * cap);
-        std::vector<double> tl(cap);
+        std::vector<float> g(4 * cap);                 // good_pts: up to 2 * max_cnt points (tracked before setMask + new corners)
+        std::vector<double> tl(2 * cap);
         check(vio_frontend_get_ui(h_, 0, &n, g.data(), tl.data()), "vio_frontend_get_ui");
         for (int i = 0; i < n; i++) { good_pts.push_back(Point2f{g[2 * i], g[2 * i + 1]}); track_len.push_back(tl[i]); }
         std::vector<int32_t> id(cap), cnt(cap);
