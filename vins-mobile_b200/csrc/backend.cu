@@ -150,6 +150,12 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     be->solve_smem = solve_smem_bytes(s.NP, s.NPW);
     if (be->solve_smem > 200 * 1024 || schur_ntile(s.NPW) > be->be_threads) be->solve_smem = 0;
     be->use_smem_solve = be->solve_smem > 0;
+    // reduced system in registers as DMMA tiles (be_tilechol.cuh) when it fits 16 warps x 16 tiles; VIO_SOLVE_TILES=0 keeps the packed path
+    { const char *e = getenv("VIO_SOLVE_TILES");
+      if (be->use_smem_solve && !(e && e[0] == '0') && tile_path_fits(s.NF, be->be_threads)) {
+          be->use_smem_solve = 2;
+          be->solve_smem = std::max(be->solve_smem, tile_smem_doubles(s.NF) * sizeof(double));
+      } }
     be->solve_smem = std::max(be->solve_smem, eval_smem_bytes(s.W));
     be->solve_vec_off = (int)((be->solve_smem / sizeof(double) + 3) & ~(size_t)3);
     be->solve_smem = (be->solve_vec_off + solve_vec_doubles(s.NP, s.NPX)) * sizeof(double);

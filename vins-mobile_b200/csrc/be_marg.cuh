@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
         }
         for (int i = 0; i < 2 * NF + 1; i++) pres[i] = np[i];
         iv[IV_PRIOR_VALID] = 1; iv[IV_PRIOR_N] = n;
-        { const long long _t = clock64(); _pp[13] += _t - _pt0; }
+        BE_PROF_ONLY({ const long long _t = clock64(); _pp[13] += _t - _pt0; })
         dvs[DV_PRIOR_C0] = c0;
     }
 }

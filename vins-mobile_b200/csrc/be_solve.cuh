@@ -238,8 +238,8 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
             stm(o, AR * ric); st3(o + 9, ricT * (RR * tic + d - tic)); stm(o + 12, AR); stm(o + 21, RR); st3(o + 30, d);
         }
         __syncthreads();
-        long long *pq2 = pp; long long _qt1 = clock64();
-        if (lin && tid == 0) { pq2[27] += _qt1 - _qt0; }
+        BE_PROF_ONLY(long long *pq2 = pp; long long _qt1 = clock64();
+                     if (lin && tid == 0) { pq2[27] += _qt1 - _qt0; })
         const int *fs = s.fac_sorted + (size_t)b * s.PCAP, *po = s.pair_off + (size_t)b * (NF * NF + 1);
         const double *fobs = s.fac_obs + (size_t)b * s.PCAP * 4;
         const double *lam_p = par + 16 * NF;
@@ -316,7 +316,7 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
             }
             if (!lin) continue;
             __syncthreads();
-            if (tid == 0) { const long long t = clock64(); pq2[28] += t - _qt1; _qt1 = t; }
+            BE_PROF_ONLY(if (tid == 0) { const long long t = clock64(); pq2[28] += t - _qt1; _qt1 = t; })
             // H-phase on the FP64 tensor pipe: per frame pair, [Jj^T Ji | Jj^T r], Jj^T Jj and [Ji^T Ji | Ji^T r] are 8x8 (6x7 used)
             // products with the pair's 2 m residual rows as the inner dimension -- one m8n8k4 DMMA per block and two factors.
             // A fragment: lane (g = lane >> 2, k = lane & 3) holds element [dof g][row k]; the B fragment [row k][col g] is the
@@ -352,7 +352,7 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
                 }
             }
             __syncthreads();
-            if (tid == 0) { const long long t = clock64(); pq2[29] += t - _qt1; _qt1 = t; }
+            BE_PROF_ONLY(if (tid == 0) { const long long t = clock64(); pq2[29] += t - _qt1; _qt1 = t; })
         }
         if (lin && hold) proj_flush(ws, NP, NF, npair, nwarp, warp, lane, 0, hacc);
         if (lin) {
@@ -762,6 +762,10 @@ __device__ __noinline__ void build_reduced_smem(const BeState &s, const SolveWs 
     __syncthreads();
 }
 
+}  // namespace be
+#include "be_tilechol.cuh"
+namespace be {
+
 // shared scratch evaluate() needs: IMU J buffers, then (aliased) frame / pair tables + the J store of one chunk of SOLVE_T factors
 __host__ __device__ inline size_t eval_smem_bytes(int W) {
     const size_t NF = W + 1, npair = NF * (NF - 1) / 2;
@@ -841,7 +845,11 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem,
             linear_ok = false;
             while (mu < 1.0) {
               bool ok;
-              if (use_smem) {
+              if (use_smem == 2) {
+                ok = tile_reduced_solve(s, ws.H, ws.g, ws.w, ws.hll, ws.gl, ws.sc_p, ws.sc_l, ws.d_p, ws.d_l, ws.u_l, nl, mu, ws.y, sm_dyn, &sh_flag,
+                                        s.prof + (size_t)b * 32);
+                BE_PROF(3);
+              } else if (use_smem) {
                 double *Ssm = sm_dyn, *wt = sm_dyn + ((((size_t)(NP + 1) * (NP + 2) / 2 + 8) + 1) & ~(size_t)1);   // 16-byte aligned
                 build_reduced_smem(s, ws, nl, mu, Ssm, wt);
                 BE_PROF(2);

@@ -62,11 +62,21 @@ __device__ __forceinline__ double *S_obs(const BeState &s, int b, int slot) { re
 __device__ __forceinline__ double *S_par_pose(const BeState &s, double *par, int i) { return par + 16 * i; }
 __device__ __forceinline__ double *S_par_sb(const BeState &s, double *par, int i) { return par + 16 * i + 7; }
 
-// phase timer: thread 0 accumulates the cycles since the previous mark into prof[b][slot]
+// phase timer: thread 0 accumulates the cycles since the previous mark into prof[b][slot].  Compiled in only with -DVIO_BE_PROFILE
+// (the debug library): every mark is a global read-modify-write on the CTA's critical path (~0.6 us each), dozens per solve.
+#ifdef VIO_BE_PROFILE
 #define BE_PROF_INIT long long _pt0 = clock64(); long long *_pp = s.prof + (size_t)blockIdx.x * 32
 #define BE_PROF2_INIT long long _qt0 = clock64()
 #define BE_PROF2(pp, slot) do { if (threadIdx.x == 0) { const long long _t = clock64(); (pp)[slot] += _t - _qt0; _qt0 = _t; } } while (0)
 #define BE_PROF(slot) do { if (threadIdx.x == 0) { const long long _t = clock64(); _pp[slot] += _t - _pt0; _pt0 = _t; } } while (0)
+#define BE_PROF_ONLY(...) __VA_ARGS__
+#else
+#define BE_PROF_INIT do { } while (0)
+#define BE_PROF2_INIT do { } while (0)
+#define BE_PROF2(pp, slot) do { (void)(pp); } while (0)
+#define BE_PROF(slot) do { } while (0)
+#define BE_PROF_ONLY(...)
+#endif
 
 // the predicate repeated throughout the reference: used_num >= 2 && start_frame < WINDOW_SIZE - 2
 __device__ __forceinline__ bool in_solve(const BeState &s, int nobs, int start) { return nobs >= 2 && start < s.W - 2; }
