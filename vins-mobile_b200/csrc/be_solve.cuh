@@ -115,14 +115,18 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
     const int NP = s.NP, NPW = s.NPW, nl = iv[IV_N_LM], nfac = iv[IV_N_FAC];
     double cost = 0.0;
     const int has_prior = iv[IV_PRIOR_VALID];
+    const int *pres = s.present + (size_t)b * (2 * s.NF + 1);
     if (lin) {
         // H (lower triangle; the upper one is never read) starts as the prior's J0^T J0 over the pose / speed-bias part of the
-        // canonical layout, or zero.  One warp per row: coalesced, no index arithmetic.
+        // canonical layout, or zero.  One warp per row: coalesced, no index arithmetic.  Rows of blocks the prior does not contain
+        // are zero in Hp (marg_kernel writes them so) and are not read.
         const double *Hp = s.Hp + (size_t)b * s.NPX * s.NPX;
         for (int i = warp; i < NP; i += nwarp) {
             double *row = ws.H + (size_t)i * NP;
             const double *src = Hp + (size_t)i * s.NPX;
-            for (int j = lane; j <= i; j += 32) row[j] = has_prior ? src[j] : 0.0;
+            const int fi = i / 15;
+            const bool rp = has_prior && pres[2 * fi + ((i - 15 * fi) >= 6)];
+            for (int j = lane; j <= i; j += 32) row[j] = rp ? src[j] : 0.0;
         }
         for (int i = tid; i < NP; i += blockDim.x) ws.g[i] = 0.0;
         // w_l rows: the entries of observing frames are rewritten by every linearisation and the others stay zero for the whole solve
@@ -133,38 +137,52 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
         const int NPX = s.NPX, T = blockDim.x;
         const double *Hp = s.Hp + (size_t)b * NPX * NPX, *bp = s.bp + (size_t)b * NPX;
         prior_dx(s, b, par, ws.dx);
+        // t = Hp dx over the dofs the prior contains (typically all poses + the first speed-bias block: 75 of 171): compact list cl[],
+        // rows split over P thread groups (Hp symmetric: thread ii of a group walks the column of its dof, neighbouring threads read
+        // neighbouring addresses); the loads of a thread are issued eight at a time so that the L2 latency is paid once per eight rows
+        double *part_sum = smem_scratch;                                   // [P][nc]
+        double *dxc = smem_scratch + 4 * NPX;                              // [nc] dx of the listed dofs
+        int *cl = reinterpret_cast<int *>(dxc + NPX);                      // [nc] canonical dof
+        int *ncp = cl + NPX;
+        if (tid == 0) *ncp = 0;
         __syncthreads();
-        // t = Hp dx: the rows are split over P thread groups (Hp symmetric: thread i of a group walks column i, coalesced)
-        // dx is staged in shared memory (after the P partial-sum rows); the Hp loads of a thread are issued eight at a time so that
-        // the L2 latency is paid once per eight rows
-        const int P = max(1, T / NPX), part = tid / NPX;
-        const int rows = (NPX + P - 1) / P;
-        double *dxs = smem_scratch + P * NPX;
-        for (int j = tid; j < NPX; j += T) dxs[j] = ws.dx[j];
-        __syncthreads();
-        if (part < P) {
-            const int j0 = part * rows, j1 = min(NPX, (part + 1) * rows);
-            for (int i = tid - part * NPX; i < NPX; i += (P == 1 ? T : NPX)) {
-                double t = 0;
-                const double *col = Hp + i;
-                int j = j0;
-                for (; j + 8 <= j1; j += 8) {
-                    double h[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) h[q] = __ldg(col + (size_t)(j + q) * NPX);
-#pragma unroll
-                    for (int q = 0; q < 8; q++) t += h[q] * dxs[j + q];
-                }
-                for (; j < j1; j++) t += __ldg(col + (size_t)j * NPX) * dxs[j];
-                smem_scratch[part * NPX + i] = t;
+        for (int d = tid; d < NPX; d += T) {
+            const int f = d / 15, blk = d < NP ? 2 * f + ((d - 15 * f) >= 6) : 2 * s.NF;
+            if (pres[blk]) {
+                int pos = 0;
+                for (int q = 0; q < blk; q++) pos += pres[q] ? ((q & 1) ? 9 : 6) : 0;
+                pos += d < NP ? ((blk & 1) ? d - 15 * f - 6 : d - 15 * f) : d - NP;
+                cl[pos] = d; dxc[pos] = ws.dx[d];
             }
         }
+        if (tid == 0) { int n = 0; for (int q = 0; q <= 2 * s.NF; q++) n += pres[q] ? (q == 2 * s.NF ? 6 : ((q & 1) ? 9 : 6)) : 0; *ncp = n; }
         __syncthreads();
-        for (int i2 = tid; i2 < NPX; i2 += T) {
+        const int nc = *ncp;
+        const int P = nc > 0 ? min(4, max(1, T / nc)) : 1, part = nc > 0 ? tid / nc : T;
+        const int rows = (nc + P - 1) / P;
+        if (part < P) {
+            const int ii = tid - part * nc;
+            const int j0 = part * rows, j1 = min(nc, (part + 1) * rows);
+            const double *col = Hp + cl[ii];
             double t = 0;
-            for (int q = 0; q < P; q++) t += smem_scratch[q * NPX + i2];
-            cost += 0.5 * dxs[i2] * t + bp[i2] * dxs[i2];
-            if (lin && i2 < NP) ws.g[i2] += t + bp[i2];
+            int j = j0;
+            for (; j + 8 <= j1; j += 8) {
+                double h[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) h[q] = __ldg(col + (size_t)cl[j + q] * NPX);
+#pragma unroll
+                for (int q = 0; q < 8; q++) t += h[q] * dxc[j + q];
+            }
+            for (; j < j1; j++) t += __ldg(col + (size_t)cl[j] * NPX) * dxc[j];
+            part_sum[part * nc + ii] = t;
+        }
+        __syncthreads();
+        for (int i2 = tid; i2 < nc; i2 += T) {
+            double t = 0;
+            for (int q = 0; q < P; q++) t += part_sum[q * nc + i2];
+            const int d = cl[i2];
+            cost += 0.5 * dxc[i2] * t + bp[d] * dxc[i2];
+            if (lin && d < NP) ws.g[d] += t + bp[d];
         }
         if (tid == 0) cost += 0.5 * S_dv(s, b)[DV_PRIOR_C0];
     }
