@@ -41,32 +41,64 @@ def _rank_world():
 
 
 class Clocks(threading.Thread):
-    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+    """SM-clock / throttle-reason sampler running during the timed region (B200_PROFILING.md clocks line).  NVML in-process (a sample
+    every 5 ms; the timed region of the default run lasts ~70 ms, shorter than one nvidia-smi start-up), nvidia-smi as fallback."""
     def __init__(self, dev):
         super().__init__(daemon=True)
         self.dev, self.stop_flag, self.rows = dev, False, []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _reasons(self, mask):
+        n = self.nvml
+        names = {"hw_slowdown": "nvmlClocksThrottleReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksThrottleReasonHwThermalSlowdown",
+                 "sw_thermal_slowdown": "nvmlClocksThrottleReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksThrottleReasonSwPowerCap"}
+        return [k for k, v in names.items() if mask & getattr(n, v, 0)]
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            while not self.stop_flag:
+                try:
+                    sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                    try:
+                        mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.rows.append((sm, self._reasons(mask)))
+                except Exception:
+                    pass
+                time.sleep(0.005)
+            return
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")] if out else []
+                if len(r) >= 7 and r[0].replace(".", "").isdigit():
+                    self.max_sm = float(r[1])
+                    self.rows.append((float(r[0]), [nm for i, nm in enumerate(names) if r[3 + i].lower().startswith("active")]))
             except Exception:
                 pass
             time.sleep(0.2)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({x for r in self.rows for x in r[1]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": getattr(self, "max_sm", None), "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------- data
@@ -258,18 +290,48 @@ def run_ours(args):
     n_kf_steps = len([i for i in range(args.steps) if (prologue + args.warmup + i) % FREQ == 0])
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm = peaks.get("hbm_gbs", 6650.0)
-    # roofline of the dominant HBM-bound kernel of the front end (per launch = one batch of B images)
     phases = prof.pop("_phases", None)
     kern = {k: {"launches": c, "ms_per_launch": t / c} for k, (c, t) in prof.items() if c}
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01f_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))["bytes_per_launch"]
+    # (1) the dominant kernel of the step: solve_kernel -- FP64 ALU / tensor pipe (DMMA), no HBM roofline (Jacobians are never
+    #     materialised).  Algorithmic flops per launch = SURVEY.md section 8(d) flop model with every stream's own P, L, iterations.
+    fp64 = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json"))) if os.path.exists(os.path.join(ROOT, "profiles", "fp64_peak.json")) else \
+        {"fma_per_clk_per_sm": 64.0, "sms": 148}
+    sm_mhz = (clk or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    fp64_peak = 2.0 * fp64["fma_per_clk_per_sm"] * fp64["sms"] * sm_mhz * 1e6 / 1e12
+    NPd = 15 * (W + 1)
+
+    def solve_flops(i):
+        P, L, it, npr = i["n_proj"], max(i["n_feat"], 1), i["iters"], i["prior_n"]
+        lin = 1500.0 * P + 45000.0 * W + 2.0 * npr * npr
+        schur = 2.0 * L * (6.0 * (P / L + 1.0)) ** 2
+        chol = NPd ** 3 / 3.0 + 2.0 * NPd * NPd
+        cost_only = 0.4 * (1500.0 * P + 45000.0 * W) + 2.0 * npr * npr
+        return lin + it * (lin + schur + chol + cost_only)          # first linearisation + one (re)linearisation per iteration
+    roof = None
+    if "solve_kernel" in kern and info:
+        fl = sum(solve_flops(i) for i in info)
+        ach = fl / (kern["solve_kernel"]["ms_per_launch"] * 1e-3) / 1e12
+        roof = {"kernel": "solve_kernel", "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                "traffic": traffic.get("solve_kernel"),
+                "peak_source": "FP64 (the path computes in f64; MEASURED_PEAKS.json has no FP64 figure): profiles/fp64_peak.json = 64 FMA/clk/SM "
+                               "measured with tools/ubench/dmma_rate.cu (DFMA and DMMA alike) x 148 SMs x SM clock under load",
+                "algorithmic_flops_per_launch": fl, "flop_model": "SURVEY.md section 8(d): per iteration 1500 P + 45000 Wn + 2 n_prior^2 (linearise) + "
+                "2 L (6 (P/L+1))^2 (Schur) + n_r^3/3 + 2 n_r^2 (Cholesky) + cost-only evaluation, summed over the batch with each stream's P, L, iterations"}
+    # (2) the dominant HBM-class kernel of the front end (per launch = one batch of B images)
     cand = {"pyr_down_kernel": ALGO_BYTES_PYR / 3.0, "eig_candidates_kernel": ALGO_BYTES_DETECT, "lk_kernel": ALGO_BYTES_KLT}
     dom = max((k for k in cand if k in kern), key=lambda k: kern[k]["ms_per_launch"] * (3 if k == "pyr_down_kernel" else 1), default=None)
-    roof = None
+    roof_fe = None
     if dom:
         bytes_per_launch = cand[dom] * B
         ach = bytes_per_launch / (kern[dom]["ms_per_launch"] * 1e-3) / 1e9
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-                "algorithmic_bytes_per_launch": bytes_per_launch}
+        roof_fe = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic.get(dom),
+                   "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
+                   "algorithmic_bytes_per_launch": bytes_per_launch,
+                   "note": "per-kernel times of this pass are taken while the solve of the previous keyframe occupies 128 SMs (two-stream overlap)"}
     for k in kern:
         if k in cand:
             kern[k]["achieved_GBps"] = cand[k] * B / (kern[k]["ms_per_launch"] * 1e-3) / 1e9
@@ -285,8 +347,8 @@ def run_ours(args):
                    "streams_overlap": "front end and back end on two CUDA streams, event-ordered hand-over" if not args.no_overlap else "single stream"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * cam.rows * cam.cols + B * IMU_PER_KF * 7 * 8 / FREQ),
                 "d2h_bytes_per_step": int(B * (W + 1) * 16 * 8 / FREQ), "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
-        "backend_phase_us_max_over_streams_at_1p9GHz": phases,
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_frontend": roof_fe, "kernels": kern, "cpu_baseline": cpu,
+        "backend_phase_us_max_over_streams_at_1p9GHz": phases if phases and any(phases.values()) else None,      # debug library only (VIO_LIB_NAME)
         "solve_info_stream0": info[0] if info else None,
         "solve_info_batch": {k: [min(i[k] for i in info), max(i[k] for i in info)] for k in ("iters", "n_feat", "n_proj", "prior_n", "marg_fast", "marg_sweeps", "marg_m", "chol_retry", "err")} if info else None,
     }
