@@ -189,6 +189,8 @@ def run_ours(args):
     dev = f"cuda:{local}"
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout; rank 0's stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
     abi = importlib.import_module("vins-mobile_b200.abi")
     api = importlib.import_module("vins-mobile_b200.api")
@@ -282,6 +284,9 @@ def run_ours(args):
 
     ms, launches, prof, info, clk = timed_run(False)
     ms_e2e, _, _, _, _ = timed_run(True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     total_frames = args.steps * B * world
