@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict
 //     registers (14 pixels per lane).  The 2x2 normal equations and the mismatch vector are reduced EXACTLY in
 //     integers with warp shuffles and converted to f32 once.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int LK_WARPS = 8;
+constexpr int LK_WARPS = 4;
+constexpr int LK_JP = 32;                                 // edge of the staged J neighbourhood: the 22x22 window may drift +-5 px before a re-stage
+constexpr int LK_JM = 5;
 constexpr int LK_NPIX = LK_WIN * LK_WIN;                 // 441
 constexpr int LK_PIX = (LK_NPIX + 31) / 32;              // 14 pixels per lane
 
@@ -118,6 +120,39 @@ __device__ __forceinline__ void lk_stage(uint8_t *dst, const uint8_t *__restrict
     }
 }
 
+// Stage the LK_JP x LK_JP neighbourhood of J whose top-left is (y0, x0) twice: A[r][c] = J(y0 + r, x0 + c) and B = A shifted left by one
+// byte (B[i] = A[i + 1]), so that the horizontally adjacent pair (A[i], A[i + 1]) is ONE aligned 16-bit load whatever the parity of i
+// (even: A + i, odd: B + i - 1).  One lane per row; inside the image the row is fetched as nine aligned words and re-aligned with funnel
+// shifts, otherwise byte by byte with BORDER_REFLECT_101.
+__device__ __forceinline__ void lk_stage_j(uint8_t *A, uint8_t *Bc, const uint8_t *__restrict__ im, int rows, int cols, int y0, int x0, int lane) {
+    const bool inner = x0 >= 4 && x0 + LK_JP + 4 <= cols && y0 >= 0 && y0 + LK_JP <= rows;
+    if (inner) {
+        const uint8_t *g = im + (size_t)(y0 + lane) * cols + x0;
+        const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
+        const unsigned *wp = reinterpret_cast<const unsigned *>(ga & ~(uintptr_t)3);
+        const unsigned sh = (unsigned)(ga & 3) * 8;
+        unsigned w[10];
+#pragma unroll
+        for (int i = 0; i < 10; i++) w[i] = wp[i];
+        unsigned a[8], bq[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { a[i] = __funnelshift_rc(w[i], w[i + 1], sh); }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const unsigned nx = i < 7 ? a[i + 1] : __funnelshift_rc(w[8], w[9], sh); bq[i] = __funnelshift_r(a[i], nx, 8); }
+        uint4 *da = reinterpret_cast<uint4 *>(A + lane * LK_JP), *db = reinterpret_cast<uint4 *>(Bc + lane * LK_JP);
+        da[0] = make_uint4(a[0], a[1], a[2], a[3]); da[1] = make_uint4(a[4], a[5], a[6], a[7]);
+        db[0] = make_uint4(bq[0], bq[1], bq[2], bq[3]); db[1] = make_uint4(bq[4], bq[5], bq[6], bq[7]);
+    } else {
+        const int yy = reflect101(y0 + lane, rows);
+        const uint8_t *row = im + (size_t)yy * cols;
+        uint8_t v[LK_JP + 1];
+#pragma unroll
+        for (int c = 0; c <= LK_JP; c++) v[c] = row[reflect101(x0 + c, cols)];
+#pragma unroll
+        for (int c = 0; c < LK_JP; c++) { A[lane * LK_JP + c] = v[c]; Bc[lane * LK_JP + c] = v[c + 1]; }
+    }
+}
+
 __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevels J, const float2 *__restrict__ prev_pts,
                                                            float2 *__restrict__ next_pts, uint8_t *__restrict__ status,
                                                            const int *__restrict__ n_pts, int maxp) {
@@ -125,18 +160,15 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
     // per warp: 24x24 template neighbourhood of I, 22x22 (stride 24) window of J, and the bilinear template (Iw, gx, gy) as int16.
     // Everything is shared-memory resident so that the per-pixel loops stay rolled (small code, few registers, 8 warps per CTA).
     __shared__ uint8_t sI[LK_WARPS][24 * 24];
-    __shared__ uint8_t sJ[LK_WARPS][22 * 24];
+    __shared__ __align__(16) uint8_t sJ[LK_WARPS][2][LK_JP * LK_JP];    // copy A and the one-byte-shifted copy B (lk_stage_j)
     __shared__ short4 sT[LK_WARPS][LK_NPIX];            // (Iw, gx, gy, -) per window pixel: one 8-byte load per pixel per iteration
-    __shared__ unsigned short sOff[LK_NPIX];             // window pixel -> offset y*24 + x (shared by the 8 warps)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int f = blockIdx.x * LK_WARPS + warp;
-    for (int p = threadIdx.x; p < LK_NPIX; p += LK_WARPS * 32) sOff[p] = (unsigned short)((p / LK_WIN) * 24 + (p % LK_WIN));
-    __syncthreads();
     if (f >= n_pts[b]) return;
     const float2 pt = prev_pts[(size_t)b * maxp + f];
     uint8_t *pI = sI[warp];
-    uint8_t *pJ = sJ[warp];
+    uint8_t *pJA = sJ[warp][0], *pJB = sJ[warp][1];
     short4 *tT = sT[warp];
     const float half = 10.f;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
@@ -200,6 +232,8 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
         const float Dinv = __fdiv_rn(1.f, D);
         float cx = fsub(nx, half), cy = fsub(ny, half);       // nextPt (window top-left, float)
         float pdx = 0.f, pdy = 0.f;
+        int sx0 = 0, sy0 = 0;
+        bool staged = false;
 #pragma unroll 1
         for (int j = 0; j < LK_MAX_ITERS; j++) {
             const int jx = (int)floorf(cx), jy = (int)floorf(cy);
@@ -207,17 +241,27 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
                 if (level == 0) ok = false;
                 break;
             }
-            __syncwarp();
-            lk_stage(pJ, imJ, rows, cols, jy, jx, 22, 22, lane);
-            __syncwarp();
+            // the window needs rows jy .. jy+21 and columns jx .. jx+21 of J: re-stage only when it leaves the staged neighbourhood
+            if (!staged || jx < sx0 || jx + 22 > sx0 + LK_JP || jy < sy0 || jy + 22 > sy0 + LK_JP) {
+                sx0 = jx - LK_JM; sy0 = jy - LK_JM; staged = true;
+                __syncwarp();
+                lk_stage_j(pJA, pJB, imJ, rows, cols, sy0, sx0, lane);
+                __syncwarp();
+            }
             int v00, v01, v10, v11;
             lk_weights(fsub(cx, (float)jx), fsub(cy, (float)jy), v00, v01, v10, v11);
+            const unsigned wt = (unsigned)v00 | ((unsigned)v01 << 16), wb = (unsigned)v10 | ((unsigned)v11 << 16);
+            const int o0 = (jy - sy0) * LK_JP + (jx - sx0);
             int b1 = 0, b2 = 0;
 #pragma unroll 2
             for (int p = lane; p < LK_NPIX; p += 32) {
-                const uint8_t *q = pJ + sOff[p];
+                const int y = (p * 3121) >> 16;                          // p / 21 for p < 441
+                const int off = o0 + p + (LK_JP - LK_WIN) * y;            // (jy - sy0 + y) * LK_JP + (jx - sx0 + x)
+                const uint8_t *src = (off & 1) ? pJB - 1 : pJA;           // aligned 16-bit load of (A[off], A[off + 1])
+                const unsigned top = *reinterpret_cast<const unsigned short *>(src + off);
+                const unsigned bot = *reinterpret_cast<const unsigned short *>(src + off + LK_JP);
                 const short4 t = tT[p];
-                const int jv = (q[0] * v00 + q[1] * v01 + q[24] * v10 + q[25] * v11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                const int jv = (int)(__dp2a_lo(wt, top, __dp2a_lo(wb, bot, (unsigned)(1 << (W_BITS - 5 - 1)))) >> (W_BITS - 5));
                 const int diff = jv - t.x;
                 b1 += diff * t.y;
                 b2 += diff * t.z;
