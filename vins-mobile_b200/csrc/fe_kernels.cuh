@@ -194,24 +194,33 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
         __syncwarp();
         int w00, w01, w10, w11;
         lk_weights(fsub(px, (float)ipx), fsub(py, (float)ipy), w00, w01, w10, w11);
-        int a11 = 0, a12 = 0, a22 = 0;
-#pragma unroll 1
-        for (int p = lane; p < LK_NPIX; p += 32) {
-            const int y = p / LK_WIN, x = p - y * LK_WIN;
-            int iv = 0, dxv = 0, dyv = 0;
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const int yy = y + (t >> 1), xx = x + (t & 1);           // window pixel (yy,xx) in 0..21
-                const int wgt = t == 0 ? w00 : t == 1 ? w01 : t == 2 ? w10 : w11;
-                const uint8_t *q = pI + (yy + 1) * 24 + (xx + 1);
-                iv += wgt * q[0];
-                const int gyi = ipy + yy, gxi = ipx + xx;
-                if (gyi >= 0 && gyi < rows && gxi >= 0 && gxi < cols) {
-                    const int tl = q[-25], tc = q[-24], tr = q[-23], ml = q[-1], mr = q[1], bl = q[23], bc = q[24], br = q[25];
-                    dxv += wgt * (3 * (tr - tl) + 10 * (mr - ml) + 3 * (br - bl));
-                    dyv += wgt * (3 * (bl - tl) + 10 * (bc - tc) + 3 * (br - tr));
-                }
+        // pass 1: Scharr derivatives at the 22x22 source pixels of the bilinear window (window pixel (yy, xx) = patch (yy+1, xx+1)),
+        // zero where the source lies outside the image -- each is used by up to four window pixels.  The J staging area is free here.
+        short2 *sD = reinterpret_cast<short2 *>(pJA);
+        for (int i = lane; i < 22 * 22; i += 32) {
+            const int yy = (i * 2979) >> 16, xx = i - 22 * yy;           // i / 22 for i < 484
+            const uint8_t *q = pI + (yy + 1) * 24 + (xx + 1);
+            const int gyi = ipy + yy, gxi = ipx + xx;
+            short2 d = make_short2(0, 0);
+            if (gyi >= 0 && gyi < rows && gxi >= 0 && gxi < cols) {
+                const int tl = q[-25], tc = q[-24], tr = q[-23], ml = q[-1], mr = q[1], bl = q[23], bc = q[24], br = q[25];
+                d.x = (short)(3 * (tr - tl) + 10 * (mr - ml) + 3 * (br - bl));
+                d.y = (short)(3 * (bl - tl) + 10 * (bc - tc) + 3 * (br - tr));
             }
+            sD[i] = d;
+        }
+        __syncwarp();
+        // pass 2: bilinear template (Iw, gx, gy) per window pixel
+        int a11 = 0, a12 = 0, a22 = 0;
+#pragma unroll 2
+        for (int p = lane; p < LK_NPIX; p += 32) {
+            const int y = (p * 3121) >> 16, x = p - LK_WIN * y;
+            const uint8_t *q = pI + (y + 1) * 24 + (x + 1);
+            const short2 *dq = sD + y * 22 + x;
+            const short2 d00 = dq[0], d01 = dq[1], d10 = dq[22], d11 = dq[23];
+            const int iv = w00 * q[0] + w01 * q[1] + w10 * q[24] + w11 * q[25];
+            const int dxv = w00 * d00.x + w01 * d01.x + w10 * d10.x + w11 * d11.x;
+            const int dyv = w00 * d00.y + w01 * d01.y + w10 * d10.y + w11 * d11.y;
             const int ivs = (iv + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
             const int gxs = (dxv + (1 << (W_BITS - 1))) >> W_BITS;
             const int gys = (dyv + (1 << (W_BITS - 1))) >> W_BITS;
