@@ -227,9 +227,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
             tT[p] = make_short4((short)ivs, (short)gxs, (short)gys, 0);
             a11 += gxs * gxs; a12 += gxs * gys; a22 += gys * gys;
         }
-        const float A11 = fmul(__ll2float_rn(warp_sum_ll(a11)), FLT_SCALE);
-        const float A12 = fmul(__ll2float_rn(warp_sum_ll(a12)), FLT_SCALE);
-        const float A22 = fmul(__ll2float_rn(warp_sum_ll(a22)), FLT_SCALE);
+        const float A11 = fmul(__ll2float_rn(warp_sum_split(a11)), FLT_SCALE);
+        const float A12 = fmul(__ll2float_rn(warp_sum_split(a12)), FLT_SCALE);
+        const float A22 = fmul(__ll2float_rn(warp_sum_split(a22)), FLT_SCALE);
         const float D = fsub(fmul(A11, A22), fmul(A12, A12));
         const float d12 = fsub(A11, A22);
         const float mineig = __fdiv_rn(fsub(fadd(A22, A11), __fsqrt_rn(fadd(fmul(d12, d12), fmul(fmul(4.f, A12), A12)))),
@@ -275,8 +275,8 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
                 b1 += diff * t.y;
                 b2 += diff * t.z;
             }
-            const float B1 = fmul(__ll2float_rn(warp_sum_ll(b1)), FLT_SCALE);
-            const float B2 = fmul(__ll2float_rn(warp_sum_ll(b2)), FLT_SCALE);
+            const float B1 = fmul(__ll2float_rn(warp_sum_split(b1)), FLT_SCALE);
+            const float B2 = fmul(__ll2float_rn(warp_sum_split(b2)), FLT_SCALE);
             const float dx = fmul(fsub(fmul(A12, B2), fmul(A22, B1)), Dinv);
             const float dy = fmul(fsub(fmul(A12, B1), fmul(A11, B2)), Dinv);
             cx = fadd(cx, dx); cy = fadd(cy, dy);
