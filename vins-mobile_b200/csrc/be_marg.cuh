@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
             const double *pr = S_pre(s, b, 1);
             double *J = tv + NPX;                           // 930 doubles of scratch after tv
             double *Jw = J + 450, *rr = J + 900, *rw = J + 915;
-            if (lane == 0) imu_residual(pr, s.gravity, par, par + 7, par + 16, par + 23, rr, J);
+            imu_residual_warp(pr, s.gravity, par, par + 7, par + 16, par + 23, rr, J, lane);
             __syncwarp();
             const double *U = pr + PR_SQI;
             if (lane < 15) { double t = 0; for (int k = lane; k < 15; k++) t += U[lane * 15 + k] * rr[k]; rw[lane] = t; }

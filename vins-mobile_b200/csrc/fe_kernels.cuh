@@ -42,14 +42,20 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict
         const uint8_t *row = src + (size_t)y * ic;
         int v[11];
         if (aligned) {
-            // the 11-byte footprint [2ox0-2, 2ox0+8] sits inside 16 bytes starting at 2ox0-4: u32 + u64 + u32 (all naturally aligned)
+            // the 11-byte footprint [2ox0-2, 2ox0+8] sits inside 16 bytes starting at 2ox0-4: u32 + u64 + u32 (all naturally aligned).
+            // Horizontal taps (1 4 6 4 | 1) times the vertical weight as two byte dot products (dp4a) per output: no byte extraction.
             const uint32_t w0 = *reinterpret_cast<const uint32_t *>(row + 2 * ox0 - 4);
             const uint2 w12 = *reinterpret_cast<const uint2 *>(row + 2 * ox0);
             const uint32_t w3 = *reinterpret_cast<const uint32_t *>(row + 2 * ox0 + 8);
-            v[0] = (w0 >> 16) & 0xff; v[1] = w0 >> 24;
-            v[2] = w12.x & 0xff; v[3] = (w12.x >> 8) & 0xff; v[4] = (w12.x >> 16) & 0xff; v[5] = w12.x >> 24;
-            v[6] = w12.y & 0xff; v[7] = (w12.y >> 8) & 0xff; v[8] = (w12.y >> 16) & 0xff; v[9] = w12.y >> 24;
-            v[10] = w3 & 0xff;
+            const unsigned kv = (unsigned)kw[dy + 2];
+            const unsigned k4 = kv * 0x04060401u;                       // bytes (1,4,6,4) * kv  (<= 36)
+            const unsigned kb0 = kv, kb2 = kv << 16;                    // the fifth tap sits in byte 0 / byte 2 of the next word
+            const unsigned f0 = __funnelshift_r(w0, w12.x, 16), f1 = __funnelshift_r(w12.x, w12.y, 16);
+            acc[0] = (int)__dp4a(f0, k4, __dp4a(w12.x, kb2, (unsigned)acc[0]));
+            acc[1] = (int)__dp4a(w12.x, k4, __dp4a(w12.y, kb0, (unsigned)acc[1]));
+            acc[2] = (int)__dp4a(f1, k4, __dp4a(w12.y, kb2, (unsigned)acc[2]));
+            acc[3] = (int)__dp4a(w12.y, k4, __dp4a(w3, kb0, (unsigned)acc[3]));
+            continue;
         } else if (2 * ox0 - 2 >= 0 && 2 * ox0 + 8 < ic) {
 #pragma unroll
             for (int k = 0; k < 11; k++) v[k] = row[2 * ox0 - 2 + k];
