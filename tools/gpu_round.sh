@@ -19,9 +19,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 if [ "$DO_FULL" = "full" ]; then
   # back end: skip the prologue (first solves), capture one steady-state launch of each heavy kernel
   # (the first ten launches of each are no-ops while the window fills; tools/ncu_summary.py lists every captured launch)
-  timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:(^|:)solve_kernel' --launch-skip 11 --launch-count 3 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:(^|:)solve_kernel' --launch-skip 12 --launch-count 1 \
     -o gpurun_out/${TAG}_be -f python bench.py --steps 6 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_be.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'marg_kernel' --launch-skip 11 --launch-count 3 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'marg_kernel' --launch-skip 12 --launch-count 1 \
     -o gpurun_out/${TAG}_marg -f python bench.py --steps 6 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_marg.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'lk_kernel|eig_candidates_kernel|pyr_down_kernel|post_track_kernel|select_kernel' \
     --launch-skip 140 --launch-count 8 -o gpurun_out/${TAG}_fe -f python bench.py --steps 6 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_fe.log 2>&1
