@@ -101,10 +101,16 @@ int vio_frontend_get_stats(vio_frontend *fe, int s, int32_t stats[8]);
 /* Device-resident SoA views (valid until the next call): counts[batch], ids[batch*max_cnt],
  * norm_xyz[batch*max_cnt*3] -- what vio_backend_process_image_dev consumes. */
 int vio_frontend_image_msg_dev(vio_frontend *fe, const int32_t **counts, const int32_t **ids, const double **norm_xyz);
+/* Optional pre-processing of every frame handed to vio_frontend_read_images[_dev]: cv::createCLAHE() + setClipLimit(clip_limit) +
+ * apply(), the step the reference runs on the camera frame right before FeatureTracker::readImage (ViewController.mm:438-441:
+ * clip_limit 3.0, default 8x8 tiles).  Bit-identical to OpenCV 4.13's CLAHE.  rows / cols must be divisible by tiles_y / tiles_x
+ * (OpenCV pads otherwise; VIO_ERR_ARG here).  enable = 0 switches it off (default). */
+int vio_frontend_set_clahe(vio_frontend *fe, int enable, double clip_limit, int tiles_x, int tiles_y);
 /* Number of CUDA kernels launched by this handle since creation. */
 int64_t vio_frontend_launch_count(const vio_frontend *fe);
 /* Primitive entry points used by the parity tests (single image, host in/out).  */
 int vio_prim_pyramid(const vio_config *cfg, const uint8_t *img, uint8_t *l1, uint8_t *l2, uint8_t *l3);
+int vio_prim_clahe(const vio_config *cfg, const uint8_t *img, double clip_limit, int tiles_x, int tiles_y, uint8_t *out);
 int vio_prim_min_eig_candidates(const vio_config *cfg, const uint8_t *img, const float *kept_xy, int n_kept,
                                 int max_corners, float *corners_xy, int *n_corners, float *max_val);
 int vio_prim_lk(const vio_config *cfg, const uint8_t *prev, const uint8_t *next, const float *pts_xy, int n,

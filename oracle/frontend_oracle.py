@@ -857,3 +857,67 @@ class FeatureTrackerOracle:
         published = self.img_cnt == 0
         self.img_cnt = (self.img_cnt + 1) % self.freq          # ViewController.mm:494
         return good_pts, track_len, published
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# CLAHE -- the pre-processing the reference applies to the camera frame right before readImage (ViewController.mm:438-441:
+# cv::createCLAHE(); setClipLimit(3); apply()).  Restatement of OpenCV's clahe.cpp (CLAHE_CalcLut_Body / CLAHE_Interpolation_Body) for
+# 8-bit images whose size is divisible by the tile grid; pinned bit-exact against the cv2 binary in tests/test_oracle_frontend.py.
+# ---------------------------------------------------------------------------------------------------------------------------------
+def cv2_clahe(img, clip_limit=3.0, tiles=(8, 8)):
+    import cv2
+    c = cv2.createCLAHE(clipLimit=float(clip_limit), tileGridSize=(int(tiles[0]), int(tiles[1])))
+    return c.apply(np.ascontiguousarray(img, np.uint8))
+
+
+def r_clahe(img, clip_limit=3.0, tiles=(8, 8)):
+    img = np.ascontiguousarray(img, np.uint8)
+    rows, cols = img.shape
+    tx, ty = int(tiles[0]), int(tiles[1])
+    assert cols % tx == 0 and rows % ty == 0, "OpenCV pads with BORDER_REFLECT_101 otherwise (not restated)"
+    tw, th = cols // tx, rows // ty
+    area = tw * th
+    lut_scale = np.float32(np.float32(255) / np.float32(area))
+    clip = max(int(clip_limit * area / 256), 1) if clip_limit > 0 else 0
+    lut = np.zeros((ty * tx, 256), np.uint8)
+    for k in range(tx * ty):
+        y0, x0 = (k // tx) * th, (k % tx) * tw
+        h = np.bincount(img[y0:y0 + th, x0:x0 + tw].ravel(), minlength=256).astype(np.int64)
+        if clip > 0:
+            clipped = int(np.maximum(h - clip, 0).sum())
+            h = np.minimum(h, clip)
+            batch = clipped // 256
+            resid = clipped - batch * 256
+            h += batch
+            if resid:
+                step = max(256 // resid, 1)
+                i = 0
+                while i < 256 and resid > 0:
+                    h[i] += 1
+                    i += step
+                    resid -= 1
+        v = np.cumsum(h).astype(np.float32) * lut_scale
+        lut[k] = np.clip(np.rint(v), 0, 255).astype(np.uint8)                 # saturate_cast<uchar>(float) = cvRound
+    one, half = np.float32(1.0), np.float32(0.5)
+    inv_tw, inv_th = one / np.float32(tw), one / np.float32(th)
+    txf = np.arange(cols, dtype=np.float32) * inv_tw - half
+    tx1 = np.floor(txf).astype(np.int32)
+    xa = (txf - tx1.astype(np.float32)).astype(np.float32)
+    xa1 = one - xa
+    tx2 = np.minimum(tx1 + 1, tx - 1)
+    tx1 = np.maximum(tx1, 0)
+    tyf = np.arange(rows, dtype=np.float32) * inv_th - half
+    ty1 = np.floor(tyf).astype(np.int32)
+    ya = (tyf - ty1.astype(np.float32)).astype(np.float32)
+    ya1 = one - ya
+    ty2 = np.minimum(ty1 + 1, ty - 1)
+    ty1 = np.maximum(ty1, 0)
+    L = lut.astype(np.float32)
+    out = np.zeros_like(img)
+    for y in range(rows):
+        v = img[y].astype(np.int64)
+        l11, l12 = L[ty1[y] * tx + tx1, v], L[ty1[y] * tx + tx2, v]
+        l21, l22 = L[ty2[y] * tx + tx1, v], L[ty2[y] * tx + tx2, v]
+        res = (l11 * xa1 + l12 * xa) * ya1[y] + (l21 * xa1 + l22 * xa) * ya[y]     # every f32 operation rounded separately
+        out[y] = np.clip(np.rint(res), 0, 255).astype(np.uint8)
+    return out

@@ -206,3 +206,28 @@ def test_config_c4_1280x720_300_features(api, abi, synth):
         assert np.array_equal(g["pts"].view(np.uint32), tr.cur_pts.view(np.uint32))
     assert len(tr.ids) >= 250
     fe.close()
+
+
+def test_clahe_bit_exact_and_tracker_on_equalised_frames(api, abi, get_stream):
+    """K0: the CUDA CLAHE equals the restated OpenCV CLAHE byte for byte (640x480 and 1280x720, clip 3, 8x8 tiles), and a tracker with
+    vio_frontend_set_clahe() enabled publishes exactly what the oracle tracker publishes on frames equalised by the oracle."""
+    from conftest import texture_pair
+    c = abi.default_config(batch=1, max_cnt=150)
+    s = get_stream(0, 7)
+    for im in (s.images[0].numpy(), texture_pair(11)[0], np.random.default_rng(1).integers(0, 256, (640, 480)).astype(np.uint8)):
+        assert np.array_equal(api.prim_clahe(c, im), fo.r_clahe(im))
+    big = texture_pair(2, rows=720, cols=1280)[0]
+    assert np.array_equal(api.prim_clahe(abi.default_config(batch=1, max_cnt=150, rows=720, cols=1280), big), fo.r_clahe(big))
+    with pytest.raises(api.VioError):
+        api.prim_clahe(c, s.images[0].numpy(), 3.0, 7, 8)                  # 480 % 7 != 0: OpenCV would pad
+    fe = api.FrontEnd(c)
+    fe.set_clahe(True, 3.0, 8, 8)
+    tr = fo.FeatureTrackerOracle(max_cnt=150, backend="restated")
+    for k in range(7):
+        im = s.images[k].numpy()
+        fe.read_images(im[None])
+        tr.read_image(fo.r_clahe(im))
+        g = fe.stream(0)
+        assert np.array_equal(g["ids"], tr.ids), f"frame {k}"
+        assert np.array_equal(g["pts"].view(np.uint32), tr.cur_pts.view(np.uint32)), f"frame {k}"
+    fe.close()

@@ -108,3 +108,17 @@ def test_tracker_cv2_vs_restated_short_stream(get_stream):
             assert np.abs(a.cur_pts - b.cur_pts).max() < 2e-3
     assert len(a.ids) == 150
     assert a.image_msg.keys() == b.image_msg.keys()
+
+
+def test_clahe_restatement_matches_cv2():
+    """ViewController.mm:438-441 runs cv::createCLAHE(), setClipLimit(3), apply() on every frame before readImage: the restatement
+    must be bit-identical to the OpenCV binary (textured, noisy, low-contrast and constant images; 640x480 and 1280x720)."""
+    r = np.random.default_rng(3)
+    imgs = [texture_pair(5)[0], texture_pair(9)[1]]
+    imgs.append(r.integers(0, 256, (640, 480)).astype(np.uint8))
+    imgs.append((r.integers(0, 40, (640, 480)) + 100).astype(np.uint8))
+    imgs.append(np.full((640, 480), 77, np.uint8))
+    imgs.append(texture_pair(2, rows=720, cols=1280)[0])
+    for k, im in enumerate(imgs):
+        assert np.array_equal(fo.r_clahe(im), fo.cv2_clahe(im)), f"image {k}"
+    assert np.array_equal(fo.r_clahe(imgs[0], 2.0, (4, 8)), fo.cv2_clahe(imgs[0], 2.0, (4, 8)))

@@ -55,6 +55,8 @@ def lib():
         L.vio_frontend_use_stream.argtypes = [vp, vp]
         L.vio_frontend_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
         L.vio_prim_pyramid.argtypes = [cfgp, UP, UP, UP, UP]
+        L.vio_frontend_set_clahe.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int]
+        L.vio_prim_clahe.argtypes = [cfgp, UP, C.c_double, C.c_int, C.c_int, UP]
         L.vio_prim_min_eig_candidates.argtypes = [cfgp, UP, FP, C.c_int, C.c_int, FP, C.POINTER(C.c_int), FP]
         L.vio_prim_lk.argtypes = [cfgp, UP, UP, FP, C.c_int, FP, UP]
         L.vio_prim_ransac_f.argtypes = [cfgp, FP, FP, C.c_int, UP, C.POINTER(C.c_int)]
@@ -165,6 +167,10 @@ class FrontEnd:
     def use_stream(self, cuda_stream: int):
         _check(lib().vio_frontend_use_stream(self.h, cuda_stream), "vio_frontend_use_stream")
 
+    def set_clahe(self, enable=True, clip_limit=3.0, tiles_x=8, tiles_y=8):
+        """cv::createCLAHE(); setClipLimit(3); apply() on every incoming frame (ViewController.mm:438-441)."""
+        _check(lib().vio_frontend_set_clahe(self.h, int(enable), float(clip_limit), tiles_x, tiles_y), "vio_frontend_set_clahe")
+
     def profile(self, enable: bool) -> dict:
         buf = C.create_string_buffer(4096)
         _check(lib().vio_frontend_profile(self.h, int(enable), buf, 4096), "vio_frontend_profile")
@@ -192,6 +198,13 @@ def prim_pyramid(cfg, img):
         outs.append(np.zeros((r, c), np.uint8))
     _check(lib().vio_prim_pyramid(C.byref(cfg), ptr(img, C.c_uint8), *[ptr(o, C.c_uint8) for o in outs]), "vio_prim_pyramid")
     return outs
+
+
+def prim_clahe(cfg, img, clip_limit=3.0, tiles_x=8, tiles_y=8):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros_like(img)
+    _check(lib().vio_prim_clahe(C.byref(cfg), ptr(img, C.c_uint8), float(clip_limit), tiles_x, tiles_y, ptr(out, C.c_uint8)), "vio_prim_clahe")
+    return out
 
 
 def prim_good_features(cfg, img, kept_xy, max_corners):

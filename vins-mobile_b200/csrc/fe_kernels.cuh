@@ -82,6 +82,88 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K0  CLAHE (cv::createCLAHE(), clipLimit 3, 8x8 tiles: ViewController.mm:438-441, the step upstream of readImage; oracle r_clahe).
+//     clahe_lut_kernel: one CTA per tile -- 256-bin histogram (shared-memory atomics), clip at max(1, int(clip * area / 256)), excess
+//     redistributed as OpenCV does (uniform batch + one extra count every `step` bins), LUT[i] = cvRound(cdf[i] * 255 / area) in f32.
+//     clahe_apply_kernel: per pixel the bilinear blend of the four neighbouring tile LUTs, every f32 operation rounded separately in
+//     OpenCV's order ((l11 xa1 + l12 xa) ya1 + (l21 xa1 + l22 xa) ya), cvRound, saturate.  In place (each pixel reads only itself).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t *__restrict__ img, size_t img_stride, int cols, int tw, int th, int tiles_x,
+                                                        int clip, float lut_scale, uint8_t *__restrict__ lut) {
+    __shared__ int hist[256];
+    __shared__ int wsum[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, b = blockIdx.y;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const uint8_t *src = img + (size_t)b * img_stride + (size_t)(ty * th) * cols + tx * tw;
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < tw * th; i += 256) { const int y = i / tw, x = i - y * tw; atomicAdd(&hist[src[(size_t)y * cols + x]], 1); }
+    __syncthreads();
+    int h = hist[tid];
+    if (clip > 0) {
+        int ex = max(h - clip, 0);
+        h = min(h, clip);
+        ex = warp_sum_i(ex);
+        if (lane == 0) wsum[warp] = ex;
+        __syncthreads();
+        int clipped = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) clipped += wsum[w];
+        const int batch = clipped / 256, resid = clipped - batch * 256;
+        h += batch;
+        if (resid > 0) { const int step = max(256 / resid, 1); if (tid % step == 0 && tid / step < resid) h++; }
+        __syncthreads();
+    }
+    // inclusive prefix sum over the 256 bins
+    int v = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += n; }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; w++) base += wsum[w];
+    const int cdf = v + base;
+    const int r = __float2int_rn(fmul((float)cdf, lut_scale));
+    lut[((size_t)b * gridDim.x + tile) * 256 + tid] = (uint8_t)min(max(r, 0), 255);
+}
+
+__global__ void __launch_bounds__(256) clahe_apply_kernel(uint8_t *__restrict__ img, size_t img_stride, int rows, int cols, int tw, int th,
+                                                          int tiles_x, int tiles_y, const uint8_t *__restrict__ lut) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, b = blockIdx.z;
+    if (x0 >= cols) return;
+    uint8_t *row = img + (size_t)b * img_stride + (size_t)y * cols;
+    const uint8_t *L = lut + (size_t)b * tiles_x * tiles_y * 256;
+    const float inv_tw = __fdiv_rn(1.f, (float)tw), inv_th = __fdiv_rn(1.f, (float)th);
+    const float tyf = fsub(fmul((float)y, inv_th), 0.5f);
+    int ty1 = (int)floorf(tyf);
+    const float ya = fsub(tyf, (float)ty1), ya1 = fsub(1.f, ya);
+    const int ty2 = min(ty1 + 1, tiles_y - 1);
+    ty1 = max(ty1, 0);
+    const uint8_t *P1 = L + (size_t)ty1 * tiles_x * 256, *P2 = L + (size_t)ty2 * tiles_x * 256;
+    uint8_t out[4];
+    const bool vec = (x0 + 3 < cols) && ((cols & 3) == 0) && ((img_stride & 3) == 0);
+    uint8_t in[4];
+    if (vec) { const uchar4 q = *reinterpret_cast<const uchar4 *>(row + x0); in[0] = q.x; in[1] = q.y; in[2] = q.z; in[3] = q.w; }
+    else for (int k = 0; k < 4; k++) in[k] = x0 + k < cols ? row[x0 + k] : 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x = x0 + k;
+        const float txf = fsub(fmul((float)x, inv_tw), 0.5f);
+        int tx1 = (int)floorf(txf);
+        const float xa = fsub(txf, (float)tx1), xa1 = fsub(1.f, xa);
+        const int tx2 = min(tx1 + 1, tiles_x - 1);
+        tx1 = max(tx1, 0);
+        const int sv = in[k];
+        const float l11 = (float)P1[tx1 * 256 + sv], l12 = (float)P1[tx2 * 256 + sv], l21 = (float)P2[tx1 * 256 + sv], l22 = (float)P2[tx2 * 256 + sv];
+        const float res = fadd(fmul(fadd(fmul(l11, xa1), fmul(l12, xa)), ya1), fmul(fadd(fmul(l21, xa1), fmul(l22, xa)), ya));
+        out[k] = (uint8_t)min(max(__float2int_rn(res), 0), 255);
+    }
+    if (vec) *reinterpret_cast<uchar4 *>(row + x0) = make_uchar4(out[0], out[1], out[2], out[3]);
+    else for (int k = 0; k < 4; k++) if (x0 + k < cols) row[x0 + k] = out[k];
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K4  pyramidal LK, one warp per feature (cv::calcOpticalFlowPyrLK(Size(21,21), 3); oracle r_lk_track).
 //     Template: 24x24 u8 patch of I (REFLECT_101) staged in shared memory, Scharr gradients formed on the fly
 //     (zero outside the image), 14-bit fixed-point bilinear weights, int16-range template values held in

@@ -32,6 +32,9 @@ struct vio_frontend {
     cudaEvent_t ev_up[2], ev_free[2];
     int up_idx;
     bool stage_used[2];
+    // optional CLAHE pre-processing (vio_frontend_set_clahe)
+    int clahe_on, clahe_tx, clahe_ty, clahe_clip;
+    uint8_t *clahe_lut;
 };
 
 template <typename T>
@@ -154,10 +157,41 @@ static PyrLevels levels_of(const vio_frontend *fe, int k) {
     return L;
 }
 
+// CLAHE of the B images at `img` (in place): two launches
+static void run_clahe(vio_frontend *fe, uint8_t *img, cudaStream_t s) {
+    const int rows = fe->cfg.rows, cols = fe->cfg.cols, tw = cols / fe->clahe_tx, th = rows / fe->clahe_ty;
+    const float lut_scale = 255.f / (float)(tw * th);
+    VIO_LAUNCH(fe->timer, s, "clahe_lut_kernel", (clahe_lut_kernel<<<dim3(fe->clahe_tx * fe->clahe_ty, fe->B), 256, 0, s>>>(img, fe->lsz[0], cols, tw, th, fe->clahe_tx,
+               fe->clahe_clip, lut_scale, fe->clahe_lut)));
+    VIO_LAUNCH(fe->timer, s, "clahe_apply_kernel", (clahe_apply_kernel<<<dim3((cols + 1023) / 1024, rows, fe->B), 256, 0, s>>>(img, fe->lsz[0], rows, cols, tw, th,
+               fe->clahe_tx, fe->clahe_ty, fe->clahe_lut)));
+    fe->launches += 2;
+}
+
+extern "C" int vio_frontend_set_clahe(vio_frontend *fe, int enable, double clip_limit, int tiles_x, int tiles_y) {
+    if (!fe) return VIO_ERR_ARG;
+    if (!enable) { fe->clahe_on = 0; return VIO_OK; }
+    if (tiles_x < 1 || tiles_y < 1 || tiles_x * tiles_y > 4096 || fe->cfg.cols % tiles_x || fe->cfg.rows % tiles_y) return VIO_ERR_ARG;   // OpenCV pads otherwise
+    VIO_CUDA_TRY(cudaSetDevice(fe->cfg.device));
+    VIO_CUDA_TRY(cudaStreamSynchronize(fe->stream));
+    if (!fe->clahe_lut || tiles_x * tiles_y > fe->clahe_tx * fe->clahe_ty) {
+        void *p = nullptr;
+        VIO_CUDA_TRY(vio_dev_alloc(&p, (size_t)fe->B * tiles_x * tiles_y * 256, fe->allocs));
+        VIO_CUDA_TRY(cudaDeviceSynchronize());
+        fe->clahe_lut = (uint8_t *)p;
+    }
+    const int area = (fe->cfg.cols / tiles_x) * (fe->cfg.rows / tiles_y);
+    fe->clahe_tx = tiles_x; fe->clahe_ty = tiles_y;
+    fe->clahe_clip = clip_limit > 0.0 ? std::max((int)(clip_limit * area / 256), 1) : 0;      // clahe.cpp: clipLimit = max(int(clip * tileArea / histSize), 1)
+    fe->clahe_on = 1;
+    return VIO_OK;
+}
+
 // The body of readImage once the new frame sits in pyr[forw][0].
 static int run_frame(vio_frontend *fe, int *published) {
     const int forw = fe->cur ^ 1, B = fe->B;
     cudaStream_t s = fe->stream;
+    if (fe->clahe_on) run_clahe(fe, fe->pyr[forw][0], s);
     for (int l = 0; l < 3; l++) {                                           // K1
         dim3 blk(32, 8), grd((fe->lc[l + 1] + 127) / 128, (fe->lr[l + 1] + 7) / 8, B);
         VIO_LAUNCH(fe->timer, s, "pyr_down_kernel", (pyr_down_kernel<<<grd, blk, 0, s>>>(fe->pyr[forw][l], fe->pyr[forw][l + 1], fe->lr[l], fe->lc[l],
@@ -331,6 +365,21 @@ extern "C" int vio_prim_pyramid(const vio_config *cfg, const uint8_t *img, uint8
     }
     uint8_t *outs[3] = {l1, l2, l3};
     for (int l = 0; l < 3; l++) cudaMemcpyAsync(outs[l], fe->pyr[0][l + 1], fe->lsz[l + 1], cudaMemcpyDeviceToHost, fe->stream);
+    cudaError_t e = cudaStreamSynchronize(fe->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    vio_frontend_destroy(fe);
+    return e == cudaSuccess ? VIO_OK : VIO_ERR_CUDA;
+}
+
+extern "C" int vio_prim_clahe(const vio_config *cfg, const uint8_t *img, double clip_limit, int tiles_x, int tiles_y, uint8_t *out) {
+    vio_frontend *fe = nullptr;
+    int rc = make_single(cfg, &fe);
+    if (rc) return rc;
+    rc = vio_frontend_set_clahe(fe, 1, clip_limit, tiles_x, tiles_y);
+    if (rc) { vio_frontend_destroy(fe); return rc; }
+    cudaMemcpyAsync(fe->pyr[0][0], img, fe->lsz[0], cudaMemcpyHostToDevice, fe->stream);
+    run_clahe(fe, fe->pyr[0][0], fe->stream);
+    cudaMemcpyAsync(out, fe->pyr[0][0], fe->lsz[0], cudaMemcpyDeviceToHost, fe->stream);
     cudaError_t e = cudaStreamSynchronize(fe->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     vio_frontend_destroy(fe);

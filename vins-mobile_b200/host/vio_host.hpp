@@ -35,6 +35,11 @@ class FeatureTracker {
         ids.reserve(cfg_.max_cnt);
     }
     ~FeatureTracker() { vio_frontend_destroy(h_); }
+    // ViewController.mm:438-441 equalises every camera frame (cv::createCLAHE(); setClipLimit(3); apply()) before readImage: with this
+    // switched on the caller hands the raw gray frame to readImage and the equalisation runs on the device
+    void setClahe(bool enable, double clip_limit = 3.0, int tiles_x = 8, int tiles_y = 8) {
+        check(vio_frontend_set_clahe(h_, enable ? 1 : 0, clip_limit, tiles_x, tiles_y), "vio_frontend_set_clahe");
+    }
     FeatureTracker(const FeatureTracker &) = delete;
 
     // void readImage(const cv::Mat &_img, cv::Mat &result, int _frame_cnt, vector<Point2f> &good_pts, vector<double> &track_len,
