@@ -287,6 +287,28 @@ def run_ours(args):
 
     ms, launches, prof, info, clk = timed_run(False)
     ms_e2e, _, _, _, _ = timed_run(True)
+
+    def single_stream_run():
+        """BASELINE.json configs[1]: ONE stream on one B200 (latency-bound: one CTA per back-end kernel), device-resident frames."""
+        cfg1 = abi.default_config(batch=1, max_cnt=150, window_size=10, device=local)
+        f1 = frames[:, :1].contiguous()
+        imu1 = tuple(torch.as_tensor(np.ascontiguousarray(x[:, :, :1]), device=dev) for x in (dt, acc, gyr))
+        pipe = Pipeline(api, cfg1, stream.cuda_stream, stream_b.cuda_stream, gt[:1], False)
+        with torch.cuda.stream(stream):
+            for i in range(prologue + args.warmup):
+                pipe.step(f1[i].data_ptr(), lambda k: tuple(x[k].data_ptr() for x in imu1))
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); stream_b.wait_stream(stream)
+            for i in range(prologue + args.warmup, prologue + args.warmup + args.steps):
+                pipe.step(f1[i].data_ptr(), lambda k: tuple(x[k].data_ptr() for x in imu1))
+            stream.wait_stream(stream_b); b.record(stream)
+            torch.cuda.synchronize()
+        t = a.elapsed_time(b)
+        pipe.close()
+        return {"workload": "BASELINE.json configs[1]: single stream 640x480@30fps + 200 Hz IMU, 150 feats, 10-KF window, 1 GPU", "frames_per_s": args.steps / (t * 1e-3),
+                "ms_per_frame": t / args.steps, "real_time_factor_at_30fps": args.steps / (t * 1e-3) / 30.0}
+    single = single_stream_run() if (world == 1 and rank == 0) else None
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -355,7 +377,7 @@ def run_ours(args):
                    "streams_overlap": "front end and back end on two CUDA streams, event-ordered hand-over" if not args.no_overlap else "single stream"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * cam.rows * cam.cols + B * IMU_PER_KF * 7 * 8 / FREQ),
                 "d2h_bytes_per_step": int(B * (W + 1) * 16 * 8 / FREQ), "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_frontend": roof_fe, "kernels": kern, "cpu_baseline": cpu,
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_frontend": roof_fe, "kernels": kern, "cpu_baseline": cpu, "single_stream": single,
         "backend_phase_us_max_over_streams_at_1p9GHz": phases if phases and any(phases.values()) else None,      # debug library only (VIO_LIB_NAME)
         "solve_info_stream0": info[0] if info else None,
         "solve_info_batch": {k: [min(i[k] for i in info), max(i[k] for i in info)] for k in ("iters", "n_feat", "n_proj", "prior_n", "marg_fast", "marg_sweeps", "marg_m", "chol_retry", "err")} if info else None,

@@ -231,15 +231,20 @@ __device__ __noinline__ bool tile_reduced_solve(const BeState &s, const double *
             double d0 = (2 * t <= g) ? Lp[rb + 8 * k + 2 * t] : 0.0, d1 = (2 * t + 1 <= g) ? Lp[rb + 8 * k + 2 * t + 1] : 0.0;
             double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, h0_ = 0.0, h1_ = 0.0;   // four accumulators: a quarter of the dependent DMMA chain
             const double *pa = Lp + rb + t;
+            // operands of the next group are loaded before the MMAs of the current one are issued (software pipelining by hand)
             int j = 0;
-            for (; j + 3 < 2 * k; j += 4) {
-                const double a0 = pa[4 * j], a1 = pa[4 * j + 4], a2 = pa[4 * j + 8], a3 = pa[4 * j + 12];
+            const int nk = 2 * k;
+            double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+            if (nk >= 4) { n0 = pa[0]; n1 = pa[4]; n2 = pa[8]; n3 = pa[12]; }
+            for (; j + 3 < nk; j += 4) {
+                const double a0 = n0, a1 = n1, a2 = n2, a3 = n3;
+                if (j + 7 < nk) { n0 = pa[4 * j + 16]; n1 = pa[4 * j + 20]; n2 = pa[4 * j + 24]; n3 = pa[4 * j + 28]; }
                 tc_dmma(d0, d1, -a0, a0);
                 tc_dmma(e0, e1, -a1, a1);
                 tc_dmma(f0, f1, -a2, a2);
                 tc_dmma(h0_, h1_, -a3, a3);
             }
-            if (j < 2 * k) {
+            if (j < nk) {
                 const double a0 = pa[4 * j], a1 = pa[4 * j + 4];
                 tc_dmma(d0, d1, -a0, a0);
                 tc_dmma(e0, e1, -a1, a1);
@@ -261,8 +266,12 @@ __device__ __noinline__ bool tile_reduced_solve(const BeState &s, const double *
             if (h1) {
                 y0 = Lp[rb1 + 8 * k + 2 * t]; y1 = Lp[rb1 + 8 * k + 2 * t + 1];
                 double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
-                for (int j = 0; j + 1 < 2 * k; j += 2) {
-                    const double b0 = pb[4 * j], a0 = p0[4 * j], c0 = p1[4 * j], b1 = pb[4 * j + 4], a1 = p0[4 * j + 4], c1 = p1[4 * j + 4];
+                const int nk = 2 * k;
+                double nb0 = 0.0, na0 = 0.0, nc0 = 0.0, nb1 = 0.0, na1 = 0.0, nc1 = 0.0;
+                if (nk >= 2) { nb0 = pb[0]; na0 = p0[0]; nc0 = p1[0]; nb1 = pb[4]; na1 = p0[4]; nc1 = p1[4]; }
+                for (int j = 0; j + 1 < nk; j += 2) {
+                    const double b0 = nb0, a0 = na0, c0 = nc0, b1 = nb1, a1 = na1, c1 = nc1;
+                    if (j + 3 < nk) { nb0 = pb[4 * j + 8]; na0 = p0[4 * j + 8]; nc0 = p1[4 * j + 8]; nb1 = pb[4 * j + 12]; na1 = p0[4 * j + 12]; nc1 = p1[4 * j + 12]; }
                     tc_dmma(x0, x1, -a0, b0);
                     tc_dmma(y0, y1, -c0, b0);
                     tc_dmma(e0, e1, -a1, b1);
@@ -272,15 +281,26 @@ __device__ __noinline__ bool tile_reduced_solve(const BeState &s, const double *
             } else {
                 double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, q0 = 0.0, q1 = 0.0;
                 int j = 0;
-                for (; j + 3 < 2 * k; j += 4) {
-                    const double b0 = pb[4 * j], a0 = p0[4 * j], b1 = pb[4 * j + 4], a1 = p0[4 * j + 4];
-                    const double b2 = pb[4 * j + 8], a2 = p0[4 * j + 8], b3 = pb[4 * j + 12], a3 = p0[4 * j + 12];
-                    tc_dmma(x0, x1, -a0, b0);
-                    tc_dmma(e0, e1, -a1, b1);
-                    tc_dmma(f0, f1, -a2, b2);
-                    tc_dmma(q0, q1, -a3, b3);
+                const int nk = 2 * k;
+                double nb[4] = {0.0, 0.0, 0.0, 0.0}, na[4] = {0.0, 0.0, 0.0, 0.0};
+                if (nk >= 4) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) { nb[q] = pb[4 * q]; na[q] = p0[4 * q]; }
                 }
-                if (j < 2 * k) {
+                for (; j + 3 < nk; j += 4) {
+                    double b[4], a[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) { b[q] = nb[q]; a[q] = na[q]; }
+                    if (j + 7 < nk) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { nb[q] = pb[4 * (j + 4 + q)]; na[q] = p0[4 * (j + 4 + q)]; }
+                    }
+                    tc_dmma(x0, x1, -a[0], b[0]);
+                    tc_dmma(e0, e1, -a[1], b[1]);
+                    tc_dmma(f0, f1, -a[2], b[2]);
+                    tc_dmma(q0, q1, -a[3], b[3]);
+                }
+                if (j < nk) {
                     const double b0 = pb[4 * j], a0 = p0[4 * j], b1 = pb[4 * j + 4], a1 = p0[4 * j + 4];
                     tc_dmma(x0, x1, -a0, b0);
                     tc_dmma(e0, e1, -a1, b1);
