@@ -39,6 +39,15 @@ def lib():
         L.vref_preintegrate.argtypes = [C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
         L.vref_imu_factor.argtypes = [DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP]
         L.vref_projection_factor.argtypes = [C.c_double, DP, DP, DP, DP, DP, DP, C.c_double, DP, DP]
+        if hasattr(L, "vpnp_create"):
+            L.vpnp_create.restype = C.c_void_p
+            L.vpnp_create.argtypes = [C.POINTER(_abi.VioConfig)]
+            L.vpnp_destroy.argtypes = [C.c_void_p]
+            L.vpnp_set_init.argtypes = [C.c_void_p, C.c_double, DP, DP, DP, DP, DP]
+            L.vpnp_process_imu.argtypes = [C.c_void_p, C.c_double, DP, DP]
+            L.vpnp_process_image.argtypes = [C.c_void_p, C.c_int, IP, DP, DP, IP, C.c_double, C.c_int]
+            L.vpnp_get_state.argtypes = [C.c_void_p, DP, DP, DP, DP, DP, DP, IP, IP]
+            L.vpnp_perspective_factor.argtypes = [DP, DP, C.c_int, C.c_double, DP, DP, DP, DP, DP]
         _lib = L
     return _lib
 
@@ -140,3 +149,56 @@ def projection_factor(fx, tic, ric, pts_i, pts_j, pi, pj, inv_dep):
     p = lambda x: _abi.ptr(x, C.c_double)
     lib().vref_projection_factor(float(fx), *[p(x) for x in a], float(inv_dep), p(res), p(J))
     return res, J
+
+
+class RefPnP:
+    """The reference's motion-only PnP tracker (vinsPnP, vins_pnp.cpp; FeatureTracker::solveVinsPnP feeds it, feature_tracker.cpp:107-160)
+    behind oracle/pnp_ref.cpp.  SURVEY.md section 8(f) rank 3: the oracle for the next widening step."""
+
+    def __init__(self, cfg):
+        self.h = lib().vpnp_create(C.byref(cfg))
+        if not self.h:
+            raise RuntimeError("vpnp_create failed")
+        self.n = lib().vpnp_size() + 1
+
+    def close(self):
+        if self.h:
+            lib().vpnp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_init(self, header, P, R, V, Ba, Bg):
+        a = [_d(x) for x in (P, R, V, Ba, Bg)]
+        lib().vpnp_set_init(self.h, float(header), *[_abi.ptr(x, C.c_double) for x in a])
+
+    def process_imu(self, dt, acc, gyr):
+        a, g = _d(acc), _d(gyr)
+        lib().vpnp_process_imu(self.h, float(dt), _abi.ptr(a, C.c_double), _abi.ptr(g, C.c_double))
+
+    def process_image(self, ids, obs_xy, pos_xyz, track_num, header, use_pnp=True):
+        ids = np.ascontiguousarray(ids, np.int32); tn = np.ascontiguousarray(track_num, np.int32)
+        o, p = _d(obs_xy), _d(pos_xyz)
+        lib().vpnp_process_image(self.h, len(ids), _abi.ptr(ids, C.c_int32), _abi.ptr(o, C.c_double), _abi.ptr(p, C.c_double),
+                                 _abi.ptr(tn, C.c_int32), float(header), int(use_pnp))
+
+    def state(self):
+        n = self.n
+        P, V, Ba, Bg = (np.zeros((n, 3)) for _ in range(4))
+        R = np.zeros((n, 3, 3)); H = np.zeros(n); fs = np.zeros(n, np.int32); fc = np.zeros(1, np.int32)
+        lib().vpnp_get_state(self.h, *[_abi.ptr(x, C.c_double) for x in (P, R, V, Ba, Bg, H)], _abi.ptr(fs, C.c_int32), _abi.ptr(fc, C.c_int32))
+        return dict(P=P, R=R, V=V, Ba=Ba, Bg=Bg, headers=H, find_solved=fs, frame_count=int(fc[0]))
+
+
+def perspective_factor(obs_xy, pos_xyz, track_num, fx, pose7, ex7):
+    """PerspectiveFactor::Evaluate (perspective_factor.cpp:16-67): residual (2,), d/dpose (2,6), d/dex_pose (2,6)."""
+    res = np.zeros(2); Jp = np.zeros((2, 6)); Je = np.zeros((2, 6))
+    a = [_d(x) for x in (obs_xy, pos_xyz)]
+    b = [_d(x) for x in (pose7, ex7)]
+    lib().vpnp_perspective_factor(_abi.ptr(a[0], C.c_double), _abi.ptr(a[1], C.c_double), int(track_num), float(fx), _abi.ptr(b[0], C.c_double),
+                                  _abi.ptr(b[1], C.c_double), *[_abi.ptr(x, C.c_double) for x in (res, Jp, Je)])
+    return res, Jp, Je

@@ -57,3 +57,19 @@ def quat_err(qa, qb):
     """max over frames of min(|qa-qb|, |qa+qb|) (q and -q are the same rotation)."""
     qa, qb = np.asarray(qa), np.asarray(qb)
     return float(np.minimum(np.abs(qa - qb).max(-1), np.abs(qa + qb).max(-1)).max())
+
+
+def drive_pnp(pnp, seq, k, last_t):
+    """One camera frame of FeatureTracker::solveVinsPnP (feature_tracker.cpp:107-160): the estimator result of frame k - lag (if any),
+    the IMU samples since the previous frame, then the frame's features.  Returns the new `last_t`."""
+    import numpy as np
+    if k >= seq["lag"]:
+        j = k - seq["lag"]
+        pnp.set_init(seq["t"][j], seq["P"][j], seq["R"][j], seq["V"][j], np.zeros(3), np.zeros(3))
+    sel = (seq["imu_t"] > last_t + 1e-9) & (seq["imu_t"] <= seq["t"][k] + 1e-9)
+    tt = last_t
+    for ti, a, g in zip(seq["imu_t"][sel], seq["acc"][sel], seq["gyr"][sel]):
+        pnp.process_imu(ti - tt, a, g)
+        tt = ti
+    pnp.process_image(seq["ids"], seq["obs"][k], seq["X"], seq["track_num"], seq["t"][k], True)
+    return seq["t"][k]

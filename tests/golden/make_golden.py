@@ -21,7 +21,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 import cv2
 import backend_oracle as bo
 import frontend_oracle as fo
-from be_common import Quiet, drive
+from be_common import Quiet, drive, drive_pnp
 from conftest import texture_pair, two_view_points
 
 synth = importlib.import_module("vins-mobile_b200.synth")
@@ -81,7 +81,32 @@ def backend():
                         states=np.array(states), infos=np.array(infos), track_seed=3, n_kf=16, max_cnt=80)
 
 
+def pnp():
+    """pnp_golden.npz: the reference's motion-only PnP tracker (vins_pnp.cpp via oracle/pnp_ref.cpp) on synth.make_pnp_sequence(seed 3):
+    window state after every camera frame, plus one PerspectiveFactor evaluation (perspective_factor.cpp:16-67)."""
+    cfg = abi.default_config(batch=1, max_cnt=150)
+    seq = synth.make_pnp_sequence(3, 16)
+    with Quiet():
+        h = bo.RefPnP(cfg)
+    states, last_t = [], 0.0
+    for k in range(16):
+        with Quiet():
+            last_t = drive_pnp(h, seq, k, last_t)
+            s = h.state()
+        states.append(np.concatenate([s["P"], s["R"].reshape(-1, 9), s["V"], s["headers"][:, None], s["find_solved"][:, None].astype(float)], 1))
+    r = np.random.default_rng(9)
+    q = np.array([0.1, -0.2, 0.05, 1.0]); q /= np.linalg.norm(q)
+    pose = np.concatenate([r.normal(0, 0.3, 3), q])
+    qe = np.array([1.0, 0.0, 0.0, 0.0])                       # ric = ypr2R(0, 0, 180 deg): quaternion (x, y, z, w) = (1, 0, 0, 0)
+    ex = np.concatenate([np.array(cfg.tic[:]), qe])
+    pos = pose[:3] + np.array([0.4, -0.3, -3.0]); ob = np.array([0.12, -0.07])
+    pr, pJp, pJe = bo.perspective_factor(ob, pos, 7, cfg.fx, pose, ex)
+    np.savez_compressed(os.path.join(HERE, "pnp_golden.npz"), states=np.array(states), seed=3, n_frames=16, pf_pose=pose, pf_ex=ex, pf_pos=pos, pf_obs=ob,
+                        pf_track=7, pf_r=pr, pf_Jp=pJp, pf_Je=pJe)
+
+
 if __name__ == "__main__":
     frontend()
     backend()
+    pnp()
     print("golden vectors written to", HERE)

@@ -126,6 +126,48 @@ def test_backend_oracle_reproduces_golden(abi, synth):
         assert [i["marg_flag"], i["n_feat"], i["n_proj"], i["prior_n"]] == g["infos"][k][[0, 1, 2, 4]].tolist()
 
 
+def test_pnp_oracle_reproduces_golden_and_tracks_ground_truth(abi, synth):
+    """SURVEY section 8(f) rank 3 (motion-only PnP tracker): the reference's vins_pnp.cpp / perspective_factor.cpp / imu_factor_pnp.h,
+    compiled unmodified into oracle/_ref, reproduce the committed golden vectors (the solve has no wall-time cap in the oracle, so it is
+    deterministic) and follow the synthetic ground truth to better than 1 cm once the 7-frame window is full."""
+    import backend_oracle as bo
+    if not bo.available() or not hasattr(bo.lib(), "vpnp_create"):
+        pytest.skip("oracle/_ref not built")
+    from be_common import Quiet, drive_pnp
+    g = np.load(os.path.join(GOLD, "pnp_golden.npz"))
+    r, Jp, Je = bo.perspective_factor(g["pf_obs"], g["pf_pos"], int(g["pf_track"]), abi.default_config().fx, g["pf_pose"], g["pf_ex"])
+    assert np.allclose(r, g["pf_r"], rtol=1e-13, atol=0) and np.allclose(Jp, g["pf_Jp"], rtol=1e-13, atol=1e-300) and np.allclose(Je, g["pf_Je"], rtol=1e-13, atol=1e-300)
+    # residual = sqrt_info * (proj - obs) * track_num / 10 and its pose Jacobian against central differences (tangent-space perturbation)
+    def res_at(dp):
+        pose = g["pf_pose"].copy()
+        pose[:3] += dp[:3]
+        x, y, z, w = pose[3:]
+        dq = np.array([0.5 * dp[3], 0.5 * dp[4], 0.5 * dp[5], 1.0])
+        q = np.array([w * dq[0] + x * dq[3] + y * dq[2] - z * dq[1], w * dq[1] - x * dq[2] + y * dq[3] + z * dq[0],
+                      w * dq[2] + x * dq[1] - y * dq[0] + z * dq[3], w * dq[3] - x * dq[0] - y * dq[1] - z * dq[2]])
+        pose[3:] = q / np.linalg.norm(q)
+        return bo.perspective_factor(g["pf_obs"], g["pf_pos"], int(g["pf_track"]), abi.default_config().fx, pose, g["pf_ex"])[0]
+    num = np.stack([(res_at(np.eye(6)[i] * 1e-6) - res_at(-np.eye(6)[i] * 1e-6)) / 2e-6 for i in range(6)], 1)
+    assert np.allclose(num, Jp, rtol=1e-5, atol=1e-4)
+    cfg = abi.default_config(batch=1, max_cnt=150)
+    seq = synth.make_pnp_sequence(int(g["seed"]), int(g["n_frames"]))
+    with Quiet():
+        h = bo.RefPnP(cfg)
+    last_t = 0.0
+    for k in range(int(g["n_frames"])):
+        with Quiet():
+            last_t = drive_pnp(h, seq, k, last_t)
+            s = h.state()
+        got = np.concatenate([s["P"], s["R"].reshape(-1, 9), s["V"], s["headers"][:, None], s["find_solved"][:, None].astype(float)], 1)
+        assert np.allclose(got, g["states"][k], rtol=0, atol=1e-9), f"frame {k}"
+        if k >= 7:
+            i = h.n - 2                                          # FeatureTracker reads vins_pnp.Ps[PNP_SIZE - 1] (feature_tracker.cpp:156)
+            j = int(round(s["headers"][i] * 30.0))
+            assert np.linalg.norm(s["P"][i] - seq["P"][j]) < 0.01, f"frame {k}"
+            assert np.abs(s["R"][i] - seq["R"][j]).max() < 5e-3
+    h.close()
+
+
 # ------------------------------------------------------------------------------- N > 1 host logic over gloo
 _WORKER = r'''
 import importlib, os, sys

@@ -291,3 +291,31 @@ def make_tracks(stream_id: int, n_kf: int, max_cnt: int = 150, cam: Camera | Non
         xyz = np.stack([(un_ - cam.cx) / cam.fx, (vn_ - cam.cy) / cam.fy, np.ones(len(u))], -1)
         frames.append((ids_live.astype(np.int32).copy(), xyz))
     return dict(frames=frames, t_kf=t_kf, imu_t=it, acc=acc, gyr=gyr, per=per, P=P, R=R, V=V, cam=cam)
+
+
+def make_pnp_sequence(stream_id: int, n_frames: int = 16, n_lm: int = 60, cam: Camera | None = None, fps: float = 30.0, imu_hz: float = 200.0,
+                      px_noise: float = 0.1, lag: int = 3):
+    """Input of the motion-only PnP tracker (FeatureTracker::solveVinsPnP, feature_tracker.cpp:107-160): a fixed set of landmarks
+    with known world positions seen in every camera frame (id, normalised observation, position, track_num), the IMU samples between
+    frames, and the estimator results (`solved_vins`) that reach the tracker `lag` frames late.  Ground truth P/R/V per frame."""
+    cam = cam or Camera()
+    traj = Trajectory(stream_id)
+    rng = np.random.default_rng(5000 + stream_id)
+    t = np.arange(n_frames) / fps
+    P, V, R = traj.pos(t), traj.pos(t, 1), traj.R(t)
+    ric = np.array(cam.ric).reshape(3, 3)
+    tic = np.array(cam.tic)
+    c0, Rwc0 = P[0] + R[0] @ tic, R[0] @ ric
+    u = rng.uniform(0.25 * cam.cols, 0.75 * cam.cols, n_lm)
+    v = rng.uniform(0.25 * cam.rows, 0.75 * cam.rows, n_lm)
+    d = np.stack([(u - cam.cx) / cam.fx, (v - cam.cy) / cam.fy, np.ones(n_lm)], -1) @ Rwc0.T
+    X = c0 + d * rng.uniform(2.5, 4.5, (n_lm, 1))
+    imu_t = (np.arange(int(round((n_frames - 1) / fps * imu_hz))) + 1) / imu_hz
+    acc = np.einsum("nji,nj->ni", traj.R(imu_t), traj.pos(imu_t, 2) + np.array([0.0, 0.0, GRAVITY]))
+    gyr = traj.omega_body(imu_t)
+    obs = []
+    for k in range(n_frames):
+        pc = (X - (P[k] + R[k] @ tic)) @ (R[k] @ ric)
+        obs.append(pc[:, :2] / pc[:, 2:3] + rng.normal(0, px_noise / cam.fx, (n_lm, 2)))
+    return dict(t=t, P=P, V=V, R=R, X=X, ids=np.arange(n_lm, dtype=np.int32), track_num=np.full(n_lm, 10, np.int32), obs=np.array(obs),
+                imu_t=imu_t, acc=acc, gyr=gyr, lag=lag)
