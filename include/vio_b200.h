@@ -198,6 +198,29 @@ int vio_prim_projection_factor(const vio_config *cfg, const double pts_i[3], con
                                const double pose_i[7], const double pose_j[7], double inv_dep,
                                double *residual /*2*/, double *J /*2x13 row-major: [pi6 pj6 lambda1]*/);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Motion-only PnP tracker: FeatureTracker::solveVinsPnP (feature_tracker.cpp:107-160) and the
+ * vinsPnP object it drives (vins_pnp.hpp:40-91, vins_pnp.cpp).  `batch` independent 7-frame windows advancing in lock-step.
+ * Replaces: vinsPnP::setInit (:63-83), processIMU (:197-233), processImage (:236-256) incl. updateFeatures / solve_ceres /
+ * slideWindow, PerspectiveFactor::Evaluate (perspective_factor.cpp:16-67), IMUFactorPnP::Evaluate (imu_factor_pnp.h).
+ * The 10 ms wall-time cap of the reference's solve is not reproduced (machine dependent).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct vio_pnp vio_pnp;
+int vio_pnp_create(const vio_config *cfg, vio_pnp **out);
+void vio_pnp_destroy(vio_pnp *p);
+/* solved_vins of every stream (ViewController.mm:734-739): header[batch], P[batch][3], R[batch][9] row-major, V, Ba, Bg [batch][3] */
+int vio_pnp_set_init(vio_pnp *p, const double *header, const double *P, const double *R, const double *V, const double *Ba, const double *Bg);
+/* n consecutive IMU samples: dt[n][batch], acc[n][batch][3], gyr[n][batch][3] */
+int vio_pnp_process_imu(vio_pnp *p, int n, const double *dt, const double *acc, const double *gyr);
+/* the frame's landmarks with a solved position (ids ascending per stream): counts[batch], ids[batch][max_cnt], obs_xy[batch][max_cnt][2]
+ * (normalised image coordinates), pos_xyz[batch][max_cnt][3] (world), track_num[batch][max_cnt], headers[batch] */
+int vio_pnp_process_image(vio_pnp *p, const int32_t *counts, const int32_t *ids, const double *obs_xy, const double *pos_xyz,
+                          const int32_t *track_num, const double *headers, int use_pnp);
+/* window of stream s: P[7][3], R[7][9], V[7][3], headers[7], find_solved[7]; info = {frame_count, error, iterations}; cost = {initial, final}.
+ * FeatureTracker::solveVinsPnP returns index PNP_SIZE - 1 = 5. */
+int vio_pnp_get_state(vio_pnp *p, int s, double *P, double *R, double *V, double *headers, int32_t *find_solved, int32_t info[3], double cost[2]);
+int64_t vio_pnp_launch_count(const vio_pnp *p);
+
 #ifdef __cplusplus
 }
 #endif

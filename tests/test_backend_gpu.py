@@ -276,3 +276,55 @@ def test_marginalisation_eigen_paths(api, cfg, synth, monkeypatch, eig, slow, ex
         except AssertionError as e:
             errors.append(str(e).splitlines()[0] if str(e) else "assertion")
     raise AssertionError(f"three comparisons against fresh reference objects failed: {errors}")
+
+
+
+def test_pnp_tracker_matches_reference(api, abi, synth, capsys):
+    """the batched CUDA motion-only PnP tracker against the reference's own vins_pnp.cpp (oracle/pnp_ref.cpp)
+    on synthetic sequences -- the 7-frame window (P, R, V, headers, find_solved) after every camera frame, two streams in one batch."""
+    from be_common import drive_pnp
+    if not hasattr(bo.lib(), "vpnp_create"):
+        pytest.skip("oracle/_ref built without the PnP tracker")
+    B, n_frames = 2, 16
+    cfg = abi.default_config(batch=B, max_cnt=150)
+    cfg1 = abi.default_config(batch=1, max_cnt=150)
+    seqs = [synth.make_pnp_sequence(3 + b, n_frames) for b in range(B)]
+    with Quiet():
+        refs = [bo.RefPnP(cfg1) for _ in range(B)]
+    gpu = api.PnP(cfg)
+    last = [0.0] * B
+    worst = 0.0
+    for k in range(n_frames):
+        with Quiet():
+            for b in range(B):
+                last[b] = drive_pnp(refs[b], seqs[b], k, last[b])
+        # the same calls, batched: estimator result of frame k - lag, IMU samples since the previous frame, the frame's landmarks
+        s0 = seqs[0]
+        if k >= s0["lag"]:
+            j = k - s0["lag"]
+            gpu.set_init([q["t"][j] for q in seqs], [q["P"][j] for q in seqs], [q["R"][j] for q in seqs], [q["V"][j] for q in seqs],
+                         np.zeros((B, 3)), np.zeros((B, 3)))
+        t_prev = s0["t"][k - 1] if k > 0 else 0.0
+        sel = (s0["imu_t"] > t_prev + 1e-9) & (s0["imu_t"] <= s0["t"][k] + 1e-9)
+        if sel.any():
+            tt = np.concatenate([[t_prev], s0["imu_t"][sel]])
+            gpu.process_imu(np.repeat(np.diff(tt)[:, None], B, 1), np.stack([q["acc"][sel] for q in seqs], 1), np.stack([q["gyr"][sel] for q in seqs], 1))
+        n = len(s0["ids"])
+        ids = np.zeros((B, 150), np.int32); obs = np.zeros((B, 150, 2)); pos = np.zeros((B, 150, 3)); tn = np.zeros((B, 150), np.int32)
+        for b, q in enumerate(seqs):
+            ids[b, :n] = q["ids"]; obs[b, :n] = q["obs"][k]; pos[b, :n] = q["X"]; tn[b, :n] = q["track_num"]
+        gpu.process_image(np.full(B, n), ids, obs, pos, tn, [q["t"][k] for q in seqs], True)
+        for b in range(B):
+            with Quiet():
+                r = refs[b].state()
+            g = gpu.state(b)
+            assert g["err"] == 0 and g["frame_count"] == r["frame_count"], f"frame {k} stream {b}"
+            assert np.array_equal(g["find_solved"], r["find_solved"]) and np.array_equal(g["headers"], r["headers"]), f"frame {k} stream {b}"
+            e = max(np.abs(g["P"] - r["P"]).max(), np.abs(g["R"] - r["R"]).max(), np.abs(g["V"] - r["V"]).max())
+            worst = max(worst, e)
+            assert e < 1e-6, f"frame {k} stream {b}: window differs by {e} (iters {g['iters']}, cost {g['cost0']} -> {g['cost1']})"
+    with capsys.disabled():
+        print(f"\n[pnp] worst |gpu - reference| over {n_frames} frames x {B} streams: {worst:.3e}")
+    gpu.close()
+    for r in refs:
+        r.close()

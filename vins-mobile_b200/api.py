@@ -60,6 +60,15 @@ def lib():
         L.vio_prim_min_eig_candidates.argtypes = [cfgp, UP, FP, C.c_int, C.c_int, FP, C.POINTER(C.c_int), FP]
         L.vio_prim_lk.argtypes = [cfgp, UP, UP, FP, C.c_int, FP, UP]
         L.vio_prim_ransac_f.argtypes = [cfgp, FP, FP, C.c_int, UP, C.POINTER(C.c_int)]
+        if hasattr(L, "vio_pnp_create"):
+            L.vio_pnp_create.argtypes = [cfgp, C.POINTER(vp)]
+            L.vio_pnp_destroy.argtypes = [vp]
+            L.vio_pnp_set_init.argtypes = [vp, DP, DP, DP, DP, DP, DP]
+            L.vio_pnp_process_imu.argtypes = [vp, C.c_int, DP, DP, DP]
+            L.vio_pnp_process_image.argtypes = [vp, IP, IP, DP, DP, IP, DP, C.c_int]
+            L.vio_pnp_get_state.argtypes = [vp, C.c_int, DP, DP, DP, DP, IP, IP, DP]
+            L.vio_pnp_launch_count.restype = C.c_int64
+            L.vio_pnp_launch_count.argtypes = [vp]
         if hasattr(L, "vio_backend_create"):
             L.vio_backend_create.argtypes = [cfgp, C.POINTER(vp)]
             L.vio_backend_destroy.argtypes = [vp]
@@ -398,3 +407,52 @@ def prim_projection_factor(cfg, pts_i, pts_j, pi, pj, inv_dep):
     p = lambda x: ptr(x, C.c_double)
     _check(lib().vio_prim_projection_factor(C.byref(cfg), *[p(x) for x in a], float(inv_dep), p(res), p(J)), "vio_prim_projection_factor")
     return res, J
+
+
+class PnP:
+    """Batched vinsPnP (vins_pnp.hpp:40-91): the motion-only tracker FeatureTracker::solveVinsPnP drives (feature_tracker.cpp:107-160)."""
+    N = 7
+
+    def __init__(self, cfg: VioConfig):
+        self.cfg, self.B, self.maxp = cfg, cfg.batch, cfg.max_cnt
+        self.h = C.c_void_p()
+        _check(lib().vio_pnp_create(C.byref(cfg), C.byref(self.h)), "vio_pnp_create")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().vio_pnp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_init(self, header, P, R, V, Ba, Bg):
+        d = lambda a, *shape: np.ascontiguousarray(a, np.float64).reshape(self.B, *shape)
+        a = [d(header), d(P, 3), d(R, 9), d(V, 3), d(Ba, 3), d(Bg, 3)]
+        _check(lib().vio_pnp_set_init(self.h, *[ptr(x, C.c_double) for x in a]), "vio_pnp_set_init")
+
+    def process_imu(self, dt, acc, gyr):
+        dt = np.ascontiguousarray(dt, np.float64).reshape(-1, self.B)
+        n = dt.shape[0]
+        acc = np.ascontiguousarray(acc, np.float64).reshape(n, self.B, 3); gyr = np.ascontiguousarray(gyr, np.float64).reshape(n, self.B, 3)
+        _check(lib().vio_pnp_process_imu(self.h, n, ptr(dt, C.c_double), ptr(acc, C.c_double), ptr(gyr, C.c_double)), "vio_pnp_process_imu")
+
+    def process_image(self, counts, ids, obs_xy, pos_xyz, track_num, headers, use_pnp=True):
+        counts = np.ascontiguousarray(counts, np.int32).reshape(self.B)
+        ids = np.ascontiguousarray(ids, np.int32).reshape(self.B, self.maxp); tn = np.ascontiguousarray(track_num, np.int32).reshape(self.B, self.maxp)
+        obs = np.ascontiguousarray(obs_xy, np.float64).reshape(self.B, self.maxp, 2); pos = np.ascontiguousarray(pos_xyz, np.float64).reshape(self.B, self.maxp, 3)
+        hdr = np.ascontiguousarray(headers, np.float64).reshape(self.B)
+        _check(lib().vio_pnp_process_image(self.h, ptr(counts, C.c_int32), ptr(ids, C.c_int32), ptr(obs, C.c_double), ptr(pos, C.c_double),
+                                           ptr(tn, C.c_int32), ptr(hdr, C.c_double), int(use_pnp)), "vio_pnp_process_image")
+
+    def state(self, s=0):
+        n = self.N
+        P, V = np.zeros((n, 3)), np.zeros((n, 3))
+        R = np.zeros((n, 3, 3)); H = np.zeros(n); fs = np.zeros(n, np.int32); info = np.zeros(3, np.int32); cost = np.zeros(2)
+        _check(lib().vio_pnp_get_state(self.h, s, ptr(P, C.c_double), ptr(R, C.c_double), ptr(V, C.c_double), ptr(H, C.c_double), ptr(fs, C.c_int32),
+                                       ptr(info, C.c_int32), ptr(cost, C.c_double)), "vio_pnp_get_state")
+        return dict(P=P, R=R, V=V, headers=H, find_solved=fs, frame_count=int(info[0]), err=int(info[1]), iters=int(info[2]), cost0=float(cost[0]),
+                    cost1=float(cost[1]))

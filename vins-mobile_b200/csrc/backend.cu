@@ -544,3 +544,177 @@ extern "C" int vio_prim_projection_factor(const vio_config *cfg, const double pt
     memcpy(res, out, 16); memcpy(J, out + 2, 26 * 8);
     return VIO_OK;
 }
+
+// ================================================================== motion-only PnP tracker
+#include "be_pnp.cuh"
+
+struct vio_pnp {
+    vio_config cfg;
+    PnpState s;
+    cudaStream_t stream;
+    std::vector<void *> allocs;
+    int64_t launches;
+    int *d_counts, *d_ids, *d_track;
+    double *d_obs, *d_pos, *d_hdr, *d_imu, *d_init;
+    size_t imu_cap;
+    size_t smem;
+};
+
+template <typename T>
+static int palloc(vio_pnp *p, T **ptr, size_t n) {
+    VIO_CUDA_TRY(vio_dev_alloc((void **)ptr, n * sizeof(T), p->allocs));
+    return VIO_OK;
+}
+__global__ void pnp_fill_kernel(double *p, size_t n, double v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void pnp_identity_kernel(double *R, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) R[i] = (i % 9) % 4 == 0 ? 1.0 : 0.0;
+}
+
+extern "C" void vio_pnp_destroy(vio_pnp *p) {
+    if (!p) return;
+    cudaSetDevice(p->cfg.device);
+    cudaStreamSynchronize(p->stream);
+    for (void *q : p->allocs) cudaFree(q);
+    cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+extern "C" int vio_pnp_create(const vio_config *cfg, vio_pnp **out) {
+    if (!cfg || !out || cfg->batch < 1 || cfg->max_cnt < 1 || cfg->max_cnt > VIO_MAXP) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(cfg->device));
+    vio_pnp *p = new (std::nothrow) vio_pnp();
+    if (!p) return VIO_ERR_ARG;
+    p->cfg = *cfg; p->launches = 0;
+    VIO_CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    PnpState &s = p->s;
+    memset(&s, 0, sizeof(s));
+    s.B = cfg->batch; s.MAXF = cfg->max_cnt; s.max_iters = 5;                 // options.max_num_iterations = 5 (vins_pnp.cpp:320)
+    s.gravity = cfg->gravity; s.sqrt_info = cfg->fx / 1.5;                    // PerspectiveFactor::sqrt_info (vins_pnp.cpp:17-20)
+    s.noise[0] = s.noise[2] = cfg->acc_n * cfg->acc_n; s.noise[1] = s.noise[3] = cfg->gyr_n * cfg->gyr_n;
+    s.noise[4] = cfg->acc_w * cfg->acc_w; s.noise[5] = cfg->gyr_w * cfg->gyr_w;
+    memcpy(s.tic, cfg->tic, sizeof(s.tic)); memcpy(s.ric, cfg->ric, sizeof(s.ric));
+    const size_t B = s.B, N = PNP_N, F = s.MAXF;
+    int rc = VIO_OK;
+    if (!rc) rc = palloc(p, &s.Ps, B * N * 3);
+    if (!rc) rc = palloc(p, &s.Rs, B * N * 9);
+    if (!rc) rc = palloc(p, &s.Vs, B * N * 3);
+    if (!rc) rc = palloc(p, &s.Bas, B * N * 3);
+    if (!rc) rc = palloc(p, &s.Bgs, B * N * 3);
+    if (!rc) rc = palloc(p, &s.Headers, B * N);
+    if (!rc) rc = palloc(p, &s.iv, B * 8);
+    if (!rc) rc = palloc(p, &s.solved, B * N);
+    if (!rc) rc = palloc(p, &s.dv, B * 8);
+    if (!rc) rc = palloc(p, &s.pre, B * N * PR_STRIDE);
+    if (!rc) rc = palloc(p, &s.f_n, B * N);
+    if (!rc) rc = palloc(p, &s.f_id, B * N * F);
+    if (!rc) rc = palloc(p, &s.f_track, B * N * F);
+    if (!rc) rc = palloc(p, &s.f_obs, B * N * F * 2);
+    if (!rc) rc = palloc(p, &s.f_pos, B * N * F * 3);
+    if (!rc) rc = palloc(p, &p->d_counts, B);
+    if (!rc) rc = palloc(p, &p->d_ids, B * F);
+    if (!rc) rc = palloc(p, &p->d_track, B * F);
+    if (!rc) rc = palloc(p, &p->d_obs, B * F * 2);
+    if (!rc) rc = palloc(p, &p->d_pos, B * F * 3);
+    if (!rc) rc = palloc(p, &p->d_hdr, B);
+    if (!rc) rc = palloc(p, &p->d_init, B * 22);
+    p->imu_cap = 64;
+    if (!rc) rc = palloc(p, &p->d_imu, p->imu_cap * B * 7);
+    if (rc) { vio_pnp_destroy(p); return rc; }
+    VIO_CUDA_TRY(cudaDeviceSynchronize());                                     // zero-fills run on the legacy default stream
+    // clearState (vins_pnp.cpp:22-52): identity rotations; Headers start at -1 (the reference leaves them uninitialised)
+    pnp_identity_kernel<<<64, 256, 0, p->stream>>>(s.Rs, B * N * 9);
+    pnp_fill_kernel<<<64, 256, 0, p->stream>>>(s.Headers, B * N, -1.0);
+    p->smem = pnp_smem_doubles() * sizeof(double);
+    VIO_CUDA_TRY(cudaFuncSetAttribute(pnp_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    VIO_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    p->launches += 2;
+    *out = p;
+    return VIO_OK;
+}
+
+// solved_vins of every stream (ViewController.mm:734-739): header[B], P[B][3], R[B][9] row-major, V[B][3], Ba[B][3], Bg[B][3]
+extern "C" int vio_pnp_set_init(vio_pnp *p, const double *header, const double *P, const double *R, const double *V, const double *Ba, const double *Bg) {
+    if (!p || !header || !P || !R || !V || !Ba || !Bg) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(p->cfg.device));
+    const size_t B = p->s.B;
+    double *d = p->d_init;
+    double *dh = d, *dP = dh + B, *dR = dP + 3 * B, *dV = dR + 9 * B, *dBa = dV + 3 * B, *dBg = dBa + 3 * B;
+    VIO_CUDA_TRY(cudaMemcpyAsync(dh, header, B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(dP, P, 3 * B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(dR, R, 9 * B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(dV, V, 3 * B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(dBa, Ba, 3 * B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(dBg, Bg, 3 * B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    pnp_set_init_kernel<<<(p->s.B + 127) / 128, 128, 0, p->stream>>>(p->s, dh, dP, dR, dV, dBa, dBg);
+    p->launches++;
+    VIO_CUDA_TRY(cudaGetLastError());
+    VIO_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+
+// vinsPnP::processIMU for n consecutive samples: dt[n][B], acc[n][B][3], gyr[n][B][3]
+extern "C" int vio_pnp_process_imu(vio_pnp *p, int n, const double *dt, const double *acc, const double *gyr) {
+    if (!p || n < 0 || (n > 0 && (!dt || !acc || !gyr))) return VIO_ERR_ARG;
+    if (n == 0) return VIO_OK;
+    VIO_CUDA_TRY(cudaSetDevice(p->cfg.device));
+    const size_t B = p->s.B;
+    if ((size_t)n > p->imu_cap) {
+        VIO_CUDA_TRY(cudaStreamSynchronize(p->stream));
+        double *q;
+        VIO_CUDA_TRY(cudaMalloc((void **)&q, (size_t)n * B * 7 * sizeof(double)));
+        p->allocs.push_back(q);
+        p->d_imu = q; p->imu_cap = n;
+    }
+    double *d_dt = p->d_imu, *d_acc = d_dt + (size_t)n * B, *d_gyr = d_acc + (size_t)n * B * 3;
+    VIO_CUDA_TRY(cudaMemcpyAsync(d_dt, dt, (size_t)n * B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(d_acc, acc, (size_t)n * B * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(d_gyr, gyr, (size_t)n * B * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    pnp_imu_kernel<<<(p->s.B + 3) / 4, 128, 0, p->stream>>>(p->s, n, d_dt, d_acc, d_gyr);
+    p->launches++;
+    VIO_CUDA_TRY(cudaGetLastError());
+    VIO_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+
+// vinsPnP::processImage: the landmarks solveVinsPnP matched in this frame (feature_tracker.cpp:119-132), ids ascending per stream:
+// counts[B], ids[B][max_cnt], obs_xy[B][max_cnt][2] (normalised image coordinates), pos_xyz[B][max_cnt][3] (world), track_num[B][max_cnt]
+extern "C" int vio_pnp_process_image(vio_pnp *p, const int32_t *counts, const int32_t *ids, const double *obs_xy, const double *pos_xyz,
+                                     const int32_t *track_num, const double *headers, int use_pnp) {
+    if (!p || !counts || !ids || !obs_xy || !pos_xyz || !track_num || !headers) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(p->cfg.device));
+    const size_t B = p->s.B, F = p->s.MAXF;
+    VIO_CUDA_TRY(cudaMemcpyAsync(p->d_counts, counts, B * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(p->d_ids, ids, B * F * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(p->d_track, track_num, B * F * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(p->d_obs, obs_xy, B * F * 2 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(p->d_pos, pos_xyz, B * F * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(p->d_hdr, headers, B * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    pnp_image_kernel<<<p->s.B, PNP_T, p->smem, p->stream>>>(p->s, p->d_counts, p->d_ids, p->d_obs, p->d_pos, p->d_track, p->d_hdr, use_pnp ? 1 : 0);
+    p->launches++;
+    VIO_CUDA_TRY(cudaGetLastError());
+    VIO_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+
+// window of stream s after the last call: P[7][3], R[7][9] row-major, V[7][3], headers[7], find_solved[7]; info = {frame_count, err,
+// iterations of the last solve}; cost = {initial, final} of the last solve.  FeatureTracker reads index PNP_SIZE - 1 = 5 (feature_tracker.cpp:156).
+extern "C" int vio_pnp_get_state(vio_pnp *p, int s, double *P, double *R, double *V, double *headers, int32_t *find_solved, int32_t info[3], double cost[2]) {
+    if (!p || s < 0 || s >= p->s.B) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(p->cfg.device));
+    const size_t k = (size_t)s * PNP_N;
+    int iv[8]; double dv[8];
+    if (P) VIO_CUDA_TRY(cudaMemcpyAsync(P, p->s.Ps + 3 * k, PNP_N * 3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (R) VIO_CUDA_TRY(cudaMemcpyAsync(R, p->s.Rs + 9 * k, PNP_N * 9 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (V) VIO_CUDA_TRY(cudaMemcpyAsync(V, p->s.Vs + 3 * k, PNP_N * 3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (headers) VIO_CUDA_TRY(cudaMemcpyAsync(headers, p->s.Headers + k, PNP_N * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (find_solved) VIO_CUDA_TRY(cudaMemcpyAsync(find_solved, p->s.solved + k, PNP_N * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(iv, p->s.iv + (size_t)s * 8, sizeof(iv), cudaMemcpyDeviceToHost, p->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(dv, p->s.dv + (size_t)s * 8, sizeof(dv), cudaMemcpyDeviceToHost, p->stream));
+    VIO_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (info) { info[0] = iv[0]; info[1] = iv[2]; info[2] = iv[3]; }
+    if (cost) { cost[0] = dv[6]; cost[1] = dv[7]; }
+    return VIO_OK;
+}
+extern "C" int64_t vio_pnp_launch_count(const vio_pnp *p) { return p ? p->launches : 0; }
