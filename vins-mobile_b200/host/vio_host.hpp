@@ -6,6 +6,7 @@
 // :701-882 compiles against them with the OpenCV / Eigen types swapped for the plain structs below.  One object = one stream
 // (batch 1); batched use goes through the C-ABI directly.  Everything numerical happens in libvio_b200.so on the GPU.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <map>
@@ -26,10 +27,66 @@ inline void check(int rc, const char *what) {
     if (rc != VIO_OK) throw std::runtime_error(std::string(what) + " failed with code " + std::to_string(rc));
 }
 
+// vins_pnp.hpp:27-39
+struct VINS_RESULT { double header; Vector3d Ba, Bg, P; Matrix3d R; Vector3d V; };
+struct Vector2d { double x, y; };
+struct IMG_MSG_LOCAL { int id; Vector2d observation; Vector3d position; int track_num; };
+struct IMU_MSG_LOCAL { double header; Vector3d acc, gyr; };            // feature_tracker.hpp:30-35
+
+// vins_pnp.hpp:40-91 -- the motion-only tracker behind FeatureTracker::solveVinsPnP (7-frame window, landmarks fixed)
+class vinsPnP {
+  public:
+    static constexpr int PNP_SIZE = 6;                                   // global_param.hpp:29
+    explicit vinsPnP(const vio_config &cfg) : cfg_(cfg), frame_count(0) {
+        cfg_.batch = 1;
+        check(vio_pnp_create(&cfg_, &h_), "vio_pnp_create");
+    }
+    ~vinsPnP() { vio_pnp_destroy(h_); }
+    vinsPnP(const vinsPnP &) = delete;
+    void setIMUModel() {}                                                // PerspectiveFactor::sqrt_info = fx / 1.5 comes from vio_config
+    void setExtrinsic() {}
+    void setInit(const VINS_RESULT &r) {                                 // vins_pnp.cpp:63-83
+        check(vio_pnp_set_init(h_, &r.header, &r.P.x, r.R.m, &r.V.x, &r.Ba.x, &r.Bg.x), "vio_pnp_set_init");
+    }
+    void processIMU(double dt, const Vector3d &acc, const Vector3d &gyr) {     // vins_pnp.cpp:197-233
+        check(vio_pnp_process_imu(h_, 1, &dt, &acc.x, &gyr.x), "vio_pnp_process_imu");
+    }
+    void processImage(std::vector<IMG_MSG_LOCAL> &feature_msg, double header, bool use_pnp) {      // vins_pnp.cpp:236-256
+        const int cap = cfg_.max_cnt;
+        if ((int)feature_msg.size() > cap) throw std::length_error("vinsPnP::processImage: more than max_cnt features");
+        std::vector<int32_t> ids(cap, 0), tn(cap, 0);
+        std::vector<double> obs(2 * cap, 0.0), pos(3 * cap, 0.0);
+        int32_t n = 0;
+        for (auto &f : feature_msg) {
+            ids[n] = f.id; tn[n] = f.track_num; obs[2 * n] = f.observation.x; obs[2 * n + 1] = f.observation.y;
+            pos[3 * n] = f.position.x; pos[3 * n + 1] = f.position.y; pos[3 * n + 2] = f.position.z; n++;
+        }
+        check(vio_pnp_process_image(h_, &n, ids.data(), obs.data(), pos.data(), tn.data(), &header, use_pnp ? 1 : 0), "vio_pnp_process_image");
+        double P[21], R[63], V[21], H[7];
+        int32_t fs[7], info[3];
+        check(vio_pnp_get_state(h_, 0, P, R, V, H, fs, info, nullptr), "vio_pnp_get_state");
+        for (int i = 0; i <= PNP_SIZE; i++) {
+            Ps[i] = Vector3d{P[3 * i], P[3 * i + 1], P[3 * i + 2]}; Vs[i] = Vector3d{V[3 * i], V[3 * i + 1], V[3 * i + 2]};
+            for (int k = 0; k < 9; k++) Rs[i].m[k] = R[9 * i + k];
+            Headers[i] = H[i]; find_solved[i] = fs[i] != 0;
+        }
+        frame_count = info[0];
+    }
+    int frame_count;
+    Vector3d Ps[PNP_SIZE + 1], Vs[PNP_SIZE + 1];
+    Matrix3d Rs[PNP_SIZE + 1];
+    double Headers[PNP_SIZE + 1];
+    bool find_solved[PNP_SIZE + 1];
+
+  private:
+    vio_config cfg_;
+    vio_pnp *h_ = nullptr;
+};
+
 // feature_tracker.hpp:52-90
 class FeatureTracker {
   public:
-    explicit FeatureTracker(const vio_config &cfg) : cfg_(cfg), img_cnt(0), update_finished(false), use_pnp(false) {
+    explicit FeatureTracker(const vio_config &cfg) : cfg_(cfg), img_cnt(0), update_finished(false), use_pnp(false), vins_pnp(cfg), current_time(-1.0) {
         cfg_.batch = 1;
         check(vio_frontend_create(&cfg_, &h_), "vio_frontend_create");
         ids.reserve(cfg_.max_cnt);
@@ -44,11 +101,11 @@ class FeatureTracker {
 
     // void readImage(const cv::Mat &_img, cv::Mat &result, int _frame_cnt, vector<Point2f> &good_pts, vector<double> &track_len,
     //                double header, Vector3d &P, Matrix3d &R, bool vins_normal)               feature_tracker.hpp:59
-    // P / R are outputs of the motion-only PnP tracker (solveVinsPnP), which is out of scope (use_pnp defaults to false,
-    // ViewController.mm:144): they are left untouched.
+    // P / R are outputs of the motion-only PnP tracker (solveVinsPnP below; use_pnp defaults to false, ViewController.mm:144):
+    // written when vins_normal is true, as in feature_tracker.cpp:203-208.
     void readImage(const Mat &_img, Mat &result, int _frame_cnt, std::vector<Point2f> &good_pts, std::vector<double> &track_len, double header,
                    Vector3d &P, Matrix3d &R, bool vins_normal) {
-        (void)_frame_cnt; (void)header; (void)P; (void)R; (void)vins_normal;
+        (void)_frame_cnt;
         if (_img.rows != cfg_.rows || _img.cols != cfg_.cols) throw std::invalid_argument("readImage: image size differs from vio_config");
         result = _img;
         int published = 0;
@@ -71,8 +128,39 @@ class FeatureTracker {
             image_msg.clear();
             for (int i = 0; i < n; i++) image_msg[ids[i]] = Vector3d{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
         }
+        solveVinsPnP(header, P, R, vins_normal);                            // feature_tracker.cpp:203-208 (after the tracking step)
         update_finished = true;
         img_cnt = (img_cnt + 1) % cfg_.freq;                                // the caller does this at ViewController.mm:494
+    }
+
+    // bool solveVinsPnP(double header, Vector3d &P, Matrix3d &R, bool vins_normal)                 feature_tracker.cpp:107-160
+    bool solveVinsPnP(double header, Vector3d &P, Matrix3d &R, bool vins_normal) {
+        if (!vins_normal) return false;
+        // The reference matches solved_features against ids with a merge that assumes ascending ids and runs between the first
+        // RANSAC rejection and setMask (feature_tracker.cpp:119-132,207).  The C-ABI exposes the tracker state after the whole
+        // frame, so the match is done by id on that state: on a detecting frame the points setMask dropped are not offered.
+        std::vector<IMG_MSG_LOCAL> feature_msg;
+        std::map<int, size_t> where;
+        for (size_t i = 0; i < ids.size(); i++) where[ids[i]] = i;
+        for (auto &it : solved_features) {
+            auto f = where.find(it.id);
+            if (f == where.end()) continue;
+            IMG_MSG_LOCAL tmp = it;
+            tmp.observation = Vector2d{(cur_pts[f->second].x - cfg_.cx) / cfg_.fx, (cur_pts[f->second].y - cfg_.cy) / cfg_.fy};
+            feature_msg.push_back(tmp);
+        }
+        std::sort(feature_msg.begin(), feature_msg.end(), [](const IMG_MSG_LOCAL &a, const IMG_MSG_LOCAL &b) { return a.id < b.id; });
+        vins_pnp.setInit(solved_vins);
+        for (auto &it : imu_msgs) {
+            if (current_time < 0) current_time = it.header;
+            const double dt = it.header - current_time;
+            current_time = it.header;
+            vins_pnp.processIMU(dt, it.acc, it.gyr);
+        }
+        vins_pnp.processImage(feature_msg, header, use_pnp);
+        P = vins_pnp.Ps[vinsPnP::PNP_SIZE - 1];
+        R = vins_pnp.Rs[vinsPnP::PNP_SIZE - 1];
+        return true;
     }
 
     std::vector<Point2f> cur_pts;
@@ -81,6 +169,11 @@ class FeatureTracker {
     std::map<int, Vector3d> image_msg;
     bool update_finished;
     bool use_pnp;
+    std::vector<IMG_MSG_LOCAL> solved_features;          // feature_tracker.hpp:77-79: filled by the caller from the estimator (ViewController.mm:445-447)
+    VINS_RESULT solved_vins{};
+    std::vector<IMU_MSG_LOCAL> imu_msgs;
+    vinsPnP vins_pnp;
+    double current_time;
     vio_frontend *handle() { return h_; }
 
   private:
