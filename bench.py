@@ -323,9 +323,10 @@ def run_ours(args):
     phases = prof.pop("_phases", None)
     kern = {k: {"launches": c, "ms_per_launch": t / c} for k, (c, t) in prof.items() if c}
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r01h_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp))["bytes_per_launch"]
+    import glob
+    tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))          # newest committed ncu capture (names sort by round)
+    if tps:
+        traffic = json.load(open(tps[-1]))["bytes_per_launch"]
     # (1) the dominant kernel of the step: solve_kernel -- FP64 ALU / tensor pipe (DMMA), no HBM roofline (Jacobians are never
     #     materialised).  Algorithmic flops per launch = SURVEY.md section 8(d) flop model with every stream's own P, L, iterations.
     fp64 = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json"))) if os.path.exists(os.path.join(ROOT, "profiles", "fp64_peak.json")) else \
