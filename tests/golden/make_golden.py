@@ -6,6 +6,9 @@
                         pre-integration, IMUFactor, ProjectionFactor, and the window state after every keyframe of a 16-keyframe
                         synthetic track sequence (synth.make_tracks(seed 3), regenerated deterministically by the tests).
 
+  clahe_golden.npz    : cv2 CLAHE (clip 3, 8x8 tiles) of a 160x128 image
+  pnp_golden.npz      : the reference's motion-only PnP tracker (oracle/pnp_ref.cpp) on a synthetic sequence
+
     python tests/golden/make_golden.py
 """
 import importlib
@@ -81,6 +84,12 @@ def backend():
                         states=np.array(states), infos=np.array(infos), track_seed=3, n_kf=16, max_cnt=80)
 
 
+def clahe():
+    """clahe_golden.npz: what the OpenCV 4.13 binary returns for createCLAHE(clipLimit=3, tileGridSize=(8,8)).apply on a 160x128 image."""
+    img0, _ = texture_pair(seed=11, rows=160, cols=128)
+    np.savez_compressed(os.path.join(HERE, "clahe_golden.npz"), img=img0, out=fo.cv2_clahe(img0, 3.0, (8, 8)), cv2_version=np.array(cv2.__version__))
+
+
 def pnp():
     """pnp_golden.npz: the reference's motion-only PnP tracker (vins_pnp.cpp via oracle/pnp_ref.cpp) on synth.make_pnp_sequence(seed 3):
     window state after every camera frame, plus one PerspectiveFactor evaluation (perspective_factor.cpp:16-67)."""
@@ -108,5 +117,6 @@ def pnp():
 if __name__ == "__main__":
     frontend()
     backend()
+    clahe()
     pnp()
     print("golden vectors written to", HERE)

@@ -97,6 +97,12 @@ def test_frontend_oracle_reproduces_golden():
     assert np.array_equal(fo.r_find_fundamental(g["f_x1"], g["f_x2"]), g["f_mask"])
 
 
+def test_clahe_oracle_reproduces_golden():
+    import frontend_oracle as fo
+    g = np.load(os.path.join(GOLD, "clahe_golden.npz"))
+    assert np.array_equal(fo.r_clahe(g["img"], 3.0, (8, 8)), g["out"])
+
+
 def test_backend_oracle_reproduces_golden(abi, synth):
     import backend_oracle as bo
     if not bo.available():
