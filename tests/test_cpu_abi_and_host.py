@@ -57,6 +57,10 @@ def test_no_cpu_fallback(api, abi):
         api.BackEnd(abi.default_config())
     with pytest.raises(api.VioError):
         api.prim_pyramid(abi.default_config(), np.zeros((640, 480), np.uint8))
+    with pytest.raises(api.VioError):
+        api.PnP(abi.default_config())
+    with pytest.raises(api.VioError):
+        api.prim_clahe(abi.default_config(), np.zeros((640, 480), np.uint8))
 
 
 def test_product_path_does_not_touch_oracle():
@@ -76,6 +80,11 @@ def test_argument_validation(api, abi):
     bad = abi.default_config()
     bad.window_size = 100
     assert api.lib().vio_backend_create(C.byref(bad), C.byref(h)) == 1
+    bad = abi.default_config()
+    bad.max_cnt = 100000
+    assert api.lib().vio_pnp_create(C.byref(bad), C.byref(h)) == 1
+    assert api.lib().vio_frontend_set_clahe(None, 1, 3.0, 8, 8) == 1
+    assert api.lib().vio_pnp_process_imu(None, 1, None, None, None) == 1
 
 
 # ------------------------------------------------------------------------------- golden vectors vs the oracle
