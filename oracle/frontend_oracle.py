@@ -13,7 +13,7 @@ Two layers live here:
 * `cv2_*`  : thin calls into the real OpenCV binary with exactly the arguments
              the reference passes (feature_tracker.cpp:95,181,198,263).
 * `r_*`    : numpy restatements of the same routines with an EXPLICIT operation
-             order (integer-exact window sums, named f32 / f64 steps).  These are
+             order (named f32 / f64 steps, cv2's SIMD-lane summation order).  These are
              what the CUDA kernels are compared against bit-for-bit, and they are
              themselves pinned against `cv2_*` (tests/test_oracle_frontend.py and
              the committed fixtures in tests/golden/).
@@ -136,11 +136,49 @@ def _bilin(win, w00, w01, w10, w11, shift):
     return (v + (1 << (shift - 1))) >> shift
 
 
+def _seq_sum_f32(vals):
+    """Sequential f32 accumulation along the last axis, starting from +0 (one rounding per add)."""
+    acc = np.zeros(vals.shape[:-1], f32)
+    for k in range(vals.shape[-1]):
+        acc = (acc + vals[..., k]).astype(f32)
+    return acc
+
+
+def _lk_sum_cov(p):
+    """sum of the (N,21,21) exact integer products gx*gx / gx*gy / gy*gy in the order of OpenCV 4.13's LKTrackerInvoker
+    (modules/video/src/lkpyramid.cpp, the CV_SIMD128 branch of the baseline SSE3 build -- the file is not dispatched):
+    columns 0..15 of every row go through two 4-lane groups, lane k accumulating RN_f32(product) of columns k, k+4, k+8, k+12 row
+    after row with separate mul/add (no FMA); columns 16..20 are added one by one, row-major, into the scalar accumulator;
+    iA += v_reduce_sum(q) with the SSE reduction ((l0+l2)+(l1+l3)).  Pinned bit-exact against cv2 in tests/test_oracle_frontend.py."""
+    pf = p.astype(f32)                                                   # RN of the exact product == f32 multiply of the int16s
+    n = p.shape[0]
+    lanes = _seq_sum_f32(np.stack([pf[:, :, [k, k + 4, k + 8, k + 12]].reshape(n, -1) for k in range(4)], 1))    # (N,4)
+    tail = _seq_sum_f32(pf[:, :, 16:21].reshape(n, -1))
+    red = ((lanes[:, 0] + lanes[:, 2]).astype(f32) + (lanes[:, 1] + lanes[:, 3]).astype(f32)).astype(f32)
+    return (tail + red).astype(f32)
+
+
+def _lk_sum_mismatch(pd):
+    """sum of the (N,21,21) exact integer products diff*gx (or diff*gy), same source: v_dotprod adds the products of columns (k, k+4)
+    and (k+8, k+12) exactly in int32, v_cvt_f32 rounds, and four f32 lanes k = 0..3 accumulate them row after row; the scalar tail
+    takes columns 16..20 one by one; ib += ((l0+l2) + (l1+l3))."""
+    n = pd.shape[0]
+    ch = []
+    for k in range(4):
+        a = (pd[:, :, k] + pd[:, :, k + 4]).astype(f32)
+        b = (pd[:, :, k + 8] + pd[:, :, k + 12]).astype(f32)
+        ch.append(np.stack([a, b], 2).reshape(n, -1))
+    lanes = _seq_sum_f32(np.stack(ch, 1))
+    tail = _seq_sum_f32(pd[:, :, 16:21].astype(f32).reshape(n, -1))
+    red = ((lanes[:, 0] + lanes[:, 2]).astype(f32) + (lanes[:, 1] + lanes[:, 3]).astype(f32)).astype(f32)
+    return (tail + red).astype(f32)
+
+
 def r_lk_track(prev_pyr, next_pyr, prev_pts: np.ndarray):
     """Restatement of calcOpticalFlowPyrLK(prev, next, pts, Size(21,21), 3) with default
-    criteria/flags (feature_tracker.cpp:181).  Window sums are formed EXACTLY in integers and
-    converted to f32 once (cv2 accumulates in f32 in SIMD order: results agree to ~1e-4 px,
-    status agrees).  Returns (next_pts f32 (N,2), status u8 (N,))."""
+    criteria/flags (feature_tracker.cpp:181).  Window products are exact integers; they are ACCUMULATED in f32 in the lane
+    order of cv2's SSE code (_lk_sum_cov / _lk_sum_mismatch), which makes positions bit-identical to cv2.
+    Returns (next_pts f32 (N,2), status u8 (N,))."""
     n = len(prev_pts)
     prev_pts = np.asarray(prev_pts, f32).reshape(n, 2)
     next_pts = np.zeros((n, 2), f32)
@@ -150,7 +188,11 @@ def r_lk_track(prev_pyr, next_pyr, prev_pts: np.ndarray):
     half = f32((LK_WIN - 1) * 0.5)
     win = LK_WIN
     eps2 = f64(LK_EPS) * f64(LK_EPS)
-    for level in range(LK_LEVELS, -1, -1):
+    # buildOpticalFlowPyramid stops at the last level whose successor would not be larger than the window in both directions
+    top = 0
+    while top < min(LK_LEVELS, len(prev_pyr) - 1) and min(prev_pyr[top + 1].shape) > win:
+        top += 1
+    for level in range(top, -1, -1):
         I = prev_pyr[level]
         J = next_pyr[level]
         rows, cols = I.shape
@@ -162,7 +204,7 @@ def r_lk_track(prev_pyr, next_pyr, prev_pts: np.ndarray):
 
         scale = f32(1.0 / (1 << level))
         prev = prev_pts * scale
-        if level == LK_LEVELS:
+        if level == top:
             nxt = prev.copy()
         else:
             nxt = next_pts * f32(2.0)
@@ -184,9 +226,9 @@ def r_lk_track(prev_pyr, next_pyr, prev_pts: np.ndarray):
         gy = _bilin(_gather(dyp, ipy_s, ipx_s, win + 1), w00, w01, w10, w11, W_BITS)
         gx = gx.astype(np.int64)
         gy = gy.astype(np.int64)
-        A11 = (gx * gx).sum((1, 2)).astype(f32) * FLT_SCALE
-        A12 = (gx * gy).sum((1, 2)).astype(f32) * FLT_SCALE
-        A22 = (gy * gy).sum((1, 2)).astype(f32) * FLT_SCALE
+        A11 = _lk_sum_cov(gx * gx) * FLT_SCALE
+        A12 = _lk_sum_cov(gx * gy) * FLT_SCALE
+        A22 = _lk_sum_cov(gy * gy) * FLT_SCALE
         D = A11 * A22 - A12 * A12
         d12 = A11 - A22
         min_eig = ((A22 + A11) - np.sqrt(d12 * d12 + (f32(4.0) * A12) * A12)) / f32(2 * win * win)
@@ -218,8 +260,8 @@ def r_lk_track(prev_pyr, next_pyr, prev_pts: np.ndarray):
             v00, v01, v10, v11 = _weights(nxt[:, 0] - inx.astype(f32), nxt[:, 1] - iny.astype(f32))
             Jw = _bilin(_gather(Jpad, iny_s, inx_s, win + 1), v00, v01, v10, v11, W_BITS - 5)
             diff = (Jw - Iw).astype(np.int64)
-            b1 = (diff * gx).sum((1, 2)).astype(f32) * FLT_SCALE
-            b2 = (diff * gy).sum((1, 2)).astype(f32) * FLT_SCALE
+            b1 = _lk_sum_mismatch(diff * gx) * FLT_SCALE
+            b2 = _lk_sum_mismatch(diff * gy) * FLT_SCALE
             dxv = ((A12 * b2 - A22 * b1) * Dinv).astype(f32)
             dyv = ((A12 * b1 - A11 * b2) * Dinv).astype(f32)
             delta = np.stack([dxv, dyv], 1)
@@ -436,12 +478,19 @@ def _solve_cubic(c):
     return [float(r) for r in roots]
 
 
+# cv::SVD (JacobiSVDImpl_, modules/core/src/lapack.cpp) completes the two null-space rows of the FULL_UV decomposition of the 7x9
+# system from pseudo-random vectors: entries +-1/9 with the sign of bit 8 of successive draws of cv::RNG(0x12345678), projected off
+# the rows found so far and normalised.  The generator is re-seeded on every call, so the two vectors are constants:
+_SVD_FILL_SIGNS = ((-1, -1, 1, -1, -1, -1, -1, 1, 1), (1, -1, 1, 1, 1, 1, 1, -1, 1))
+
+
 def _null_space_7x9(A):
-    """Orthonormal basis (f1, f2) of the null space of the 7x9 epipolar system.  OpenCV takes the
-    last two right singular vectors of its SVD; any orthonormal basis spans the same pencil of F,
-    and every F is renormalised to F[8]=1 afterwards, so the set of candidate F is basis-independent
-    (only the ORDER of the up-to-3 roots may differ).  Explicit Householder QR of A^T (9x7), columns
-    8 and 9 of Q -- the same algorithm, step for step, as run_7point() in csrc/fe_ransac.cuh."""
+    """The basis (f1, f2) of the null space of the 7x9 epipolar system that run7Point() takes from cv::SVDecomp(FULL_UV): rows 7 and
+    8 of Vt.  Both singular values are zero there, so OpenCV's Jacobi SVD GENERATES those rows (see _SVD_FILL_SIGNS): f1 is the
+    normalised null-space component of the constant vector r1, f2 that of r2 made orthogonal to f1.  The basis matters: it fixes the
+    ORDER in which solveCubic emits the up-to-three F candidates, and RANSAC keeps the first of equally good models.  The null space
+    itself comes from an explicit Householder QR of A^T (9x7), columns 8 and 9 of Q -- the same algorithm, step for step, as
+    run_7point() in csrc/fe_ransac.cuh; (f1, f2) agree with cv2.SVDecomp to round-off (checked in tests/test_oracle_frontend.py)."""
     M = A.T.astype(f64).copy()                        # 9 x 7
     beta = np.zeros(7)
     for k in range(7):
@@ -465,15 +514,57 @@ def _null_space_7x9(A):
             for r in range(k, 9):
                 y[r] -= s * M[r, k]
         out.append(y)
-    return out[0], out[1]
+    n1, n2 = out
+    # coordinates of r1, r2 in the orthonormal null-space basis (n1, n2); the common factor 1/9 drops out in the normalisation
+    a1 = sum(_SVD_FILL_SIGNS[0][r] * n1[r] for r in range(9))
+    a2 = sum(_SVD_FILL_SIGNS[0][r] * n2[r] for r in range(9))
+    b1 = sum(_SVD_FILL_SIGNS[1][r] * n1[r] for r in range(9))
+    b2 = sum(_SVD_FILL_SIGNS[1][r] * n2[r] for r in range(9))
+    na = np.sqrt(a1 * a1 + a2 * a2)
+    if na == 0:
+        return n1, n2
+    a1 /= na
+    a2 /= na
+    d = b1 * a1 + b2 * a2
+    b1 -= d * a1
+    b2 -= d * a2
+    nb = np.sqrt(b1 * b1 + b2 * b2)
+    if nb == 0:
+        return n1, n2
+    b1 /= nb
+    b2 /= nb
+    return a1 * n1 + a2 * n2, b1 * n1 + b2 * n2
 
 
 def r_run_7point(m1, m2, null_space=_null_space_7x9):
-    """run7Point: up to three F (row-major 9-vectors, F[8]=1)."""
+    """run7Point of OpenCV 4.13 (modules/calib3d/src/fundam.cpp): the seven pairs are first normalised like the 8-point algorithm
+    (centroid to the origin, mean distance sqrt 2), the null-space basis is rows 7, 8 of the FULL_UV SVD (_null_space_7x9), the
+    cubic det(lambda f1' + f2) = 0 gives up to three F, each scaled to F[8] = 1, de-normalised (T2^T F T1) and scaled to F[8] = 1
+    again.  The normalisation matters for parity: it changes the parametrisation of the pencil and with it the ORDER of the roots
+    (checked against cv2.findFundamentalMat(FM_7POINT), which returns the candidates in that order).  Returns row-major 9-vectors."""
+    m1 = np.asarray(m1, f32)
+    m2 = np.asarray(m2, f32)
+    c1x = c1y = c2x = c2y = f64(0)
+    for i in range(7):
+        c1x += f64(m1[i, 0]); c1y += f64(m1[i, 1]); c2x += f64(m2[i, 0]); c2y += f64(m2[i, 1])
+    t = f64(1.0) / 7
+    c1x *= t; c1y *= t; c2x *= t; c2y *= t
+    sc1 = sc2 = f64(0)
+    for i in range(7):
+        dx, dy = f64(m1[i, 0]) - c1x, f64(m1[i, 1]) - c1y
+        sc1 += np.sqrt(dx * dx + dy * dy)
+        dx, dy = f64(m2[i, 0]) - c2x, f64(m2[i, 1]) - c2y
+        sc2 += np.sqrt(dx * dx + dy * dy)
+    sc1 *= t
+    sc2 *= t
+    if sc1 < f64(FLT_EPSILON) or sc2 < f64(FLT_EPSILON):
+        return []
+    sc1 = np.sqrt(f64(2.0)) / sc1
+    sc2 = np.sqrt(f64(2.0)) / sc2
     A = np.zeros((7, 9), f64)
     for i in range(7):
-        x0, y0 = f64(m1[i, 0]), f64(m1[i, 1])
-        x1, y1 = f64(m2[i, 0]), f64(m2[i, 1])
+        x0, y0 = (f64(m1[i, 0]) - c1x) * sc1, (f64(m1[i, 1]) - c1y) * sc1
+        x1, y1 = (f64(m2[i, 0]) - c2x) * sc2, (f64(m2[i, 1]) - c2y) * sc2
         A[i] = [x1 * x0, x1 * y0, x1, y1 * x0, y1 * y0, y1, x0, y0, 1.0]
     f1, f2 = null_space(A)
     # f1 := f1 - f2 so that F = lambda*f1' + f2  (det(lambda*f1 + (1-lambda)*f2) = 0)
@@ -506,12 +597,29 @@ def r_run_7point(m1, m2, null_space=_null_space_7x9):
     for lam in roots:
         mu = 1.0
         s = f1[8] * lam + f2[8]
+        G = np.zeros(9, f64)
         if abs(s) > np.finfo(f64).eps:
             mu = 1.0 / s
             lam *= mu
-            F = f1 * lam + f2 * mu
-            F[8] = 1.0
-            out.append(F)
+            G[8] = 1.0
+        for i in range(8):
+            G[i] = f1[i] * lam + f2[i] * mu
+        # de-normalise: F = T2^T G T1 with T = [s 0 -s cx; 0 s -s cy; 0 0 1]
+        #   H = G T1 (columns), then F = T2^T H (rows)
+        H = np.zeros(9, f64)
+        for r in range(3):
+            g0, g1, g2 = G[3 * r], G[3 * r + 1], G[3 * r + 2]
+            H[3 * r] = g0 * sc1
+            H[3 * r + 1] = g1 * sc1
+            H[3 * r + 2] = g2 - (g0 * c1x + g1 * c1y) * sc1
+        F = np.zeros(9, f64)
+        for k in range(3):
+            F[k] = H[k] * sc2
+            F[3 + k] = H[3 + k] * sc2
+            F[6 + k] = H[6 + k] - (H[k] * c2x + H[3 + k] * c2y) * sc2
+        if abs(F[8]) > f64(FLT_EPSILON):
+            F = F * (1.0 / F[8])
+        out.append(F)
     return out
 
 

@@ -102,7 +102,7 @@ def test_frontend_oracle_reproduces_golden():
     assert np.array_equal(fo.r_good_features(g["img0"], mask, 20), g["corners"])
     nxt, st = fo.r_lk_track(fo.r_build_pyramid(g["img0"]), fo.r_build_pyramid(g["img1"]), g["lk_pts"])
     assert np.array_equal(st, g["lk_status"])
-    assert np.abs(nxt - g["lk_next"])[st == 1].max() < 2e-3
+    assert np.array_equal(nxt[st == 1].view(np.uint32), g["lk_next"][st == 1].view(np.uint32))      # bitwise the cv2 output
     assert np.array_equal(fo.r_find_fundamental(g["f_x1"], g["f_x2"]), g["f_mask"])
 
 

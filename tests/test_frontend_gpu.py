@@ -54,7 +54,26 @@ def test_lk_bit_exact_vs_oracle_and_status_vs_cv2(api, cfg, pair):
     assert np.array_equal(n_g[ok].view(np.uint32), n_r[ok].view(np.uint32)), "LK positions must be bit-identical to the oracle"
     n_c, s_c = fo.cv2_lk_track(img0, img1, pts)
     assert np.array_equal(s_g, s_c)
-    assert np.abs(n_g - n_c)[ok].max() < 2e-3
+    assert np.array_equal(n_g[ok].view(np.uint32), n_c[ok].view(np.uint32)), "LK positions must be bit-identical to cv2.calcOpticalFlowPyrLK"
+
+
+def test_lk_negative_fourth_bilinear_weight(api, cfg, pair):
+    """The three rounded 14-bit bilinear weights can add up to 2^14 + 1, which makes the fourth one -1 (OpenCV keeps it as a signed
+    short).  Regression: the J-window sampler packed the weights as unsigned 16-bit halves (one gross LK error in ~20 000 tracks)."""
+    img0, _ = pair
+    rng = np.random.default_rng(1)
+    fr = []
+    while len(fr) < 40:
+        a, b = rng.uniform(0, 0.02, 2).astype(np.float32)
+        w = fo._weights(np.array([a]), np.array([b]))
+        if int(w[3][0]) < 0:
+            fr.append((a, b))
+    base = fo.cv2_good_features(img0, None, 40)
+    pts = (base + np.array(fr, np.float32)[:len(base)]).astype(np.float32)
+    n_g, s_g = api.prim_lk(cfg, img0, img0, pts)          # identical images: the first J window sits exactly on the template position
+    n_c, s_c = fo.cv2_lk_track(img0, img0, pts)
+    assert np.array_equal(s_g, s_c) and s_c.all()
+    assert np.array_equal(n_g.view(np.uint32), n_c.view(np.uint32))
 
 
 def test_good_features_identical(api, cfg, pair):
@@ -126,13 +145,32 @@ def test_stream_ids_bit_exact_vs_restated_oracle(api, abi, get_stream):
                 assert tuple(xyz) == msg[int(i)]
 
 
-def test_stream_vs_cv2_tracker(api, abi, get_stream):
-    """Against the OpenCV binary itself ids stay identical until the first threshold decision that falls inside cv2's f32
-    summation-order noise (hard parts); 19 frames of stream 0 are clear of such an event."""
-    s = get_stream(0, 19)
-    for k, (g, ids, pts, cnt, msg, st, st_o) in enumerate(_run_stream(api, abi, "cv2", s, 19)):
-        assert np.array_equal(g["ids"], ids), f"frame {k}"
-        assert np.abs(g["pts"] - pts).max() < 2e-3
+def test_stream_vs_cv2_tracker(api, abi, synth):
+    """The headline front-end parity claim against the OpenCV binary itself (the stand-in for the reference's arithmetic, SURVEY
+    section 8(c)): 8 streams x 300 frames (the stream length of SURVEY section 8(d)) through one batch-8 handle; after EVERY frame the
+    tracked ids, the positions (bitwise), the track counts and -- on publishing frames -- image_msg equal those of a
+    FeatureTracker restatement whose KLT / RANSAC-F / goodFeaturesToTrack calls go to cv2 (feature_tracker.cpp:162-321)."""
+    nb, nf = 8, 300
+    streams = [synth.make_stream(i, nf, device="cuda") for i in range(nb)]
+    c = abi.default_config(batch=nb, max_cnt=150)
+    fe = api.FrontEnd(c)
+    trs = [fo.FeatureTrackerOracle(max_cnt=150, backend="cv2") for _ in range(nb)]
+    for k in range(nf):
+        ims = np.stack([s.images[k].cpu().numpy() for s in streams])
+        pub = fe.read_images(ims)
+        for b, tr in enumerate(trs):
+            _, _, pub_o = tr.read_image(ims[b])
+            assert pub == pub_o
+            g = fe.stream(b)
+            assert np.array_equal(g["ids"], tr.ids), f"stream {b} frame {k}: ids differ"
+            assert np.array_equal(g["pts"].view(np.uint32), tr.cur_pts.view(np.uint32)), f"stream {b} frame {k}: points differ"
+            assert np.array_equal(g["track_cnt"], tr.track_cnt), f"stream {b} frame {k}"
+            if pub:
+                assert {int(i) for i in g["ids"]} == set(tr.image_msg.keys())
+                for i, xyz in zip(g["ids"], g["norm_xyz"]):
+                    assert tuple(xyz) == tr.image_msg[int(i)]
+    fe.close()
+    assert all(len(tr.ids) > 100 for tr in trs)
 
 
 def test_batch_equals_single(api, abi, get_stream):
@@ -184,7 +222,7 @@ def test_frontend_golden_vectors(api, abi):
     assert np.array_equal(corners, g["corners"])
     nxt, st = api.prim_lk(c, img0, img1, g["lk_pts"])
     assert np.array_equal(st, g["lk_status"])
-    assert np.abs(nxt - g["lk_next"])[st == 1].max() < 2e-3
+    assert np.array_equal(nxt[st == 1].view(np.uint32), g["lk_next"][st == 1].view(np.uint32))      # bitwise the cv2 output
     m, _ = api.prim_ransac_f(c, g["f_x1"], g["f_x2"])
     assert np.array_equal(m, g["f_mask"])
 

@@ -167,14 +167,22 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(uint8_t *__restrict__ 
 // K4  pyramidal LK, one warp per feature (cv::calcOpticalFlowPyrLK(Size(21,21), 3); oracle r_lk_track).
 //     Template: 24x24 u8 patch of I (REFLECT_101) staged in shared memory, Scharr gradients formed on the fly
 //     (zero outside the image), 14-bit fixed-point bilinear weights, int16-range template values held in
-//     registers (14 pixels per lane).  The 2x2 normal equations and the mismatch vector are reduced EXACTLY in
-//     integers with warp shuffles and converted to f32 once.
+//     registers (14 window pixels per lane).  All window PRODUCTS are exact integers; they are ACCUMULATED in f32 in the
+//     order of OpenCV's SSE code (oracle _lk_sum_cov / _lk_sum_mismatch): per sum four "SIMD lane" chains (columns k, k+4, k+8,
+//     k+12 of rows 0..20) and one scalar-tail chain (columns 16..20), each a strictly sequential f32 accumulation, combined as
+//     tail + ((c0 + c2) + (c1 + c3)).  That order is what makes positions bit-identical to cv2, so it is reproduced literally:
+//     the lanes that own the window pixels write their addends to shared memory in chain order and one lane per chain adds
+//     them up (15 chains for the covariance sums once per level, 10 chains for the mismatch vector once per iteration).
+//     Pixel ownership: lanes 0..23 = (SIMD lane k = lane / 6, sixth j = lane % 6) own the pair addends 7j..7j+6 of chain k
+//     (addend a = row a >> 1, columns k + 8 (a & 1) and that + 4); lanes 24..31 own 14 consecutive tail pixels each.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int LK_WARPS = 4;
 constexpr int LK_JP = 32;                                 // edge of the staged J neighbourhood: the 22x22 window may drift +-5 px before a re-stage
 constexpr int LK_JM = 5;
-constexpr int LK_NPIX = LK_WIN * LK_WIN;                 // 441
-constexpr int LK_PIX = (LK_NPIX + 31) / 32;              // 14 pixels per lane
+constexpr int LK_IP = 32;                                 // row stride of the staged 24x24 I patch
+constexpr int LK_PIX = 14;                                // window pixels per lane (32 * 14 = 448 >= 441)
+constexpr int LK_QS = 448;                                // covariance phase: floats per sum (4 chains x 84 + tail 105, padded to 112)
+constexpr int LK_ACC = 3 * LK_QS;                         // mismatch phase uses 8 x 48 + 2 x 112 = 608 of them
 
 __device__ __forceinline__ void lk_weights(float fx, float fy, int &w00, int &w01, int &w10, int &w11) {
     const float s = (float)(1 << W_BITS);
@@ -185,7 +193,7 @@ __device__ __forceinline__ void lk_weights(float fx, float fy, int &w00, int &w0
     w11 = (1 << W_BITS) - w00 - w01 - w10;
 }
 
-// stage an (nr x nc) u8 window whose top-left is (y0, x0) into dst (row stride 24), 4 loads in flight per lane
+// stage an (nr x nc) u8 window whose top-left is (y0, x0) into dst (row stride LK_IP), 4 loads in flight per lane
 __device__ __forceinline__ void lk_stage(uint8_t *dst, const uint8_t *__restrict__ im, int rows, int cols, int y0, int x0, int nr, int nc,
                                          int lane) {
     const int total = nr * nc;
@@ -198,7 +206,7 @@ __device__ __forceinline__ void lk_stage(uint8_t *dst, const uint8_t *__restrict
         for (int t = 0; t < 4; t++) {
             const int i = i0 + 32 * t;
             const int r = i / nc, c = i - r * nc;
-            d[t] = r * 24 + c;
+            d[t] = r * LK_IP + c;
             if (i < total)
                 v[t] = inner ? base[r * cols + c] : im[(size_t)reflect101(y0 + r, rows) * cols + reflect101(x0 + c, cols)];
         }
@@ -241,15 +249,42 @@ __device__ __forceinline__ void lk_stage_j(uint8_t *A, uint8_t *Bc, const uint8_
     }
 }
 
-__global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevels J, const float2 *__restrict__ prev_pts,
+// two-way dot product of SIGNED 16-bit weights (low/high half of a) with the two low UNSIGNED bytes of b, plus c.  The fourth bilinear
+// weight 2^14 - w00 - w01 - w10 is -1 when the three rounded weights add up to 2^14 + 1 (OpenCV keeps it as a signed short too).
+__device__ __forceinline__ int lk_dp2a(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// one chain: strictly sequential f32 accumulation of 4 * n4 addends starting from +0 (adding the +0 pads changes nothing)
+__device__ __forceinline__ float lk_chain(const float *p, int n4) {
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    float acc = 0.f;
+#pragma unroll 3
+    for (int i = 0; i < n4; i++) {
+        const float4 v = q[i];
+        acc = fadd(acc, v.x); acc = fadd(acc, v.y); acc = fadd(acc, v.z); acc = fadd(acc, v.w);
+    }
+    return acc;
+}
+// tail + ((c0 + c2) + (c1 + c3)): v_reduce_sum of the SSE accumulator, then added to the scalar accumulator
+__device__ __forceinline__ float lk_combine(float r, int l0) {
+    const float c0 = __shfl_sync(0xffffffffu, r, l0), c1 = __shfl_sync(0xffffffffu, r, l0 + 1), c2 = __shfl_sync(0xffffffffu, r, l0 + 2),
+                c3 = __shfl_sync(0xffffffffu, r, l0 + 3);
+    return fadd(fadd(c0, c2), fadd(c1, c3));
+}
+
+#ifndef LK_MINB
+#define LK_MINB 1
+#endif
+__global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I, PyrLevels J, const float2 *__restrict__ prev_pts,
                                                            float2 *__restrict__ next_pts, uint8_t *__restrict__ status,
                                                            const int *__restrict__ n_pts, int maxp) {
     VIO_POISON(256u);
-    // per warp: 24x24 template neighbourhood of I, 22x22 (stride 24) window of J, and the bilinear template (Iw, gx, gy) as int16.
-    // Everything is shared-memory resident so that the per-pixel loops stay rolled (small code, few registers, 8 warps per CTA).
-    __shared__ uint8_t sI[LK_WARPS][24 * 24];
+    __shared__ __align__(16) uint8_t sI[LK_WARPS][24 * LK_IP];          // rows ipy-1 .. ipy+22, cols ipx-1 .. ipx+22 (stride 32)
     __shared__ __align__(16) uint8_t sJ[LK_WARPS][2][LK_JP * LK_JP];    // copy A and the one-byte-shifted copy B (lk_stage_j)
-    __shared__ short4 sT[LK_WARPS][LK_NPIX];            // (Iw, gx, gy, -) per window pixel: one 8-byte load per pixel per iteration
+    __shared__ __align__(16) float sAcc[LK_WARPS][LK_ACC];              // addends in chain order
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int f = blockIdx.x * LK_WARPS + warp;
@@ -257,19 +292,49 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
     const float2 pt = prev_pts[(size_t)b * maxp + f];
     uint8_t *pI = sI[warp];
     uint8_t *pJA = sJ[warp][0], *pJB = sJ[warp][1];
-    short4 *tT = sT[warp];
+    float *acc = sAcc[warp];
     const float half = 10.f;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
     float nx = 0.f, ny = 0.f;          // nextPts[ptidx] (level coordinates, window centre)
     bool ok = true;                    // status[ptidx]
 
-    for (int level = LK_LEVELS; level >= 0; level--) {
+    // window pixels owned by this lane: woff = y * 32 + x (window coordinates), nvalid of them real
+    const bool is_tail = lane >= 24;
+    const int ck = lane / 6, cj = lane - 6 * ck, ct = lane - 24;
+    int woff[LK_PIX];
+#pragma unroll
+    for (int i = 0; i < LK_PIX; i++) {
+        if (!is_tail) {
+            const int a = 7 * cj + (i >> 1);
+            woff[i] = (a >> 1) * LK_JP + ck + 8 * (a & 1) + 4 * (i & 1);
+        } else {
+            const int a = min(14 * ct + i, 104);
+            const int y = (a * 13108) >> 16;                             // a / 5 for a < 105
+            woff[i] = y * LK_JP + 16 + a - 5 * y;
+        }
+    }
+    const int nvalid = is_tail ? min(105 - 14 * ct, LK_PIX) : LK_PIX;
+    // where this lane's addends go: covariance phase (per sum q: + q * LK_QS) and mismatch phase (sum 0; sum 1 at + off_b2)
+    const int off_a = is_tail ? 336 + 14 * ct : 84 * ck + 14 * cj;
+    const int off_b = is_tail ? 384 + 14 * ct : 48 * ck + 8 * cj;
+    const int off_b2 = is_tail ? 112 : 192;
+    // which chain this lane adds up: covariance phase lane = 5 q + c (c = 4: tail), mismatch phase lanes 0..7 = 4 s + k, lanes 8, 9 tails
+    const int qa = lane / 5, ca = lane - 5 * qa;
+    const float *chain_a = acc + qa * LK_QS + (ca < 4 ? 84 * ca : 336);
+    const int n4_a = lane < 15 ? (ca < 4 ? 21 : 27) : 0;
+    const float *chain_b = acc + (lane < 8 ? 48 * lane : 384 + 112 * (lane - 8));
+    const int n4_b = lane < 8 ? 12 : (lane < 10 ? 27 : 0);
+
+    // cv::buildOpticalFlowPyramid stops at the last level whose successor would not be larger than the window in both directions
+    int top = 0;
+    while (top < LK_LEVELS && min(I.rows[top + 1], I.cols[top + 1]) > LK_WIN) top++;
+    for (int level = top; level >= 0; level--) {
         const int rows = I.rows[level], cols = I.cols[level];
         const uint8_t *__restrict__ imI = I.p[level] + (size_t)b * I.stride[level];
         const uint8_t *__restrict__ imJ = J.p[level] + (size_t)b * J.stride[level];
         const float scale = 1.f / (float)(1 << level);
         float px = fmul(pt.x, scale), py = fmul(pt.y, scale);
-        if (level == LK_LEVELS) { nx = px; ny = py; }
+        if (level == top) { nx = px; ny = py; }
         else { nx = fmul(nx, 2.f); ny = fmul(ny, 2.f); }
         px = fsub(px, half); py = fsub(py, half);
         const int ipx = (int)floorf(px), ipy = (int)floorf(py);
@@ -287,37 +352,49 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
         short2 *sD = reinterpret_cast<short2 *>(pJA);
         for (int i = lane; i < 22 * 22; i += 32) {
             const int yy = (i * 2979) >> 16, xx = i - 22 * yy;           // i / 22 for i < 484
-            const uint8_t *q = pI + (yy + 1) * 24 + (xx + 1);
+            const uint8_t *q = pI + (yy + 1) * LK_IP + (xx + 1);
             const int gyi = ipy + yy, gxi = ipx + xx;
             short2 d = make_short2(0, 0);
             if (gyi >= 0 && gyi < rows && gxi >= 0 && gxi < cols) {
-                const int tl = q[-25], tc = q[-24], tr = q[-23], ml = q[-1], mr = q[1], bl = q[23], bc = q[24], br = q[25];
+                const int tl = q[-LK_IP - 1], tc = q[-LK_IP], tr = q[-LK_IP + 1], ml = q[-1], mr = q[1], bl = q[LK_IP - 1], bc = q[LK_IP], br = q[LK_IP + 1];
                 d.x = (short)(3 * (tr - tl) + 10 * (mr - ml) + 3 * (br - bl));
                 d.y = (short)(3 * (bl - tl) + 10 * (bc - tc) + 3 * (br - tr));
             }
             sD[i] = d;
         }
         __syncwarp();
-        // pass 2: bilinear template (Iw, gx, gy) per window pixel
-        int a11 = 0, a12 = 0, a22 = 0;
-#pragma unroll 2
-        for (int p = lane; p < LK_NPIX; p += 32) {
-            const int y = (p * 3121) >> 16, x = p - LK_WIN * y;
-            const uint8_t *q = pI + (y + 1) * 24 + (x + 1);
-            const short2 *dq = sD + y * 22 + x;
-            const short2 d00 = dq[0], d01 = dq[1], d10 = dq[22], d11 = dq[23];
-            const int iv = w00 * q[0] + w01 * q[1] + w10 * q[24] + w11 * q[25];
-            const int dxv = w00 * d00.x + w01 * d01.x + w10 * d10.x + w11 * d11.x;
-            const int dyv = w00 * d00.y + w01 * d01.y + w10 * d10.y + w11 * d11.y;
-            const int ivs = (iv + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-            const int gxs = (dxv + (1 << (W_BITS - 1))) >> W_BITS;
-            const int gys = (dyv + (1 << (W_BITS - 1))) >> W_BITS;
-            tT[p] = make_short4((short)ivs, (short)gxs, (short)gys, 0);
-            a11 += gxs * gxs; a12 += gxs * gys; a22 += gys * gys;
+        // pass 2: bilinear template (Iw, gx, gy) of the lane's own window pixels, kept in registers; covariance products to the chains
+        int tI[LK_PIX], tG[LK_PIX];                                      // Iw ; gx | gy << 16
+#pragma unroll
+        for (int i = 0; i < LK_PIX; i += 2) {
+            float pa[2], pb[2], pc[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int y = woff[i + h] >> 5, x = woff[i + h] & 31;
+                const uint8_t *q = pI + (y + 1) * LK_IP + (x + 1);
+                const short2 *dq = sD + y * 22 + x;
+                const short2 d00 = dq[0], d01 = dq[1], d10 = dq[22], d11 = dq[23];
+                const int iv = w00 * q[0] + w01 * q[1] + w10 * q[LK_IP] + w11 * q[LK_IP + 1];
+                const int dxv = w00 * d00.x + w01 * d01.x + w10 * d10.x + w11 * d11.x;
+                const int dyv = w00 * d00.y + w01 * d01.y + w10 * d10.y + w11 * d11.y;
+                const bool valid = i + h < nvalid;
+                const int ivs = valid ? (iv + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5) : 0;
+                const int gxs = valid ? (dxv + (1 << (W_BITS - 1))) >> W_BITS : 0;
+                const int gys = valid ? (dyv + (1 << (W_BITS - 1))) >> W_BITS : 0;
+                tI[i + h] = ivs;
+                tG[i + h] = (gxs & 0xffff) | (gys << 16);
+                pa[h] = (float)(gxs * gxs); pb[h] = (float)(gxs * gys); pc[h] = (float)(gys * gys);     // RN of the exact product, as the f32 multiply
+            }
+            *reinterpret_cast<float2 *>(acc + off_a + i) = make_float2(pa[0], pa[1]);
+            *reinterpret_cast<float2 *>(acc + LK_QS + off_a + i) = make_float2(pb[0], pb[1]);
+            *reinterpret_cast<float2 *>(acc + 2 * LK_QS + off_a + i) = make_float2(pc[0], pc[1]);
         }
-        const float A11 = fmul(__ll2float_rn(warp_sum_split(a11)), FLT_SCALE);
-        const float A12 = fmul(__ll2float_rn(warp_sum_split(a12)), FLT_SCALE);
-        const float A22 = fmul(__ll2float_rn(warp_sum_split(a22)), FLT_SCALE);
+        __syncwarp();
+        const float ra = lk_chain(chain_a, n4_a);
+        __syncwarp();
+        const float A11 = fmul(fadd(__shfl_sync(0xffffffffu, ra, 4), lk_combine(ra, 0)), FLT_SCALE);
+        const float A12 = fmul(fadd(__shfl_sync(0xffffffffu, ra, 9), lk_combine(ra, 5)), FLT_SCALE);
+        const float A22 = fmul(fadd(__shfl_sync(0xffffffffu, ra, 14), lk_combine(ra, 10)), FLT_SCALE);
         const float D = fsub(fmul(A11, A22), fmul(A12, A12));
         const float d12 = fsub(A11, A22);
         const float mineig = __fdiv_rn(fsub(fadd(A22, A11), __fsqrt_rn(fadd(fmul(d12, d12), fmul(fmul(4.f, A12), A12)))),
@@ -347,24 +424,41 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(PyrLevels I, PyrLevel
             }
             int v00, v01, v10, v11;
             lk_weights(fsub(cx, (float)jx), fsub(cy, (float)jy), v00, v01, v10, v11);
-            const unsigned wt = (unsigned)v00 | ((unsigned)v01 << 16), wb = (unsigned)v10 | ((unsigned)v11 << 16);
+            const unsigned wt = ((unsigned)v00 & 0xffffu) | ((unsigned)v01 << 16), wb = ((unsigned)v10 & 0xffffu) | ((unsigned)v11 << 16);
             const int o0 = (jy - sy0) * LK_JP + (jx - sx0);
-            int b1 = 0, b2 = 0;
-#pragma unroll 2
-            for (int p = lane; p < LK_NPIX; p += 32) {
-                const int y = (p * 3121) >> 16;                          // p / 21 for p < 441
-                const int off = o0 + p + (LK_JP - LK_WIN) * y;            // (jy - sy0 + y) * LK_JP + (jx - sx0 + x)
+            int p1[LK_PIX], p2[LK_PIX];
+#pragma unroll
+            for (int i = 0; i < LK_PIX; i++) {
+                const int off = o0 + woff[i];                             // (jy - sy0 + y) * LK_JP + (jx - sx0 + x)
                 const uint8_t *src = (off & 1) ? pJB - 1 : pJA;           // aligned 16-bit load of (A[off], A[off + 1])
                 const unsigned top = *reinterpret_cast<const unsigned short *>(src + off);
                 const unsigned bot = *reinterpret_cast<const unsigned short *>(src + off + LK_JP);
-                const short4 t = tT[p];
-                const int jv = (int)(__dp2a_lo(wt, top, __dp2a_lo(wb, bot, (unsigned)(1 << (W_BITS - 5 - 1)))) >> (W_BITS - 5));
-                const int diff = jv - t.x;
-                b1 += diff * t.y;
-                b2 += diff * t.z;
+                const int jv = lk_dp2a(wt, top, lk_dp2a(wb, bot, 1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                const int diff = jv - tI[i];
+                p1[i] = diff * (int)(short)(tG[i] & 0xffff);
+                p2[i] = diff * (tG[i] >> 16);
             }
-            const float B1 = fmul(__ll2float_rn(warp_sum_split(b1)), FLT_SCALE);
-            const float B2 = fmul(__ll2float_rn(warp_sum_split(b2)), FLT_SCALE);
+            // addends in chain order: a SIMD lane adds the int32 dot product of two pixels (v_dotprod), the tail one pixel at a time
+            if (!is_tail) {
+                float4 u0, u1, v0, v1;
+                u0.x = (float)(p1[0] + p1[1]); u0.y = (float)(p1[2] + p1[3]); u0.z = (float)(p1[4] + p1[5]); u0.w = (float)(p1[6] + p1[7]);
+                u1.x = (float)(p1[8] + p1[9]); u1.y = (float)(p1[10] + p1[11]); u1.z = (float)(p1[12] + p1[13]); u1.w = 0.f;
+                v0.x = (float)(p2[0] + p2[1]); v0.y = (float)(p2[2] + p2[3]); v0.z = (float)(p2[4] + p2[5]); v0.w = (float)(p2[6] + p2[7]);
+                v1.x = (float)(p2[8] + p2[9]); v1.y = (float)(p2[10] + p2[11]); v1.z = (float)(p2[12] + p2[13]); v1.w = 0.f;
+                float4 *d1 = reinterpret_cast<float4 *>(acc + off_b), *d2 = reinterpret_cast<float4 *>(acc + off_b + off_b2);
+                d1[0] = u0; d1[1] = u1; d2[0] = v0; d2[1] = v1;
+            } else {
+#pragma unroll
+                for (int i = 0; i < LK_PIX; i += 2) {
+                    *reinterpret_cast<float2 *>(acc + off_b + i) = make_float2((float)p1[i], (float)p1[i + 1]);
+                    *reinterpret_cast<float2 *>(acc + off_b + off_b2 + i) = make_float2((float)p2[i], (float)p2[i + 1]);
+                }
+            }
+            __syncwarp();
+            const float rb = lk_chain(chain_b, n4_b);
+            __syncwarp();
+            const float B1 = fmul(fadd(__shfl_sync(0xffffffffu, rb, 8), lk_combine(rb, 0)), FLT_SCALE);
+            const float B2 = fmul(fadd(__shfl_sync(0xffffffffu, rb, 9), lk_combine(rb, 4)), FLT_SCALE);
             const float dx = fmul(fsub(fmul(A12, B2), fmul(A22, B1)), Dinv);
             const float dy = fmul(fsub(fmul(A12, B1), fmul(A11, B2)), Dinv);
             cx = fadd(cx, dx); cy = fadd(cy, dy);

@@ -102,11 +102,29 @@ __device__ inline int solve_cubic(const double c[4], double r[3]) {          // 
     return 1;
 }
 
-// run7Point: null space of the 7x9 epipolar system by Householder QR of A^T (columns 8,9 of Q), cubic in lambda.
+// run7Point of OpenCV 4.13 (oracle r_run_7point): Hartley normalisation of the seven pairs, null space of the 7x9 epipolar system by
+// Householder QR of A^T (columns 8, 9 of Q) rotated to the basis cv::SVDecomp(FULL_UV) generates for its two zero singular values
+// (normalised null-space components of two constant +-1/9 vectors: oracle _SVD_FILL_SIGNS), cubic in lambda, de-normalisation.
+// The basis and the normalisation fix the ORDER of the up-to-three candidates, and RANSAC keeps the first of equally good models.
 __device__ inline int run_7point(const float2 *p1, const float2 *p2, const int *idx, double Fout[3][9]) {
+    double c1x = 0, c1y = 0, c2x = 0, c2y = 0;
+    for (int i = 0; i < 7; i++) { c1x += (double)p1[idx[i]].x; c1y += (double)p1[idx[i]].y; c2x += (double)p2[idx[i]].x; c2y += (double)p2[idx[i]].y; }
+    const double tt = 1.0 / 7;
+    c1x *= tt; c1y *= tt; c2x *= tt; c2y *= tt;
+    double sc1 = 0, sc2 = 0;
+    for (int i = 0; i < 7; i++) {
+        double dx = (double)p1[idx[i]].x - c1x, dy = (double)p1[idx[i]].y - c1y;
+        sc1 += sqrt(dx * dx + dy * dy);
+        dx = (double)p2[idx[i]].x - c2x; dy = (double)p2[idx[i]].y - c2y;
+        sc2 += sqrt(dx * dx + dy * dy);
+    }
+    sc1 *= tt; sc2 *= tt;
+    if (sc1 < (double)FLT_EPSILON || sc2 < (double)FLT_EPSILON) return 0;
+    sc1 = sqrt(2.0) / sc1; sc2 = sqrt(2.0) / sc2;
     double M[9][7];                                    // A^T
     for (int i = 0; i < 7; i++) {
-        const double x0 = p1[idx[i]].x, y0 = p1[idx[i]].y, x1 = p2[idx[i]].x, y1 = p2[idx[i]].y;
+        const double x0 = ((double)p1[idx[i]].x - c1x) * sc1, y0 = ((double)p1[idx[i]].y - c1y) * sc1;
+        const double x1 = ((double)p2[idx[i]].x - c2x) * sc2, y1 = ((double)p2[idx[i]].y - c2y) * sc2;
         M[0][i] = x1 * x0; M[1][i] = x1 * y0; M[2][i] = x1; M[3][i] = y1 * x0; M[4][i] = y1 * y0; M[5][i] = y1;
         M[6][i] = x0; M[7][i] = y0; M[8][i] = 1.0;
     }
@@ -128,15 +146,39 @@ __device__ inline int run_7point(const float2 *p1, const float2 *p2, const int *
             for (int r = k; r < 9; r++) M[r][j] -= s * M[r][k];
         }
     }
-    double f1[9], f2[9];
+    double n1[9], n2[9];
     for (int c = 0; c < 2; c++) {
-        double *y = c == 0 ? f1 : f2;
+        double *y = c == 0 ? n1 : n2;
         for (int r = 0; r < 9; r++) y[r] = (r == 7 + c) ? 1.0 : 0.0;
         for (int k = 6; k >= 0; k--) {
             double s = 0;
             for (int r = k; r < 9; r++) s += M[r][k] * y[r];
             s *= beta[k];
             for (int r = k; r < 9; r++) y[r] -= s * M[r][k];
+        }
+    }
+    // rotate (n1, n2) to the basis of cv::SVD: f1 ~ null-space part of r1, f2 ~ that of r2 made orthogonal to f1
+    double f1[9], f2[9];
+    {
+        const double sg1[9] = {-1, -1, 1, -1, -1, -1, -1, 1, 1}, sg2[9] = {1, -1, 1, 1, 1, 1, 1, -1, 1};
+        double a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+        for (int r = 0; r < 9; r++) a1 += sg1[r] * n1[r];
+        for (int r = 0; r < 9; r++) a2 += sg1[r] * n2[r];
+        for (int r = 0; r < 9; r++) b1 += sg2[r] * n1[r];
+        for (int r = 0; r < 9; r++) b2 += sg2[r] * n2[r];
+        const double na = sqrt(a1 * a1 + a2 * a2);
+        bool rot = na != 0;
+        if (rot) {
+            a1 /= na; a2 /= na;
+            const double d = b1 * a1 + b2 * a2;
+            b1 -= d * a1; b2 -= d * a2;
+            const double nb = sqrt(b1 * b1 + b2 * b2);
+            rot = nb != 0;
+            if (rot) { b1 /= nb; b2 /= nb; }
+        }
+        for (int r = 0; r < 9; r++) {
+            f1[r] = rot ? a1 * n1[r] + a2 * n2[r] : n1[r];
+            f2[r] = rot ? b1 * n1[r] + b2 * n2[r] : n2[r];
         }
     }
     for (int i = 0; i < 9; i++) f1[i] -= f2[i];
@@ -153,18 +195,26 @@ __device__ inline int run_7point(const float2 *p1, const float2 *p2, const int *
     c[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
     double roots[3];
     const int n = solve_cubic(c, roots);
-    int m = 0;
     for (int k = 0; k < n; k++) {
         double lambda = roots[k], mu = 1.0;
         const double s = f1[8] * lambda + f2[8];
-        if (fabs(s) > DBL_EPSILON) {
-            mu = 1.0 / s; lambda *= mu;
-            for (int i = 0; i < 8; i++) Fout[m][i] = f1[i] * lambda + f2[i] * mu;
-            Fout[m][8] = 1.0;
-            m++;
+        double G[9];
+        G[8] = 0.0;
+        if (fabs(s) > DBL_EPSILON) { mu = 1.0 / s; lambda *= mu; G[8] = 1.0; }
+        for (int i = 0; i < 8; i++) G[i] = f1[i] * lambda + f2[i] * mu;
+        // de-normalise F = T2^T G T1, T = [s 0 -s cx; 0 s -s cy; 0 0 1]
+        double H[9];
+        for (int r = 0; r < 3; r++) {
+            const double g0 = G[3 * r], g1 = G[3 * r + 1], g2 = G[3 * r + 2];
+            H[3 * r] = g0 * sc1; H[3 * r + 1] = g1 * sc1; H[3 * r + 2] = g2 - (g0 * c1x + g1 * c1y) * sc1;
         }
+        double *F = Fout[k];
+        for (int q = 0; q < 3; q++) {
+            F[q] = H[q] * sc2; F[3 + q] = H[3 + q] * sc2; F[6 + q] = H[6 + q] - (H[q] * c2x + H[3 + q] * c2y) * sc2;
+        }
+        if (fabs(F[8]) > (double)FLT_EPSILON) { const double inv = 1.0 / F[8]; for (int i = 0; i < 9; i++) F[i] *= inv; }
     }
-    return m;
+    return n;
 }
 
 __device__ __forceinline__ float fm_error(const double *F, float2 a, float2 b2) {
