@@ -182,7 +182,7 @@ constexpr int LK_JM = 5;
 constexpr int LK_IP = 32;                                 // row stride of the staged 24x24 I patch
 constexpr int LK_PIX = 14;                                // window pixels per lane (32 * 14 = 448 >= 441)
 constexpr int LK_QS = 448;                                // covariance phase: floats per sum (4 chains x 84 + tail 105, padded to 112)
-constexpr int LK_ACC = 3 * LK_QS;                         // mismatch phase uses 8 x 48 + 2 x 112 = 608 of them
+constexpr int LK_ACC = 3 * LK_QS;                         // the mismatch phase uses the first two thirds
 
 __device__ __forceinline__ void lk_weights(float fx, float fy, int &w00, int &w01, int &w10, int &w11) {
     const float s = (float)(1 << W_BITS);
@@ -241,11 +241,13 @@ __device__ __forceinline__ void lk_stage_j(uint8_t *A, uint8_t *Bc, const uint8_
     } else {
         const int yy = reflect101(y0 + lane, rows);
         const uint8_t *row = im + (size_t)yy * cols;
-        uint8_t v[LK_JP + 1];
-#pragma unroll
-        for (int c = 0; c <= LK_JP; c++) v[c] = row[reflect101(x0 + c, cols)];
-#pragma unroll
-        for (int c = 0; c < LK_JP; c++) { A[lane * LK_JP + c] = v[c]; Bc[lane * LK_JP + c] = v[c + 1]; }
+        uint8_t prev = row[reflect101(x0, cols)];
+#pragma unroll 4
+        for (int c = 0; c < LK_JP; c++) {
+            const uint8_t nxt = row[reflect101(x0 + c + 1, cols)];
+            A[lane * LK_JP + c] = prev; Bc[lane * LK_JP + c] = nxt;
+            prev = nxt;
+        }
     }
 }
 
@@ -276,7 +278,7 @@ __device__ __forceinline__ float lk_combine(float r, int l0) {
 }
 
 #ifndef LK_MINB
-#define LK_MINB 1
+#define LK_MINB 4            // 128 registers: measured best on B200 (163 unconstrained, 96 and 80 spill in the iteration loop)
 #endif
 __global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I, PyrLevels J, const float2 *__restrict__ prev_pts,
                                                            float2 *__restrict__ next_pts, uint8_t *__restrict__ status,
@@ -298,36 +300,40 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I,
     float nx = 0.f, ny = 0.f;          // nextPts[ptidx] (level coordinates, window centre)
     bool ok = true;                    // status[ptidx]
 
-    // window pixels owned by this lane: woff = y * 32 + x (window coordinates), nvalid of them real
+    // window pixels owned by this lane: woff = y * 32 + x (window coordinates), two per register; nvalid of them are real
     const bool is_tail = lane >= 24;
     const int ck = lane / 6, cj = lane - 6 * ck, ct = lane - 24;
-    int woff[LK_PIX];
+    unsigned woffp[LK_PIX / 2];
 #pragma unroll
-    for (int i = 0; i < LK_PIX; i++) {
-        if (!is_tail) {
-            const int a = 7 * cj + (i >> 1);
-            woff[i] = (a >> 1) * LK_JP + ck + 8 * (a & 1) + 4 * (i & 1);
-        } else {
-            const int a = min(14 * ct + i, 104);
-            const int y = (a * 13108) >> 16;                             // a / 5 for a < 105
-            woff[i] = y * LK_JP + 16 + a - 5 * y;
+    for (int s2 = 0; s2 < LK_PIX / 2; s2++) {
+        int wo[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (!is_tail) {
+                const int a = 7 * cj + s2;
+                wo[h] = (a >> 1) * LK_JP + ck + 8 * (a & 1) + 4 * h;
+            } else {
+                const int a = min(14 * ct + 2 * s2 + h, 104);
+                const int y = (a * 13108) >> 16;                         // a / 5 for a < 105
+                wo[h] = y * LK_JP + 16 + a - 5 * y;
+            }
         }
+        woffp[s2] = (unsigned)wo[0] | ((unsigned)wo[1] << 16);
     }
     const int nvalid = is_tail ? min(105 - 14 * ct, LK_PIX) : LK_PIX;
-    // where this lane's addends go: covariance phase (per sum q: + q * LK_QS) and mismatch phase (sum 0; sum 1 at + off_b2)
+    // where this lane's addends go (same layout for the covariance sums q = 0..2 and the mismatch sums q = 0, 1: + q * LK_QS): a SIMD
+    // lane chain holds 6 x 14 floats, the tail chain 8 x 14.  In the mismatch phase a SIMD-lane owner writes (pair sum, +0) per two
+    // pixels -- adding +0 changes nothing -- so that both kinds of lanes issue the same 8-byte stores.
     const int off_a = is_tail ? 336 + 14 * ct : 84 * ck + 14 * cj;
-    const int off_b = is_tail ? 384 + 14 * ct : 48 * ck + 8 * cj;
-    const int off_b2 = is_tail ? 112 : 192;
-    // which chain this lane adds up: covariance phase lane = 5 q + c (c = 4: tail), mismatch phase lanes 0..7 = 4 s + k, lanes 8, 9 tails
+    // which chain this lane adds up: covariance phase lane = 5 q + c (c = 4: tail), mismatch phase the same with q = 0, 1
     const int qa = lane / 5, ca = lane - 5 * qa;
     const float *chain_a = acc + qa * LK_QS + (ca < 4 ? 84 * ca : 336);
     const int n4_a = lane < 15 ? (ca < 4 ? 21 : 27) : 0;
-    const float *chain_b = acc + (lane < 8 ? 48 * lane : 384 + 112 * (lane - 8));
-    const int n4_b = lane < 8 ? 12 : (lane < 10 ? 27 : 0);
-
+    const int n4_b = lane < 10 ? n4_a : 0;
     // cv::buildOpticalFlowPyramid stops at the last level whose successor would not be larger than the window in both directions
     int top = 0;
     while (top < LK_LEVELS && min(I.rows[top + 1], I.cols[top + 1]) > LK_WIN) top++;
+#pragma unroll 1
     for (int level = top; level >= 0; level--) {
         const int rows = I.rows[level], cols = I.cols[level];
         const uint8_t *__restrict__ imI = I.p[level] + (size_t)b * I.stride[level];
@@ -363,14 +369,18 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I,
             sD[i] = d;
         }
         __syncwarp();
-        // pass 2: bilinear template (Iw, gx, gy) of the lane's own window pixels, kept in registers; covariance products to the chains
-        int tI[LK_PIX], tG[LK_PIX];                                      // Iw ; gx | gy << 16
+        // pass 2: bilinear template (Iw, gx, gy) of the lane's own window pixels, kept in registers (Iw | gx << 16; the gy of two
+        // pixels share a register); covariance products to the chains
+        int tIG[LK_PIX];
+        unsigned tGy[LK_PIX / 2];
 #pragma unroll
         for (int i = 0; i < LK_PIX; i += 2) {
             float pa[2], pb[2], pc[2];
+            int gyp[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const int y = woff[i + h] >> 5, x = woff[i + h] & 31;
+                const int wo = h ? (int)(woffp[i >> 1] >> 16) : (int)(woffp[i >> 1] & 0xffffu);
+                const int y = wo >> 5, x = wo & 31;
                 const uint8_t *q = pI + (y + 1) * LK_IP + (x + 1);
                 const short2 *dq = sD + y * 22 + x;
                 const short2 d00 = dq[0], d01 = dq[1], d10 = dq[22], d11 = dq[23];
@@ -378,13 +388,14 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I,
                 const int dxv = w00 * d00.x + w01 * d01.x + w10 * d10.x + w11 * d11.x;
                 const int dyv = w00 * d00.y + w01 * d01.y + w10 * d10.y + w11 * d11.y;
                 const bool valid = i + h < nvalid;
-                const int ivs = valid ? (iv + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5) : 0;
+                const int ivs = valid ? (iv + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5) : 0;      // 0 .. 8160
                 const int gxs = valid ? (dxv + (1 << (W_BITS - 1))) >> W_BITS : 0;
                 const int gys = valid ? (dyv + (1 << (W_BITS - 1))) >> W_BITS : 0;
-                tI[i + h] = ivs;
-                tG[i + h] = (gxs & 0xffff) | (gys << 16);
+                tIG[i + h] = ivs | (gxs << 16);
+                gyp[h] = gys;
                 pa[h] = (float)(gxs * gxs); pb[h] = (float)(gxs * gys); pc[h] = (float)(gys * gys);     // RN of the exact product, as the f32 multiply
             }
+            tGy[i >> 1] = ((unsigned)gyp[0] & 0xffffu) | ((unsigned)gyp[1] << 16);
             *reinterpret_cast<float2 *>(acc + off_a + i) = make_float2(pa[0], pa[1]);
             *reinterpret_cast<float2 *>(acc + LK_QS + off_a + i) = make_float2(pb[0], pb[1]);
             *reinterpret_cast<float2 *>(acc + 2 * LK_QS + off_a + i) = make_float2(pc[0], pc[1]);
@@ -426,39 +437,33 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I,
             lk_weights(fsub(cx, (float)jx), fsub(cy, (float)jy), v00, v01, v10, v11);
             const unsigned wt = ((unsigned)v00 & 0xffffu) | ((unsigned)v01 << 16), wb = ((unsigned)v10 & 0xffffu) | ((unsigned)v11 << 16);
             const int o0 = (jy - sy0) * LK_JP + (jx - sx0);
-            int p1[LK_PIX], p2[LK_PIX];
-#pragma unroll
-            for (int i = 0; i < LK_PIX; i++) {
-                const int off = o0 + woff[i];                             // (jy - sy0 + y) * LK_JP + (jx - sx0 + x)
-                const uint8_t *src = (off & 1) ? pJB - 1 : pJA;           // aligned 16-bit load of (A[off], A[off + 1])
-                const unsigned top = *reinterpret_cast<const unsigned short *>(src + off);
-                const unsigned bot = *reinterpret_cast<const unsigned short *>(src + off + LK_JP);
-                const int jv = lk_dp2a(wt, top, lk_dp2a(wb, bot, 1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                const int diff = jv - tI[i];
-                p1[i] = diff * (int)(short)(tG[i] & 0xffff);
-                p2[i] = diff * (tG[i] >> 16);
-            }
             // addends in chain order: a SIMD lane adds the int32 dot product of two pixels (v_dotprod), the tail one pixel at a time
-            if (!is_tail) {
-                float4 u0, u1, v0, v1;
-                u0.x = (float)(p1[0] + p1[1]); u0.y = (float)(p1[2] + p1[3]); u0.z = (float)(p1[4] + p1[5]); u0.w = (float)(p1[6] + p1[7]);
-                u1.x = (float)(p1[8] + p1[9]); u1.y = (float)(p1[10] + p1[11]); u1.z = (float)(p1[12] + p1[13]); u1.w = 0.f;
-                v0.x = (float)(p2[0] + p2[1]); v0.y = (float)(p2[2] + p2[3]); v0.z = (float)(p2[4] + p2[5]); v0.w = (float)(p2[6] + p2[7]);
-                v1.x = (float)(p2[8] + p2[9]); v1.y = (float)(p2[10] + p2[11]); v1.z = (float)(p2[12] + p2[13]); v1.w = 0.f;
-                float4 *d1 = reinterpret_cast<float4 *>(acc + off_b), *d2 = reinterpret_cast<float4 *>(acc + off_b + off_b2);
-                d1[0] = u0; d1[1] = u1; d2[0] = v0; d2[1] = v1;
-            } else {
 #pragma unroll
-                for (int i = 0; i < LK_PIX; i += 2) {
-                    *reinterpret_cast<float2 *>(acc + off_b + i) = make_float2((float)p1[i], (float)p1[i + 1]);
-                    *reinterpret_cast<float2 *>(acc + off_b + off_b2 + i) = make_float2((float)p2[i], (float)p2[i + 1]);
+            for (int i = 0; i < LK_PIX; i += 2) {
+                int p1[2], p2[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int wo = h ? (int)(woffp[i >> 1] >> 16) : (int)(woffp[i >> 1] & 0xffffu);
+                    const int off = o0 + wo;                              // (jy - sy0 + y) * LK_JP + (jx - sx0 + x)
+                    const uint8_t *src = pJA + off + (off & 1) * (LK_JP * LK_JP - 1);     // odd: copy B at off - 1 -> aligned 16-bit load of (A[off], A[off + 1])
+                    const unsigned top = *reinterpret_cast<const unsigned short *>(src);
+                    const unsigned bot = *reinterpret_cast<const unsigned short *>(src + LK_JP);
+                    const int jv = lk_dp2a(wt, top, lk_dp2a(wb, bot, 1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                    const int diff = jv - (tIG[i + h] & 0xffff);
+                    const int gy = h ? (int)tGy[i >> 1] >> 16 : (int)(short)(tGy[i >> 1] & 0xffffu);
+                    p1[h] = diff * (tIG[i + h] >> 16);
+                    p2[h] = diff * gy;
                 }
+                const float2 u = is_tail ? make_float2((float)p1[0], (float)p1[1]) : make_float2((float)(p1[0] + p1[1]), 0.f);
+                const float2 v = is_tail ? make_float2((float)p2[0], (float)p2[1]) : make_float2((float)(p2[0] + p2[1]), 0.f);
+                *reinterpret_cast<float2 *>(acc + off_a + i) = u;
+                *reinterpret_cast<float2 *>(acc + LK_QS + off_a + i) = v;
             }
             __syncwarp();
-            const float rb = lk_chain(chain_b, n4_b);
+            const float rb = lk_chain(chain_a, n4_b);
             __syncwarp();
-            const float B1 = fmul(fadd(__shfl_sync(0xffffffffu, rb, 8), lk_combine(rb, 0)), FLT_SCALE);
-            const float B2 = fmul(fadd(__shfl_sync(0xffffffffu, rb, 9), lk_combine(rb, 4)), FLT_SCALE);
+            const float B1 = fmul(fadd(__shfl_sync(0xffffffffu, rb, 4), lk_combine(rb, 0)), FLT_SCALE);
+            const float B2 = fmul(fadd(__shfl_sync(0xffffffffu, rb, 9), lk_combine(rb, 5)), FLT_SCALE);
             const float dx = fmul(fsub(fmul(A12, B2), fmul(A22, B1)), Dinv);
             const float dy = fmul(fsub(fmul(A12, B1), fmul(A11, B2)), Dinv);
             cx = fadd(cx, dx); cy = fadd(cy, dy);
