@@ -61,6 +61,16 @@ typedef struct vio_config {
     int32_t max_imu_per_frame;   /* capacity of dt_buf[] etc.  VINS.hpp:103-105          */
     int32_t batch;               /* number of independent streams in the handle          */
     int32_t device;              /* CUDA device ordinal                                   */
+    /* How the back end computes (all 0 by default; results agree within the parity tolerance whichever is chosen): */
+    int32_t marg_mode;           /* 0: new prior formed directly in information form (H = A_r, b, c0).  1: the reference's route,
+                                    eigendecomposition of A_r -> linearized_jacobians / residuals (marginalization_factor.cpp:270-294) */
+    int32_t marg_eig;            /* eigen-solver used by marg_mode 1 and by the pseudo-inverse of Amm: 0 Householder tridiagonalisation
+                                    + implicit QL, 1 parallel Jacobi */
+    int32_t marg_amm_eig;        /* 1: Amm^+ always through its eigendecomposition with the 1e-8 cut (marginalization_factor.cpp:270-276);
+                                    0: structured inverse guarded by an eigenvalue bound, falling back to the eigendecomposition */
+    int32_t solve_path;          /* reduced-system solve: 0 auto (FP64 tensor-pipe tiles when the window fits one SM, else global memory),
+                                    1 packed Cholesky in shared memory without DMMA tiles */
+    int32_t be_threads;          /* threads per stream in the solve / marginalisation kernels: 0 = 512, or 256 */
 } vio_config;
 
 /* Fills `cfg` with the reference's iPhone7P defaults (global_param.cpp:26-39) and the
@@ -154,6 +164,10 @@ int vio_backend_process_image_from_frontend(vio_backend *be, vio_frontend *fe, c
 int vio_backend_get_state(vio_backend *be, int s, double *P, double *Q, double *V, double *Ba, double *Bg, double *headers);
 /* Whole-batch device pointer to the packed state [batch][W+1][16] = P3,Q4(xyzw),V3,Ba3,Bg3 (for NCCL gathers). */
 int vio_backend_state_dev(vio_backend *be, const double **state, int64_t *n_doubles);
+/* Per-stream error flag.  A capacity overflow inside a kernel (IMU buffer beyond max_imu_per_frame, feature table beyond
+ * (window_size + 2) * max_cnt entries) cannot fail the call that enqueued the kernel, so it is latched per stream: the state getters
+ * (vio_backend_get_state / _get_post_solve) return it, VIO_ERR_CAPACITY, until it is cleared here (clear != 0) or by vio_backend_clear(). */
+int vio_backend_get_error(vio_backend *be, int s, int clear, int32_t *code);
 /* info[0] solver_flag (0 INITIAL,1 NON_LINEAR) [1] marginalization_flag (0 OLD,1 SECOND_NEW) [2] frame_count
  * [3] failure_occur [4] feature count in solve [5] projection factors [6] iterations run [7] last_track_num
  * dinfo[0] initial cost [1] final cost [2] prior size n */

@@ -26,6 +26,7 @@
 #include <map>
 #include <unordered_map>
 #include <algorithm>
+#include <sys/mman.h>
 
 #include "global_param.hpp"
 #include "utility.hpp"
@@ -66,7 +67,12 @@ struct Est {
     std::vector<std::vector<Vector3d>> acc_buf, gyr_buf;
     Vector3d acc_0, gyr_0, tic;
     Matrix3d ric;
-    std::vector<double> para_Pose, para_SB, para_Feature, para_Ex;
+    // para_Pose / para_SpeedBias / para_Feature / para_Ex_Pose (VINS.hpp:79-82): consecutive arrays, as in the reference object,
+    // placed in an arena at a FIXED virtual address (ParaArena below)
+    struct Span { double *p = nullptr; size_t n = 0; double *data() { return p; } double &operator[](size_t i) { return p[i]; }
+                  const double &operator[](size_t i) const { return p[i]; } };
+    Span para_Pose, para_SB, para_Feature, para_Ex;
+    int arena_slot = -1;
     MarginalizationInfo *last_marg = nullptr;
     std::vector<double *> last_marg_blocks;
     int failure_occur = 0;
@@ -84,6 +90,35 @@ struct Est {
     double *sb(int i) { return &para_SB[9 * i]; }
     double *feat_p(int i) { return &para_Feature[i]; }
 };
+
+// MarginalizationInfo keys its maps by reinterpret_cast<long>(parameter address) and fixes the block order of the prior by ITERATING an
+// unordered_map over those keys (marginalization_factor.cpp:185-200): with heap-allocated parameter arrays the
+// order -- and with it the round-off of every prior -- changes from one estimator object (and one process) to the next.  The oracle
+// pins it: the parameter arrays of estimator slot k live at the fixed address ARENA_BASE + k * ARENA_STRIDE (lowest free slot
+// first), so a fresh estimator always sees the same addresses and the reference arithmetic becomes reproducible.
+namespace ParaArena {
+const uintptr_t ARENA_BASE = 0x5f0000000000ull;
+const size_t ARENA_STRIDE = 1u << 20;
+const int SLOTS = 64;
+bool used[SLOTS];
+double *claim(int *slot, size_t doubles) {
+    if (doubles * sizeof(double) > ARENA_STRIDE) return nullptr;
+    for (int k = 0; k < SLOTS; k++) {
+        if (used[k]) continue;
+        void *want = (void *)(ARENA_BASE + (uintptr_t)k * ARENA_STRIDE);
+        void *got = mmap(want, ARENA_STRIDE, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_FIXED_NOREPLACE, -1, 0);
+        if (got != want) { if (got != MAP_FAILED) munmap(got, ARENA_STRIDE); continue; }
+        used[k] = true; *slot = k;
+        return (double *)got;
+    }
+    return nullptr;
+}
+void release(int slot) {
+    if (slot < 0) return;
+    munmap((void *)(ARENA_BASE + (uintptr_t)slot * ARENA_STRIDE), ARENA_STRIDE);
+    used[slot] = false;
+}
+}  // namespace ParaArena
 
 bool in_solve(const Est &e, const Track &t) { return (int)t.obs.size() >= 2 && t.start < e.W - 2; }
 
@@ -417,17 +452,24 @@ int process_image(Est &e, int n, const int *ids, const double *xyz, double heade
     e.Headers[e.frame_count] = header;
     if (e.solver_flag == 0) {
         if (e.frame_count == e.W) {
+            if (e.last_track_num < 20) { clear_state(e); return 2; }      // VINS.cpp:401-405
             if (e.init_pending) {
                 e.init_pending = false;
                 for (int i = 0; i <= e.W; i++) { e.Ps[i] = e.iP[i]; e.Rs[i] = e.iQ[i].normalized().toRotationMatrix(); e.Vs[i] = e.iV[i]; e.Bas[i] = e.iBa; e.Bgs[i] = e.iBg; }
                 for (auto &t : e.feat) t.depth = -1.0;       // clearDepth(-1), VINS.cpp:1047-1050
                 triangulate(e);
                 solve(e);
-                e.failure_occur = 0;
-                e.solver_flag = 1;
-                slide_window(e);
-                remove_failures(e);
-                e.last_R = e.Rs[e.W]; e.last_P = e.Ps[e.W]; e.last_R_old = e.Rs[0]; e.last_P_old = e.Ps[0];
+                if (e.cost1 > 200) {                         // VINS.cpp:416-425: initialisation rejected
+                    delete e.last_marg; e.last_marg = nullptr;
+                    e.solver_flag = 0;
+                    slide_window(e);
+                } else {
+                    e.failure_occur = 0;
+                    e.solver_flag = 1;
+                    slide_window(e);
+                    remove_failures(e);
+                    e.last_R = e.Rs[e.W]; e.last_P = e.Ps[e.W]; e.last_R_old = e.Rs[0]; e.last_P_old = e.Ps[0];
+                }
             } else {
                 slide_window(e);
             }
@@ -458,15 +500,20 @@ void *vref_create(const vio_config *cfg) {
     }
     Est *e = new Est();
     e->c = *cfg; e->W = cfg->window_size;
-    e->para_Pose.assign(7 * (e->W + 1), 0); e->para_SB.assign(9 * (e->W + 1), 0);
-    e->para_Feature.assign(cfg->num_of_f, 0); e->para_Ex.assign(7, 0);
+    {
+        const size_t nP = 7 * (e->W + 1), nS = 9 * (e->W + 1), nF = cfg->num_of_f, nE = 7;
+        double *a = ParaArena::claim(&e->arena_slot, nP + nS + nF + nE);
+        if (!a) { fprintf(stderr, "vref_create: no parameter arena slot free\n"); delete e; return nullptr; }
+        e->para_Pose.p = a; e->para_Pose.n = nP; e->para_SB.p = a + nP; e->para_SB.n = nS;
+        e->para_Feature.p = a + nP + nS; e->para_Feature.n = nF; e->para_Ex.p = a + nP + nS + nF; e->para_Ex.n = nE;      // mmap memory is zeroed
+    }
     FOCUS_LENGTH_X = cfg->fx; FOCUS_LENGTH_Y = cfg->fy; PX = cfg->cx; PY = cfg->cy;
     ProjectionFactor::sqrt_info = cfg->fx / 1.5 * Matrix2d::Identity();     // VINS::setIMUModel, VINS.cpp:29-32
     e->last_P.setZero(); e->last_R.setIdentity(); e->last_P_old.setZero(); e->last_R_old.setIdentity();
     clear_state(*e);
     return e;
 }
-void vref_destroy(void *h) { Est *e = (Est *)h; clear_state(*e); delete e; }
+void vref_destroy(void *h) { Est *e = (Est *)h; clear_state(*e); ParaArena::release(e->arena_slot); delete e; }
 void vref_clear(void *h) { clear_state(*(Est *)h); }
 void vref_process_imu(void *h, double dt, const double *a, const double *g) {
     process_imu(*(Est *)h, dt, Vector3d(a[0], a[1], a[2]), Vector3d(g[0], g[1], g[2]));

@@ -48,6 +48,28 @@ def drive(est, tr, k, W, single=True):
         est.process_image(ids, xyz, tr["t_kf"][k])
 
 
+def outlier_tracks(sid, n_kf, max_cnt=150, n_out=6, seed=0, mag=0.15):
+    """synth.make_tracks with `n_out` tracks turned into gross outliers (the observation slides across the image, inconsistent with any
+    static point): their inverse depth goes negative in a solve, removeFailures() (feature_manager.cpp:289-298) erases them while the
+    front end keeps publishing the id, and the id is appended again BEHIND larger ids -- the reference's feature list stops being
+    sorted by id (from keyframe 16 on for stream 0).  Returns (tracks, outlier ids)."""
+    tr = synth.make_tracks(sid, n_kf, max_cnt=max_cnt)
+    rng = np.random.default_rng(seed)
+    born = {}
+    for k, (ids, _xyz) in enumerate(tr["frames"]):
+        for i in ids:
+            born.setdefault(int(i), k)
+    cand = [i for i, k in born.items() if 12 <= k <= 16]
+    pick = rng.choice(cand, n_out, replace=False)
+    drift = {int(i): rng.normal(0, mag, 2) for i in pick}
+    for k, (ids, xyz) in enumerate(tr["frames"]):
+        for j, i in enumerate(ids):
+            i = int(i)
+            if i in drift and k > born[i]:
+                xyz[j, :2] += drift[i] * (k - born[i])
+    return tr, pick
+
+
 def rel_err(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return float(np.abs(a - b).max() / max(1e-12, np.abs(b).max()))

@@ -54,6 +54,7 @@ def lib():
         L.vio_frontend_stream.restype = vp
         L.vio_frontend_use_stream.argtypes = [vp, vp]
         L.vio_frontend_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
+        L.vio_backend_get_error.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int32)]
         L.vio_prim_pyramid.argtypes = [cfgp, UP, UP, UP, UP]
         L.vio_frontend_set_clahe.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int]
         L.vio_prim_clahe.argtypes = [cfgp, UP, C.c_double, C.c_int, C.c_int, UP]
@@ -379,6 +380,12 @@ class BackEnd:
 
     def sync(self):
         _check(lib().vio_backend_sync(self.h), "vio_backend_sync")
+
+    def error(self, s=0, clear=False):
+        """latched per-stream error code (VIO_ERR_CAPACITY ...), optionally cleared"""
+        code = C.c_int32(0)
+        _check(lib().vio_backend_get_error(self.h, s, int(clear), C.byref(code)), "vio_backend_get_error")
+        return code.value
 
 
 def prim_preintegrate(cfg, dt, acc, gyr, acc0, gyr0, ba, bg):

@@ -75,9 +75,9 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     vio_backend *be = new (std::nothrow) vio_backend();
     if (!be) return VIO_ERR_ARG;
     be->cfg = *cfg; be->launches = 0; be->own_stream = true; be->consumed_valid = false; be->record_consumed = false;
-    VIO_CUDA_TRY(cudaEventCreateWithFlags(&be->evt_ready, cudaEventDisableTiming));
-    VIO_CUDA_TRY(cudaEventCreateWithFlags(&be->evt_consumed, cudaEventDisableTiming));
-    VIO_CUDA_TRY(cudaStreamCreateWithFlags(&be->stream, cudaStreamNonBlocking));
+    VIO_CUDA_TRY_OR(cudaEventCreateWithFlags(&be->evt_ready, cudaEventDisableTiming), vio_backend_destroy(be));
+    VIO_CUDA_TRY_OR(cudaEventCreateWithFlags(&be->evt_consumed, cudaEventDisableTiming), vio_backend_destroy(be));
+    VIO_CUDA_TRY_OR(cudaStreamCreateWithFlags(&be->stream, cudaStreamNonBlocking), vio_backend_destroy(be));
     BeState &s = be->s;
     memset(&s, 0, sizeof(s));
     s.B = cfg->batch; s.W = cfg->window_size; s.NF = s.W + 1; s.NP = 15 * s.NF; s.NPX = s.NP + 6; s.NPW = 6 * s.NF;
@@ -91,10 +91,10 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     s.noise[0] = s.noise[2] = cfg->acc_n * cfg->acc_n; s.noise[1] = s.noise[3] = cfg->gyr_n * cfg->gyr_n;
     s.noise[4] = cfg->acc_w * cfg->acc_w; s.noise[5] = cfg->gyr_w * cfg->gyr_w;
     s.max_iters = cfg->max_iters;
-    { const char *e = getenv("VIO_EIG"); s.eig_mode = (e && !strcmp(e, "jacobi")) ? 0 : 1; }
-    { const char *e = getenv("VIO_BE_THREADS"); be->be_threads = (e && atoi(e) == 256) ? 256 : 512; }
-    { const char *e = getenv("VIO_MARG_SLOW"); s.force_slow_marg = (e && e[0] == '1') ? 1 : 0; }
-    { const char *e = getenv("VIO_MARG_EXACT"); s.marg_direct = (e && e[0] == '1') ? 0 : 1; }
+    s.eig_mode = cfg->marg_eig == 1 ? 0 : 1;
+    be->be_threads = cfg->be_threads == 256 ? 256 : 512;
+    s.force_slow_marg = cfg->marg_amm_eig ? 1 : 0;
+    s.marg_direct = cfg->marg_mode == 1 ? 0 : 1;
     const size_t B = s.B, NF = s.NF;
     int rc = VIO_OK;
     if (!rc) rc = dalloc(be, &s.Ps, B * NF * 3);
@@ -145,29 +145,32 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     if (!rc) rc = dalloc(be, &be->d_imu, be->imu_cap * B * 7);
     if (!rc && cudaMallocHost((void **)&be->h_headers_pinned, B * sizeof(double)) != cudaSuccess) rc = VIO_ERR_CUDA;
     if (rc) { vio_backend_destroy(be); return rc; }
-    VIO_CUDA_TRY(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s.FCAP + 64));
+    size_t dyn_max = 0;
+    VIO_CUDA_TRY_OR(vio_allow_max_dynamic_smem(finish_kernel, cfg->device, &dyn_max), vio_backend_destroy(be));
+    if ((size_t)s.FCAP + 64 > dyn_max) { vio_backend_destroy(be); return VIO_ERR_CAPACITY; }
     // reduced system resident in shared memory when it fits one SM (W = 10: 110 KB packed); otherwise the global-memory path
     be->solve_smem = solve_smem_bytes(s.NP, s.NPW);
     if (be->solve_smem > 200 * 1024 || schur_ntile(s.NPW) > be->be_threads) be->solve_smem = 0;
     be->use_smem_solve = be->solve_smem > 0;
-    // reduced system in registers as DMMA tiles (be_tilechol.cuh) when it fits 16 warps x 16 tiles; VIO_SOLVE_TILES=0 keeps the packed path
-    { const char *e = getenv("VIO_SOLVE_TILES");
-      if (be->use_smem_solve && !(e && e[0] == '0') && tile_path_fits(s.NF, be->be_threads)) {
-          be->use_smem_solve = 2;
-          be->solve_smem = std::max(be->solve_smem, tile_smem_doubles(s.NF) * sizeof(double));
-      } }
+    // reduced system in registers as DMMA tiles (be_tilechol.cuh) when it fits 16 warps x 16 tiles; vio_config::solve_path = 1 keeps the packed path
+    if (be->use_smem_solve && cfg->solve_path != 1 && tile_path_fits(s.NF, be->be_threads)) {
+        be->use_smem_solve = 2;
+        be->solve_smem = std::max(be->solve_smem, tile_smem_doubles(s.NF) * sizeof(double));
+    }
     be->solve_smem = std::max(be->solve_smem, eval_smem_bytes(s.W));
     be->solve_vec_off = (int)((be->solve_smem / sizeof(double) + 3) & ~(size_t)3);
     be->solve_smem = (be->solve_vec_off + solve_vec_doubles(s.NP, s.NPX)) * sizeof(double);
-    VIO_CUDA_TRY(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->solve_smem));
+    VIO_CUDA_TRY_OR(vio_allow_max_dynamic_smem(solve_kernel, cfg->device, &dyn_max), vio_backend_destroy(be));
+    if (be->solve_smem > dyn_max) { vio_backend_destroy(be); return VIO_ERR_CAPACITY; }
     be->marg_smem = sizeof(MargSmem) + 16 + (size_t)2 * MARG_NCAP * MARG_NCAP * sizeof(double);
-    VIO_CUDA_TRY(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->marg_smem));
+    VIO_CUDA_TRY_OR(vio_allow_max_dynamic_smem(marg_kernel, cfg->device, &dyn_max), vio_backend_destroy(be));
+    if (be->marg_smem > dyn_max) { vio_backend_destroy(be); return VIO_ERR_CAPACITY; }
     // dalloc() zero-fills with cudaMemset on the legacy default stream, which does not order against this handle's non-blocking
     // stream (nor against a caller's non-blocking stream given to vio_backend_use_stream): finish the fills before any kernel
-    VIO_CUDA_TRY(cudaDeviceSynchronize());
+    VIO_CUDA_TRY_OR(cudaDeviceSynchronize(), vio_backend_destroy(be));
     rc = vio_backend_clear(be);
     if (rc) { vio_backend_destroy(be); return rc; }
-    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    VIO_CUDA_TRY_OR(cudaStreamSynchronize(be->stream), vio_backend_destroy(be));
     *out = be;
     return VIO_OK;
 }
@@ -175,11 +178,12 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
 extern "C" void vio_backend_destroy(vio_backend *be) {
     if (!be) return;
     cudaSetDevice(be->cfg.device);
-    cudaStreamSynchronize(be->stream);
+    if (be->stream) cudaStreamSynchronize(be->stream);
     for (void *p : be->allocs) cudaFree(p);
-    cudaEventDestroy(be->evt_ready); cudaEventDestroy(be->evt_consumed);
+    if (be->evt_ready) cudaEventDestroy(be->evt_ready);
+    if (be->evt_consumed) cudaEventDestroy(be->evt_consumed);
     if (be->h_headers_pinned) cudaFreeHost(be->h_headers_pinned);
-    if (be->own_stream) cudaStreamDestroy(be->stream);
+    if (be->own_stream && be->stream) cudaStreamDestroy(be->stream);
     delete be;
 }
 
@@ -315,6 +319,17 @@ static int stream_err(vio_backend *be, int s) {
     VIO_CUDA_TRY(cudaMemcpyAsync(&e, be->s.iv + (size_t)s * IV_COUNT + IV_ERR, sizeof(int), cudaMemcpyDeviceToHost, be->stream));
     VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
     return e;
+}
+
+extern "C" int vio_backend_get_error(vio_backend *be, int s, int clear, int32_t *code) {
+    if (!be || s < 0 || s >= be->s.B || !code) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    int e = 0;
+    VIO_CUDA_TRY(cudaMemcpyAsync(&e, be->s.iv + (size_t)s * IV_COUNT + IV_ERR, sizeof(int), cudaMemcpyDeviceToHost, be->stream));
+    if (clear) VIO_CUDA_TRY(cudaMemsetAsync(be->s.iv + (size_t)s * IV_COUNT + IV_ERR, 0, sizeof(int), be->stream));
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    *code = e;
+    return VIO_OK;
 }
 
 template <typename T>
@@ -575,9 +590,9 @@ __global__ void pnp_identity_kernel(double *R, size_t n) {
 extern "C" void vio_pnp_destroy(vio_pnp *p) {
     if (!p) return;
     cudaSetDevice(p->cfg.device);
-    cudaStreamSynchronize(p->stream);
+    if (p->stream) cudaStreamSynchronize(p->stream);
     for (void *q : p->allocs) cudaFree(q);
-    cudaStreamDestroy(p->stream);
+    if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
 
@@ -587,7 +602,7 @@ extern "C" int vio_pnp_create(const vio_config *cfg, vio_pnp **out) {
     vio_pnp *p = new (std::nothrow) vio_pnp();
     if (!p) return VIO_ERR_ARG;
     p->cfg = *cfg; p->launches = 0;
-    VIO_CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    VIO_CUDA_TRY_OR(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking), vio_pnp_destroy(p));
     PnpState &s = p->s;
     memset(&s, 0, sizeof(s));
     s.B = cfg->batch; s.MAXF = cfg->max_cnt; s.max_iters = 5;                 // options.max_num_iterations = 5 (vins_pnp.cpp:320)
@@ -622,13 +637,15 @@ extern "C" int vio_pnp_create(const vio_config *cfg, vio_pnp **out) {
     p->imu_cap = 64;
     if (!rc) rc = palloc(p, &p->d_imu, p->imu_cap * B * 7);
     if (rc) { vio_pnp_destroy(p); return rc; }
-    VIO_CUDA_TRY(cudaDeviceSynchronize());                                     // zero-fills run on the legacy default stream
+    VIO_CUDA_TRY_OR(cudaDeviceSynchronize(), vio_pnp_destroy(p));                                     // zero-fills run on the legacy default stream
     // clearState (vins_pnp.cpp:22-52): identity rotations; Headers start at -1 (the reference leaves them uninitialised)
     pnp_identity_kernel<<<64, 256, 0, p->stream>>>(s.Rs, B * N * 9);
     pnp_fill_kernel<<<64, 256, 0, p->stream>>>(s.Headers, B * N, -1.0);
     p->smem = pnp_smem_doubles() * sizeof(double);
-    VIO_CUDA_TRY(cudaFuncSetAttribute(pnp_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-    VIO_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    size_t dyn_max = 0;
+    VIO_CUDA_TRY_OR(vio_allow_max_dynamic_smem(pnp_image_kernel, cfg->device, &dyn_max), vio_pnp_destroy(p));
+    if (p->smem > dyn_max) { vio_pnp_destroy(p); return VIO_ERR_CAPACITY; }
+    VIO_CUDA_TRY_OR(cudaStreamSynchronize(p->stream), vio_pnp_destroy(p));
     p->launches += 2;
     *out = p;
     return VIO_OK;

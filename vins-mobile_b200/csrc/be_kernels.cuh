@@ -111,13 +111,14 @@ __global__ void __launch_bounds__(256) addfeat_kernel(BeState s, const int *__re
     const int *mid = ids + (size_t)b * s.MAXCNT;
     const double *mx = xyz + (size_t)b * s.MAXCNT * 3;
     for (int i = tid; i < n; i += 256) {
+        // find_if over the list in list order (feature_manager.cpp:113-116).  The table is in INSERTION order like the reference's
+        // std::list, which is not sorted by id once removeFailures() has erased a landmark the front end keeps tracking (its id comes
+        // back and is appended behind larger ids), so the lookup is a scan, not a bisection.  All lanes read the same address.
         const int id = mid[i];
-        int lo = 0, hi = nf - 1, slot = -1;
-        while (lo <= hi) {
-            const int m = (lo + hi) >> 1, v = s.f_id[fo + m];
-            if (v == id) { slot = m; break; }
-            if (v < id) lo = m + 1; else hi = m - 1;
-        }
+        int slot = -1;
+#pragma unroll 8
+        for (int m = 0; m < nf; m++)
+            if (slot < 0 && s.f_id[fo + m] == id) slot = m;
         sh_new[i] = slot < 0;
         if (slot >= 0) {
             const int k = s.f_nobs[fo + slot];
@@ -171,8 +172,11 @@ __global__ void __launch_bounds__(256) addfeat_kernel(BeState s, const int *__re
         iv[IV_LAST_TRACK] = last_track;
         s.Headers[(size_t)b * s.NF + fc] = headers[b];
         int act;
-        if (iv[IV_SOLVER_FLAG] == 0) act = (fc == s.W) ? (iv[IV_INIT_PENDING] ? ACT_INIT_SOLVE : ACT_SLIDE_ONLY) : ACT_ACCUMULATE;
-        else act = ACT_NL_SOLVE;
+        if (iv[IV_SOLVER_FLAG] == 0) {
+            if (fc != s.W) act = ACT_ACCUMULATE;
+            else if (last_track < 20) act = ACT_CLEAR;                   // VINS.cpp:401-405: too few tracked points to initialise -> clearState()
+            else act = iv[IV_INIT_PENDING] ? ACT_INIT_SOLVE : ACT_SLIDE_ONLY;
+        } else act = ACT_NL_SOLVE;
         iv[IV_ACTION] = act;
         iv[IV_N_LM] = 0; iv[IV_N_FAC] = 0; iv[IV_ITERS] = 0; iv[IV_CHOL_RETRY] = 0; iv[IV_MARG_SWEEPS] = 0; iv[IV_MARG_FAST] = 0;
     }
@@ -442,6 +446,9 @@ __device__ inline void clear_state_cta(const BeState &s, int b) {      // VINS::
         st3(S_Bas(s, b, i), v3(0, 0, 0)); st3(S_Bgs(s, b, i), v3(0, 0, 0));
         S_pre(s, b, i)[PR_VALID] = 0.0;
         s.imu_cnt[(size_t)b * s.NF + i] = 0;
+        double *o = s.state_out + ((size_t)b * s.NF + i) * 16;           // what vio_backend_get_state / copy_state read
+        st3(o, v3(0, 0, 0)); o[3] = 0; o[4] = 0; o[5] = 0; o[6] = 1; st3(o + 7, v3(0, 0, 0)); st3(o + 10, v3(0, 0, 0)); st3(o + 13, v3(0, 0, 0));
+        s.Headers[(size_t)b * s.NF + i] = 0.0;
     }
     if (tid == 0) {
         iv[IV_FRAME_COUNT] = 0; iv[IV_FIRST_IMU] = 0; iv[IV_SOLVER_FLAG] = 0; iv[IV_NFEAT] = 0; iv[IV_PRIOR_VALID] = 0; iv[IV_PRIOR_N] = 0;
@@ -462,8 +469,12 @@ __global__ void __launch_bounds__(256) finish_kernel(BeState s) {
     const size_t fo = (size_t)b * s.FCAP;
     double *tmp = s.scratch + (size_t)b * s.scratch_stride;
     if (act == ACT_ACCUMULATE) { if (tid == 0) iv[IV_FRAME_COUNT] += 1; }
+    else if (act == ACT_CLEAR) clear_state_cta(s, b);
     else if (act != ACT_NONE) {
-        const bool solved = (act == ACT_INIT_SOLVE || act == ACT_NL_SOLVE);
+        // initialisation check (VINS.cpp:415-425): a first solve that ends above cost 200 is discarded -- the prior it built is deleted,
+        // solver_flag stays INITIAL and the window only slides (no removeFailures, last_R / last_P untouched, failure_occur untouched)
+        const bool init_rejected = act == ACT_INIT_SOLVE && dv[DV_COST1] > 200.0;
+        const bool solved = (act == ACT_INIT_SOLVE || act == ACT_NL_SOLVE) && !init_rejected;
         if (tid == 0) {
             sh_fail = 0;
             if (act == ACT_NL_SOLVE) {                       // failureDetection(), VINS.cpp:214-265
@@ -485,7 +496,10 @@ __global__ void __launch_bounds__(256) finish_kernel(BeState s) {
             __syncthreads();
             clear_state_cta(s, b);
         } else {
-            if (act == ACT_INIT_SOLVE && tid == 0) iv[IV_SOLVER_FLAG] = 1;
+            if (act == ACT_INIT_SOLVE && tid == 0) {
+                if (init_rejected) { iv[IV_PRIOR_VALID] = 0; iv[IV_PRIOR_N] = 0; }
+                else iv[IV_SOLVER_FLAG] = 1;
+            }
             __syncthreads();
             const int marg = iv[IV_MARG_FLAG];
             const int nonlinear = iv[IV_SOLVER_FLAG] == 1;

@@ -13,7 +13,7 @@ enum { IV_FRAME_COUNT = 0, IV_FIRST_IMU, IV_SOLVER_FLAG, IV_MARG_FLAG, IV_FAILUR
 enum { DV_ACC0 = 0, DV_GYR0 = 3, DV_LAST_P = 6, DV_LAST_P_OLD = 9, DV_BACK_P0 = 12, DV_LAST_R = 15, DV_LAST_R_OLD = 24, DV_BACK_R0 = 33,
        DV_COST0 = 42, DV_COST1 = 43, DV_PRIOR_C0 = 44, DV_TIC = 45, DV_RIC = 48, DV_COUNT = 64 };
 // IV_ACTION values decided by the feature kernel (VINS::processImage control flow, VINS.cpp:377-478)
-enum { ACT_ACCUMULATE = 0, ACT_INIT_SOLVE = 1, ACT_SLIDE_ONLY = 2, ACT_NL_SOLVE = 3, ACT_NONE = 4 };
+enum { ACT_ACCUMULATE = 0, ACT_INIT_SOLVE = 1, ACT_SLIDE_ONLY = 2, ACT_NL_SOLVE = 3, ACT_NONE = 4, ACT_CLEAR = 5 /* track_num < 20 at frame_count == W: clearState(), VINS.cpp:401-405 */ };
 
 struct BeState {
     int B, W, NF;            // NF = W + 1 frames
@@ -33,7 +33,7 @@ struct BeState {
     double *imu_buf; int *imu_cnt;                    // [B][NF][MAXIMU][7], [B][NF]
     int *iv; double *dv;                              // [B][IV_COUNT], [B][DV_COUNT]
     double *init_state;                               // [B][NF*10 + 6]  P3 Q4 V3 per frame, Ba3 Bg3
-    // feature table (FeatureManager::feature, always sorted by feature id)
+    // feature table (FeatureManager::feature, in the list's insertion order; compacted order-preservingly)
     int *f_id, *f_start, *f_nobs, *f_flag; double *f_depth; double *f_obs;   // [B][FCAP], obs [B][FCAP][NF][2]
     // prior (MarginalizationInfo in information form, canonical layout [pose_i(6) sb_i(9)]_i ex(6))
     double *Hp, *bp; double *x0;                      // [B][NPX*NPX], [B][NPX], [B][NF*16+7]

@@ -16,6 +16,34 @@
         }                                                                                      \
     } while (0)
 
+// inside vio_*_create after the handle exists: a failing CUDA call frees the handle before returning
+#define VIO_CUDA_TRY_OR(expr, cleanup)                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            fprintf(stderr, "[vio_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e),   \
+                    __FILE__, __LINE__, cudaGetErrorString(_e));                               \
+            cleanup;                                                                           \
+            return VIO_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the kernel FUNCTION, not of a handle: raise it once to everything the
+// device allows (opt-in maximum minus the kernel's static shared memory) so that handles with different requirements can coexist;
+// each launch is then validated against *max_dynamic by its caller.
+template <typename K>
+inline cudaError_t vio_allow_max_dynamic_smem(K kernel, int device, size_t *max_dynamic) {
+    int optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    const size_t dyn = (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : 0;
+    if (max_dynamic) *max_dynamic = dyn;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+}
+
 // Debug build only (-DVIO_DEBUG_POISON, libvio_b200_dbg.so): fill the CTA's whole shared-memory window (static + dynamic) with a
 // NaN / -1 pattern at kernel entry so that a read of uninitialised shared memory shows up deterministically.  kernel_bit selects
 // the kernel in the VIO_POISON_MASK environment variable read at library load (tools/poison_check.py).

@@ -94,7 +94,7 @@ extern "C" int vio_frontend_create(const vio_config *cfg, vio_frontend **out) {
     if (!fe) return VIO_ERR_ARG;
     fe->cfg = *cfg; fe->B = cfg->batch; fe->maxp = cfg->max_cnt;
     fe->cur = 0; fe->has_cur = false; fe->img_cnt = 0; fe->launches = 0; fe->own_stream = true;
-    VIO_CUDA_TRY(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking));
+    VIO_CUDA_TRY_OR(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking), vio_frontend_destroy(fe));
     int r = cfg->rows, c = cfg->cols;
     for (int l = 0; l < 4; l++) {
         fe->lr[l] = r; fe->lc[l] = c; fe->lsz[l] = (size_t)r * c;
@@ -130,9 +130,12 @@ extern "C" int vio_frontend_create(const vio_config *cfg, vio_frontend **out) {
     if (!rc) rc = dev_alloc(fe, &fe->err_flag_dev, 1);
     A.err_flag = fe->err_flag_dev;
     if (rc) { vio_frontend_destroy(fe); return rc; }
-    VIO_CUDA_TRY(cudaDeviceSynchronize());       // dev_alloc() zero-fills on the legacy default stream; fe->stream is non-blocking
-    VIO_CUDA_TRY(cudaFuncSetAttribute(post_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrackSmem)));
-    VIO_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelectSmem)));
+    VIO_CUDA_TRY_OR(cudaDeviceSynchronize(), vio_frontend_destroy(fe));       // dev_alloc() zero-fills on the legacy default stream; fe->stream is non-blocking
+    size_t dyn_max = 0;
+    VIO_CUDA_TRY_OR(vio_allow_max_dynamic_smem(post_track_kernel, cfg->device, &dyn_max), vio_frontend_destroy(fe));
+    if (sizeof(TrackSmem) > dyn_max) { vio_frontend_destroy(fe); return VIO_ERR_CAPACITY; }
+    VIO_CUDA_TRY_OR(vio_allow_max_dynamic_smem(select_kernel, cfg->device, &dyn_max), vio_frontend_destroy(fe));
+    if (sizeof(SelectSmem) > dyn_max) { vio_frontend_destroy(fe); return VIO_ERR_CAPACITY; }
     *out = fe;
     return VIO_OK;
 }
@@ -140,14 +143,14 @@ extern "C" int vio_frontend_create(const vio_config *cfg, vio_frontend **out) {
 extern "C" void vio_frontend_destroy(vio_frontend *fe) {
     if (!fe) return;
     cudaSetDevice(fe->cfg.device);
-    cudaStreamSynchronize(fe->stream);
+    if (fe->stream) cudaStreamSynchronize(fe->stream);
     if (fe->up_stream) {
         cudaStreamSynchronize(fe->up_stream);
         for (int i = 0; i < 2; i++) { cudaEventDestroy(fe->ev_up[i]); cudaEventDestroy(fe->ev_free[i]); }
         cudaStreamDestroy(fe->up_stream);
     }
     for (void *p : fe->allocs) cudaFree(p);
-    if (fe->own_stream) cudaStreamDestroy(fe->stream);
+    if (fe->own_stream && fe->stream) cudaStreamDestroy(fe->stream);
     delete fe;
 }
 
@@ -474,7 +477,7 @@ extern "C" int vio_prim_ransac_f(const vio_config *cfg, const float *p1_xy, cons
     VIO_CUDA_TRY(cudaMalloc(&dok, 2 * sizeof(int)));
     VIO_CUDA_TRY(cudaMemcpy(d1, p1_xy, sizeof(float2) * n, cudaMemcpyHostToDevice));
     VIO_CUDA_TRY(cudaMemcpy(d2, p2_xy, sizeof(float2) * n, cudaMemcpyHostToDevice));
-    VIO_CUDA_TRY(cudaFuncSetAttribute(ransac_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrackSmem)));
+    VIO_CUDA_TRY(vio_allow_max_dynamic_smem(ransac_test_kernel, cfg->device, nullptr));
     ransac_test_kernel<<<1, 256, sizeof(TrackSmem)>>>(d1, d2, n, cfg->f_threshold, dm, dok, dok + 1);
     int h[2] = {0, 0};
     VIO_CUDA_TRY(cudaMemcpy(h, dok, sizeof(h), cudaMemcpyDeviceToHost));
