@@ -821,6 +821,10 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem,
 
     double radius = 1e4, mu = 1e-8, alpha = 0.0, dogleg_norm = 0.0, x_norm = -1.0, mu_gn = 0.0, g2_lin = 0.0, gHg_lin = 0.0;
     bool reuse = false;
+    // The candidate is evaluated WITH its linearisation (speculatively): an accepted step -- the usual case -- then needs no second
+    // pass over the factors (Ceres evaluates the candidate cost-only and re-evaluates with Jacobians after accepting; same numbers).
+    // After a rejected candidate H / g / w belong to the candidate; lin_valid says whether they belong to the current point.
+    bool lin_valid = true;
     int iter = 0, invalid_run = 0;
     bool step_ok = true;                                   // iteration 0 counts as successful
     while (true) {
@@ -839,6 +843,7 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem,
         bool linear_ok = true;
         if (!reuse) {
             reuse = true;
+            if (!lin_valid) { (void)evaluate(s, b, ws, par, 1, sh_red, sm_dyn); lin_valid = true; }     // rejected candidate, then an invalid step
             for (int i = tid; i < NP; i += T) {
                 const double sc = ws.sc_p[i];
                 const double d = sqrt(fmin(fmax(ws.H[(size_t)i * NP + i] * sc * sc, 1e-6), 1e32));
@@ -991,7 +996,8 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem,
         }
         for (int l = tid; l < nl; l += T) cand[16 * NF + l] = par[16 * NF + l] + ws.u_l[l];
         __syncthreads();
-        const double cand_cost = evaluate(s, b, ws, cand, 0, sh_red, sm_dyn);
+        const double cand_cost = evaluate(s, b, ws, cand, 1, sh_red, sm_dyn);
+        lin_valid = false;
         BE_PROF(5);
         // ParameterToleranceReached / FunctionToleranceReached (trust_region_minimizer.cc:662-705)
         double sn = 0;
@@ -1007,8 +1013,8 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem,
             for (int i = tid; i < 16 * NF + nl; i += T) xn += par[i] * par[i];
             x_norm = sqrt(block_sum_d(xn, sh_red));
             BE_PROF(6);
-            x_cost = evaluate(s, b, ws, par, 1, sh_red, sm_dyn);
-            BE_PROF(0);
+            x_cost = cand_cost;                                       // H, g, w already hold the linearisation at the accepted point
+            lin_valid = true;
             step_ok = true;
             if (quality < 0.25) radius *= 0.5;                        // DoglegStrategy::StepAccepted
             if (quality > 0.75) radius = fmax(radius, 3.0 * dogleg_norm);

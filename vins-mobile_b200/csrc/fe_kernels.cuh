@@ -490,132 +490,162 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I,
 
 // ---------------------------------------------------------------------------------------------------------
 // K2  Shi-Tomasi response + 3x3 NMS + mask test, candidate compaction (cv::goodFeaturesToTrack front half;
-//     oracle r_min_eig_map / r_good_features).  The eig map is never written to HBM: a 32x32 tile computes
-//     Sobel (f32, the exact fma pattern cv2 uses), covariance products, 3x3 box sums in f64, min-eigenvalue,
-//     and emits (value, address) of every masked interior local maximum plus the masked global maximum.
+//     oracle r_min_eig_map / r_good_features).  The eig map is never written to HBM.  One WARP streams down a vertical strip:
+//     lane = image column (32 input columns -> 26 output columns, 3 columns of halo on either side), one image row per step,
+//     everything the separable pipeline needs from the rows above kept in registers:
+//       pixel row -> Sobel (f32, the exact fma pattern cv2 uses) -> covariance products -> 3x3 box sums in f64 in cv2's order
+//       (row sum (left + centre) + right first, then (above + row) + below) -> min-eigenvalue -> 3x3 NMS,
+//     horizontal neighbours through warp shuffles.  Borders: pixels are REFLECT_101 for the Sobel stage; the box filter reflects
+//     the COVARIANCE image (column -1 := column 1, row -1 := row 1 -- not the same thing: dx changes sign under pixel reflection),
+//     which is a matter of which lane / which register a neighbour is taken from.
+//     Emits (value, address) of every masked interior local maximum plus the masked global maximum.
 //     The min-distance mask of setMask() is evaluated analytically: a pixel is masked iff it lies within
 //     min_dist of a kept point's ROUNDED centre (cv::circle raster == Euclidean disc).
 //     NMS is threshold independent: (e > thr) && (e == dilate(threshold(e)))  <=>  (e > thr) && e >= 8 nbrs.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int ET = 32;                 // tile edge
-__global__ void __launch_bounds__(256) eig_candidates_kernel(const uint8_t *__restrict__ img, size_t img_stride, int rows,
-                                                             int cols, const int2 *__restrict__ kept, const int *__restrict__ n_kept,
-                                                             int maxp, int min_dist, unsigned *__restrict__ max_bits,
-                                                             unsigned long long *__restrict__ cand, int *__restrict__ cand_cnt) {
+constexpr int EG_W = 26;               // output columns per warp (32 lanes - 2 x 3 halo)
+constexpr int EG_ROWS = 64;            // output rows per warp (4 rows of halo are recomputed per chunk)
+constexpr int EG_WARPS = 4;
+constexpr int EG_KCAP = 64;            // kept points whose disc can reach one strip chunk
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__device__ __forceinline__ float eg_min_eig(double sxx, double sxy, double syy) {
+    const float fa = (float)sxx, fb = (float)sxy, fc = (float)syy;
+    const float ha = fmul(fa, 0.5f), hc = fmul(fc, 0.5f);
+    const float t = fsub(ha, hc);
+    return fsub(fadd(ha, hc), __fsqrt_rn(fadd(fmul(t, t), fmul(fb, fb))));
+}
+
+__global__ void __launch_bounds__(EG_WARPS * 32) eig_candidates_kernel(const uint8_t *__restrict__ img, size_t img_stride, int rows,
+                                                                       int cols, const int2 *__restrict__ kept, const int *__restrict__ n_kept,
+                                                                       int maxp, int min_dist, unsigned *__restrict__ max_bits,
+                                                                       unsigned long long *__restrict__ cand, int *__restrict__ cand_cnt) {
     VIO_POISON(512u);
-    __shared__ float sp[(ET + 6) * (ET + 6)];        // pixels as f32, origin (ty0-3, tx0-3)
-    __shared__ float sdx[(ET + 4) * (ET + 4)];       // origin (ty0-2, tx0-2)
-    __shared__ float sdy[(ET + 4) * (ET + 4)];
-    __shared__ double srs[3][(ET + 4) * (ET + 2)];   // f64 ROW sums of dx*dx, dx*dy, dy*dy: rows origin ty0-2, cols origin tx0-1
-    float *se = sp;                                  // eig, origin (ty0-1, tx0-1): aliases sp (dead once dx/dy exist)
-    __shared__ int2 sk[64];
-    __shared__ int nk;
+    __shared__ int2 sk[EG_WARPS][EG_KCAP];
+    __shared__ short sw[128];                                        // chord half widths of the min-distance disc (min_dist <= 127)
+    constexpr unsigned FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.z;
-    const int tx0 = blockIdx.x * ET, ty0 = blockIdx.y * ET;
-    const uint8_t *im = img + (size_t)b * img_stride;
-    const int tid = threadIdx.x;
-    if (tid == 0) nk = 0;
+    for (int d = threadIdx.x; d <= min(min_dist, 127); d += blockDim.x) {
+        const int v = min_dist * min_dist - d * d;
+        int w = (int)sqrtf((float)v);
+        while (w * w > v) w--;
+        while ((w + 1) * (w + 1) <= v) w++;
+        sw[d] = (short)w;
+    }
     __syncthreads();
-    // kept points whose disc can touch this tile
+    const int x0 = (blockIdx.x * EG_WARPS + warp) * EG_W;
+    if (x0 >= cols) return;                                          // whole warp
+    const int y0 = blockIdx.y * EG_ROWS, y1 = min(y0 + EG_ROWS, rows);
+    const uint8_t *im = img + (size_t)b * img_stride;
+    // kept points whose disc can touch this strip chunk (warp-level compaction)
+    int nk = 0;
     {
         const int n = n_kept[b];
-        for (int i = tid; i < n; i += 256) {
-            const int2 c = kept[(size_t)b * maxp + i];
-            if (c.x >= tx0 - min_dist && c.x < tx0 + ET + min_dist && c.y >= ty0 - min_dist && c.y < ty0 + ET + min_dist) {
-                const int s = atomicAdd(&nk, 1);
-                if (s < 64) sk[s] = c;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            bool near = false;
+            int2 c = make_int2(0, 0);
+            if (i < n) {
+                c = kept[(size_t)b * maxp + i];
+                near = c.x >= x0 - min_dist && c.x < x0 + EG_W + min_dist && c.y >= y0 - min_dist && c.y < y1 + min_dist;
             }
+            const unsigned m = __ballot_sync(FULL, near);
+            const int pos = nk + __popc(m & ((1u << lane) - 1u));
+            if (near && pos < EG_KCAP) sk[warp][pos] = c;
+            nk += __popc(m);
         }
+        nk = min(nk, EG_KCAP);
+        __syncwarp();
     }
-    constexpr int PW = ET + 6, DW = ET + 4, EW = ET + 2;
-    for (int i = tid; i < PW * PW; i += 256) {
-        const int r = i / PW, c = i - r * PW;
-        const int y = reflect101(ty0 - 3 + r, rows), x = reflect101(tx0 - 3 + c, cols);
-        sp[i] = (float)im[(size_t)y * cols + x];
-    }
-    __syncthreads();
+    const int md2 = min_dist * min_dist;
+    const int xin = x0 - 3 + lane;                                   // image column of this lane
+    const int xr = reflect101(xin, cols);                            // where its pixels come from (Sobel: BORDER_REFLECT_101)
+    const bool own_x = lane >= 3 && lane < 3 + EG_W && xin < cols;   // columns whose results this warp publishes
+    const int pl = max(lane - 1, 0), pr = min(lane + 1, 31);         // pixel neighbours
+    const int cl = (xin == 0) ? pr : pl, cr = (xin == cols - 1) ? pl : pr;      // covariance neighbours (box filter border)
     const float a = (float)(1.0 / 3060.0);
     const float a2 = fmul(2.f, a);
-    for (int i = tid; i < DW * DW; i += 256) {
-        const int r = i / DW, c = i - r * DW;
-        const float *q = sp + (r + 1) * PW + (c + 1);      // pixel (ty0-2+r, tx0-2+c)
-        // dx = fma(r[-1]+r[+1], a, r[0]*2a),  r[k] = p[k][+1]-p[k][-1]
-        const float rm = fsub(q[-PW + 1], q[-PW - 1]), r0 = fsub(q[1], q[-1]), rp = fsub(q[PW + 1], q[PW - 1]);
-        sdx[i] = ffma(fadd(rm, rp), a, fmul(r0, a2));
-        // dy = s[+1]-s[-1],  s[k] = fma(p[k][+1], a, fma(p[k][0], 2a, a*p[k][-1]))
-        const float sm = ffma(q[-PW + 1], a, ffma(q[-PW], a2, fmul(a, q[-PW - 1])));
-        const float spv = ffma(q[PW + 1], a, ffma(q[PW], a2, fmul(a, q[PW - 1])));
-        sdy[i] = fsub(spv, sm);
-    }
-    __syncthreads();
-    // separable 3x3 box filter, exactly cv2's order: row sums (c0+c1)+c2 in f64 first, then column sums (r0+r1)+r2
-    for (int i = tid; i < DW * EW; i += 256) {
-        const int r = i / EW, c = i - r * EW;
-        const int gy = ty0 - 2 + r, gx = tx0 - 1 + c;
-        if (gy < 0 || gy >= rows || gx < 0 || gx >= cols) continue;
-        double pa[3], pb[3], pc[3];
-#pragma unroll
-        for (int dx = -1; dx <= 1; dx++) {
-            const int xx = reflect101(gx + dx, cols) - (tx0 - 2);
-            const float vx = sdx[r * DW + xx], vy = sdy[r * DW + xx];
-            pa[dx + 1] = (double)fmul(vx, vx); pb[dx + 1] = (double)fmul(vx, vy); pc[dx + 1] = (double)fmul(vy, vy);
-        }
-        srs[0][i] = __dadd_rn(__dadd_rn(pa[0], pa[1]), pa[2]);
-        srs[1][i] = __dadd_rn(__dadd_rn(pb[0], pb[1]), pb[2]);
-        srs[2][i] = __dadd_rn(__dadd_rn(pc[0], pc[1]), pc[2]);
-    }
-    __syncthreads();
-    for (int i = tid; i < EW * EW; i += 256) {
-        const int r = i / EW, c = i - r * EW;
-        const int gy = ty0 - 1 + r, gx = tx0 - 1 + c;
-        float e = -1.f;
-        if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
-            const int y0 = reflect101(gy - 1, rows) - (ty0 - 2), y1 = gy - (ty0 - 2), y2 = reflect101(gy + 1, rows) - (ty0 - 2);
-            const float fa = (float)__dadd_rn(__dadd_rn(srs[0][y0 * EW + c], srs[0][y1 * EW + c]), srs[0][y2 * EW + c]);
-            const float fb = (float)__dadd_rn(__dadd_rn(srs[1][y0 * EW + c], srs[1][y1 * EW + c]), srs[1][y2 * EW + c]);
-            const float fc = (float)__dadd_rn(__dadd_rn(srs[2][y0 * EW + c], srs[2][y1 * EW + c]), srs[2][y2 * EW + c]);
-            const float ha = fmul(fa, 0.5f), hc = fmul(fc, 0.5f);
-            const float t = fsub(ha, hc);
-            e = fsub(fadd(ha, hc), __fsqrt_rn(fadd(fmul(t, t), fmul(fb, fb))));
-        }
-        se[i] = e;
-    }
-    __syncthreads();
-    const int nkk = min(nk, 64);
-    const int md2 = min_dist * min_dist;
+    const int r_start = max(0, y0 - 2), r_end = min(rows - 1, y1 + 1);
+    auto ldpix = [&](int r) { return (float)im[(size_t)reflect101(r, rows) * cols + xr]; };
+    // per pixel row k: rd[k] = p[k][x+1] - p[k][x-1],  sv[k] = fma(p[k][x+1], a, fma(p[k][x], 2a, a p[k][x-1]))
+    auto row_terms = [&](float p, float &rd, float &sv) {
+        const float L = __shfl_sync(FULL, p, pl), R = __shfl_sync(FULL, p, pr);
+        rd = fsub(R, L);
+        sv = ffma(R, a, ffma(p, a2, fmul(a, L)));
+    };
+    float rd_a, sv_a, rd_b, sv_b, rd_c, sv_c;
+    row_terms(ldpix(r_start - 1), rd_a, sv_a);
+    row_terms(ldpix(r_start), rd_b, sv_b);
+    float q0 = ldpix(r_start + 1), q1 = ldpix(r_start + 2), q2 = ldpix(r_start + 3);      // pixel rows in flight (three steps ahead)
+    double xx0 = 0, xy0 = 0, yy0 = 0, xx1 = 0, xy1 = 0, yy1 = 0;     // row sums of rows r-2, r-1
+    float e0 = -1.f, e1 = -1.f, e2 = -1.f;                           // eig rows ye-2, ye-1, ye
     float local_max = 0.f;
-    for (int i = tid; i < ET * ET; i += 256) {
-        const int r = i / ET, c = i - r * ET;
-        const int gy = ty0 + r, gx = tx0 + c;
-        if (gy >= rows || gx >= cols) continue;
-        const float *q = se + (r + 1) * EW + (c + 1);
-        const float e = q[0];
-        // the (analytic) mask only matters for a pixel that would raise the running maximum or that is an interior local maximum,
-        // so it is evaluated lazily
-        bool is_cand = false;
-        if (e > 0.f && gy >= 1 && gy < rows - 1 && gx >= 1 && gx < cols - 1) {
-            const float m = fmaxf(fmaxf(fmaxf(q[-EW - 1], q[-EW]), fmaxf(q[-EW + 1], q[-1])),
-                                  fmaxf(fmaxf(q[1], q[EW - 1]), fmaxf(q[EW], q[EW + 1])));
-            is_cand = e >= m;
+    unsigned mrow1 = 0, mrow2 = 0;                                   // lanes masked by a kept point's disc in eig rows ye-1, ye
+    unsigned long long *cout = cand + (size_t)b * CAND_CAP;
+    // setMask() for one image row as a lane bit mask: lane k owns kept point k, turns its disc's chord on that row (half width
+    // sw[|dy|] = floor(sqrt(min_dist^2 - dy^2)), tabulated once per CTA) into a run of lane bits; the runs are OR-ed across the warp
+    auto row_mask = [&](int gy) {
+        unsigned m = 0;
+        for (int k0 = 0; k0 < nk; k0 += 32) {
+            unsigned bits = 0;
+            if (k0 + lane < nk) {
+                const int2 c = sk[warp][k0 + lane];
+                const int dy = abs(gy - c.y);
+                if (dy <= min_dist) {
+                    const int w = sw[dy];
+                    const int lo = max(c.x - w - (x0 - 3), 0), hi = min(c.x + w - (x0 - 3), 31);
+                    if (lo <= hi) bits = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+                }
+            }
+            m |= __reduce_or_sync(FULL, bits);
         }
-        if (!is_cand && !(e > local_max)) continue;
-        bool masked = false;
-        for (int k = 0; k < nkk; k++) {
-            const int ddx = gx - sk[k].x, ddy = gy - sk[k].y;
-            masked |= (ddx * ddx + ddy * ddy <= md2);
+        return m;
+    };
+    // a new eig row ye: (1) running masked maximum over the pixels this warp owns, (2) NMS of row ye - 1
+    auto push_eig = [&](float e, int ye) {
+        e0 = e1; e1 = e2; e2 = e;
+        mrow1 = mrow2; mrow2 = nk ? row_mask(ye) : 0u;
+        if (own_x && ye >= y0 && ye < y1 && !((mrow2 >> lane) & 1u)) local_max = fmaxf(local_max, e);
+        const int y = ye - 1;
+        const float vm = fmaxf(fmaxf(e0, e1), e2);
+        const float vl = __shfl_sync(FULL, vm, pl), vr = __shfl_sync(FULL, vm, pr);
+        if (own_x && y >= y0 && y < y1 && y >= 1 && y < rows - 1 && xin >= 1 && xin < cols - 1 && e1 > 0.f && !((mrow1 >> lane) & 1u)) {
+            const float m = fmaxf(fmaxf(vl, vr), fmaxf(e0, e2));
+            if (e1 >= m) {
+                const int sl = atomicAdd(&cand_cnt[b], 1);
+                if (sl < CAND_CAP) cout[sl] = ((unsigned long long)__float_as_uint(e1) << 32) | (unsigned)(y * cols + xin);
+            }
         }
-        if (masked) continue;
-        local_max = fmaxf(local_max, e);
-        if (is_cand) {
-            const int s = atomicAdd(&cand_cnt[b], 1);
-            if (s < CAND_CAP)
-                cand[(size_t)b * CAND_CAP + s] = ((unsigned long long)__float_as_uint(e) << 32) | (unsigned)(gy * cols + gx);
+    };
+#pragma unroll 1
+    for (int r = r_start; r <= r_end; r++) {
+        row_terms(q0, rd_c, sv_c);
+        q0 = q1; q1 = q2;
+        if (r + 4 <= r_end + 1) {                                    // pixel row r + 1 is needed at step r: loads run three steps ahead
+            const int rr = r + 4 < rows ? r + 4 : 2 * rows - 2 - (r + 4);
+            q2 = (float)im[(size_t)rr * cols + xr];
         }
+        const float dx = ffma(fadd(rd_a, rd_c), a, fmul(rd_b, a2));
+        const float dy = fsub(sv_c, sv_a);
+        rd_a = rd_b; sv_a = sv_b; rd_b = rd_c; sv_b = sv_c;
+        const double pxx = (double)fmul(dx, dx), pxy = (double)fmul(dx, dy), pyy = (double)fmul(dy, dy);
+        const double xx2 = __dadd_rn(__dadd_rn(shfl_d(pxx, cl), pxx), shfl_d(pxx, cr));
+        const double xy2 = __dadd_rn(__dadd_rn(shfl_d(pxy, cl), pxy), shfl_d(pxy, cr));
+        const double yy2 = __dadd_rn(__dadd_rn(shfl_d(pyy, cl), pyy), shfl_d(pyy, cr));
+        if (r == 1)                                                  // eig row 0: box rows (1, 0, 1)
+            push_eig(eg_min_eig(__dadd_rn(__dadd_rn(xx2, xx1), xx2), __dadd_rn(__dadd_rn(xy2, xy1), xy2), __dadd_rn(__dadd_rn(yy2, yy1), yy2)), 0);
+        if (r - r_start >= 2)                                        // eig row r - 1: box rows (r - 2, r - 1, r)
+            push_eig(eg_min_eig(__dadd_rn(__dadd_rn(xx0, xx1), xx2), __dadd_rn(__dadd_rn(xy0, xy1), xy2), __dadd_rn(__dadd_rn(yy0, yy1), yy2)), r - 1);
+        if (r == rows - 1 && r >= 1)                                 // eig row rows - 1: box rows (rows - 2, rows - 1, rows - 2)
+            push_eig(eg_min_eig(__dadd_rn(__dadd_rn(xx1, xx2), xx1), __dadd_rn(__dadd_rn(xy1, xy2), xy1), __dadd_rn(__dadd_rn(yy1, yy2), yy1)), rows - 1);
+        xx0 = xx1; xy0 = xy1; yy0 = yy1; xx1 = xx2; xy1 = xy2; yy1 = yy2;
     }
     // masked global maximum (positive floats order like their bit patterns)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
-    if ((tid & 31) == 0 && local_max > 0.f) atomicMax(&max_bits[b], __float_as_uint(local_max));
+    for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(FULL, local_max, o));
+    if (lane == 0 && local_max > 0.f) atomicMax(&max_bits[b], __float_as_uint(local_max));
 }
 
 }  // namespace fe

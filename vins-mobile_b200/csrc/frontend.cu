@@ -84,7 +84,7 @@ extern "C" void vio_config_default(vio_config *c) {
 
 extern "C" int vio_frontend_create(const vio_config *cfg, vio_frontend **out) {
     if (!cfg || !out || cfg->batch < 1 || cfg->max_cnt < 1 || cfg->max_cnt > VIO_MAXP || cfg->rows < 64 || cfg->cols < 64 ||
-        cfg->min_dist < 1 || cfg->freq < 1)
+        cfg->min_dist < 1 || cfg->min_dist > 127 || cfg->freq < 1)
         return VIO_ERR_ARG;
     const int gw = (cfg->cols + cfg->min_dist - 1) / cfg->min_dist, gh = (cfg->rows + cfg->min_dist - 1) / cfg->min_dist;
     if (gw * gh > 2048) return VIO_ERR_ARG;
@@ -212,8 +212,8 @@ static int run_frame(vio_frontend *fe, int *published) {
                fe->cfg.min_dist, fe->cfg.f_threshold, detect, fe->has_cur ? 1 : 0)));
     fe->launches++;
     if (detect) {
-        dim3 grd((fe->cfg.cols + ET - 1) / ET, (fe->cfg.rows + ET - 1) / ET, B);
-        VIO_LAUNCH(fe->timer, s, "eig_candidates_kernel", (eig_candidates_kernel<<<grd, 256, 0, s>>>(fe->pyr[forw][0], fe->lsz[0], fe->cfg.rows,
+        dim3 grd(((fe->cfg.cols + EG_W - 1) / EG_W + EG_WARPS - 1) / EG_WARPS, (fe->cfg.rows + EG_ROWS - 1) / EG_ROWS, B);
+        VIO_LAUNCH(fe->timer, s, "eig_candidates_kernel", (eig_candidates_kernel<<<grd, EG_WARPS * 32, 0, s>>>(fe->pyr[forw][0], fe->lsz[0], fe->cfg.rows,
                    fe->cfg.cols, fe->A.kept, fe->A.n_kept, fe->maxp, fe->cfg.min_dist, fe->A.max_bits, fe->A.cand, fe->A.cand_cnt)));
         VIO_LAUNCH(fe->timer, s, "select_kernel", (select_kernel<<<B, 256, sizeof(SelectSmem), s>>>(fe->A, fe->maxp, fe->cfg.rows, fe->cfg.cols,
                    fe->cfg.max_cnt, fe->cfg.min_dist, fe->cfg.fx, fe->cfg.fy, fe->cfg.cx, fe->cfg.cy)));
@@ -437,8 +437,8 @@ extern "C" int vio_prim_min_eig_candidates(const vio_config *cfg, const uint8_t 
     cudaMemcpyAsync(fe->A.forw_pts, kp.data(), sizeof(float2) * n_kept, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(fe->A.n_kept, &n_kept, sizeof(int), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(fe->A.n, &n_kept, sizeof(int), cudaMemcpyHostToDevice, s);
-    dim3 grd((c.cols + ET - 1) / ET, (c.rows + ET - 1) / ET, 1);
-    eig_candidates_kernel<<<grd, 256, 0, s>>>(fe->pyr[0][0], fe->lsz[0], c.rows, c.cols, fe->A.kept, fe->A.n_kept, fe->maxp, c.min_dist,
+    dim3 grd(((c.cols + EG_W - 1) / EG_W + EG_WARPS - 1) / EG_WARPS, (c.rows + EG_ROWS - 1) / EG_ROWS, 1);
+    eig_candidates_kernel<<<grd, EG_WARPS * 32, 0, s>>>(fe->pyr[0][0], fe->lsz[0], c.rows, c.cols, fe->A.kept, fe->A.n_kept, fe->maxp, c.min_dist,
                                               fe->A.max_bits, fe->A.cand, fe->A.cand_cnt);
     select_kernel<<<1, 256, sizeof(SelectSmem), s>>>(fe->A, fe->maxp, c.rows, c.cols, c.max_cnt, c.min_dist, c.fx, c.fy, c.cx, c.cy);
     int n = 0;
