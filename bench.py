@@ -30,10 +30,30 @@ sys.path.insert(0, ROOT)
 
 FREQ = 3
 IMU_PER_KF = 20
-ALGO_BYTES_PER_FRAME = 1_247_562          # 640x480, N=150, FREQ=3
-ALGO_BYTES_PYR = 407_962                  # 1.328*HW read L0 + write L1..L3
-ALGO_BYTES_DETECT = 614_400               # 2*HW on a detect frame
-ALGO_BYTES_KLT = 634_800                  # 4232*N
+# BASELINE.json configs -> concrete shapes.  c2 (= c3 at 8 GPUs) is the workload `value` is quoted on; c1 and c4 are measured as
+# extra lines ("configs" in the JSON) or on their own with --config.
+CONFIGS = {
+    "c1": dict(rows=640, cols=480, max_cnt=150, window=10, batch=1,
+               name="BASELINE.json configs[1]: single stream 640x480@30fps + 200 Hz IMU, 150 feats, 10-KF window"),
+    "c2": dict(rows=640, cols=480, max_cnt=150, window=10, batch=128,
+               name="batch 128 independent streams per GPU, 640x480@30fps + 200 Hz IMU, 150 feats, 10-KF window, FREQ=3 "
+                    "(BASELINE.json configs[2]; configs[3] at 8 GPUs)"),
+    "c4": dict(rows=720, cols=1280, max_cnt=300, window=20, batch=32,
+               name="BASELINE.json configs[4]: 1280x720, 300 feats, 20-KF window, 32 streams per GPU (batch 256 across 8 GPUs)"),
+}
+
+
+def algo_bytes(rows, cols, n):
+    """algorithmic bytes per camera frame -- pyramid 1.328 HW (read L0, write L1..L3), KLT 4232 N,
+    detection 2 HW on a detect frame."""
+    hw = rows * cols
+    lv = [hw]
+    r, c = rows, cols
+    for _ in range(3):
+        r, c = (r + 1) // 2, (c + 1) // 2
+        lv.append(r * c)
+    pyr = hw + sum(lv[1:])
+    return dict(pyr=pyr, detect=2 * hw, klt=4232 * n, frame=pyr + 4232 * n + 2 * hw / FREQ)
 
 
 def _rank_world():
@@ -182,67 +202,96 @@ class Pipeline:
         self.be.close()
 
 
-def run_ours(args):
-    import torch
-    rank, local, world = _rank_world()
-    torch.cuda.set_device(local)
-    dev = f"cuda:{local}"
-    if world > 1:
-        import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout; rank 0's stdout carries ONE JSON line
-        dist.init_process_group("nccl", device_id=torch.device(dev))
-    abi = importlib.import_module("vins-mobile_b200.abi")
-    api = importlib.import_module("vins-mobile_b200.api")
-    synth = importlib.import_module("vins-mobile_b200.synth")
-    B = args.batch
-    cfg = abi.default_config(batch=B, max_cnt=150, window_size=10, device=local)
-    W = cfg.window_size
-    prologue = FREQ * (W + 1)                       # fills the window and runs the first (initialising) solve
-    n_frames = prologue + args.warmup + args.steps + FREQ
-    t0 = time.time()
-    frames, dt, acc, gyr, gt, cam = make_data(synth, B, n_frames, rank * B, dev)
-    t_data = time.time() - t0
-    dt_d, acc_d, gyr_d = (torch.as_tensor(x, device=dev).contiguous() for x in (dt, acc, gyr))
-    stream = torch.cuda.Stream(device=dev)          # front end
-    # the back end is the critical path (one CTA per stream, a full SM each): its kernels get the free SMs first
-    stream_b = torch.cuda.Stream(device=dev, priority=-1) if not args.no_overlap else stream      # back end
+def _solve_flops(i, W):
+    """SURVEY.md section 8(d) flop model of one window solve with the stream's own P, L, iterations."""
+    NPd = 15 * (W + 1)
+    P, L, it, npr = i["n_proj"], max(i["n_feat"], 1), i["iters"], i["prior_n"]
+    lin = 1500.0 * P + 45000.0 * W + 2.0 * npr * npr
+    schur = 2.0 * L * (6.0 * (P / L + 1.0)) ** 2
+    chol = NPd ** 3 / 3.0 + 2.0 * NPd * NPd
+    cost_only = 0.4 * (1500.0 * P + 45000.0 * W) + 2.0 * npr * npr
+    return lin + it * (lin + schur + chol + cost_only)          # first linearisation + one (re)linearisation per iteration
 
-    def imu_dev(k):
-        return dt_d[k].data_ptr(), acc_d[k].data_ptr(), gyr_d[k].data_ptr()
 
-    dt_p, acc_p, gyr_p = (torch.as_tensor(np.ascontiguousarray(x)).pin_memory().numpy() for x in (dt, acc, gyr))   # pinned host IMU
+class Bench:
+    """Everything one rank needs to time a configuration: data, handles, streams."""
 
-    def imu_host(k):
-        return dt_p[k], acc_p[k], gyr_p[k]
-
-    gather_buf = None
-    if world > 1:
-        gather_buf = torch.empty((world, B, W + 1, 16), dtype=torch.float64, device=dev)
-        send_buf = torch.empty((B, W + 1, 16), dtype=torch.float64, device=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
+    def __init__(self, args, conf, rank, local, world):
+        import torch
+        self.torch = torch
+        self.args, self.conf, self.rank, self.local, self.world = args, conf, rank, local, world
+        self.dev = f"cuda:{local}"
+        self.abi = importlib.import_module("vins-mobile_b200.abi")
+        self.api = importlib.import_module("vins-mobile_b200.api")
+        self.synth = importlib.import_module("vins-mobile_b200.synth")
+        self.B, self.W = conf["batch"], conf["window"]
+        self.prologue = FREQ * (self.W + 1)                  # fills the window and runs the first (initialising) solve
+        self.n_frames = self.prologue + args.warmup + args.steps + FREQ
+        self.cam = self.synth.Camera() if (conf["rows"], conf["cols"]) == (640, 480) else self.synth.Camera().scaled(conf["rows"], conf["cols"])
+        t0 = time.time()
+        self.frames, self.dt, self.acc, self.gyr, self.gt, _ = make_data(self.synth, self.B, self.n_frames, rank * self.B, self.dev, self.cam)
+        self.t_data = time.time() - t0
+        self.dt_d, self.acc_d, self.gyr_d = (torch.as_tensor(x, device=self.dev).contiguous() for x in (self.dt, self.acc, self.gyr))
+        self.dt_p, self.acc_p, self.gyr_p = (torch.as_tensor(np.ascontiguousarray(x)).pin_memory().numpy() for x in (self.dt, self.acc, self.gyr))
+        self.stream = torch.cuda.Stream(device=self.dev)          # front end
+        # the back end is the critical path (one CTA per stream, a full SM each): its kernels get the free SMs first
+        self.stream_b = torch.cuda.Stream(device=self.dev, priority=-1) if not args.no_overlap else self.stream
+        self.stream_c = torch.cuda.Stream(device=self.dev)        # NCCL gather of the window states, off the critical path
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            self.gather_buf = torch.empty((world, self.B, self.W + 1, 16), dtype=torch.float64, device=self.dev)
+            self.send_buf = [torch.empty((self.B, self.W + 1, 16), dtype=torch.float64, device=self.dev) for _ in range(2)]
 
-    def timed_run(host_inputs):
-        pipe = Pipeline(api, cfg, stream.cuda_stream, stream_b.cuda_stream, gt, host_inputs)
-        src = frames.cpu().pin_memory().numpy() if host_inputs else None
+    def cfg(self, **over):
+        c = self.abi.default_config(batch=self.B, max_cnt=self.conf["max_cnt"], window_size=self.W, rows=self.conf["rows"], cols=self.conf["cols"],
+                                    device=self.local)
+        for k, v in over.items():
+            setattr(c, k, v)
+        return c
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed_run(self, host_inputs, cfg=None, clahe=False, profile=True):
+        torch, args, B, W, world = self.torch, self.args, self.B, self.W, self.world
+        cfg = cfg or self.cfg()
+        stream, stream_b, stream_c = self.stream, self.stream_b, self.stream_c
+        pipe = Pipeline(self.api, cfg, stream.cuda_stream, stream_b.cuda_stream, self.gt, host_inputs)
+        if clahe:
+            pipe.fe.set_clahe(True, 3.0, 8, 8)
+        src = self.frames.cpu().pin_memory().numpy() if host_inputs else None
+        imu_host = lambda k: (self.dt_p[k], self.acc_p[k], self.gyr_p[k])
+        imu_dev = lambda k: (self.dt_d[k].data_ptr(), self.acc_d[k].data_ptr(), self.gyr_d[k].data_ptr())
+        ev_copy, ev_gather, nkf = [None, None], [None, None], [0]
+        prologue = self.prologue
         with torch.cuda.stream(stream):
             def one(i):
-                pub = pipe.step(src[i] if host_inputs else frames[i].data_ptr(), imu_host if host_inputs else imu_dev)
+                pub = pipe.step(src[i] if host_inputs else self.frames[i].data_ptr(), imu_host if host_inputs else imu_dev)
                 if pub and world > 1:
+                    # the only collective: all-gather of the packed window states.  The copy into the (double-buffered) send buffer is
+                    # stream-ordered behind the solve; the gather itself runs on a third stream behind an event, so the next keyframe's
+                    # back-end kernels never queue behind NCCL
+                    import torch.distributed as dist
+                    k2 = nkf[0] & 1
+                    nkf[0] += 1
+                    if ev_gather[k2] is not None:
+                        stream_b.wait_event(ev_gather[k2])
                     with torch.cuda.stream(stream_b):
-                        pipe.be.copy_state(send_buf.data_ptr(), True)
-                        dist.all_gather_into_tensor(gather_buf.view(world * B, W + 1, 16), send_buf)
+                        pipe.be.copy_state(self.send_buf[k2].data_ptr(), True)
+                    ev_copy[k2] = torch.cuda.Event(); ev_copy[k2].record(stream_b)
+                    stream_c.wait_event(ev_copy[k2])
+                    with torch.cuda.stream(stream_c):
+                        dist.all_gather_into_tensor(self.gather_buf.view(world * B, W + 1, 16), self.send_buf[k2])
+                    ev_gather[k2] = torch.cuda.Event(); ev_gather[k2].record(stream_c)
             for i in range(prologue + args.warmup):
                 one(i)
-            barrier()
+            self.barrier()
             l0 = pipe.fe.launch_count() + pipe.be.launch_count()
-            clocks = Clocks(local)
-            if rank == 0 and not os.environ.get("VIO_BENCH_NO_CLOCKS"):
+            clocks = Clocks(self.local)
+            if self.rank == 0 and not os.environ.get("VIO_BENCH_NO_CLOCKS"):
                 clocks.start()
             trace = [] if os.environ.get("VIO_BENCH_TRACE") else None
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -253,107 +302,167 @@ def run_ours(args):
                 if trace is not None:
                     trace.append(time.perf_counter())
             stream.wait_stream(stream_b)
+            stream.wait_stream(stream_c)
             e1.record(stream)
-            barrier()
+            self.barrier()
             clocks.stop_flag = True
             ms = e0.elapsed_time(e1)
             if trace:
                 print("host ms per step (host_inputs=%s): " % host_inputs + " ".join(f"{(b - a) * 1e3:.2f}" for a, b in zip(trace, trace[1:])), file=sys.stderr)
             launches = pipe.fe.launch_count() + pipe.be.launch_count() - l0
-            # per-kernel CUDA-event pass (separate, untimed): one more keyframe period with both handles on ONE stream, so that every
-            # kernel is timed alone (under the two-stream overlap a front-end kernel's event time includes waiting for SMs the solve holds)
-            torch.cuda.synchronize()
-            pipe.be.use_stream(stream.cuda_stream)
-            pipe.fe.profile(True); pipe.be.profile(True); pipe.be.phase_cycles(True)
-            base = prologue + args.warmup + args.steps
-            for i in range(base, base + FREQ):
-                one(i)
-            prof = {}
-            prof.update(pipe.fe.profile(False)); prof.update(pipe.be.profile(False))
-            info = [pipe.be.info(b) for b in range(B)]
-            ph = pipe.be.phase_cycles(True).astype(float)
-            names = ["solve.linearize", "solve.scale_cauchy", "solve.schur", "solve.cholesky", "solve.dogleg_model", "solve.cost_eval", "solve.accept", "",
-                     "marg.setup", "marg.accumulate", "marg.slow_amm", "marg.amm_inv+schur", "marg.eig", "marg.recompose", "", "",
-                     "lin.prior", "lin.imu", "lin.projection", "lin.cost_sum", "chol.trailing_update", "chol.diag_kloop", "chol.diag_factor",
-                     "chol.backward", "chol.wait_A(eig.tred2)", "chol.phase_B(eig.accumulate)", "eig.tql2", "proj.pair_tables", "proj.jacobians", "proj.block_sums", "cost.prior", "cost.imu"]
-            phase_us = {nm: round(float(ph[:, i].max()) / 1.9e3, 1) for i, nm in enumerate(names) if nm}
+            prof, info, phase_us = {}, [], None
+            if profile:
+                # per-kernel CUDA-event pass (separate, untimed): one more keyframe period with both handles on ONE stream, so that every
+                # kernel is timed alone (under the two-stream overlap a front-end kernel's event time includes waiting for SMs the solve holds)
+                torch.cuda.synchronize()
+                pipe.be.use_stream(stream.cuda_stream)
+                pipe.fe.profile(True); pipe.be.profile(True); pipe.be.phase_cycles(True)
+                base = prologue + args.warmup + args.steps
+                for i in range(base, base + FREQ):
+                    one(i)
+                prof.update(pipe.fe.profile(False)); prof.update(pipe.be.profile(False))
+                info = [pipe.be.info(b) for b in range(B)]
+                ph = pipe.be.phase_cycles(True).astype(float)
+                names = ["solve.linearize", "solve.scale_cauchy", "solve.schur", "solve.cholesky", "solve.dogleg_model", "solve.cost_eval", "solve.accept", "",
+                         "marg.setup", "marg.accumulate", "marg.slow_amm", "marg.amm_inv+schur", "marg.eig", "marg.recompose", "", "",
+                         "lin.prior", "lin.imu", "lin.projection", "lin.cost_sum", "chol.trailing_update", "chol.diag_kloop", "chol.diag_factor",
+                         "chol.backward", "chol.wait_A(eig.tred2)", "chol.phase_B(eig.accumulate)", "eig.tql2", "proj.pair_tables", "proj.jacobians", "proj.block_sums", "cost.prior", "cost.imu"]
+                phase_us = {nm: round(float(ph[:, i].max()) / 1.9e3, 1) for i, nm in enumerate(names) if nm}
         if world > 1:
-            t = torch.tensor([ms], device=dev)
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=self.dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         pipe.close()
-        prof["_phases"] = phase_us
-        return ms, launches, prof, info, clocks.summary() if rank == 0 else None
+        return dict(ms=ms, launches=launches, prof=prof, info=info, phases=phase_us, clocks=clocks.summary() if self.rank == 0 else None)
 
-    ms, launches, prof, info, clk = timed_run(False)
-    ms_e2e, _, _, _, _ = timed_run(True)
+    def n_frames_parity_cap(self):
+        return 100000
 
-    def single_stream_run():
-        """BASELINE.json configs[1]: ONE stream on one B200 (latency-bound: one CTA per back-end kernel), device-resident frames."""
-        cfg1 = abi.default_config(batch=1, max_cnt=150, window_size=10, device=local)
-        f1 = frames[:, :1].contiguous()
-        imu1 = tuple(torch.as_tensor(np.ascontiguousarray(x[:, :, :1]), device=dev) for x in (dt, acc, gyr))
-        pipe = Pipeline(api, cfg1, stream.cuda_stream, stream_b.cuda_stream, gt[:1], False)
-        with torch.cuda.stream(stream):
-            for i in range(prologue + args.warmup):
-                pipe.step(f1[i].data_ptr(), lambda k: tuple(x[k].data_ptr() for x in imu1))
+    def parity_states_on(self, frames_host, dt, acc, gyr, gt, nb, last_frame):
+        """Untimed pass for `parity_in_bench`: a batch-nb pipeline of this library through the host frames the CPU arm consumed
+        (frames_host [n][nb][rows][cols]); returns the packed window states and the tracker state after the last frame."""
+        torch = self.torch
+        cfg = self.abi.default_config(batch=nb, max_cnt=150, window_size=10, device=self.local)
+        pipe = Pipeline(self.api, cfg, self.stream.cuda_stream, self.stream.cuda_stream, gt[:nb], True)
+        imu = lambda k: (np.ascontiguousarray(dt[k][:, :nb]), np.ascontiguousarray(acc[k][:, :nb]), np.ascontiguousarray(gyr[k][:, :nb]))
+        with torch.cuda.stream(self.stream):
+            for i in range(last_frame + 1):
+                pipe.step(np.ascontiguousarray(frames_host[i]), imu)
             torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream); stream_b.wait_stream(stream)
-            for i in range(prologue + args.warmup, prologue + args.warmup + args.steps):
-                pipe.step(f1[i].data_ptr(), lambda k: tuple(x[k].data_ptr() for x in imu1))
-            stream.wait_stream(stream_b); b.record(stream)
-            torch.cuda.synchronize()
-        t = a.elapsed_time(b)
+            st = pipe.be.state_all()
+            tr = [pipe.fe.stream(b) for b in range(nb)]
         pipe.close()
-        return {"workload": "BASELINE.json configs[1]: single stream 640x480@30fps + 200 Hz IMU, 150 feats, 10-KF window, 1 GPU", "frames_per_s": args.steps / (t * 1e-3),
-                "ms_per_frame": t / args.steps, "real_time_factor_at_30fps": args.steps / (t * 1e-3) / 30.0}
-    single = single_stream_run() if (world == 1 and rank == 0) else None
+        return st, tr
+
+
+def _kernel_table(prof, B, ab):
+    kern = {k: {"launches": c, "ms_per_launch": t / c} for k, (c, t) in prof.items() if c}
+    cand = {"pyr_down_kernel": ab["pyr"] / 3.0, "eig_candidates_kernel": ab["detect"], "lk_kernel": ab["klt"]}
+    for k in kern:
+        if k in cand:
+            kern[k]["achieved_GBps"] = cand[k] * B / (kern[k]["ms_per_launch"] * 1e-3) / 1e9
+    return kern, cand
+
+
+def run_ours(args):
+    import torch
+    rank, local, world = _rank_world()
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout; rank 0's stdout carries ONE JSON line
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    conf = dict(CONFIGS[args.config])
+    if args.batch:
+        conf["batch"] = args.batch
+    bn = Bench(args, conf, rank, local, world)
+    B, W = bn.B, bn.W
+    ab = algo_bytes(conf["rows"], conf["cols"], conf["max_cnt"])
+    main = bn.timed_run(False)
+    e2e = bn.timed_run(True, profile=False)
+    extras = {}
+    if world == 1 and not args.no_extras:
+        # (a) the reference's own marginalisation route on the GPU (eigendecompositions of Amm and A_r, marginalization_factor.cpp:270-294)
+        #     -- the like-for-like number next to the default information-form prior
+        r = bn.timed_run(False, cfg=bn.cfg(marg_mode=1, marg_amm_eig=1), profile=True)
+        extras["marg_reference_route"] = {"value": args.steps * B / (r["ms"] * 1e-3), "unit": "frames/s", "ms_per_step": r["ms"] / args.steps,
+                                          "marg_kernel_ms": r["prof"].get("marg_kernel", (1, float("nan")))[1] / max(r["prof"].get("marg_kernel", (1, 0))[0], 1),
+                                          "what": "vio_config marg_mode=1, marg_amm_eig=1: Amm^+ and the new prior through symmetric eigendecompositions as the reference does"}
+        # (b) CLAHE pre-processing switched on (ViewController.mm:438-441 runs it before every readImage)
+        r = bn.timed_run(False, clahe=True, profile=True)
+        extras["clahe_on"] = {"value": args.steps * B / (r["ms"] * 1e-3), "unit": "frames/s", "ms_per_step": r["ms"] / args.steps,
+                              "kernels_ms": {k: v[1] / v[0] for k, v in r["prof"].items() if k.startswith("clahe")}}
+    single = None
+    configs_extra = {}
+    if world == 1 and rank == 0 and not args.no_extras and args.config == "c2":
+        # BASELINE.json configs[1]: ONE stream (latency-bound: one CTA per back-end kernel), same frames as stream 0
+        b1 = Bench.__new__(Bench)
+        b1.__dict__.update(bn.__dict__)
+        b1.conf = dict(CONFIGS["c1"]); b1.B = 1
+        b1.frames = bn.frames[:, :1].contiguous()
+        b1.dt_d, b1.acc_d, b1.gyr_d = (torch.as_tensor(np.ascontiguousarray(x[:, :, :1]), device=bn.dev) for x in (bn.dt, bn.acc, bn.gyr))
+        b1.dt_p, b1.acc_p, b1.gyr_p = (np.ascontiguousarray(x[:, :, :1]) for x in (bn.dt, bn.acc, bn.gyr))
+        b1.gt = bn.gt[:1]
+        r1 = b1.timed_run(False, profile=False)
+        single = {"workload": CONFIGS["c1"]["name"] + ", 1 GPU", "frames_per_s": args.steps / (r1["ms"] * 1e-3), "ms_per_frame": r1["ms"] / args.steps,
+                  "real_time_factor_at_30fps": args.steps / (r1["ms"] * 1e-3) / 30.0, "gpu_launches": int(r1["launches"])}
+        configs_extra["c1"] = single
+        del b1
+        # BASELINE.json configs[4] at one GPU's share (32 of the 256 streams): short run, device-resident + end to end
+        try:
+            a4 = argparse.Namespace(**vars(args)); a4.steps = min(args.steps, 12); a4.warmup = 3
+            del bn.frames
+            torch.cuda.empty_cache()
+            b4 = Bench(a4, dict(CONFIGS["c4"]), rank, local, world)
+            r4 = b4.timed_run(False)
+            r4e = b4.timed_run(True, profile=False)
+            k4, _ = _kernel_table(r4["prof"], b4.B, algo_bytes(720, 1280, 300))
+            fl4 = sum(_solve_flops(i, b4.W) for i in r4["info"])
+            configs_extra["c4"] = {"workload": CONFIGS["c4"]["name"], "value": a4.steps * b4.B / (r4["ms"] * 1e-3), "unit": "frames/s",
+                                   "ms_per_step": r4["ms"] / a4.steps, "steps": a4.steps, "e2e": a4.steps * b4.B / (r4e["ms"] * 1e-3),
+                                   "kernels": k4, "solve_TFLOPs": fl4 / (k4["solve_kernel"]["ms_per_launch"] * 1e-3) / 1e12 if "solve_kernel" in k4 else None,
+                                   "solve_info_batch": {k: [min(i[k] for i in r4["info"]), max(i[k] for i in r4["info"])] for k in ("iters", "n_feat", "n_proj", "prior_n", "err")}}
+            del b4
+        except Exception as e:          # the extra line must never cost the headline
+            configs_extra["c4"] = {"error": repr(e)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
+    ms, launches, prof, info, clk = main["ms"], main["launches"], main["prof"], main["info"], main["clocks"]
     total_frames = args.steps * B * world
     value = total_frames / (ms * 1e-3)
-    e2e = total_frames / (ms_e2e * 1e-3)
-    n_kf_steps = len([i for i in range(args.steps) if (prologue + args.warmup + i) % FREQ == 0])
+    e2e_v = total_frames / (e2e["ms"] * 1e-3)
+    n_kf_steps = len([i for i in range(args.steps) if (bn.prologue + args.warmup + i) % FREQ == 0])
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm = peaks.get("hbm_gbs", 6650.0)
-    phases = prof.pop("_phases", None)
-    kern = {k: {"launches": c, "ms_per_launch": t / c} for k, (c, t) in prof.items() if c}
-    traffic = {}
+    kern, cand = _kernel_table(prof, B, ab)
+    traffic, traffic_src = {}, None
     import glob
     tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))          # newest committed ncu capture (names sort by round)
-    if tps:
-        traffic = json.load(open(tps[-1]))["bytes_per_launch"]
+    if tps and args.config == "c2":
+        tj = json.load(open(tps[-1]))
+        traffic, traffic_src = tj["bytes_per_launch"], {"file": os.path.relpath(tps[-1], ROOT), "captured_at_commit": tj.get("commit"), "note": tj.get("note")}
     # (1) the dominant kernel of the step: solve_kernel -- FP64 ALU / tensor pipe (DMMA), no HBM roofline (Jacobians are never
     #     materialised).  Algorithmic flops per launch = SURVEY.md section 8(d) flop model with every stream's own P, L, iterations.
     fp64 = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json"))) if os.path.exists(os.path.join(ROOT, "profiles", "fp64_peak.json")) else \
         {"fma_per_clk_per_sm": 64.0, "sms": 148}
     sm_mhz = (clk or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     fp64_peak = 2.0 * fp64["fma_per_clk_per_sm"] * fp64["sms"] * sm_mhz * 1e6 / 1e12
-    NPd = 15 * (W + 1)
-
-    def solve_flops(i):
-        P, L, it, npr = i["n_proj"], max(i["n_feat"], 1), i["iters"], i["prior_n"]
-        lin = 1500.0 * P + 45000.0 * W + 2.0 * npr * npr
-        schur = 2.0 * L * (6.0 * (P / L + 1.0)) ** 2
-        chol = NPd ** 3 / 3.0 + 2.0 * NPd * NPd
-        cost_only = 0.4 * (1500.0 * P + 45000.0 * W) + 2.0 * npr * npr
-        return lin + it * (lin + schur + chol + cost_only)          # first linearisation + one (re)linearisation per iteration
     roof = None
     if "solve_kernel" in kern and info:
-        fl = sum(solve_flops(i) for i in info)
+        fl = sum(_solve_flops(i, W) for i in info)
         ach = fl / (kern["solve_kernel"]["ms_per_launch"] * 1e-3) / 1e12
         roof = {"kernel": "solve_kernel", "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                "traffic": traffic.get("solve_kernel"),
+                "traffic": traffic.get("solve_kernel"), "traffic_source": traffic_src,
                 "peak_source": "FP64 (the path computes in f64; MEASURED_PEAKS.json has no FP64 figure): profiles/fp64_peak.json = 64 FMA/clk/SM "
                                "measured with tools/ubench/dmma_rate.cu (DFMA and DMMA alike) x 148 SMs x SM clock under load",
                 "algorithmic_flops_per_launch": fl, "flop_model": "SURVEY.md section 8(d): per iteration 1500 P + 45000 Wn + 2 n_prior^2 (linearise) + "
                 "2 L (6 (P/L+1))^2 (Schur) + n_r^3/3 + 2 n_r^2 (Cholesky) + cost-only evaluation, summed over the batch with each stream's P, L, iterations"}
     # (2) the dominant HBM-class kernel of the front end (per launch = one batch of B images)
-    cand = {"pyr_down_kernel": ALGO_BYTES_PYR / 3.0, "eig_candidates_kernel": ALGO_BYTES_DETECT, "lk_kernel": ALGO_BYTES_KLT}
     dom = max((k for k in cand if k in kern), key=lambda k: kern[k]["ms_per_launch"] * kern[k]["launches"], default=None)     # time per keyframe period
     roof_fe = None
     if dom:
@@ -363,23 +472,22 @@ def run_ours(args):
                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
                    "algorithmic_bytes_per_launch": bytes_per_launch,
                    "note": "kernel timed alone (single-stream profile pass after the timed region)"}
-    for k in kern:
-        if k in cand:
-            kern[k]["achieved_GBps"] = cand[k] * B / (kern[k]["ms_per_launch"] * 1e-3) / 1e9
-    cpu = cpu_baseline(args, frames[:, :min(B, os.cpu_count() or 1)].cpu().numpy(), dt, acc, gyr, gt, prologue) if world == 1 and not args.no_cpu else None
+    cpu = parity = None
+    if world == 1 and not args.no_cpu and args.config == "c2":
+        cpu, parity = cpu_baselines(args, bn)
     line = {
         "metric": "VIO frames/sec (640x480, 150 feats, 10-KF window)", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/f32 front end, f64 back end", "data": "synthetic",
-        "config": {"workload": f"batch {B} independent streams per GPU, 640x480@30fps + 200 Hz IMU, 150 feats, 10-KF window, FREQ=3 "
-                               "(BASELINE.json configs[2]; configs[3] at 8 GPUs)", "batch_per_gpu": B, "streams": B * world, "freq": FREQ,
+        "config": {"workload": conf["name"], "batch_per_gpu": B, "streams": B * world, "freq": FREQ,
                    "keyframe_steps_timed": n_kf_steps, "l2": "inputs change every step and the working set exceeds L2; no explicit flush",
-                   "prologue_frames_untimed": prologue, "data_gen_s": round(t_data, 1),
-                   "streams_overlap": "front end and back end on two CUDA streams, event-ordered hand-over" if not args.no_overlap else "single stream"},
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * cam.rows * cam.cols + B * IMU_PER_KF * 7 * 8 / FREQ),
-                "d2h_bytes_per_step": int(B * (W + 1) * 16 * 8 / FREQ), "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_frontend": roof_fe, "kernels": kern, "cpu_baseline": cpu, "single_stream": single,
-        "backend_phase_us_max_over_streams_at_1p9GHz": phases if phases and any(phases.values()) else None,      # debug library only (VIO_LIB_NAME)
+                   "prologue_frames_untimed": bn.prologue, "data_gen_s": round(bn.t_data, 1),
+                   "streams_overlap": "front end and back end on two CUDA streams, event-ordered hand-over; NCCL gather on a third" if not args.no_overlap else "single stream"},
+        "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": int(B * bn.cam.rows * bn.cam.cols + B * IMU_PER_KF * 7 * 8 / FREQ),
+                "d2h_bytes_per_step": int(B * (W + 1) * 16 * 8 / FREQ), "ms_per_step": e2e["ms"] / args.steps},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_frontend": roof_fe, "kernels": kern, "cpu_baseline": cpu,
+        "parity_in_bench": parity, "variants": extras or None, "configs": configs_extra or None, "single_stream": single,
+        "backend_phase_us_max_over_streams_at_1p9GHz": main["phases"] if main["phases"] and any(main["phases"].values()) else None,      # debug library only (VIO_LIB_NAME)
         "solve_info_stream0": info[0] if info else None,
         "solve_info_batch": {k: [min(i[k] for i in info), max(i[k] for i in info)] for k in ("iters", "n_feat", "n_proj", "prior_n", "marg_fast", "marg_sweeps", "marg_m", "chol_retry", "err")} if info else None,
     }
@@ -403,11 +511,14 @@ class Quiet:
 
 def _cpu_worker(payload):
     """One stream through the CPU reference path: cv2 (OpenCV binary) KLT / RANSAC-F / goodFeaturesToTrack driven by the restated
-    readImage, then the reference's factors + vendored Ceres 1.12 driven by the restated estimator loop."""
-    frames, dt, acc, gyr, gt, prologue, n_time, threads = payload
+    readImage, then the reference's factors + vendored Ceres 1.12 driven by the restated estimator loop.  Returns the wall time of the
+    timed frames, its split per stage, and the final tracker / window state (for parity_in_bench)."""
+    frames, dt, acc, gyr, gt, prologue, n_time, cv_threads, ref_lib = payload
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    if ref_lib:
+        os.environ["VINS_REF_LIB"] = ref_lib
     import cv2
-    cv2.setNumThreads(threads)
+    cv2.setNumThreads(cv_threads)
     import frontend_oracle as fo
     import backend_oracle as bo
     abi = importlib.import_module("vins-mobile_b200.abi")
@@ -417,6 +528,7 @@ def _cpu_worker(payload):
     est = bo.RefEstimator(cfg)
     kf = 0
     t_start = None
+    t_fe = 0.0
     # the reference prints from destructors too ("release marginlizationinfo"): this worker's stdout stays on /dev/null for good,
     # results travel back through the pool's pipe
     os.dup2(os.open(os.devnull, os.O_WRONLY), 1)
@@ -424,7 +536,11 @@ def _cpu_worker(payload):
         for i in range(prologue + n_time):
             if i == prologue:
                 t_start = time.perf_counter()
+                est.stage_seconds(reset=True)
+                t_fe = 0.0
+            t0 = time.perf_counter()
             _, _, pub = tr.read_image(frames[i])
+            t_fe += time.perf_counter() - t0
             if pub:
                 if kf > 0:
                     for j in range(IMU_PER_KF):
@@ -435,48 +551,113 @@ def _cpu_worker(payload):
                 xyz = np.array([tr.image_msg[k] for k in ids])
                 est.process_image(ids, xyz, i / 30.0)
                 kf += 1
-    return time.perf_counter() - t_start
+    total = time.perf_counter() - t_start
+    st = est.stage_seconds()
+    s = est.state()
+    packed = np.concatenate([s["P"], s["Q"], s["V"], s["Ba"], s["Bg"]], 1)
+    return dict(total=total, front_end=t_fe, ceres_solve=st["ceres_solve"], marginalise=st["marginalise"], process_imu=st["process_imu"],
+                process_image=st["process_image"], state=packed, ids=tr.ids.copy(), pts=tr.cur_pts.copy())
 
 
-def cpu_baseline(args, frames_cpu, dt, acc, gyr, gt, prologue, n_time=None):
-    """Throughput-fair CPU baseline: one single-threaded stream per host core, aggregate frames/s."""
+def _cpu_pool(payloads):
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    n_streams = min(cores, frames_cpu.shape[1])
-    n_time = n_time or min(args.steps + args.warmup, frames_cpu.shape[0] - prologue)
-    n_time -= n_time % FREQ
-    payloads = [(frames_cpu[:, b], dt[:, :, b], acc[:, :, b], gyr[:, :, b], gt[b], prologue, n_time, 1) for b in range(n_streams)]
     ctx = mp.get_context("spawn")
-    with ctx.Pool(n_streams) as pool:
-        times = pool.map(_cpu_worker, payloads)
-    v = n_streams * n_time / max(times)
-    return {"value": v, "unit": "frames/s", "cores": n_streams, "kind": "reference",
-            "sample": f"{n_streams} streams x {n_time} frames (same frames/IMU as GPU streams 0..{n_streams - 1}), one process per core, "
-                      "cv2.setNumThreads(1); front end = OpenCV 4.13 binary (the reference's OpenCV fork is not vendored) driven by the "
-                      "restated readImage, back end = reference factor code + vendored Ceres 1.12 (oracle/_ref)",
-            "per_stream_frames_per_s": n_time / (sum(times) / len(times))}
+    with ctx.Pool(len(payloads)) as pool:
+        return pool.map_async(_cpu_worker, payloads).get(timeout=900)       # a crashed worker must not hang the bench
+
+
+def _cpu_make_data(synth, n_streams, n_frames, dev):
+    return make_data(synth, n_streams, n_frames, 0, dev)
+
+
+def cpu_baselines(args, bn=None, n_time=None):
+    """BASELINE.md section 3, both baselines, on the host cores of this box, >= 300 timed frames per stream:
+      (2) throughput-fair (the headline `value`): independent single-threaded streams, one process per core, aggregate frames/s.  The
+          reference's marginalisation spawns 4 pthreads per stream (marginalization_factor.hpp:18), so `cores` streams oversubscribe;
+          the arm is therefore run with cores, cores/2 and cores/4 streams and the BEST aggregate is reported;
+      (1) reference-faithful single stream: cv2 with its default thread pool, Ceres num_threads 1, 4 marginalisation pthreads.
+    Each with the split front end / ceres::Solve / marginalisation, for the default -O2 oracle build and for -O3 -march=x86-64-v3.
+    Also returns parity_in_bench: the GPU pipeline's window states / tracker ids against these CPU runs on the same frames."""
+    import torch
+    synth = importlib.import_module("vins-mobile_b200.synth")
+    cores = os.cpu_count() or 1
+    prologue = FREQ * 11
+    n_time = n_time or max(args.cpu_frames, FREQ)
+    n_time -= n_time % FREQ
+    n_frames = prologue + n_time + FREQ
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    frames, dt, acc, gyr, gt, _ = _cpu_make_data(synth, cores, n_frames, dev)
+    fr = frames.cpu().numpy()
+    del frames
+
+    def payloads(n, threads, lib):
+        return [(fr[:, b], dt[:, :, b], acc[:, :, b], gyr[:, :, b], gt[b], prologue, n_time, threads, lib) for b in range(n)]
+
+    def summarise(res, n):
+        tmax = max(r["total"] for r in res)
+        tot = sum(r["total"] for r in res)
+        return {"value": n * n_time / tmax, "streams": n, "per_stream_frames_per_s": n_time * n / tot,
+                "split_fraction": {k: sum(r[k] for r in res) / tot for k in ("front_end", "ceres_solve", "marginalise", "process_imu")},
+                "ms_per_frame_per_stream": {k: 1e3 * sum(r[k] for r in res) / (n * n_time) for k in ("front_end", "ceres_solve", "marginalise")}}
+
+    out = {}
+    best = None
+    res_full = None
+    for lib, tag in ((None, "O2"), ("libvins_ref_o3.so", "O3_x86-64-v3")):
+        if lib and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", lib)):
+            continue
+        runs = []
+        for n in sorted({cores, max(cores // 2, 1), max(cores // 4, 1)}, reverse=True):
+            res = _cpu_pool(payloads(n, 1, lib))
+            if lib is None and n == cores:
+                res_full = res
+            runs.append(summarise(res, n))
+        out[f"throughput_fair_{tag}"] = {"runs": runs, "best": max(runs, key=lambda r: r["value"])}
+        single = _cpu_pool(payloads(1, -1, lib))       # cv2.setNumThreads(-1) restores OpenCV's default pool
+        out[f"single_stream_faithful_{tag}"] = summarise(single, 1)
+        cand = out[f"throughput_fair_{tag}"]["best"]
+        if best is None or cand["value"] > best[1]["value"]:
+            best = (tag, cand)
+    cpu = {"value": best[1]["value"], "unit": "frames/s", "cores": cores, "kind": "reference", "build": best[0], "streams": best[1]["streams"],
+           "sample": f"{n_time} timed frames per stream after {prologue} untimed (window fill + first solve), same frames / IMU as GPU streams 0..{cores - 1}; "
+                     "front end = OpenCV 4.13 binary (the reference's OpenCV fork is not vendored) driven by the restated readImage, back end = reference "
+                     "factor code + vendored Ceres 1.12 (oracle/_ref); value = best aggregate over {cores, cores/2, cores/4} concurrent streams and both builds",
+           "per_stream_frames_per_s": best[1]["per_stream_frames_per_s"], "detail": out}
+    parity = None
+    if bn is not None and res_full is not None:
+        # the GPU pipeline on the very same frames (frames are a deterministic function of (stream id, frame index))
+        last = prologue + n_time - 1
+        nb = min(cores, bn.B)
+        if last < bn.n_frames_parity_cap():
+            st, trk = bn.parity_states_on(fr[:last + 1, :nb], dt, acc, gyr, gt, nb, last)
+            ids_equal, pts_equal, worst = True, True, 0.0
+            for b in range(nb):
+                ids_equal &= bool(np.array_equal(trk[b]["ids"], res_full[b]["ids"]))
+                pts_equal &= bool(np.array_equal(trk[b]["ids"], res_full[b]["ids"]) and
+                                  np.array_equal(trk[b]["pts"].view(np.uint32), res_full[b]["pts"].view(np.uint32)))
+                g, r = st[b], res_full[b]["state"]
+                for sl in (slice(0, 3), slice(7, 10)):
+                    worst = max(worst, float(np.abs(g[:, sl] - r[:, sl]).max() / max(np.abs(r[:, sl]).max(), 1e-12)))
+                q = np.minimum(np.abs(g[:, 3:7] - r[:, 3:7]).max(), np.abs(g[:, 3:7] + r[:, 3:7]).max())
+                worst = max(worst, float(q))
+            parity = {"streams": nb, "frames": last + 1, "ids_equal": ids_equal, "points_bitwise_equal": pts_equal, "max_rel_err": worst,
+                      "what": "GPU pipeline (device path) vs the CPU reference arm (-O2 build) on the same frames: tracker ids / positions after the last "
+                              "frame, window P, V (relative to the largest entry) and Q (absolute) after the last keyframe"}
+    return cpu, parity
 
 
 def run_reference(args):
     rank, local, world = _rank_world()
     if rank != 0:
         return
-    synth = importlib.import_module("vins-mobile_b200.synth")
     cores = os.cpu_count() or 1
-    prologue = FREQ * 11
-    n_time = args.steps + args.warmup
-    n_time -= n_time % FREQ
-    n_time = max(n_time, FREQ)
-    n_frames = prologue + n_time + FREQ
-    import torch
-    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-    frames, dt, acc, gyr, gt, cam = make_data(synth, cores, n_frames, 0, dev)
-    cpu = cpu_baseline(args, frames.cpu().numpy(), dt, acc, gyr, gt, prologue, n_time)
+    args.cpu_frames = min(args.cpu_frames, max(FREQ, (args.steps + args.warmup) * 10))
+    cpu, _ = cpu_baselines(args, None)
     line = {"impl": "reference", "metric": "VIO frames/sec (640x480, 150 feats, 10-KF window)", "value": cpu["value"], "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cores / cpu["value"],
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cpu["streams"] / cpu["value"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32 front end, f64 back end", "data": "synthetic",
             "config": {"workload": "independent streams, 640x480@30fps + 200 Hz IMU, 150 feats, 10-KF window, FREQ=3 "
-                                   "(one stream per host core)", "streams": cores, "freq": FREQ},
+                                   "(one stream per host core or fewer, best aggregate)", "streams": cpu["streams"], "freq": FREQ, "host_cores": cores},
             "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -487,8 +668,11 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default c2 = the headline workload)")
+    ap.add_argument("--batch", type=int, default=0, help="streams per GPU (default: the configuration's)")
+    ap.add_argument("--cpu-frames", type=int, default=300, help="timed frames per stream of the cpu_baseline legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the variant / extra-configuration lines (profiling runs)")
     ap.add_argument("--no-overlap", action="store_true", help="front end and back end on ONE CUDA stream (no overlap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -12,7 +12,8 @@ import numpy as np
 _abi = importlib.import_module("vins-mobile_b200.abi")
 DP, IP = _abi.DP, _abi.IP
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libvins_ref.so")
+# VINS_REF_LIB selects another build of the same sources (bench.py times libvins_ref_o3.so, -O3 -march=x86-64-v3, next to the default -O2)
+LIB_PATH = os.path.join(_HERE, "_ref", os.environ.get("VINS_REF_LIB", "libvins_ref.so"))
 _lib = None
 
 
@@ -36,6 +37,7 @@ def lib():
         L.vref_get_info.argtypes = [C.c_void_p, IP, DP]
         L.vref_get_features.argtypes = [C.c_void_p, C.c_int, IP, IP, IP, IP, DP, IP]
         L.vref_get_prior.argtypes = [C.c_void_p, DP, DP, IP, DP]
+        L.vref_stage_seconds.argtypes = [C.c_void_p, DP, C.c_int]
         L.vref_preintegrate.argtypes = [C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
         L.vref_imu_factor.argtypes = [DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP]
         L.vref_projection_factor.argtypes = [C.c_double, DP, DP, DP, DP, DP, DP, C.c_double, DP, DP]
@@ -76,6 +78,12 @@ class RefEstimator:
             self.close()
         except Exception:
             pass
+
+    def stage_seconds(self, reset=False):
+        """wall-clock seconds in processImage (total), ceres::Solve, marginalisation, processIMU since creation / the last reset"""
+        out = np.zeros(4)
+        lib().vref_stage_seconds(self.h, out.ctypes.data_as(DP), int(reset))
+        return dict(process_image=float(out[0]), ceres_solve=float(out[1]), marginalise=float(out[2]), process_imu=float(out[3]))
 
     def process_imu(self, dt, acc, gyr):
         a, g = _d(acc), _d(gyr)

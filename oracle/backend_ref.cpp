@@ -26,6 +26,7 @@
 #include <map>
 #include <unordered_map>
 #include <algorithm>
+#include <chrono>
 #include <sys/mman.h>
 
 #include "global_param.hpp"
@@ -73,6 +74,8 @@ struct Est {
                   const double &operator[](size_t i) const { return p[i]; } };
     Span para_Pose, para_SB, para_Feature, para_Ex;
     int arena_slot = -1;
+    // wall-clock per stage (bench.py cpu_baseline split): [0] processImage total, [1] ceres::Solve, [2] marginalisation, [3] processIMU
+    double t_stage[4] = {0, 0, 0, 0};
     MarginalizationInfo *last_marg = nullptr;
     std::vector<double *> last_marg_blocks;
     int failure_occur = 0;
@@ -342,7 +345,11 @@ void solve(Est &e) {                 // VINS::solve_ceres, VINS.cpp:480-831
     o.max_num_iterations = e.c.max_iters;
     o.logging_type = ceres::SILENT;
     ceres::Solver::Summary sum;
-    ceres::Solve(o, &problem, &sum);
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        ceres::Solve(o, &problem, &sum);
+        e.t_stage[1] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
     e.cost0 = sum.initial_cost; e.cost1 = sum.final_cost;
     e.iters = (int)sum.iterations.size() - 1;
     new2old(e);
@@ -356,7 +363,11 @@ void solve(Est &e) {                 // VINS::solve_ceres, VINS.cpp:480-831
     std::vector<ceres::ResidualBlockId> rs;
     problem.GetResidualBlocks(&rs);
     // Problem owns cost functions; the MarginalizationFactor added above must not delete last_marg (it does not).
-    if (e.marg_flag == 0) marginalize_old(e, loss); else marginalize_second_new(e);
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        if (e.marg_flag == 0) marginalize_old(e, loss); else marginalize_second_new(e);
+        e.t_stage[2] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
 }
 
 bool failure_detection(Est &e) {     // VINS.cpp:214-265
@@ -516,7 +527,14 @@ void *vref_create(const vio_config *cfg) {
 void vref_destroy(void *h) { Est *e = (Est *)h; clear_state(*e); ParaArena::release(e->arena_slot); delete e; }
 void vref_clear(void *h) { clear_state(*(Est *)h); }
 void vref_process_imu(void *h, double dt, const double *a, const double *g) {
+    const auto t0 = std::chrono::steady_clock::now();
     process_imu(*(Est *)h, dt, Vector3d(a[0], a[1], a[2]), Vector3d(g[0], g[1], g[2]));
+    ((Est *)h)->t_stage[3] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// seconds spent so far in [0] processImage, [1] ceres::Solve, [2] marginalisation, [3] processIMU; reset != 0 zeroes them
+void vref_stage_seconds(void *h, double *out, int reset) {
+    Est &e = *(Est *)h;
+    for (int i = 0; i < 4; i++) { out[i] = e.t_stage[i]; if (reset) e.t_stage[i] = 0; }
 }
 void vref_set_init_window(void *h, const double *P, const double *Q, const double *V, const double *Ba, const double *Bg) {
     Est &e = *(Est *)h;
@@ -530,7 +548,10 @@ void vref_set_init_window(void *h, const double *P, const double *Q, const doubl
     e.init_pending = true;
 }
 int vref_process_image(void *h, int n, const int *ids, const double *xyz, double header) {
-    return process_image(*(Est *)h, n, ids, xyz, header);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = process_image(*(Est *)h, n, ids, xyz, header);
+    ((Est *)h)->t_stage[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
 }
 static void pack_state(Est &e, double *P, double *Q, double *V, double *Ba, double *Bg, double *H) {
     for (int i = 0; i <= e.W; i++) {
