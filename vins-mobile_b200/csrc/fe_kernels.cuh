@@ -3,6 +3,7 @@
 // pinned to cv2 4.13; reference call sites are /root/reference/VINS_ios/feature_tracker.cpp:95,181,198,263.
 #pragma once
 #include "common.cuh"
+#include <cuda.h>                      // CUtensorMap (the descriptors are encoded on the host through the driver entry point)
 
 namespace fe {
 
@@ -18,6 +19,34 @@ struct PyrLevels {
     int rows[4], cols[4];
     size_t stride[4];                 // bytes between consecutive streams at this level
 };
+
+// TMA descriptors of the pyramid levels, rank 3 (x, y, stream), u8, box LK_BOX x 32 x 1 (48 x 32 x 1), no swizzle, out-of-bounds elements read as 0.
+// The box must START on a 16-byte boundary in global memory (measured on B200: an unaligned x coordinate raises "illegal instruction",
+// tools/ubench/tma_box2.cu), so a window is fetched as the aligned 48-column box that contains its 33 columns.  A level gets a
+// descriptor only when its row stride is a multiple of 16 bytes (a tensor-map requirement: 480 and 240 at 640x480; every level at
+// 1280x720); ok[l] = 0 keeps the level on the register-staged path.
+struct LkMaps {
+    const CUtensorMap *I, *J;         // [4] each, in global memory (64-byte aligned)
+    int ok[4];
+};
+
+// ---- TMA / mbarrier primitives (PTX ISA: cp.async.bulk.tensor, mbarrier) ---------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, void *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // K1  pyrDown: 5-tap [1 4 6 4 1] x [1 4 6 4 1], REFLECT_101, (s + 128) >> 8, output ((H+1)/2,(W+1)/2)
@@ -179,7 +208,11 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(uint8_t *__restrict__ 
 constexpr int LK_WARPS = 4;
 constexpr int LK_JP = 32;                                 // edge of the staged J neighbourhood: the 22x22 window may drift +-5 px before a re-stage
 constexpr int LK_JM = 5;
-constexpr int LK_IP = 32;                                 // row stride of the staged 24x24 I patch
+#ifndef LK_IP_V
+#define LK_IP_V 32
+#endif
+constexpr int LK_IP = LK_IP_V;                            // row stride of the staged 24 x 24 I patch
+constexpr int LK_BOX = 48;                                // width of the TMA box: a 16-byte aligned start + up to 33 columns
 constexpr int LK_PIX = 14;                                // window pixels per lane (32 * 14 = 448 >= 441)
 constexpr int LK_QS = 448;                                // covariance phase: floats per sum (4 chains x 84 + tail 105, padded to 112)
 constexpr int LK_ACC = 3 * LK_QS;                         // the mismatch phase uses the first two thirds
@@ -220,35 +253,38 @@ __device__ __forceinline__ void lk_stage(uint8_t *dst, const uint8_t *__restrict
 // byte (B[i] = A[i + 1]), so that the horizontally adjacent pair (A[i], A[i + 1]) is ONE aligned 16-bit load whatever the parity of i
 // (even: A + i, odd: B + i - 1).  One lane per row; inside the image the row is fetched as nine aligned words and re-aligned with funnel
 // shifts, otherwise byte by byte with BORDER_REFLECT_101.
+// one row of the J neighbourhood: 33 bytes starting at g (any alignment, global or shared) -> row `lane` of copy A and of the shifted copy B
+__device__ __forceinline__ void lk_repack_row(uint8_t *A, uint8_t *Bc, const uint8_t *g, int lane) {
+    const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
+    const unsigned *wp = reinterpret_cast<const unsigned *>(ga & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)(ga & 3) * 8;
+    unsigned w[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) w[i] = wp[i];
+    unsigned a[8], bq[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = __funnelshift_rc(w[i], w[i + 1], sh); }
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const unsigned nx = i < 7 ? a[i + 1] : __funnelshift_rc(w[8], w[9], sh); bq[i] = __funnelshift_r(a[i], nx, 8); }
+    uint4 *da = reinterpret_cast<uint4 *>(A + lane * LK_JP), *db = reinterpret_cast<uint4 *>(Bc + lane * LK_JP);
+    da[0] = make_uint4(a[0], a[1], a[2], a[3]); da[1] = make_uint4(a[4], a[5], a[6], a[7]);
+    db[0] = make_uint4(bq[0], bq[1], bq[2], bq[3]); db[1] = make_uint4(bq[4], bq[5], bq[6], bq[7]);
+}
+// border case (cold): byte by byte with BORDER_REFLECT_101
+__device__ __forceinline__ void lk_stage_j_border(uint8_t *A, uint8_t *Bc, const uint8_t *__restrict__ im, int rows, int cols, int y0, int x0, int lane) {
+    const int yy = reflect101(y0 + lane, rows);
+    const uint8_t *row = im + (size_t)yy * cols;
+    uint8_t prev = row[reflect101(x0, cols)];
+    for (int c = 0; c < LK_JP; c++) {
+        const uint8_t nxt = row[reflect101(x0 + c + 1, cols)];
+        A[lane * LK_JP + c] = prev; Bc[lane * LK_JP + c] = nxt;
+        prev = nxt;
+    }
+}
 __device__ __forceinline__ void lk_stage_j(uint8_t *A, uint8_t *Bc, const uint8_t *__restrict__ im, int rows, int cols, int y0, int x0, int lane) {
     const bool inner = x0 >= 4 && x0 + LK_JP + 4 <= cols && y0 >= 0 && y0 + LK_JP <= rows;
-    if (inner) {
-        const uint8_t *g = im + (size_t)(y0 + lane) * cols + x0;
-        const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
-        const unsigned *wp = reinterpret_cast<const unsigned *>(ga & ~(uintptr_t)3);
-        const unsigned sh = (unsigned)(ga & 3) * 8;
-        unsigned w[10];
-#pragma unroll
-        for (int i = 0; i < 10; i++) w[i] = wp[i];
-        unsigned a[8], bq[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) { a[i] = __funnelshift_rc(w[i], w[i + 1], sh); }
-#pragma unroll
-        for (int i = 0; i < 8; i++) { const unsigned nx = i < 7 ? a[i + 1] : __funnelshift_rc(w[8], w[9], sh); bq[i] = __funnelshift_r(a[i], nx, 8); }
-        uint4 *da = reinterpret_cast<uint4 *>(A + lane * LK_JP), *db = reinterpret_cast<uint4 *>(Bc + lane * LK_JP);
-        da[0] = make_uint4(a[0], a[1], a[2], a[3]); da[1] = make_uint4(a[4], a[5], a[6], a[7]);
-        db[0] = make_uint4(bq[0], bq[1], bq[2], bq[3]); db[1] = make_uint4(bq[4], bq[5], bq[6], bq[7]);
-    } else {
-        const int yy = reflect101(y0 + lane, rows);
-        const uint8_t *row = im + (size_t)yy * cols;
-        uint8_t prev = row[reflect101(x0, cols)];
-#pragma unroll 4
-        for (int c = 0; c < LK_JP; c++) {
-            const uint8_t nxt = row[reflect101(x0 + c + 1, cols)];
-            A[lane * LK_JP + c] = prev; Bc[lane * LK_JP + c] = nxt;
-            prev = nxt;
-        }
-    }
+    if (inner) lk_repack_row(A, Bc, im + (size_t)(y0 + lane) * cols + x0, lane);
+    else lk_stage_j_border(A, Bc, im, rows, cols, y0, x0, lane);
 }
 
 // two-way dot product of SIGNED 16-bit weights (low/high half of a) with the two low UNSIGNED bytes of b, plus c.  The fourth bilinear
@@ -277,22 +313,40 @@ __device__ __forceinline__ float lk_combine(float r, int l0) {
     return fadd(fadd(c0, c2), fadd(c1, c3));
 }
 
+#ifndef LK_TMA_I
+#define LK_TMA_I 1            // template patches through TMA
+#endif
+#ifndef LK_TMA_J
+#define LK_TMA_J 0            // 1: J neighbourhoods through TMA as well (measured slower on B200: DESIGN.md section 4)
+#endif
 #ifndef LK_MINB
 #define LK_MINB 4            // 128 registers: measured best on B200 (163 unconstrained, 96 and 80 spill in the iteration loop)
 #endif
-__global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I, PyrLevels J, const float2 *__restrict__ prev_pts,
+__global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I, PyrLevels J, LkMaps maps,
+                                                           const float2 *__restrict__ prev_pts,
                                                            float2 *__restrict__ next_pts, uint8_t *__restrict__ status,
                                                            const int *__restrict__ n_pts, int maxp) {
     VIO_POISON(256u);
-    __shared__ __align__(16) uint8_t sI[LK_WARPS][24 * LK_IP];          // rows ipy-1 .. ipy+22, cols ipx-1 .. ipx+22 (stride 32)
-    __shared__ __align__(16) uint8_t sJ[LK_WARPS][2][LK_JP * LK_JP];    // copy A and the one-byte-shifted copy B (lk_stage_j)
+    __shared__ __align__(16) uint8_t sI[LK_WARPS][24 * LK_IP];          // I patch: rows ipy-1 .. ipy+22, cols ipx-1 .. ipx+22 (stride 32)
+    __shared__ __align__(128) uint8_t sB[LK_WARPS][(1 + LK_TMA_J) * LK_BOX * 32];   // TMA landing boxes: [0] I patch, [1] J neighbourhood; re-aligned into sI / sJ
+    __shared__ __align__(128) uint8_t sJ[LK_WARPS][2][LK_JP * LK_JP];   // copy A and the one-byte-shifted copy B (lk_stage_j)
     __shared__ __align__(16) float sAcc[LK_WARPS][LK_ACC];              // addends in chain order
+    __shared__ __align__(8) unsigned long long sBar[LK_WARPS][2];       // two mbarriers per warp: [0] I-patch loads, [1] J-box loads
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int f = blockIdx.x * LK_WARPS + warp;
     if (f >= n_pts[b]) return;
+    if (lane == 0) { mbar_init(&sBar[warp][0], 1); mbar_init(&sBar[warp][1], 1); fence_proxy_async_smem(); }
+    __syncwarp();
+    // TMA loads are issued ahead of their use so that their latency hides behind the template build: the I patch of level l - 1 while
+    // level l iterates, the first J box of a level while its template is built.  ipend / jpend = a load is in flight on the barrier.
+    unsigned phI = 0, phJ = 0;
+    bool ipend = false, jpend = false;
+    int jp_x = 0, jp_y = 0;
+    void *barI = &sBar[warp][0], *barJ = &sBar[warp][1];
+    uint8_t *sIb = sB[warp], *sJb = sB[warp] + LK_TMA_J * LK_BOX * 32;
     const float2 pt = prev_pts[(size_t)b * maxp + f];
-    uint8_t *pI = sI[warp];
+    uint8_t *sS = sI[warp];
     uint8_t *pJA = sJ[warp][0], *pJB = sJ[warp][1];
     float *acc = sAcc[warp];
     const float half = 10.f;
@@ -349,7 +403,53 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I,
             continue;
         }
         __syncwarp();
-        lk_stage(pI, imI, rows, cols, ipy - 1, ipx - 1, 24, 24, lane);      // rows ipy-1 .. ipy+22, cols ipx-1 .. ipx+22
+        if (jpend) { mbar_wait(barJ, phJ); phJ ^= 1u; jpend = false; }          // an unused prefetch of the previous level
+        const uint8_t *pI = sS;                                          // patch origin = image (ipy - 1, ipx - 1)
+        const bool tma_i = LK_TMA_I && maps.ok[level] && ipx >= 1 && ipx + 23 <= cols && ipy >= 1 && ipy + 23 <= rows;
+        if (tma_i) {
+            // the 24 x 24 template neighbourhood lies inside the image: it arrives as ONE TMA box that starts at the 16-byte boundary below
+            // its first column (what hangs over the right / bottom edge reads as 0 and is never used); normally the box was requested
+            // while the previous level iterated
+            const int xa = (ipx - 1) & ~15;
+            if (!ipend) {
+                if (lane == 0) {
+                    fence_proxy_async_smem();                           // earlier generic-proxy accesses of this warp to the buffer are done (__syncwarp above)
+                    mbar_expect_tx(barI, LK_BOX * 32);
+                    tma_load_3d(sIb, maps.I + level, xa, ipy - 1, b, barI);
+                }
+            }
+#if LK_TMA_J
+            // the first J neighbourhood of this level is known already (nextPt of the level above): fetch it while the template is built
+            {
+                const int jx0 = (int)floorf(fsub(nx, half)) - LK_JM, jy0 = (int)floorf(fsub(ny, half)) - LK_JM;
+                if (jx0 >= 0 && jx0 + LK_JP + 1 <= cols && jy0 >= 0 && jy0 + LK_JP <= rows) {
+                    if (lane == 0) {
+                        fence_proxy_async_smem();
+                        mbar_expect_tx(barJ, LK_BOX * 32);
+                        tma_load_3d(sJb, maps.J + level, jx0 & ~15, jy0, b, barJ);
+                    }
+                    jpend = true; jp_x = jx0; jp_y = jy0;
+                }
+            }
+#endif
+            mbar_wait(barI, phI);
+            phI ^= 1u; ipend = false;
+            // re-align the box into the patch layout the template build uses (fixed origin, stride 32): 24 rows x 3 eight-byte pieces
+            {
+                const int d = ipx - 1 - xa;
+                for (int t = lane; t < 72; t += 32) {
+                    const int r = (t * 21846) >> 16, c8 = (t - 3 * r) * 8;                 // t / 3 for t < 72
+                    const uint8_t *g = sIb + r * LK_BOX + d + c8;
+                    const unsigned *wp = reinterpret_cast<const unsigned *>(g - ((d + c8) & 3));   // rows start 16-byte aligned
+                    const unsigned sh = (unsigned)((d + c8) & 3) * 8;
+                    const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
+                    *reinterpret_cast<uint2 *>(sS + r * LK_IP + c8) = make_uint2(__funnelshift_rc(w0, w1, sh), __funnelshift_rc(w1, w2, sh));
+                }
+            }
+        } else {
+            if (ipend) { mbar_wait(barI, phI); phI ^= 1u; ipend = false; }        // cannot happen (a prefetch is only issued for a TMA-able level); keeps the phase honest
+            lk_stage(sS, imI, rows, cols, ipy - 1, ipx - 1, 24, 24, lane);      // rows ipy-1 .. ipy+22, cols ipx-1 .. ipx+22
+        }
         __syncwarp();
         int w00, w01, w10, w11;
         lk_weights(fsub(px, (float)ipx), fsub(py, (float)ipy), w00, w01, w10, w11);
@@ -401,6 +501,20 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I,
             *reinterpret_cast<float2 *>(acc + 2 * LK_QS + off_a + i) = make_float2(pc[0], pc[1]);
         }
         __syncwarp();
+        if (level > 0) {
+            // the I patch is dead from here on: fetch the next level's patch (its position depends on the point alone)
+            const int nrows = I.rows[level - 1], ncols = I.cols[level - 1];
+            const float sc2 = 1.f / (float)(1 << (level - 1));
+            const int qx = (int)floorf(fsub(fmul(pt.x, sc2), half)), qy = (int)floorf(fsub(fmul(pt.y, sc2), half));
+            if (LK_TMA_I && maps.ok[level - 1] && qx >= 1 && qx + 23 <= ncols && qy >= 1 && qy + 23 <= nrows) {
+                if (lane == 0) {
+                    fence_proxy_async_smem();
+                    mbar_expect_tx(barI, LK_BOX * 32);
+                    tma_load_3d(sIb, maps.I + (level - 1), (qx - 1) & ~15, qy - 1, b, barI);
+                }
+                ipend = true;
+            }
+        }
         const float ra = lk_chain(chain_a, n4_a);
         __syncwarp();
         const float A11 = fmul(fadd(__shfl_sync(0xffffffffu, ra, 4), lk_combine(ra, 0)), FLT_SCALE);
@@ -430,7 +544,26 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I,
             if (!staged || jx < sx0 || jx + 22 > sx0 + LK_JP || jy < sy0 || jy + 22 > sy0 + LK_JP) {
                 sx0 = jx - LK_JM; sy0 = jy - LK_JM; staged = true;
                 __syncwarp();
-                lk_stage_j(pJA, pJB, imJ, rows, cols, sy0, sx0, lane);
+                if (jpend) { mbar_wait(barJ, phJ); phJ ^= 1u; }                  // the prefetched box has landed (used below if it is the right one)
+                const bool hit = jpend && jp_x == sx0 && jp_y == sy0;
+                jpend = false;
+                if (LK_TMA_J && maps.ok[level] && sx0 >= 0 && sx0 + LK_JP + 1 <= cols && sy0 >= 0 && sy0 + LK_JP <= rows) {
+                    // interior: the aligned 48 x 32 box that contains the 33 x 32 neighbourhood arrives by TMA; each lane then re-aligns one
+                    // row into copy A and the one-byte-shifted copy B
+                    const int xa = sx0 & ~15;
+                    if (!hit) {
+                        if (lane == 0) {
+                            fence_proxy_async_smem();
+                            mbar_expect_tx(barJ, LK_BOX * 32);
+                            tma_load_3d(sJb, maps.J + level, xa, sy0, b, barJ);
+                        }
+                        mbar_wait(barJ, phJ);
+                        phJ ^= 1u;
+                    }
+                    lk_repack_row(pJA, pJB, sJb + lane * LK_BOX + (sx0 - xa), lane);
+                } else {
+                    lk_stage_j(pJA, pJB, imJ, rows, cols, sy0, sx0, lane);
+                }
                 __syncwarp();
             }
             int v00, v01, v10, v11;
@@ -482,6 +615,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32, LK_MINB) lk_kernel(PyrLevels I,
             if (fx < -LK_WIN || fx >= cols || fy < -LK_WIN || fy >= rows) ok = false;
         }
     }
+    // no TMA write may still be in flight into this CTA's shared memory when the warp exits
+    if (jpend) mbar_wait(barJ, phJ);
+    if (ipend) mbar_wait(barI, phI);
     if (lane == 0) {
         next_pts[(size_t)b * maxp + f] = make_float2(nx, ny);
         status[(size_t)b * maxp + f] = ok ? 1 : 0;

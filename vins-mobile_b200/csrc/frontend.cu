@@ -15,6 +15,8 @@ struct vio_frontend {
     int lr[4], lc[4];
     size_t lsz[4];
     uint8_t *pyr[2][4];
+    CUtensorMap *tmap_dev;    // [2][4] TMA descriptors of the pyramid levels in device memory (lk_kernel), valid where tmap_ok[level]
+    int tmap_ok[4];
     int cur;             // index of the cur pyramid; forw = cur ^ 1
     bool has_cur;        // forw_img.empty() == false
     TrackArrays A;
@@ -82,6 +84,25 @@ extern "C" void vio_config_default(vio_config *c) {
     c->max_imu_per_frame = 256; c->batch = 1; c->device = 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+static int encode_level_map(CUtensorMap *out, const uint8_t *base, int rows, int cols, int batch) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return VIO_ERR_CUDA;
+        fn = (encode_fn)p;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)cols, (cuuint64_t)rows * cols};          // bytes, dimensions 1 and 2
+    const cuuint32_t box[3] = {LK_BOX, 32, 1}, estr[3] = {1, 1, 1};     // see LkMaps
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? VIO_OK : VIO_ERR_CUDA;
+}
+
 extern "C" int vio_frontend_create(const vio_config *cfg, vio_frontend **out) {
     if (!cfg || !out || cfg->batch < 1 || cfg->max_cnt < 1 || cfg->max_cnt > VIO_MAXP || cfg->rows < 64 || cfg->cols < 64 ||
         cfg->min_dist < 1 || cfg->min_dist > 127 || cfg->freq < 1)
@@ -104,6 +125,16 @@ extern "C" int vio_frontend_create(const vio_config *cfg, vio_frontend **out) {
     int rc = VIO_OK;
     for (int k = 0; k < 2 && !rc; k++)
         for (int l = 0; l < 4 && !rc; l++) rc = dev_alloc(fe, &fe->pyr[k][l], B * fe->lsz[l]);
+    if (!rc) rc = dev_alloc(fe, &fe->tmap_dev, 8);
+    if (!rc) {
+        alignas(64) CUtensorMap host_maps[8];
+        memset(host_maps, 0, sizeof(host_maps));
+        for (int l = 0; l < 4 && !rc; l++) {
+            fe->tmap_ok[l] = (fe->lc[l] % 16 == 0 && fe->lc[l] >= LK_BOX && fe->lr[l] >= 32) ? 1 : 0;
+            for (int k = 0; k < 2 && !rc && fe->tmap_ok[l]; k++) rc = encode_level_map(&host_maps[4 * k + l], fe->pyr[k][l], fe->lr[l], fe->lc[l], fe->B);
+        }
+        if (!rc && cudaMemcpy(fe->tmap_dev, host_maps, sizeof(host_maps), cudaMemcpyHostToDevice) != cudaSuccess) rc = VIO_ERR_CUDA;
+    }
     TrackArrays &A = fe->A;
     if (!rc) rc = dev_alloc(fe, &A.cur_pts, B * P);
     if (!rc) rc = dev_alloc(fe, &A.pre_pts, B * P);
@@ -152,6 +183,14 @@ extern "C" void vio_frontend_destroy(vio_frontend *fe) {
     for (void *p : fe->allocs) cudaFree(p);
     if (fe->own_stream && fe->stream) cudaStreamDestroy(fe->stream);
     delete fe;
+}
+
+// TMA descriptors of pyramid k (template side) and pyramid kj (search side) for lk_kernel
+static LkMaps maps_of(const vio_frontend *fe, int k, int kj) {
+    LkMaps m;
+    m.I = fe->tmap_dev + 4 * k; m.J = fe->tmap_dev + 4 * kj;
+    for (int l = 0; l < 4; l++) m.ok[l] = fe->tmap_ok[l];
+    return m;
 }
 
 static PyrLevels levels_of(const vio_frontend *fe, int k) {
@@ -204,7 +243,7 @@ static int run_frame(vio_frontend *fe, int *published) {
     const int detect = fe->img_cnt == 0;
     if (fe->has_cur) {                                                      // K4
         dim3 grd((fe->maxp + LK_WARPS - 1) / LK_WARPS, B);
-        VIO_LAUNCH(fe->timer, s, "lk_kernel", (lk_kernel<<<grd, LK_WARPS * 32, 0, s>>>(levels_of(fe, fe->cur), levels_of(fe, forw), fe->A.cur_pts,
+        VIO_LAUNCH(fe->timer, s, "lk_kernel", (lk_kernel<<<grd, LK_WARPS * 32, 0, s>>>(levels_of(fe, fe->cur), levels_of(fe, forw), maps_of(fe, fe->cur, forw), fe->A.cur_pts,
                    fe->A.forw_pts, fe->A.status, fe->A.n, fe->maxp)));
         fe->launches++;
     }
@@ -407,7 +446,7 @@ extern "C" int vio_prim_lk(const vio_config *cfg, const uint8_t *prev, const uin
     cudaMemcpyAsync(fe->A.cur_pts, pts_xy, sizeof(float2) * n, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(fe->A.n, &n, sizeof(int), cudaMemcpyHostToDevice, s);
     dim3 grd((fe->maxp + LK_WARPS - 1) / LK_WARPS, 1);
-    lk_kernel<<<grd, LK_WARPS * 32, 0, s>>>(levels_of(fe, 0), levels_of(fe, 1), fe->A.cur_pts, fe->A.forw_pts, fe->A.status, fe->A.n, fe->maxp);
+    lk_kernel<<<grd, LK_WARPS * 32, 0, s>>>(levels_of(fe, 0), levels_of(fe, 1), maps_of(fe, 0, 1), fe->A.cur_pts, fe->A.forw_pts, fe->A.status, fe->A.n, fe->maxp);
     cudaMemcpyAsync(next_xy, fe->A.forw_pts, sizeof(float2) * n, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(status, fe->A.status, n, cudaMemcpyDeviceToHost, s);
     cudaError_t e = cudaStreamSynchronize(s);
