@@ -155,6 +155,12 @@ int vio_backend_process_image(vio_backend *be, const int32_t *counts, const int3
 int vio_backend_process_image_dev(vio_backend *be, const int32_t *counts, const int32_t *ids, const double *norm_xyz,
                                   const double *headers_host);
 
+/* VINS::solve_ceres(buf_num) on its own (VINS.hpp:153, VINS.cpp:480-831) for every stream that is NON_LINEAR with a full window: problem
+ * build, <= max_iters dogleg iterations, new2old and the marginalisation chosen by the current marginalization_flag, on the window as it
+ * stands -- none of the processImage steps around it.  Read the result with vio_backend_get_post_solve / _get_state / _get_prior.
+ * (buf_num only shortens the reference's wall-time cap, which is not reproduced.) */
+int vio_backend_solve(vio_backend *be);
+
 /* processImage fed from a front end's device-resident image_msg; event-ordered hand-over when the two handles use different
  * CUDA streams (front end of the next frames overlaps the solve). */
 int vio_backend_process_image_from_frontend(vio_backend *be, vio_frontend *fe, const double *headers_host);

@@ -38,6 +38,7 @@ def lib():
         L.vref_get_features.argtypes = [C.c_void_p, C.c_int, IP, IP, IP, IP, DP, IP]
         L.vref_get_prior.argtypes = [C.c_void_p, DP, DP, IP, DP]
         L.vref_stage_seconds.argtypes = [C.c_void_p, DP, C.c_int]
+        L.vref_solve.argtypes = [C.c_void_p]
         L.vref_preintegrate.argtypes = [C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
         L.vref_imu_factor.argtypes = [DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP]
         L.vref_projection_factor.argtypes = [C.c_double, DP, DP, DP, DP, DP, DP, C.c_double, DP, DP]
@@ -78,6 +79,9 @@ class RefEstimator:
             self.close()
         except Exception:
             pass
+
+    def solve(self):
+        return lib().vref_solve(self.h)
 
     def stage_seconds(self, reset=False):
         """wall-clock seconds in processImage (total), ceres::Solve, marginalisation, processIMU since creation / the last reset"""

@@ -531,6 +531,13 @@ void vref_process_imu(void *h, double dt, const double *a, const double *g) {
     process_imu(*(Est *)h, dt, Vector3d(a[0], a[1], a[2]), Vector3d(g[0], g[1], g[2]));
     ((Est *)h)->t_stage[3] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
+// VINS::solve_ceres() alone on the current window (NON_LINEAR, full window), as vio_backend_solve does
+int vref_solve(void *h) {
+    Est &e = *(Est *)h;
+    if (e.solver_flag != 1 || e.frame_count != e.W) return 1;
+    solve(e);
+    return 0;
+}
 // seconds spent so far in [0] processImage, [1] ceres::Solve, [2] marginalisation, [3] processIMU; reset != 0 zeroes them
 void vref_stage_seconds(void *h, double *out, int reset) {
     Est &e = *(Est *)h;

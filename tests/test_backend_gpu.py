@@ -417,6 +417,41 @@ def test_too_few_tracks_at_full_window_clears(api, cfg, synth):
         ref.close(); gpu.close()
 
 
+def test_solve_entry_matches_reference_solve_ceres(api, cfg, synth):
+    """vio_backend_solve = VINS::solve_ceres() alone (VINS.hpp:153): after 13 keyframes both estimators re-solve the window as it stands
+    (problem build, <= 10 dogleg iterations, new2old, marginalisation) without any processImage bookkeeping."""
+    W = cfg.window_size
+    tr = synth.make_tracks(9, 14, max_cnt=cfg.max_cnt)
+    ref, gpu = bo.RefEstimator(cfg), api.BackEnd(cfg)
+    try:
+        for k in range(13):
+            with Quiet():
+                drive(ref, tr, k, W)
+            drive(gpu, tr, k, W)
+        # the IMU samples of the next interval (the newest pre-integration must not be empty), then the solve alone
+        per = tr["per"]
+        sl = slice(12 * per, 13 * per)
+        dts = np.diff(np.concatenate([[tr["t_kf"][12]], tr["imu_t"][sl]]))
+        gpu.process_imu(dts[:, None], tr["acc"][sl][:, None, :], tr["gyr"][sl][:, None, :])
+        for d, a, g in zip(dts, tr["acc"][sl], tr["gyr"][sl]):
+            ref.process_imu(d, a, g)
+        with Quiet():
+            assert ref.solve() == 0
+        gpu.solve()
+        ri, gi = ref.info(), gpu.info()
+        assert gi["err"] == 0 and ri["n_feat"] == gi["n_feat"] and ri["n_proj"] == gi["n_proj"] and ri["frame_count"] == gi["frame_count"]
+        assert abs(gi["cost0"] - ri["cost0"]) <= 1e-4 * abs(ri["cost0"]) and abs(gi["cost1"] - ri["cost1"]) <= 1e-4 * abs(ri["cost1"])
+        rps, gps = ref.post_solve(), gpu.post_solve()
+        assert rel_err(gps[:, :3], rps[:, :3]) < 1e-4 and rel_err(gps[:, 7:10], rps[:, 7:10]) < 1e-4
+        rs, gs = ref.state(), gpu.state()
+        assert rel_err(gs["P"], rs["P"]) < 1e-4 and quat_err(gs["Q"], rs["Q"]) < 1e-4
+        assert np.array_equal(ref.features()["ids"], gpu.features()["ids"])
+        rp, gp = ref.prior(), gpu.prior()
+        assert np.array_equal(rp["present"], gp["present"]) and rel_err(gp["H"], rp["H"]) < 1e-4
+    finally:
+        ref.close(); gpu.close()
+
+
 def test_imu_capacity_error_is_latched_and_clearable(api, abi):
     """More IMU samples in one frame interval than max_imu_per_frame: VIO_ERR_CAPACITY is latched for the stream, reported by the state
     getters and cleared through vio_backend_get_error(clear) / vio_backend_clear()."""

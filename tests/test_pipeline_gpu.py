@@ -125,3 +125,60 @@ def test_no_out_of_bounds_device_writes():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "guard_check.py"), "32", "45", "two"], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "final: corrupted guard bands = 0" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+def test_cpp_host_mirror_runs_and_matches_ctypes_path(api, abi, synth, tmp_path):
+    """vins-mobile_b200/host/vio_host.hpp executed on the GPU: host/parity_loop.cpp drives vio::FeatureTracker / vio::VINS (the reference's
+    class and member names: readImage, processIMU, processImage, solve_ceres, image_msg, img_cnt, Ps, frame_count, solver_flag ...) through
+    42 frames of a synthetic stream; every published frame must agree with the ctypes path over the same C-ABI (same kernels: equal to
+    round-off), and VINS::solve_ceres() on its own must re-solve the window (vio_backend_solve)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "vins-mobile_b200")
+    exe = str(tmp_path / "parity_loop")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(pkg, "host", "parity_loop.cpp"), "-L", pkg, "-lvio_b200", f"-Wl,-rpath,{pkg}"], check=True)
+    nf, W, per = 42, 10, 20
+    s = synth.make_stream(1, nf + 3, device="cuda")             # one more IMU interval than the frames need (stand-alone solve at the end)
+    fr = np.stack([s.images[k].cpu().numpy() for k in range(nf)])
+    n_kf = (nf + 2) // 3
+    dt = np.full((n_kf * per, 1), 1.0 / 200.0)
+    imu = np.concatenate([dt, s.acc[:n_kf * per], s.gyr[:n_kf * per]], 1)
+    P, Q, V = s.P[::3][:W + 1], synth.rot_to_quat_xyzw(s.R[::3][:W + 1]), s.V[::3][:W + 1]
+    path = str(tmp_path / "rec.bin")
+    with open(path, "wb") as f:
+        f.write(np.array([nf, 640, 480, per, W, 150], np.int32).tobytes()); f.write(fr.tobytes()); f.write(np.ascontiguousarray(imu).tobytes())
+        f.write(np.ascontiguousarray(P).tobytes()); f.write(np.ascontiguousarray(Q).tobytes()); f.write(np.ascontiguousarray(V).tobytes())
+    r = subprocess.run([exe, path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = [l.split() for l in r.stdout.splitlines() if l.startswith("kf ")]
+    assert len(rows) == n_kf
+    cfg = abi.default_config(batch=1, max_cnt=150)
+    fe, be = api.FrontEnd(cfg), api.BackEnd(cfg)
+    kf = 0
+    for k in range(nf):
+        pub = fe.read_images(fr[k][None])
+        if not pub:
+            continue
+        if kf > 0:
+            sl = slice((kf - 1) * per, kf * per)
+            be.process_imu(imu[sl, 0:1], imu[sl, None, 1:4], imu[sl, None, 4:7])
+        if kf == W:
+            be.set_init_window(P[None], Q[None], V[None], np.zeros((1, 3)), np.zeros((1, 3)))
+        g = fe.stream(0)
+        be.process_image_single(g["ids"], g["norm_xyz"], k / 30.0)
+        st, inf = be.state(), be.info()
+        row = rows[kf]
+        assert int(row[1]) == k and int(row[2]) == inf["frame_count"] and int(row[3]) == inf["solver_flag"]
+        assert int(row[4]) == len(g["ids"]) and int(row[5]) == int(g["ids"].astype(np.int64).sum())
+        # same kernels, same inputs; the solve accumulates H with floating-point atomics, so two runs agree to round-off, not to the bit
+        assert np.allclose([float(x) for x in row[6:9]], st["P"][W], rtol=1e-9, atol=1e-12), f"kf {kf}"
+        assert abs(float(row[9]) - inf["cost1"]) <= 1e-9 * max(1.0, abs(inf["cost1"]))
+        kf += 1
+    assert be.info()["solver_flag"] == 1
+    sl = slice((kf - 1) * per, kf * per)
+    be.process_imu(imu[sl, 0:1], imu[sl, None, 1:4], imu[sl, None, 4:7])
+    be.solve()
+    rs = [l.split() for l in r.stdout.splitlines() if l.startswith("resolve ")][0]
+    assert abs(float(rs[1]) - be.state()["P"][W][0]) < 1e-9 and abs(float(rs[2]) - be.info()["cost1"]) <= 1e-9 * max(1.0, be.info()["cost1"])
+    fe.close(); be.close()

@@ -54,6 +54,7 @@ def lib():
         L.vio_frontend_stream.restype = vp
         L.vio_frontend_use_stream.argtypes = [vp, vp]
         L.vio_frontend_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
+        L.vio_backend_solve.argtypes = [vp]
         L.vio_backend_get_error.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int32)]
         L.vio_prim_pyramid.argtypes = [cfgp, UP, UP, UP, UP]
         L.vio_frontend_set_clahe.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int]
@@ -380,6 +381,10 @@ class BackEnd:
 
     def sync(self):
         _check(lib().vio_backend_sync(self.h), "vio_backend_sync")
+
+    def solve(self):
+        """VINS::solve_ceres() alone on the current window of every NON_LINEAR stream"""
+        _check(lib().vio_backend_solve(self.h), "vio_backend_solve")
 
     def error(self, s=0, clear=False):
         """latched per-stream error code (VIO_ERR_CAPACITY ...), optionally cleared"""

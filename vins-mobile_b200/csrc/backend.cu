@@ -272,6 +272,37 @@ static int run_process_image(vio_backend *be, const int32_t *counts, const int32
     return VIO_OK;
 }
 
+// VINS::solve_ceres() on its own (VINS.hpp:153, VINS.cpp:480-831): problem build (old2new), <= max_iters dogleg iterations, new2old and
+// the marginalisation selected by the current marginalization_flag -- on the window as it stands, without the processImage
+// bookkeeping around it (no addFeatureCheckParallax, triangulate, failureDetection or slideWindow).  Streams that are not in the
+// NON_LINEAR state with a full window are left untouched.
+__global__ void solve_only_action_kernel(BeState s, int begin) {
+    int *iv = S_iv(s, blockIdx.x);
+    if (threadIdx.x != 0) return;
+    if (begin) {
+        const bool ready = iv[IV_SOLVER_FLAG] == 1 && iv[IV_FRAME_COUNT] == s.W;
+        iv[IV_ACTION] = ready ? ACT_NL_SOLVE : ACT_NONE;
+        iv[IV_N_LM] = 0; iv[IV_N_FAC] = 0; iv[IV_ITERS] = 0; iv[IV_CHOL_RETRY] = 0; iv[IV_MARG_SWEEPS] = 0; iv[IV_MARG_FAST] = 0;
+    } else iv[IV_ACTION] = ACT_NONE;
+}
+
+extern "C" int vio_backend_solve(vio_backend *be) {
+    if (!be) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    BeState &s = be->s;
+    cudaStream_t st = be->stream;
+    solve_only_action_kernel<<<s.B, 32, 0, st>>>(s, 1);
+    VIO_LAUNCH(be->timer, st, "prepare_kernel", (prepare_kernel<<<s.B, 256, 0, st>>>(s)));
+    VIO_LAUNCH(be->timer, st, "solve_kernel", (solve_kernel<<<s.B, be->be_threads, be->solve_smem, st>>>(s, be->use_smem_solve, be->solve_vec_off)));
+    VIO_LAUNCH(be->timer, st, "post_solve_kernel", (post_solve_kernel<<<s.B, 256, 0, st>>>(s)));
+    VIO_LAUNCH(be->timer, st, "marg_kernel", (marg_kernel<<<s.B, be->be_threads, be->marg_smem, st>>>(s)));
+    solve_only_action_kernel<<<s.B, 32, 0, st>>>(s, 0);
+    VIO_LAUNCH(be->timer, st, "finish_kernel", (finish_kernel<<<s.B, 256, s.FCAP + 64, st>>>(s)));      // action NONE: refreshes the packed state only
+    be->launches += 7;
+    VIO_CUDA_TRY(cudaGetLastError());
+    return VIO_OK;
+}
+
 extern "C" int vio_backend_process_image_dev(vio_backend *be, const int32_t *counts, const int32_t *ids, const double *xyz, const double *headers_host) {
     if (!be || !counts || !ids || !xyz || !headers_host) return VIO_ERR_ARG;
     VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));

@@ -191,7 +191,7 @@ class VINS {
                                            final_cost(0), feature_num(0) {
         cfg_.batch = 1;
         const int n = cfg_.window_size + 1;
-        Ps.resize(n); Vs.resize(n); Bas.resize(n); Bgs.resize(n); Qs.resize(n); Headers.resize(n);
+        Ps.resize(n); Vs.resize(n); Bas.resize(n); Bgs.resize(n); Qs.resize(n); Rs.resize(n); Headers.resize(n);
         check(vio_backend_create(&cfg_, &h_), "vio_backend_create");
     }
     ~VINS() { vio_backend_destroy(h_); }
@@ -227,13 +227,16 @@ class VINS {
         check(vio_backend_process_image(h_, &n, ids.data(), xyz.data(), &header), "vio_backend_process_image");
         refresh();
     }
-    void solve_ceres(int buf_num) { (void)buf_num; }      // VINS.hpp:153: fused into processImage on the device
+    // VINS.hpp:153.  processImage() already runs the solve on the device; called on its own it re-solves the current window
+    // (vio_backend_solve).  buf_num only shortens the reference's wall-time cap, which is not reproduced.
+    void solve_ceres(int buf_num) { (void)buf_num; check(vio_backend_solve(h_), "vio_backend_solve"); refresh(); }
 
     int frame_count;
     SolverFlag solver_flag;
     MarginalizationFlag marginalization_flag;
     std::vector<Vector3d> Ps, Vs, Bas, Bgs;
     std::vector<std::array<double, 4>> Qs;                 // Rs as quaternions (x,y,z,w)
+    std::vector<Matrix3d> Rs;                              // VINS.hpp:74 (row-major), refreshed together with Qs
     std::vector<double> Headers;
     bool failure_occur;
     double final_cost;
@@ -249,6 +252,9 @@ class VINS {
             Ps[i] = Vector3d{P[3 * i], P[3 * i + 1], P[3 * i + 2]}; Vs[i] = Vector3d{V[3 * i], V[3 * i + 1], V[3 * i + 2]};
             Bas[i] = Vector3d{Ba[3 * i], Ba[3 * i + 1], Ba[3 * i + 2]}; Bgs[i] = Vector3d{Bg[3 * i], Bg[3 * i + 1], Bg[3 * i + 2]};
             Qs[i] = {Q[4 * i], Q[4 * i + 1], Q[4 * i + 2], Q[4 * i + 3]};
+            const double x = Q[4 * i], y = Q[4 * i + 1], z = Q[4 * i + 2], w = Q[4 * i + 3];
+            Rs[i] = Matrix3d{{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                              2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
         }
         int32_t info[8]; double dinfo[4];
         check(vio_backend_get_info(h_, 0, info, dinfo), "vio_backend_get_info");
