@@ -71,6 +71,8 @@ typedef struct vio_config {
     int32_t solve_path;          /* reduced-system solve: 0 auto (FP64 tensor-pipe tiles when the window fits one SM, else global memory),
                                     1 packed Cholesky in shared memory without DMMA tiles */
     int32_t be_threads;          /* threads per stream in the solve / marginalisation kernels: 0 = 512, or 256 */
+    int32_t loop_closure;        /* LOOP_CLOSURE (VINS.cpp:11): 1 reserves the loop-closure pose in the window solve; the factors are added when a
+                                    match has been supplied with vio_backend_set_loop_match (VINS.cpp:571-637).  0 (default): never. */
 } vio_config;
 
 /* Fills `cfg` with the reference's iPhone7P defaults (global_param.cpp:26-39) and the
@@ -160,6 +162,18 @@ int vio_backend_process_image_dev(vio_backend *be, const int32_t *counts, const 
  * stands -- none of the processImage steps around it.  Read the result with vio_backend_get_post_solve / _get_state / _get_prior.
  * (buf_num only shortens the reference's wall-time cap, which is not reproduced.) */
 int vio_backend_solve(vio_backend *be);
+
+/* Loop-closure factors in the window solve (VINS.cpp:571-637, 664-680, 174-195; needs vio_config::loop_closure = 1).
+ * vio_backend_set_loop_match = retrive_pose_data (VINS.hpp:28-45): per stream the header of the window keyframe that was matched, the ids
+ * (ascending) and normalised image measurements [batch][max_cnt][2] of the shared features in the OLD keyframe, and the old keyframe's pose
+ * pose_old[batch][7] = P_old, Q_old (x,y,z,w).  counts[b] = 0: no match for stream b.  A match stays in force until replaced (front_pose).
+ * While the matched header is inside the window, every solve adds ProjectionFactor(first observation, old measurement) between the
+ * landmark's anchor pose and a free loop pose initialised from the matched frame.
+ * vio_backend_get_loop_result: out = relative_t[3], relative_q[4] (xyzw), relative_yaw, drift yaw (r_drift = ypr2R(yaw,0,0)), t_drift[3]
+ * of the last solve; *n_factors = 0 when that solve had no loop constraint. */
+int vio_backend_set_loop_match(vio_backend *be, const int32_t *counts, const double *headers, const int32_t *ids, const double *xy,
+                               const double *pose_old);
+int vio_backend_get_loop_result(vio_backend *be, int s, double out[12], int32_t *n_factors);
 
 /* processImage fed from a front end's device-resident image_msg; event-ordered hand-over when the two handles use different
  * CUDA streams (front end of the next frames overlaps the solve). */

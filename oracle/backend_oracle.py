@@ -39,6 +39,8 @@ def lib():
         L.vref_get_prior.argtypes = [C.c_void_p, DP, DP, IP, DP]
         L.vref_stage_seconds.argtypes = [C.c_void_p, DP, C.c_int]
         L.vref_solve.argtypes = [C.c_void_p]
+        L.vref_set_loop_match.argtypes = [C.c_void_p, C.c_int, C.c_double, IP, DP, DP]
+        L.vref_get_loop_result.argtypes = [C.c_void_p, DP]
         L.vref_preintegrate.argtypes = [C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
         L.vref_imu_factor.argtypes = [DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP]
         L.vref_projection_factor.argtypes = [C.c_double, DP, DP, DP, DP, DP, DP, C.c_double, DP, DP]
@@ -82,6 +84,15 @@ class RefEstimator:
 
     def solve(self):
         return lib().vref_solve(self.h)
+
+    def set_loop_match(self, header, ids, xy, pose_old):
+        ids = np.ascontiguousarray(ids, np.int32); xy = _d(xy); pose_old = _d(pose_old)
+        lib().vref_set_loop_match(self.h, len(ids), float(header), ids.ctypes.data_as(IP), xy.ctypes.data_as(DP), pose_old.ctypes.data_as(DP))
+
+    def loop_result(self):
+        out = np.zeros(12)
+        n = lib().vref_get_loop_result(self.h, out.ctypes.data_as(DP))
+        return out, n
 
     def stage_seconds(self, reset=False):
         """wall-clock seconds in processImage (total), ceres::Solve, marginalisation, processIMU since creation / the last reset"""

@@ -74,6 +74,11 @@ struct Est {
                   const double &operator[](size_t i) const { return p[i]; } };
     Span para_Pose, para_SB, para_Feature, para_Ex;
     int arena_slot = -1;
+    // loop closure: retrive_pose_data / front_pose (VINS.hpp:28-45, VINS.cpp:571-637)
+    double loop_hdr = -1; std::vector<int> loop_ids; std::vector<double> loop_xy; Vector3d loop_P_old = Vector3d::Zero(); Quaterniond loop_Q_old{1, 0, 0, 0};
+    double loop_pose[7] = {0, 0, 0, 0, 0, 0, 1};
+    int loop_nfac = 0, loop_frame = -1; bool loop_enable = false;
+    double loop_out[12] = {0};       // relative_t3, relative_q4 (xyzw), relative_yaw, drift_yaw, t_drift3
     // wall-clock per stage (bench.py cpu_baseline split): [0] processImage total, [1] ceres::Solve, [2] marginalisation, [3] processIMU
     double t_stage[4] = {0, 0, 0, 0};
     MarginalizationInfo *last_marg = nullptr;
@@ -229,7 +234,7 @@ void old2new(Est &e) {               // VINS.cpp:89-129
     for (auto &t : e.feat) if (in_solve(e, t)) e.para_Feature[k++] = 1.0 / t.depth;
 }
 
-void new2old(Est &e) {               // VINS.cpp:131-212 (loop branch omitted: loop_enable false)
+void new2old(Est &e) {               // VINS.cpp:131-212
     Vector3d origin_R0 = Utility::R2ypr(e.Rs[0]);
     Vector3d origin_P0 = e.Ps[0];
     if (e.failure_occur) { origin_R0 = Utility::R2ypr(e.last_R_old); origin_P0 = e.last_P_old; }
@@ -244,6 +249,20 @@ void new2old(Est &e) {               // VINS.cpp:131-212 (loop branch omitted: l
         e.Vs[i] = rot_diff * Vector3d(s[0], s[1], s[2]);
         e.Bas[i] = Vector3d(s[3], s[4], s[5]);
         e.Bgs[i] = Vector3d(s[6], s[7], s[8]);
+    }
+    if (e.c.loop_closure && e.loop_enable) {                     // VINS.cpp:174-195: r_drift / t_drift from the re-anchored loop pose
+        e.loop_enable = false;
+        if (e.loop_frame >= 0) {
+            Matrix3d Rs_loop = Quaterniond(e.loop_pose[6], e.loop_pose[3], e.loop_pose[4], e.loop_pose[5]).normalized().toRotationMatrix();
+            Vector3d Ps_loop(e.loop_pose[0], e.loop_pose[1], e.loop_pose[2]);
+            Rs_loop = rot_diff * Rs_loop;
+            Ps_loop = rot_diff * (Ps_loop - Vector3d(p0[0], p0[1], p0[2])) + origin_P0;
+            double drift_yaw = Utility::R2ypr(e.loop_Q_old.toRotationMatrix()).x() - Utility::R2ypr(Rs_loop).x();
+            Matrix3d r_drift = Utility::ypr2R(Vector3d(drift_yaw, 0, 0));
+            Vector3d t_drift = e.loop_P_old - r_drift * Ps_loop;
+            e.loop_out[8] = drift_yaw;
+            for (int k = 0; k < 3; k++) e.loop_out[9 + k] = t_drift(k);
+        }
     }
     double *x = e.para_Ex.data();
     e.tic = Vector3d(x[0], x[1], x[2]);
@@ -336,6 +355,31 @@ void solve(Est &e) {                 // VINS::solve_ceres, VINS.cpp:480-831
         }
     }
     e.n_feat_solve = fi + 1;
+    // loop-closure factors, VINS.cpp:571-637 (LOOP_CLOSURE == cfg.loop_closure)
+    e.loop_nfac = 0; e.loop_frame = -1;
+    if (e.c.loop_closure && !e.loop_ids.empty() && e.loop_hdr >= e.Headers[0]) {
+        for (int i = 0; i < e.W; i++) {
+            if (e.loop_hdr != e.Headers[i]) continue;
+            e.loop_frame = i;
+            for (int k = 0; k < 7; k++) e.loop_pose[k] = e.pose(i)[k];
+            problem.AddParameterBlock(e.loop_pose, 7, new PoseLocalParameterization());
+            size_t ri = 0;
+            int feature_index = -1;
+            for (auto &t : e.feat) {
+                if (!in_solve(e, t)) continue;
+                ++feature_index;
+                const int start = t.start, end = (int)(start + t.obs.size() - i - 1);
+                if (start <= i && end >= 0) {
+                    while (ri < e.loop_ids.size() && e.loop_ids[ri] < t.id) ri++;          // (the reference has no bound check here)
+                    if (ri < e.loop_ids.size() && e.loop_ids[ri] == t.id) {
+                        Vector3d pts_j(e.loop_xy[2 * ri], e.loop_xy[2 * ri + 1], 1.0);
+                        problem.AddResidualBlock(new ProjectionFactor(t.obs[0], pts_j), loss, e.pose(start), e.loop_pose, e.para_Ex.data(), e.feat_p(feature_index));
+                        ri++; e.loop_nfac++; e.loop_enable = true;
+                    }
+                }
+            }
+        }
+    }
     ceres::Solver::Options o;
     o.linear_solver_type = ceres::DENSE_SCHUR;
     o.num_threads = 1;
@@ -352,6 +396,20 @@ void solve(Est &e) {                 // VINS::solve_ceres, VINS.cpp:480-831
     }
     e.cost0 = sum.initial_cost; e.cost1 = sum.final_cost;
     e.iters = (int)sum.iterations.size() - 1;
+    for (int k = 0; k < 12; k++) e.loop_out[k] = 0;
+    if (e.loop_frame >= 0 && e.loop_nfac > 0) {                  // VINS.cpp:664-680
+        const int i = e.loop_frame;
+        const double *pp = e.pose(i);
+        Matrix3d Rs_i = Quaterniond(pp[6], pp[3], pp[4], pp[5]).normalized().toRotationMatrix();
+        Vector3d Ps_i(pp[0], pp[1], pp[2]);
+        Matrix3d Rs_loop = Quaterniond(e.loop_pose[6], e.loop_pose[3], e.loop_pose[4], e.loop_pose[5]).normalized().toRotationMatrix();
+        Vector3d Ps_loop(e.loop_pose[0], e.loop_pose[1], e.loop_pose[2]);
+        Vector3d rt = Rs_loop.transpose() * (Ps_i - Ps_loop);
+        Quaterniond rq(Rs_loop.transpose() * Rs_i);
+        for (int k = 0; k < 3; k++) e.loop_out[k] = rt(k);
+        e.loop_out[3] = rq.x(); e.loop_out[4] = rq.y(); e.loop_out[5] = rq.z(); e.loop_out[6] = rq.w();
+        e.loop_out[7] = Utility::normalizeAngle(Utility::R2ypr(Rs_i).x() - Utility::R2ypr(Rs_loop).x());
+    }
     new2old(e);
     e.post_solve.assign((e.W + 1) * 16, 0.0);
     for (int i = 0; i <= e.W; i++) {
@@ -530,6 +588,20 @@ void vref_process_imu(void *h, double dt, const double *a, const double *g) {
     const auto t0 = std::chrono::steady_clock::now();
     process_imu(*(Est *)h, dt, Vector3d(a[0], a[1], a[2]), Vector3d(g[0], g[1], g[2]));
     ((Est *)h)->t_stage[3] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// retrive_pose_data: header, n ids (ascending) + n x 2 measurements of the old keyframe, its pose P_old[3], Q_old (xyzw); n = 0 clears
+void vref_set_loop_match(void *h, int n, double header, const int *ids, const double *xy, const double *pose_old) {
+    Est &e = *(Est *)h;
+    e.loop_hdr = header;
+    e.loop_ids.assign(ids, ids + n); e.loop_xy.assign(xy, xy + 2 * n);
+    e.loop_P_old = Vector3d(pose_old[0], pose_old[1], pose_old[2]);
+    e.loop_Q_old = Quaterniond(pose_old[6], pose_old[3], pose_old[4], pose_old[5]);
+}
+int vref_get_loop_result(void *h, double *out) {
+    Est &e = *(Est *)h;
+    const bool valid = e.loop_frame >= 0 && e.loop_nfac > 0;
+    for (int k = 0; k < 12; k++) out[k] = valid ? e.loop_out[k] : 0.0;
+    return valid ? e.loop_nfac : 0;
 }
 // VINS::solve_ceres() alone on the current window (NON_LINEAR, full window), as vio_backend_solve does
 int vref_solve(void *h) {

@@ -452,6 +452,63 @@ def test_solve_entry_matches_reference_solve_ceres(api, cfg, synth):
         ref.close(); gpu.close()
 
 
+def test_loop_closure_factors_match_reference(api, abi, synth):
+    """loop-closure factors in the window solve (VINS.cpp:571-637, 664-680, 174-195).  A retrieved old keyframe
+    (60 shared features seen from a slightly different pose) is matched against window frame 4 at keyframe 16; from then on every solve
+    carries ProjectionFactors to a free loop pose until the matched frame leaves the window.  Window state, number of loop factors and the
+    published relative_t / relative_q / relative_yaw / drift must follow the reference."""
+    cfg = abi.default_config(batch=1, max_cnt=150)
+    cfg.loop_closure = 1
+    W = cfg.window_size
+    tr = synth.make_tracks(3, 24, max_cnt=cfg.max_cnt)
+    ref, gpu = bo.RefEstimator(cfg), api.BackEnd(cfg)
+    seen = 0
+    try:
+        for k in range(24):
+            if k == 16:
+                hdr = ref.state()["headers"][4]
+                assert hdr == gpu.state()["headers"][4]
+                kk = int(np.argmin(np.abs(tr["t_kf"] - hdr)))
+                ids, xyz = tr["frames"][kk]
+                o = np.argsort(ids)[:60]
+                ids = ids[o]
+                xy = xyz[o, :2] + np.array([0.004, -0.003]) + np.random.default_rng(1).normal(0, 2e-4, (len(o), 2))
+                pose_old = np.concatenate([tr["P"][kk] + [0.05, -0.02, 0.01], synth.rot_to_quat_xyzw(tr["R"][kk:kk + 1])[0]])
+                ref.set_loop_match(hdr, ids, xy, pose_old)
+                I = np.zeros((1, cfg.max_cnt), np.int32); X = np.zeros((1, cfg.max_cnt, 2))
+                I[0, :len(ids)] = ids; X[0, :len(ids)] = xy
+                gpu.set_loop_match([len(ids)], [hdr], I, X, pose_old[None])
+            with Quiet():
+                drive(ref, tr, k, W)
+            drive(gpu, tr, k, W)
+            ri, gi = ref.info(), gpu.info()
+            assert gi["err"] == 0
+            for key in ("solver_flag", "marg_flag", "frame_count", "failure"):
+                assert ri[key] == gi[key], f"kf {k}: {key}"
+            if k < W:
+                continue
+            assert ri["n_feat"] == gi["n_feat"] and ri["n_proj"] == gi["n_proj"], f"kf {k}"
+            rs, gs = ref.state(), gpu.state()
+            tol = 1e-7 if k == W else 1e-4
+            for key, floor in (("P", 0.0), ("V", 0.0), ("Ba", 1e-2), ("Bg", 1e-3)):
+                err = np.abs(gs[key] - rs[key]).max() / max(np.abs(rs[key]).max(), floor)
+                assert err < tol, f"kf {k}: {key} {err}"
+            assert quat_err(gs["Q"], rs["Q"]) < tol
+            ro, rn = ref.loop_result()
+            go, gn = gpu.loop_result()
+            assert rn == gn, f"kf {k}: loop factors {rn} vs {gn}"
+            if k < 16:
+                assert gn == 0
+            if rn > 0:
+                seen += 1
+                assert np.abs(go[:3] - ro[:3]).max() < 1e-5 and np.abs(go[9:12] - ro[9:12]).max() < 1e-5, f"kf {k}: {go} vs {ro}"
+                assert min(np.abs(go[3:7] - ro[3:7]).max(), np.abs(go[3:7] + ro[3:7]).max()) < 1e-6
+                assert abs(go[7] - ro[7]) < 1e-3 and abs(go[8] - ro[8]) < 1e-3          # yaw angles in degrees
+        assert seen >= 4
+    finally:
+        ref.close(); gpu.close()
+
+
 def test_imu_capacity_error_is_latched_and_clearable(api, abi):
     """More IMU samples in one frame interval than max_imu_per_frame: VIO_ERR_CAPACITY is latched for the stream, reported by the state
     getters and cleared through vio_backend_get_error(clear) / vio_backend_clear()."""

@@ -19,6 +19,7 @@ class VioConfig(C.Structure):
         ("min_parallax", C.c_double), ("init_depth", C.c_double),
         ("max_imu_per_frame", C.c_int32), ("batch", C.c_int32), ("device", C.c_int32),
         ("marg_mode", C.c_int32), ("marg_eig", C.c_int32), ("marg_amm_eig", C.c_int32), ("solve_path", C.c_int32), ("be_threads", C.c_int32),
+        ("loop_closure", C.c_int32),
     ]
 
 

@@ -55,6 +55,8 @@ def lib():
         L.vio_frontend_use_stream.argtypes = [vp, vp]
         L.vio_frontend_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
         L.vio_backend_solve.argtypes = [vp]
+        L.vio_backend_set_loop_match.argtypes = [vp, IP, DP, IP, DP, DP]
+        L.vio_backend_get_loop_result.argtypes = [vp, C.c_int, DP, C.POINTER(C.c_int32)]
         L.vio_backend_get_error.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int32)]
         L.vio_prim_pyramid.argtypes = [cfgp, UP, UP, UP, UP]
         L.vio_frontend_set_clahe.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int]
@@ -381,6 +383,19 @@ class BackEnd:
 
     def sync(self):
         _check(lib().vio_backend_sync(self.h), "vio_backend_sync")
+
+    def set_loop_match(self, counts, headers, ids, xy, pose_old):
+        """retrive_pose_data per stream: counts (B,), headers (B,), ids (B,max_cnt) ascending, xy (B,max_cnt,2), pose_old (B,7) = P_old, Q_old xyzw"""
+        counts = np.ascontiguousarray(counts, np.int32).reshape(self.B); headers = np.ascontiguousarray(headers, np.float64).reshape(self.B)
+        ids = np.ascontiguousarray(ids, np.int32).reshape(self.B, self.maxp); xy = np.ascontiguousarray(xy, np.float64).reshape(self.B, self.maxp, 2)
+        pose_old = np.ascontiguousarray(pose_old, np.float64).reshape(self.B, 7)
+        _check(lib().vio_backend_set_loop_match(self.h, ptr(counts, C.c_int32), ptr(headers, C.c_double), ptr(ids, C.c_int32), ptr(xy, C.c_double),
+                                                ptr(pose_old, C.c_double)), "vio_backend_set_loop_match")
+
+    def loop_result(self, s=0):
+        out = np.zeros(12); n = C.c_int32(0)
+        _check(lib().vio_backend_get_loop_result(self.h, s, ptr(out, C.c_double), C.byref(n)), "vio_backend_get_loop_result")
+        return out, n.value
 
     def solve(self):
         """VINS::solve_ceres() alone on the current window of every NON_LINEAR stream"""

@@ -81,9 +81,11 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     BeState &s = be->s;
     memset(&s, 0, sizeof(s));
     s.B = cfg->batch; s.W = cfg->window_size; s.NF = s.W + 1; s.NP = 15 * s.NF; s.NPX = s.NP + 6; s.NPW = 6 * s.NF;
+    s.loop_on = cfg->loop_closure ? 1 : 0; s.NFS = s.NF + s.loop_on; s.NPS = 15 * s.NFS; s.NPWS = 6 * s.NFS;
     s.MAXCNT = cfg->max_cnt;
     s.FCAP = std::min(8192, (s.NF + 1) * cfg->max_cnt);
     s.LCAP = cfg->num_of_f;
+    s.par_stride = (size_t)s.NFS * 16 + s.LCAP;
     s.PCAP = std::min(cfg->num_of_f * s.W, 16384);
     s.MAXIMU = cfg->max_imu_per_frame;
     s.gravity = cfg->gravity; s.min_parallax = cfg->min_parallax; s.init_depth = cfg->init_depth;
@@ -119,20 +121,27 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     if (!rc) rc = dalloc(be, &s.bp, B * s.NPX);
     if (!rc) rc = dalloc(be, &s.x0, B * (NF * 16 + 7));
     if (!rc) rc = dalloc(be, &s.present, B * (2 * NF + 1));
-    if (!rc) rc = dalloc(be, &s.par, B * (NF * 16 + s.LCAP));
-    if (!rc) rc = dalloc(be, &s.cand, B * (NF * 16 + s.LCAP));
+    if (!rc) rc = dalloc(be, &s.par, B * s.par_stride);
+    if (!rc) rc = dalloc(be, &s.cand, B * s.par_stride);
+    if (!rc) rc = dalloc(be, &s.loop_n, B);
+    if (!rc) rc = dalloc(be, &s.loop_hdr, B);
+    if (!rc) rc = dalloc(be, &s.loop_ids, B * (size_t)cfg->max_cnt);
+    if (!rc) rc = dalloc(be, &s.loop_xy, B * (size_t)cfg->max_cnt * 2);
+    if (!rc) rc = dalloc(be, &s.loop_old, B * 7);
+    if (!rc) rc = dalloc(be, &s.lm_loop, B * (size_t)s.LCAP);
+    if (!rc) rc = dalloc(be, &s.loop_out, B * 20);
     if (!rc) rc = dalloc(be, &s.lm_slot, B * s.LCAP);
     if (!rc) rc = dalloc(be, &s.fac_lm, B * s.PCAP);
     if (!rc) rc = dalloc(be, &s.fac_j, B * s.PCAP);
     if (!rc) rc = dalloc(be, &s.lm_fac0, B * (s.LCAP + 1));
     if (!rc) rc = dalloc(be, &s.lm_anchor, B * s.LCAP);
     if (!rc) rc = dalloc(be, &s.fac_sorted, B * s.PCAP);
-    if (!rc) rc = dalloc(be, &s.pair_off, B * (NF * NF + 1));
+    if (!rc) rc = dalloc(be, &s.pair_off, B * ((size_t)s.NFS * s.NFS + 1));
     if (!rc) rc = dalloc(be, &s.fac_obs, B * s.PCAP * 4);
     if (!rc) rc = dalloc(be, &s.post_solve, B * NF * 16);
     if (!rc) rc = dalloc(be, &s.state_out, B * NF * 16);
     if (!rc) rc = dalloc(be, &s.prof, B * 32);
-    size_t sc = solve_scratch_doubles(s.NP, s.NPX, s.NPW, s.LCAP, s.PCAP);
+    size_t sc = solve_scratch_doubles(s.NPS, s.NPX, s.NPWS, s.LCAP, s.PCAP);
     sc = std::max(sc, marg_scratch_doubles(s.NPX, s.LCAP, cfg->max_cnt));
     sc = std::max(sc, (size_t)s.FCAP * (5 + 2 * NF));
     s.scratch_stride = (sc + 15) & ~(size_t)15;
@@ -149,17 +158,17 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     VIO_CUDA_TRY_OR(vio_allow_max_dynamic_smem(finish_kernel, cfg->device, &dyn_max), vio_backend_destroy(be));
     if ((size_t)s.FCAP + 64 > dyn_max) { vio_backend_destroy(be); return VIO_ERR_CAPACITY; }
     // reduced system resident in shared memory when it fits one SM (W = 10: 110 KB packed); otherwise the global-memory path
-    be->solve_smem = solve_smem_bytes(s.NP, s.NPW);
-    if (be->solve_smem > 200 * 1024 || schur_ntile(s.NPW) > be->be_threads) be->solve_smem = 0;
+    be->solve_smem = solve_smem_bytes(s.NPS, s.NPWS);
+    if (be->solve_smem > 200 * 1024 || schur_ntile(s.NPWS) > be->be_threads) be->solve_smem = 0;
     be->use_smem_solve = be->solve_smem > 0;
     // reduced system in registers as DMMA tiles (be_tilechol.cuh) when it fits 16 warps x 16 tiles; vio_config::solve_path = 1 keeps the packed path
-    if (be->use_smem_solve && cfg->solve_path != 1 && tile_path_fits(s.NF, be->be_threads)) {
+    if (be->use_smem_solve && cfg->solve_path != 1 && tile_path_fits(s.NFS, be->be_threads)) {
         be->use_smem_solve = 2;
-        be->solve_smem = std::max(be->solve_smem, tile_smem_doubles(s.NF) * sizeof(double));
+        be->solve_smem = std::max(be->solve_smem, tile_smem_doubles(s.NFS) * sizeof(double));
     }
-    be->solve_smem = std::max(be->solve_smem, eval_smem_bytes(s.W));
+    be->solve_smem = std::max(be->solve_smem, eval_smem_bytes(s.NFS - 1));
     be->solve_vec_off = (int)((be->solve_smem / sizeof(double) + 3) & ~(size_t)3);
-    be->solve_smem = (be->solve_vec_off + solve_vec_doubles(s.NP, s.NPX)) * sizeof(double);
+    be->solve_smem = (be->solve_vec_off + solve_vec_doubles(s.NPS, s.NPX)) * sizeof(double);
     VIO_CUDA_TRY_OR(vio_allow_max_dynamic_smem(solve_kernel, cfg->device, &dyn_max), vio_backend_destroy(be));
     if (be->solve_smem > dyn_max) { vio_backend_destroy(be); return VIO_ERR_CAPACITY; }
     be->marg_smem = sizeof(MargSmem) + 16 + (size_t)2 * MARG_NCAP * MARG_NCAP * sizeof(double);
@@ -269,6 +278,40 @@ static int run_process_image(vio_backend *be, const int32_t *counts, const int32
     VIO_LAUNCH(be->timer, st, "clear_init_pending_kernel", (clear_init_pending_kernel<<<s.B, 32, 0, st>>>(s)));
     be->launches += 8;
     VIO_CUDA_TRY(cudaGetLastError());
+    return VIO_OK;
+}
+
+// retrive_pose_data (VINS.hpp:28-45, written by the loop-closure thread at ViewController.mm:964): per stream the matched old keyframe --
+// header of the window frame it was matched against, ids (ascending) and normalised measurements of the shared features in the OLD
+// keyframe, its pose (P_old, Q_old xyzw).  counts[b] = 0 clears the stream's match.  Stays in force until replaced, like front_pose.
+extern "C" int vio_backend_set_loop_match(vio_backend *be, const int32_t *counts, const double *headers, const int32_t *ids, const double *xy,
+                                          const double *pose_old) {
+    if (!be || !counts || !headers || !ids || !xy || !pose_old) return VIO_ERR_ARG;
+    if (!be->s.loop_on) return VIO_ERR_STATE;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    const size_t B = be->s.B, P = be->cfg.max_cnt;
+    for (size_t b = 0; b < B; b++) if (counts[b] < 0 || counts[b] > (int)P) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->s.loop_n, counts, B * sizeof(int), cudaMemcpyHostToDevice, be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->s.loop_hdr, headers, B * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->s.loop_ids, ids, B * P * sizeof(int), cudaMemcpyHostToDevice, be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->s.loop_xy, xy, B * P * 2 * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(be->s.loop_old, pose_old, B * 7 * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));           // the caller's buffers may be pageable and short-lived
+    return VIO_OK;
+}
+
+// what the last solve made of the match (VINS.cpp:664-680, :174-195): out[0..2] relative_t, [3..6] relative_q (xyzw), [7] relative_yaw (deg),
+// [8] drift yaw (deg; r_drift = ypr2R(drift_yaw, 0, 0)), [9..11] t_drift.  *n_factors = loop factors in that solve (0: no loop constraint).
+extern "C" int vio_backend_get_loop_result(vio_backend *be, int s, double out[12], int32_t *n_factors) {
+    if (!be || s < 0 || s >= be->s.B || !out || !n_factors) return VIO_ERR_ARG;
+    if (!be->s.loop_on) return VIO_ERR_STATE;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    double lo[20]; int iv[IV_COUNT];
+    VIO_CUDA_TRY(cudaMemcpyAsync(lo, be->s.loop_out + (size_t)s * 20, sizeof(lo), cudaMemcpyDeviceToHost, be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(iv, be->s.iv + (size_t)s * IV_COUNT, sizeof(iv), cudaMemcpyDeviceToHost, be->stream));
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    for (int i = 0; i < 12; i++) out[i] = lo[12] != 0.0 ? lo[i] : 0.0;
+    *n_factors = lo[12] != 0.0 ? iv[IV_LOOP_NFAC] : 0;
     return VIO_OK;
 }
 

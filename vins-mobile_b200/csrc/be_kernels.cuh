@@ -278,13 +278,32 @@ __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
     if (act != ACT_INIT_SOLVE && act != ACT_NL_SOLVE) return;
     const size_t fo = (size_t)b * s.FCAP;
     const int nf = iv[IV_NFEAT];
-    double *par = s.par + (size_t)b * (s.NF * 16 + s.LCAP);
+    double *par = s.par + (size_t)b * s.par_stride;
     for (int i = tid; i < s.NF; i += 256) {
         double *p = par + 16 * i;
         st3(p, ld3(S_Ps(s, b, i)));
         stq(p + 3, R2q(ldm(S_Rs(s, b, i))));
         st3(p + 7, ld3(S_Vs(s, b, i))); st3(p + 10, ld3(S_Bas(s, b, i))); st3(p + 13, ld3(S_Bgs(s, b, i)));
     }
+    // Loop closure (VINS.cpp:571-600): the retrieved keyframe must still be in the window (header >= Headers[0]) and equal the header of a
+    // frame i < WINDOW_SIZE; the loop pose ("12th pose", solve frame NF) starts from para_Pose[i].  Without a match the extra frame is inert.
+    __shared__ int sh_loop_i;
+    if (s.loop_on) {
+        if (tid == 0) {
+            int li = -1;
+            const double h = s.loop_hdr[b];
+            if (act == ACT_NL_SOLVE && s.loop_n[b] > 0 && h >= s.Headers[(size_t)b * s.NF])
+                for (int i = 0; i < s.W; i++) if (s.Headers[(size_t)b * s.NF + i] == h) li = i;
+            sh_loop_i = li;
+            iv[IV_LOOP_FRAME] = li; iv[IV_LOOP_NFAC] = 0;
+            double *p = par + 16 * s.NF;
+            for (int k = 0; k < 16; k++) p[k] = 0.0;
+            p[6] = 1.0;
+            if (li >= 0) { st3(p, ld3(S_Ps(s, b, li))); stq(p + 3, R2q(ldm(S_Rs(s, b, li)))); }
+        }
+        __syncthreads();
+    }
+    const int loop_i = s.loop_on ? sh_loop_i : -1;
     // IMUFactor(pre_integrations[i+1]): sqrt_info = LLT(cov^-1).matrixL()^T.  Cached while the covariance is unchanged (only the
     // newest frames propagate between two solves); warps 0 and 1 factor the ones that need it.
     __shared__ double sh_sqi[2][3][225];
@@ -313,7 +332,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
                 s.lm_slot[(size_t)b * s.LCAP + li] = k;
                 s.lm_fac0[(size_t)b * (s.LCAP + 1) + li] = fi;
                 s.lm_anchor[(size_t)b * s.LCAP + li] = s.f_start[fo + k];
-                par[16 * s.NF + li] = 1.0 / s.f_depth[fo + k];
+                par[16 * s.NFS + li] = 1.0 / s.f_depth[fo + k];
                 const int st = s.f_start[fo + k];
                 for (int j = 1; j <= nfac; j++) { s.fac_lm[(size_t)b * s.PCAP + fi + j - 1] = li; s.fac_j[(size_t)b * s.PCAP + fi + j - 1] = st + j; }
             } else iv[IV_ERR] = VIO_ERR_CAPACITY;
@@ -322,11 +341,40 @@ __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
     }
     const int nl = min(lm_base, s.LCAP), nfac_all = min(fac_base, s.PCAP);
     if (tid == 0) { iv[IV_N_LM] = nl; iv[IV_N_FAC] = nfac_all; s.lm_fac0[(size_t)b * (s.LCAP + 1) + nl] = nfac_all; }
+    // loop-closure factors: the reference walks the landmarks in solve order and the retrieved ids with one forward cursor (both ascending
+    // by id, VINS.cpp:603-631); a landmark observed in frame loop_i whose id is found gets ProjectionFactor(first observation, old measurement)
+    // between its anchor pose and the loop pose.  Sequential by construction (one thread).
+    int n_loop_fac = 0;
+    if (s.loop_on) {
+        int *lml = s.lm_loop + (size_t)b * s.LCAP;
+        __syncthreads();
+        for (int l = tid; l < nl; l += 256) lml[l] = -1;
+        __syncthreads();
+        if (tid == 0 && loop_i >= 0) {
+            const int n = min(s.loop_n[b], s.MAXCNT);
+            const int *lid = s.loop_ids + (size_t)b * s.MAXCNT;
+            int ri = 0, cnt = 0;
+            for (int l = 0; l < nl && ri < n; l++) {
+                const int k = s.lm_slot[(size_t)b * s.LCAP + l];
+                const int st = s.f_start[fo + k], no = s.f_nobs[fo + k], id = s.f_id[fo + k];
+                if (st <= loop_i && st + no - loop_i - 1 >= 0) {
+                    while (ri < n && lid[ri] < id) ri++;
+                    if (ri < n && lid[ri] == id && nfac_all + cnt < s.PCAP) { lml[l] = ri; ri++; cnt++; }
+                }
+            }
+            iv[IV_LOOP_NFAC] = cnt;
+        }
+        __syncthreads();
+        n_loop_fac = iv[IV_LOOP_NFAC];
+    }
+    if (tid == 0) iv[IV_N_FAC_ALL] = nfac_all + n_loop_fac;
     // the same factors ordered by (anchor frame i, observing frame j): a landmark contributes at most one factor to a pair, so
     // "landmark order within the pair" is a deterministic order.  One thread per pair counts, then places.
-    __shared__ int sh_cnt[(VIO_MAX_WIN + 1) * (VIO_MAX_WIN + 1) + 1];
-    const int NF = s.NF, nkey = NF * NF;
+    __shared__ int sh_cnt[(VIO_MAX_WIN + 2) * (VIO_MAX_WIN + 2) + 1];
+    const int NF = s.NFS, nkey = NF * NF, LF = s.NF;                 // LF: index of the loop pose among the solve frames
+    const int nfac_tot = nfac_all + n_loop_fac;
     const int *slot = s.lm_slot + (size_t)b * s.LCAP;
+    const int *lml = s.lm_loop + (size_t)b * s.LCAP;
     __shared__ unsigned short sh_lm[2048][2];                        // (anchor frame, observations) per landmark
     const int nls = min(nl, 2048);
     __syncthreads();
@@ -334,11 +382,15 @@ __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
     __syncthreads();
     auto lm_start = [&](int l) { return l < 2048 ? (int)sh_lm[l][0] : s.f_start[fo + slot[l]]; };
     auto lm_nobs = [&](int l) { return l < 2048 ? (int)sh_lm[l][1] : s.f_nobs[fo + slot[l]]; };
+    auto has_fac = [&](int l, int i, int j) {
+        if (lm_start(l) != i) return false;
+        return (s.loop_on && j == LF) ? (n_loop_fac > 0 && lml[l] >= 0) : (j < i + lm_nobs(l));
+    };
     for (int key = tid; key < nkey; key += 256) {
         const int i = key / NF, j = key - i * NF;
         int c = 0;
         if (j > i)
-            for (int l = 0; l < nl; l++) c += (lm_start(l) == i && j < i + lm_nobs(l));
+            for (int l = 0; l < nl; l++) c += has_fac(l, i, j);
         sh_cnt[key] = c;
     }
     __syncthreads();
@@ -348,20 +400,22 @@ __global__ void __launch_bounds__(256) prepare_kernel(BeState s) {
         sh_cnt[nkey] = acc;
     }
     __syncthreads();
-    int *po = s.pair_off + (size_t)b * (nkey + 1);
-    for (int key = tid; key <= nkey; key += 256) po[key] = min(sh_cnt[key], nfac_all);
+    int *po = s.pair_off + (size_t)b * ((size_t)s.NFS * s.NFS + 1);
+    for (int key = tid; key <= nkey; key += 256) po[key] = min(sh_cnt[key], nfac_tot);
     int *fs = s.fac_sorted + (size_t)b * s.PCAP;
     double *fobs = s.fac_obs + (size_t)b * s.PCAP * 4;
+    const double *lxy = s.loop_xy + (size_t)b * s.MAXCNT * 2;
     for (int key = tid; key < nkey; key += 256) {
         const int i = key / NF, j = key - i * NF;
         if (j <= i) continue;
         int pos = sh_cnt[key];
         for (int l = 0; l < nl; l++) {
-            if (lm_start(l) == i && j < i + lm_nobs(l) && pos < s.PCAP) {
+            if (has_fac(l, i, j) && pos < s.PCAP) {
                 const double *o = S_obs(s, b, slot[l]);
                 fs[pos] = l | (i << 16) | (j << 24);
                 fobs[4 * (size_t)pos] = o[0]; fobs[4 * (size_t)pos + 1] = o[1];
-                fobs[4 * (size_t)pos + 2] = o[2 * (j - i)]; fobs[4 * (size_t)pos + 3] = o[2 * (j - i) + 1];
+                if (s.loop_on && j == LF) { fobs[4 * (size_t)pos + 2] = lxy[2 * lml[l]]; fobs[4 * (size_t)pos + 3] = lxy[2 * lml[l] + 1]; }
+                else { fobs[4 * (size_t)pos + 2] = o[2 * (j - i)]; fobs[4 * (size_t)pos + 3] = o[2 * (j - i) + 1]; }
                 pos++;
             }
         }
@@ -377,13 +431,36 @@ __global__ void __launch_bounds__(256) post_solve_kernel(BeState s) {
     const int act = iv[IV_ACTION];
     if (act != ACT_INIT_SOLVE && act != ACT_NL_SOLVE) return;
     double *dv = S_dv(s, b);
-    const double *par = s.par + (size_t)b * (s.NF * 16 + s.LCAP);
+    const double *par = s.par + (size_t)b * s.par_stride;
     V3 oR0 = R2ypr(ldm(S_Rs(s, b, 0)));
     V3 oP0 = ld3(S_Ps(s, b, 0));
     if (iv[IV_FAILURE]) { oR0 = R2ypr(ldm(dv + DV_LAST_R_OLD)); oP0 = ld3(dv + DV_LAST_P_OLD); }
     const V3 oR00 = R2ypr(q2R(ldq(par + 3)));
     const M3 rot = ypr2R(v3(oR0.x - oR00.x, 0, 0));
     const V3 p0 = ld3(par);
+    if (s.loop_on && tid == 0) {
+        // loop-closure results (VINS.cpp:664-680 from the raw solved parameters, :174-195 after the yaw / P0 re-anchoring)
+        double *lo = s.loop_out + (size_t)b * 20;
+        const int li = iv[IV_LOOP_FRAME];
+        lo[12] = 0.0;
+        if (li >= 0 && iv[IV_LOOP_NFAC] > 0) {
+            const double *pl = par + 16 * s.NF, *pi = par + 16 * li;
+            const M3 Ri = q2R(qnormalized(ldq(pi + 3))), Rl = q2R(qnormalized(ldq(pl + 3)));
+            const V3 Pi = ld3(pi), Pl = ld3(pl);
+            st3(lo, tr(Rl) * (Pi - Pl));
+            stq(lo + 3, R2q(tr(Rl) * Ri));
+            double ry = R2ypr(Ri).x - R2ypr(Rl).x;                   // Utility::normalizeAngle (degrees, utility.hpp:171-179)
+            ry = ry > 0 ? ry - 360.0 * floor((ry + 180.0) / 360.0) : ry + 360.0 * floor((-ry + 180.0) / 360.0);
+            lo[7] = ry;
+            const M3 Rl2 = rot * Rl;
+            const V3 Pl2 = rot * (Pl - p0) + oP0;
+            const double *old = s.loop_old + (size_t)b * 7;
+            const double dyaw = R2ypr(q2R(ldq(old + 3))).x - R2ypr(Rl2).x;
+            lo[8] = dyaw;
+            st3(lo + 9, ld3(old) - ypr2R(v3(dyaw, 0, 0)) * Pl2);
+            lo[12] = 1.0;
+        }
+    }
     __syncthreads();                                   // everyone has read Rs[0]/Ps[0] before they are overwritten
     for (int i = tid; i < s.NF; i += 256) {
         const double *p = par + 16 * i;
@@ -399,7 +476,7 @@ __global__ void __launch_bounds__(256) post_solve_kernel(BeState s) {
     const size_t fo = (size_t)b * s.FCAP;
     for (int l = tid; l < nl; l += 256) {
         const int k = s.lm_slot[(size_t)b * s.LCAP + l];
-        const double d = 1.0 / par[16 * s.NF + l];
+        const double d = 1.0 / par[16 * s.NFS + l];
         s.f_depth[fo + k] = d;
         s.f_flag[fo + k] = d < 0 ? 2 : 1;
     }

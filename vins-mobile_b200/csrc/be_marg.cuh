@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(MARG_T) marg_kernel(BeState s) {
     const int prior_valid = iv[IV_PRIOR_VALID];
     if (marg == 1 && !(prior_valid && pres[2 * (W - 1)])) return;         // VINS.cpp:779-780: nothing to do
     double *dvs = S_dv(s, b);
-    double *par = s.par + (size_t)b * (NF * 16 + s.LCAP);
+    double *par = s.par + (size_t)b * s.par_stride;
     const size_t fo = (size_t)b * s.FCAP;
     const int nl = iv[IV_N_LM], nfac = iv[IV_N_FAC];
     BE_PROF_INIT;

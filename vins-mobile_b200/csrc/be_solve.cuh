@@ -38,9 +38,9 @@ __device__ inline SolveWs carve(const BeState &s, int b, double *sv, int nl) {
     double *p = s.scratch + (size_t)b * s.scratch_stride;
     auto take = [&](size_t n) { double *r = p; p += (n + 3) & ~(size_t)3; return r; };
     auto stake = [&](size_t n) { double *r = sv; sv += (n + 3) & ~(size_t)3; return r; };
-    w.H = take((size_t)s.NP * s.NP); w.S = take((size_t)s.NP * s.NP); w.w = take((size_t)s.LCAP * s.NPW); w.lt = take((size_t)s.PCAP * 8);
-    w.g = stake(s.NP); w.sc_p = stake(s.NP); w.d_p = stake(s.NP); w.gr_p = stake(s.NP); w.gn_p = stake(s.NP); w.st_p = stake(s.NP);
-    w.u_p = stake(s.NP); w.rhs = stake(s.NP); w.y = stake(s.NP); w.dx = stake(s.NPX);
+    w.H = take((size_t)s.NPS * s.NPS); w.S = take((size_t)s.NPS * s.NPS); w.w = take((size_t)s.LCAP * s.NPWS); w.lt = take((size_t)s.PCAP * 8);
+    w.g = stake(s.NPS); w.sc_p = stake(s.NPS); w.d_p = stake(s.NPS); w.gr_p = stake(s.NPS); w.gn_p = stake(s.NPS); w.st_p = stake(s.NPS);
+    w.u_p = stake(s.NPS); w.rhs = stake(s.NPS); w.y = stake(s.NPS); w.dx = stake(s.NPX);
     if (nl <= SOLVE_LV) {
         w.hll = stake(SOLVE_LV); w.gl = stake(SOLVE_LV); w.sc_l = stake(SOLVE_LV); w.d_l = stake(SOLVE_LV);
         w.gr_l = stake(SOLVE_LV); w.gn_l = stake(SOLVE_LV); w.st_l = stake(SOLVE_LV); w.u_l = stake(SOLVE_LV);
@@ -112,7 +112,7 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
     long long *pp = s.prof + (size_t)b * 32; BE_PROF2_INIT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int *iv = S_iv(s, b);
-    const int NP = s.NP, NPW = s.NPW, nl = iv[IV_N_LM], nfac = iv[IV_N_FAC];
+    const int NP = s.NPS, NPW = s.NPWS, NPwin = s.NP, nl = iv[IV_N_LM], nfac = iv[IV_N_FAC_ALL], nfac_reg = iv[IV_N_FAC];
     double cost = 0.0;
     const int has_prior = iv[IV_PRIOR_VALID];
     const int *pres = s.present + (size_t)b * (2 * s.NF + 1);
@@ -125,7 +125,7 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
             double *row = ws.H + (size_t)i * NP;
             const double *src = Hp + (size_t)i * s.NPX;
             const int fi = i / 15;
-            const bool rp = has_prior && pres[2 * fi + ((i - 15 * fi) >= 6)];
+            const bool rp = has_prior && fi < s.NF && pres[2 * fi + ((i - 15 * fi) >= 6)];       // the loop-closure pose has no prior
             for (int j = lane; j <= i; j += 32) row[j] = rp ? src[j] : 0.0;
         }
         for (int i = tid; i < NP; i += blockDim.x) ws.g[i] = 0.0;
@@ -147,11 +147,11 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
         if (tid == 0) *ncp = 0;
         __syncthreads();
         for (int d = tid; d < NPX; d += T) {
-            const int f = d / 15, blk = d < NP ? 2 * f + ((d - 15 * f) >= 6) : 2 * s.NF;
+            const int f = d / 15, blk = d < NPwin ? 2 * f + ((d - 15 * f) >= 6) : 2 * s.NF;
             if (pres[blk]) {
                 int pos = 0;
                 for (int q = 0; q < blk; q++) pos += pres[q] ? ((q & 1) ? 9 : 6) : 0;
-                pos += d < NP ? ((blk & 1) ? d - 15 * f - 6 : d - 15 * f) : d - NP;
+                pos += d < NPwin ? ((blk & 1) ? d - 15 * f - 6 : d - 15 * f) : d - NPwin;
                 cl[pos] = d; dxc[pos] = ws.dx[d];
             }
         }
@@ -182,7 +182,7 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
             for (int q = 0; q < P; q++) t += part_sum[q * nc + i2];
             const int d = cl[i2];
             cost += 0.5 * dxc[i2] * t + bp[d] * dxc[i2];
-            if (lin && d < NP) ws.g[d] += t + bp[d];
+            if (lin && d < NPwin) ws.g[d] += t + bp[d];
         }
         if (tid == 0) cost += 0.5 * S_dv(s, b)[DV_PRIOR_C0];
     }
@@ -237,7 +237,8 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
         const double *dv = S_dv(s, b);
         const M3 ric = ldm(dv + DV_RIC), ricT = tr(ric);
         const V3 tic = ld3(dv + DV_TIC);
-        const int T = blockDim.x, NF = s.NF, npair = NF * (NF - 1) / 2;
+        const int T = blockDim.x, NF = s.NFS, npair = NF * (NF - 1) / 2;
+        const int *lml = s.lm_loop + (size_t)b * s.LCAP;
         double *fr = smem_scratch, *prs = fr + 21 * NF, *Js = prs + 33 * npair + ((33 * npair + 21 * NF) & 1);
         for (int f = tid; f < NF; f += T) {
             const M3 R = q2R(ldq(par + 16 * f + 3));
@@ -328,7 +329,9 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
                     lt8[6] = Jl0 * Jl0 + Jl1 * Jl1; lt8[7] = Jl0 * c0r + Jl1 * c1r;
                     // terms that are sums over the landmark's factors (w_l of the anchor frame, h_ll, g_l): stored per factor in
                     // landmark order and summed by one thread per landmark after the last chunk -- no atomics
-                    double4 *dst = reinterpret_cast<double4 *>(ws.lt + 8 * (size_t)(lf0[l] + (j - i - 1)));
+                    // a loop-closure factor (observing "frame" = the loop pose, solve frame s.NF) keeps its landmark terms behind the regular ones
+                    const int lts = (s.loop_on && j == s.NF) ? nfac_reg + lml[l] : lf0[l] + (j - i - 1);
+                    double4 *dst = reinterpret_cast<double4 *>(ws.lt + 8 * (size_t)lts);
                     dst[0] = make_double4(lt8[0], lt8[1], lt8[2], lt8[3]); dst[1] = make_double4(lt8[4], lt8[5], lt8[6], lt8[7]);
                 }
             }
@@ -384,6 +387,11 @@ __device__ __noinline__ double evaluate(const BeState &s, int b, const SolveWs &
                     const double4 u = *reinterpret_cast<const double4 *>(ws.lt + 8 * (size_t)f), v = *reinterpret_cast<const double4 *>(ws.lt + 8 * (size_t)f + 4);
                     a8[0] += u.x; a8[1] += u.y; a8[2] += u.z; a8[3] += u.w; a8[4] += v.x; a8[5] += v.y; a8[6] += v.z; a8[7] += v.w;
                 }
+                if (s.loop_on && lml[l] >= 0 && nfac > nfac_reg) {
+                    const size_t f = (size_t)nfac_reg + lml[l];
+                    const double4 u = *reinterpret_cast<const double4 *>(ws.lt + 8 * f), v = *reinterpret_cast<const double4 *>(ws.lt + 8 * f + 4);
+                    a8[0] += u.x; a8[1] += u.y; a8[2] += u.z; a8[3] += u.w; a8[4] += v.x; a8[5] += v.y; a8[6] += v.z; a8[7] += v.w;
+                }
                 double *wl = ws.w + (size_t)l * NPW + 6 * anchor[l];
 #pragma unroll
                 for (int k = 0; k < 6; k++) wl[k] = a8[k];
@@ -410,7 +418,7 @@ __device__ __forceinline__ double w_dot_warp(const double *wl, const double *v, 
 // u^T H u over the full (pose/speed-bias + landmark) system.  Only the LOWER triangle of H is valid (the accumulation writes one
 // triangle); elements are visited in memory order, so the reads are coalesced.
 __device__ inline double quad_form(const BeState &s, const SolveWs &ws, int nl, const double *up, const double *ul, double *sh_red) {
-    const int tid = threadIdx.x, T = blockDim.x, NP = s.NP, NPW = s.NPW, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    const int tid = threadIdx.x, T = blockDim.x, NP = s.NPS, NPW = s.NPWS, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     double acc = 0;
     for (int i = warp; i < NP; i += nwarp) {                         // one warp per row of the lower triangle
         const double *row = ws.H + (size_t)i * NP;
@@ -720,7 +728,7 @@ constexpr int SCHUR_CHUNK = 64;
 __host__ __device__ inline int schur_ld(int NPW) { return (NPW + 1 + 3) & ~3; }
 __host__ __device__ inline int schur_ntile(int NPW) { const int rt = schur_ld(NPW) / 4; return rt * (rt + 1) / 2; }
 __device__ __noinline__ void build_reduced_smem(const BeState &s, const SolveWs &ws, int nl, double mu, double *S, double *wt) {
-    const int tid = threadIdx.x, T = blockDim.x, NP = s.NP, NPW = s.NPW;
+    const int tid = threadIdx.x, T = blockDim.x, NP = s.NPS, NPW = s.NPWS;
     for (int e = tid; e < NP * (NP + 1) / 2; e += T) {
         const int i = tri_row(e), j = e - pidx(i, 0);
         double v = ws.H[(size_t)i * NP + j] * ws.sc_p[i] * ws.sc_p[j];
@@ -805,10 +813,10 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem,
     const int act = iv[IV_ACTION];
     if (act != ACT_INIT_SOLVE && act != ACT_NL_SOLVE) return;
     double *dvs = S_dv(s, b);
-    const int NP = s.NP, NPW = s.NPW, NF = s.NF, nl = iv[IV_N_LM];
+    const int NP = s.NPS, NPW = s.NPWS, NF = s.NFS, nl = iv[IV_N_LM];
     const SolveWs ws = carve(s, b, sm_dyn + vec_off, nl);
-    double *par = s.par + (size_t)b * (NF * 16 + s.LCAP);
-    double *cand = s.cand + (size_t)b * (NF * 16 + s.LCAP);
+    double *par = s.par + (size_t)b * s.par_stride;
+    double *cand = s.cand + (size_t)b * s.par_stride;
 
     BE_PROF_INIT;
     double x_cost = evaluate(s, b, ws, par, 2, sh_red, sm_dyn);

@@ -8,7 +8,8 @@ namespace be {
 
 // per-stream integer scalars (BeState::iv)
 enum { IV_FRAME_COUNT = 0, IV_FIRST_IMU, IV_SOLVER_FLAG, IV_MARG_FLAG, IV_FAILURE, IV_NFEAT, IV_LAST_TRACK, IV_ACTION, IV_INIT_PENDING,
-       IV_PRIOR_VALID, IV_N_LM, IV_N_FAC, IV_ITERS, IV_PRIOR_N, IV_ERR, IV_MARG_FAST, IV_MARG_SWEEPS, IV_MARG_M, IV_CHOL_RETRY, IV_COUNT = 20 };
+       IV_PRIOR_VALID, IV_N_LM, IV_N_FAC, IV_ITERS, IV_PRIOR_N, IV_ERR, IV_MARG_FAST, IV_MARG_SWEEPS, IV_MARG_M, IV_CHOL_RETRY,
+       IV_N_FAC_ALL /* IV_N_FAC + loop-closure factors */, IV_LOOP_FRAME /* window frame the loop pose is tied to, -1: none */, IV_LOOP_NFAC, IV_COUNT = 24 };
 // per-stream double scalars (BeState::dv)
 enum { DV_ACC0 = 0, DV_GYR0 = 3, DV_LAST_P = 6, DV_LAST_P_OLD = 9, DV_BACK_P0 = 12, DV_LAST_R = 15, DV_LAST_R_OLD = 24, DV_BACK_R0 = 33,
        DV_COST0 = 42, DV_COST1 = 43, DV_PRIOR_C0 = 44, DV_TIC = 45, DV_RIC = 48, DV_COUNT = 64 };
@@ -20,6 +21,11 @@ struct BeState {
     int NP;                  // 15 * NF   pose+speed-bias local size
     int NPX;                 // NP + 6    (+ ex_pose)
     int NPW;                 // 6 * NF    pose-only local size (landmark coupling rows)
+    // The solve may carry one more pose than the window: the loop-closure pose ("12th pose", VINS.cpp:571-637), stored as solve frame NF.
+    // NFS = NF + loop_on; the solve's dimensions are NPS = 15 NFS (the extra speed-bias dofs have no factor: they stay exactly 0) and
+    // NPWS = 6 NFS; everything that belongs to the WINDOW (prior, IMU factors, marginalisation, slide) keeps NF / NP / NPX.
+    int loop_on, NFS, NPS, NPWS;
+    size_t par_stride;       // doubles per stream in par / cand: 16 * NFS + LCAP
     int FCAP, LCAP, PCAP, MAXIMU, MAXCNT;
     double gravity, min_parallax, init_depth, sqrt_info;
     double noise[6];         // acc_n^2, gyr_n^2, acc_n^2, gyr_n^2, acc_w^2, gyr_w^2   (integration_base.h:37-43)
@@ -47,6 +53,10 @@ struct BeState {
     double *post_solve;                               // [B][NF][16]
     double *state_out;                                // [B][NF][16] packed P,Q,V,Ba,Bg after the step
     long long *prof;                                  // [B][32] clock64 cycles per kernel phase (diagnostics)
+    // loop closure (RetriveData, VINS.hpp:28-45): matched keyframe header, ids + measurements of the old keyframe (ids ascending), its pose
+    int *loop_n; double *loop_hdr; int *loop_ids; double *loop_xy; double *loop_old;   // [B], [B], [B][MAXCNT], [B][MAXCNT][2], [B][7] P_old, Q_old (xyzw)
+    int *lm_loop;                                     // [B][LCAP] index into loop_ids/xy of the landmark's loop factor, -1: none
+    double *loop_out;                                 // [B][20] relative_t3 relative_q4(xyzw) relative_yaw1 drift_yaw1 t_drift3 (valid flag at [12])
 };
 
 __device__ __forceinline__ double *S_Ps(const BeState &s, int b, int i) { return s.Ps + ((size_t)b * s.NF + i) * 3; }

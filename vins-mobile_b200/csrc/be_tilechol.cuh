@@ -121,8 +121,8 @@ __device__ __noinline__ bool tile_reduced_solve(const BeState &s, const double *
     constexpr unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int NP = s.NP, NPW = s.NPW;
-    const TileGeom G = tile_geom(s.NF);
+    const int NP = s.NPS, NPW = s.NPWS;
+    const TileGeom G = tile_geom(s.NFS);
     const int nt = G.nt, npad = G.npad;
     const int npt = G.ppad / 8, nsy = npt * (npt + 1) / 2 + npt;       // pose tile rows; SYRK tiles = pose x pose (lower) + border x pose
     double *Lp = sm;

@@ -182,6 +182,18 @@ class FeatureTracker {
 };
 
 // VINS.hpp:51-172
+// VINS.hpp:28-45 (the fields the window solve reads and writes)
+struct RetriveData {
+    double header = -1;
+    Vector3d P_old{0, 0, 0};
+    std::array<double, 4> Q_old{0, 0, 0, 1};               // x,y,z,w
+    std::vector<Point2f> measurements;                     // normalised image coordinates in the old keyframe
+    std::vector<int> features_ids;                         // ascending
+    Vector3d relative_t{0, 0, 0};
+    std::array<double, 4> relative_q{0, 0, 0, 1};
+    double relative_yaw = 0;
+};
+
 class VINS {
   public:
     enum SolverFlag { INITIAL, NON_LINEAR };
@@ -224,6 +236,7 @@ class VINS {
             if (n >= cap) throw std::length_error("processImage: more than max_cnt features");
             ids[n] = kv.first; xyz[3 * n] = kv.second.x; xyz[3 * n + 1] = kv.second.y; xyz[3 * n + 2] = kv.second.z; n++;
         }
+        push_loop_match();
         check(vio_backend_process_image(h_, &n, ids.data(), xyz.data(), &header), "vio_backend_process_image");
         refresh();
     }
@@ -241,10 +254,38 @@ class VINS {
     bool failure_occur;
     double final_cost;
     int feature_num;
+    // loop closure (needs vio_config::loop_closure = 1): the caller (loop-closure thread, ViewController.mm:964) writes retrive_pose_data;
+    // the next solves add the loop factors (VINS.cpp:571-637) and publish relative_t / relative_q / relative_yaw in it, and the drift
+    // correction r_drift = ypr2R(drift_yaw, 0, 0), t_drift (VINS.hpp:117-118)
+    RetriveData retrive_pose_data;
+    double drift_yaw = 0;
+    Vector3d t_drift{0, 0, 0};
     vio_backend *handle() { return h_; }
 
   private:
+    void push_loop_match() {
+        if (!cfg_.loop_closure || retrive_pose_data.header == pushed_header_) return;
+        const RetriveData &r = retrive_pose_data;
+        const int cap = cfg_.max_cnt;
+        const int32_t n = (int32_t)std::min<size_t>(r.features_ids.size(), (size_t)cap);
+        std::vector<int32_t> ids(cap, 0);
+        std::vector<double> xy(2 * cap, 0.0);
+        for (int i = 0; i < n; i++) { ids[i] = r.features_ids[i]; xy[2 * i] = r.measurements[i].x; xy[2 * i + 1] = r.measurements[i].y; }
+        const double pose[7] = {r.P_old.x, r.P_old.y, r.P_old.z, r.Q_old[0], r.Q_old[1], r.Q_old[2], r.Q_old[3]};
+        check(vio_backend_set_loop_match(h_, &n, &r.header, ids.data(), xy.data(), pose), "vio_backend_set_loop_match");
+        pushed_header_ = r.header;
+    }
     void refresh() {
+        if (cfg_.loop_closure) {
+            double lo[12]; int32_t nf = 0;
+            check(vio_backend_get_loop_result(h_, 0, lo, &nf), "vio_backend_get_loop_result");
+            if (nf > 0) {
+                retrive_pose_data.relative_t = Vector3d{lo[0], lo[1], lo[2]};
+                retrive_pose_data.relative_q = {lo[3], lo[4], lo[5], lo[6]};
+                retrive_pose_data.relative_yaw = lo[7];
+                drift_yaw = lo[8]; t_drift = Vector3d{lo[9], lo[10], lo[11]};
+            }
+        }
         const int n = cfg_.window_size + 1;
         std::vector<double> P(3 * n), Q(4 * n), V(3 * n), Ba(3 * n), Bg(3 * n);
         check(vio_backend_get_state(h_, 0, P.data(), Q.data(), V.data(), Ba.data(), Bg.data(), Headers.data()), "vio_backend_get_state");
@@ -264,6 +305,7 @@ class VINS {
     }
     vio_config cfg_;
     vio_backend *h_ = nullptr;
+    double pushed_header_ = -1;
 };
 
 }  // namespace vio
