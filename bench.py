@@ -365,6 +365,48 @@ def _kernel_table(prof, B, ab):
     return kern, cand
 
 
+def pnp_bench(bn, args, n_frames=40):
+    """vio_pnp_* through the host API: per camera frame the IMU samples since the last frame + the frame's solved landmarks (60 per stream) +
+    every third frame a (lagging) estimator result, as feature_tracker.cpp:107-160 feeds vinsPnP.  Frames per second over B windows."""
+    torch = bn.torch
+    B = bn.B
+    cfg = bn.abi.default_config(batch=B, max_cnt=150, device=bn.local)
+    seqs = [bn.synth.make_pnp_sequence(b, n_frames) for b in range(min(B, 8))]        # 8 distinct sequences, tiled over the batch
+    pnp = bn.api.PnP(cfg)
+    n_lm = len(seqs[0]["ids"])
+    cnt = np.full(B, n_lm, np.int32)
+    ids = np.zeros((B, 150), np.int32); tn = np.zeros((B, 150), np.int32); pos = np.zeros((B, 150, 3)); obs = np.zeros((B, 150, 2))
+    for b in range(B):
+        q = seqs[b % len(seqs)]
+        ids[b, :n_lm] = q["ids"]; tn[b, :n_lm] = q["track_num"]; pos[b, :n_lm] = q["X"]
+    last_t = 0.0
+    t0 = None
+    for k in range(n_frames):
+        if k == 8:
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+        q0 = seqs[0]
+        if k >= q0["lag"] and k % 3 == 0:
+            j = k - q0["lag"]
+            pnp.set_init(np.full(B, q0["t"][j]), np.stack([seqs[b % len(seqs)]["P"][j] for b in range(B)]), np.stack([seqs[b % len(seqs)]["R"][j] for b in range(B)]),
+                         np.stack([seqs[b % len(seqs)]["V"][j] for b in range(B)]), np.zeros((B, 3)), np.zeros((B, 3)))
+        sel = (q0["imu_t"] > last_t + 1e-9) & (q0["imu_t"] <= q0["t"][k] + 1e-9)
+        if sel.any():
+            tt = np.concatenate([[last_t], q0["imu_t"][sel]])
+            pnp.process_imu(np.repeat(np.diff(tt)[:, None], B, 1), np.stack([seqs[b % len(seqs)]["acc"][sel] for b in range(B)], 1),
+                            np.stack([seqs[b % len(seqs)]["gyr"][sel] for b in range(B)], 1))
+        for b in range(B):
+            obs[b, :n_lm] = seqs[b % len(seqs)]["obs"][k]
+        pnp.process_image(cnt, ids, obs, pos, tn, np.full(B, q0["t"][k]), True)
+        last_t = q0["t"][k]
+    st = pnp.state(0)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    pnp.close()
+    return {"value": (n_frames - 8) * B / dt, "unit": "frames/s", "windows": B, "landmarks_per_frame": n_lm, "frames_timed": n_frames - 8,
+            "ms_per_frame_all_windows": 1e3 * dt / (n_frames - 8), "iters_last": st["iters"], "err": st["err"],
+            "what": "vinsPnP::processIMU + processImage (5 dogleg iterations on the 7-frame window) through the host C-ABI, host loop included"}
+
+
 def run_ours(args):
     import torch
     rank, local, world = _rank_world()
@@ -394,6 +436,11 @@ def run_ours(args):
         r = bn.timed_run(False, clahe=True, profile=True)
         extras["clahe_on"] = {"value": args.steps * B / (r["ms"] * 1e-3), "unit": "frames/s", "ms_per_step": r["ms"] / args.steps,
                               "kernels_ms": {k: v[1] / v[0] for k, v in r["prof"].items() if k.startswith("clahe")}}
+        # (c) the motion-only PnP tracker behind FeatureTracker::solveVinsPnP (vins_pnp.cpp), B windows in lock-step, host buffers in
+        try:
+            extras["pnp_tracker"] = pnp_bench(bn, args)
+        except Exception as e:
+            extras["pnp_tracker"] = {"error": repr(e)}
     single = None
     configs_extra = {}
     if world == 1 and rank == 0 and not args.no_extras and args.config == "c2":
