@@ -410,6 +410,11 @@ def pnp_bench(bn, args, n_frames=40):
 def run_ours(args):
     import torch
     rank, local, world = _rank_world()
+    # rank 0's stdout must carry exactly ONE JSON line: libraries that print there (NCCL's version banner at communicator creation)
+    # are sent to stderr for the duration of the run; the descriptor is restored right before the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
@@ -538,7 +543,9 @@ def run_ours(args):
         "solve_info_stream0": info[0] if info else None,
         "solve_info_batch": {k: [min(i[k] for i in info), max(i[k] for i in info)] for k in ("iters", "n_feat", "n_proj", "prior_n", "marg_fast", "marg_sweeps", "marg_m", "chol_retry", "err")} if info else None,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------- reference arm
