@@ -167,6 +167,8 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
         be->solve_smem = std::max(be->solve_smem, tile_smem_doubles(s.NFS) * sizeof(double));
     }
     be->solve_smem = std::max(be->solve_smem, eval_smem_bytes(s.NFS - 1));
+    if (!be->use_smem_solve)                       // global-memory path: Schur chunk staging and the Cholesky panel (used one after the other)
+        be->solve_smem = std::max(be->solve_smem, std::max((size_t)SCHUR_CHUNK * schur_ld(s.NPWS), chol_global_smem_doubles(s.NPS)) * sizeof(double));
     be->solve_vec_off = (int)((be->solve_smem / sizeof(double) + 3) & ~(size_t)3);
     be->solve_smem = (be->solve_vec_off + solve_vec_doubles(s.NPS, s.NPX)) * sizeof(double);
     VIO_CUDA_TRY_OR(vio_allow_max_dynamic_smem(solve_kernel, cfg->device, &dyn_max), vio_backend_destroy(be));

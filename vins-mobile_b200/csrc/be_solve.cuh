@@ -788,6 +788,188 @@ __device__ __noinline__ void build_reduced_smem(const BeState &s, const SolveWs 
     __syncthreads();
 }
 
+// ---- global-memory path (reduced system too large for one SM: W = 20 -> 315 x 315) -----------------------------------------------
+// Same mathematics as build_reduced_smem / chol_solve_packed with the matrix in the stream's global scratch (L2-resident: 0.8 MB) and
+// only the hot operands in shared memory: the landmark chunk of the Schur SYRK, and the current panel of the blocked factorisation.
+__device__ __noinline__ void build_reduced_global(const BeState &s, const SolveWs &ws, int nl, double mu, double *wt /* smem [SCHUR_CHUNK][ld] */) {
+    const int tid = threadIdx.x, T = blockDim.x, NP = s.NPS, NPW = s.NPWS;
+    for (int e = tid; e < NP * NP; e += T) {
+        const int i = e / NP, j = e - i * NP;
+        if (j <= i) {
+            double v = ws.H[e] * ws.sc_p[i] * ws.sc_p[j];
+            if (i == j) v += mu * ws.d_p[i] * ws.d_p[i];
+            ws.S[e] = v;
+        }
+    }
+    for (int i = tid; i < NP; i += T) ws.rhs[i] = ws.g[i] * ws.sc_p[i];
+    for (int l = tid; l < nl; l += T) {                             // per-landmark weight sqrt(s_l^2 / h_l) (u_l is free scratch here)
+        const double sl = ws.sc_l[l];
+        ws.u_l[l] = sqrt(sl * sl / (ws.hll[l] * sl * sl + mu * ws.d_l[l] * ws.d_l[l]));
+    }
+    const int ld = schur_ld(NPW), rt = ld / 4, ntile = rt * (rt + 1) / 2;
+    // a thread owns up to TPT 4x4 tiles of the lower triangle of the (NPW+1) x (NPW+1) SYRK (border row = right-hand side)
+    constexpr int TPT = 2;
+    int I[TPT], J[TPT];
+    double acc[TPT][4][4];
+#pragma unroll
+    for (int q = 0; q < TPT; q++) {
+        const int tile = tid + q * T;
+        if (tile < ntile) { const int ti = tri_row(tile); I[q] = 4 * ti; J[q] = 4 * (tile - ti * (ti + 1) / 2); } else { I[q] = -1; J[q] = 0; }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[q][a][c] = 0.0;
+    }
+    for (int l0 = 0; l0 < nl; l0 += SCHUR_CHUNK) {
+        const int cn = min(SCHUR_CHUNK, nl - l0);
+        __syncthreads();
+        for (int e = tid; e < cn * ld; e += T) {
+            const int cl = e / ld, a = e - cl * ld, l = l0 + cl;
+            wt[e] = (a < NPW) ? ws.w[(size_t)l * NPW + a] * ws.u_l[l] : (a == NPW ? ws.gl[l] * ws.u_l[l] : 0.0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < TPT; q++) {
+            if (I[q] < 0) continue;
+            for (int cl = 0; cl < cn; cl++) {
+                const double *row = wt + cl * ld;
+                const double2 a01 = *reinterpret_cast<const double2 *>(row + I[q]), a23 = *reinterpret_cast<const double2 *>(row + I[q] + 2);
+                const double2 b01 = *reinterpret_cast<const double2 *>(row + J[q]), b23 = *reinterpret_cast<const double2 *>(row + J[q] + 2);
+                const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[q][a][c] += av[a] * bv[c];
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < TPT; q++) {
+        if (I[q] < 0) continue;
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int ra = I[q] + a, rc = J[q] + c;
+                if (rc > ra || ra > NPW || rc >= NPW) continue;
+                const int ic = 15 * (rc / 6) + rc % 6;
+                if (ra == NPW) ws.rhs[ic] -= acc[q][a][c] * ws.sc_p[ic];          // one owner per element: no atomics
+                else { const int ia = 15 * (ra / 6) + ra % 6; ws.S[(size_t)ia * NP + ic] -= acc[q][a][c] * ws.sc_p[ia] * ws.sc_p[ic]; }
+            }
+    }
+    __syncthreads();
+}
+
+// Blocked right-looking Cholesky of the lower triangle of A (global, ld = n) with 16-column panels + the two triangular solves.
+//   per panel: (a) warp 0 factors the 16 x 16 diagonal block in shared memory; (b) one thread per row below solves its 16 entries
+//   against the block and leaves the row in the shared panel; (c) the trailing matrix gets the rank-16 update in 4x4 register tiles
+//   whose operands come from the shared panel.  smem: panel [n][16] + diag [16][17] + dinv [n] doubles.
+constexpr int GB_NB = 16;
+__host__ __device__ inline size_t chol_global_smem_doubles(int n) { return (size_t)n * GB_NB + GB_NB * (GB_NB + 1) + n + 8; }
+__device__ __noinline__ bool chol_solve_blocked_global(double *A, int n, const double *rhs, double *y, int *sh_flag, double *sm) {
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+    constexpr int NB = GB_NB, DL = GB_NB + 1;
+    double *panel = sm, *diag = panel + (size_t)n * NB, *dinv = diag + NB * DL;
+    if (tid == 0) *sh_flag = 1;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += NB) {
+        const int nb = min(NB, n - c0);
+        // (a) diagonal block -> shared, factored by warp 0 (column by column, lanes = rows)
+        for (int e = tid; e < NB * NB; e += T) { const int r = e / NB, c = e - r * NB; diag[r * DL + c] = (r < nb && c <= r) ? A[(size_t)(c0 + r) * n + c0 + c] : (r == c ? 1.0 : 0.0); }
+        __syncthreads();
+        if (tid < 32) {
+            for (int k = 0; k < nb; k++) {
+                const double piv = diag[k * DL + k];
+                if (lane == 0) { if (!(piv > 0) || !isfinite(piv)) *sh_flag = 0; }
+                const double il = fast_rsqrt(piv);
+                __syncwarp();
+                if (lane == k) { diag[k * DL + k] = piv * il; dinv[c0 + k] = il; }
+                if (lane > k && lane < nb) diag[lane * DL + k] *= il;
+                __syncwarp();
+                for (int e = lane; e < (nb - k - 1) * (nb - k - 1); e += 32) {
+                    const int r = k + 1 + e / (nb - k - 1), c = k + 1 + e % (nb - k - 1);
+                    if (c <= r) diag[r * DL + c] -= diag[r * DL + k] * diag[c * DL + k];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (!*sh_flag) return false;
+        for (int e = tid; e < nb * nb; e += T) { const int r = e / nb, c = e - r * nb; if (c <= r) A[(size_t)(c0 + r) * n + c0 + c] = diag[r * DL + c]; }
+        // (b) rows below the block
+        const int r0 = c0 + nb;
+        for (int i = r0 + tid; i < n; i += T) {
+            double *ri = A + (size_t)i * n + c0;
+            double v[NB];
+#pragma unroll
+            for (int jj = 0; jj < NB; jj++) {
+                if (jj < nb) {
+                    double w = ri[jj];
+#pragma unroll
+                    for (int t = 0; t < jj; t++) w -= v[t] * diag[jj * DL + t];
+                    v[jj] = w * dinv[c0 + jj];
+                    ri[jj] = v[jj];
+                    panel[(size_t)(i - r0) * NB + jj] = v[jj];
+                } else panel[(size_t)(i - r0) * NB + jj] = 0.0;
+            }
+        }
+        __syncthreads();
+        // (c) trailing update A[i][j] -= sum_t P[i][t] P[j][t], i >= j >= r0
+        const int R = n - r0, RT = (R + 3) >> 2, ntile = RT * (RT + 1) / 2;
+        for (int e = tid; e < ntile; e += T) {
+            const int ti = tri_row(e), tj = e - ti * (ti + 1) / 2;
+            const int I = 4 * ti, J = 4 * tj;
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
+            const double *pi_[4], *pj_[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) { pi_[a] = panel + (size_t)min(I + a, R - 1) * NB; pj_[a] = panel + (size_t)min(J + a, R - 1) * NB; }
+#pragma unroll
+            for (int t = 0; t < NB; t += 2) {
+                double2 li[4], lj[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) { li[a] = *reinterpret_cast<const double2 *>(pi_[a] + t); lj[a] = *reinterpret_cast<const double2 *>(pj_[a] + t); }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[a][c] += li[a].x * lj[c].x + li[a].y * lj[c].y;
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int i = I + a, j = J + c;
+                    if (i < R && j <= i) A[(size_t)(r0 + i) * n + r0 + j] -= acc[a][c];
+                }
+        }
+        __syncthreads();
+    }
+    // L z = rhs, L^T y = z (column sweeps; dinv = 1 / diag(L))
+    for (int i = tid; i < n; i += T) y[i] = rhs[i];
+    __syncthreads();
+    for (int k = 0; k < n; k++) {
+        if (tid == 0) y[k] *= dinv[k];
+        __syncthreads();
+        const double yk = y[k];
+        for (int i = k + 1 + tid; i < n; i += T) y[i] -= A[(size_t)i * n + k] * yk;
+        __syncthreads();
+    }
+    for (int k = n - 1; k >= 0; k--) {
+        if (tid == 0) y[k] *= dinv[k];
+        __syncthreads();
+        const double yk = y[k];
+        for (int i = tid; i < k; i += T) y[i] -= A[(size_t)k * n + i] * yk;
+        __syncthreads();
+    }
+    bool ok = true;
+    for (int i = tid; i < n; i += T) ok &= isfinite(y[i]);
+    return __syncthreads_and(ok) != 0;
+}
+
 }  // namespace be
 #include "be_tilechol.cuh"
 namespace be {
@@ -887,43 +1069,10 @@ __global__ void __launch_bounds__(SOLVE_T) solve_kernel(BeState s, int use_smem,
                 ok = chol_solve_packed(Ssm, NP, ws.rhs, ws.y, &sh_flag, wt, s.prof + (size_t)b * 32);
                 BE_PROF(3);
               } else {
-                for (int e = tid; e < NP * NP; e += T) {
-                    const int i = e / NP, j = e - i * NP;
-                    if (j <= i) {
-                        double v = ws.H[e] * ws.sc_p[i] * ws.sc_p[j];
-                        if (i == j) v += mu * ws.d_p[i] * ws.d_p[i];
-                        ws.S[e] = v;
-                    }
-                }
-                for (int i = tid; i < NP; i += T) ws.rhs[i] = ws.g[i] * ws.sc_p[i];
-                __syncthreads();
-                // S -= sum_l ws_l ws_l^T / h_l on the pose (6-dof) rows/cols; rhs -= ws_l gs_l / h_l
-                for (int e = tid; e < NPW * NPW; e += T) {
-                    const int a = e / NPW, c = e - a * NPW;
-                    if (c > a) continue;
-                    const int ia = 15 * (a / 6) + a % 6, ic = 15 * (c / 6) + c % 6;
-                    double acc = 0;
-                    for (int l = 0; l < nl; l++) {
-                        const double wa = ws.w[(size_t)l * NPW + a];
-                        if (wa == 0.0) continue;
-                        const double sl = ws.sc_l[l];
-                        const double h = ws.hll[l] * sl * sl + mu * ws.d_l[l] * ws.d_l[l];
-                        acc += wa * ws.w[(size_t)l * NPW + c] * (sl * sl / h);
-                    }
-                    ws.S[(size_t)ia * NP + ic] -= acc * ws.sc_p[ia] * ws.sc_p[ic];
-                }
-                for (int a = tid; a < NPW; a += T) {
-                    const int ia = 15 * (a / 6) + a % 6;
-                    double acc = 0;
-                    for (int l = 0; l < nl; l++) {
-                        const double sl = ws.sc_l[l];
-                        const double h = ws.hll[l] * sl * sl + mu * ws.d_l[l] * ws.d_l[l];
-                        acc += ws.w[(size_t)l * NPW + a] * ws.gl[l] * (sl * sl / h);
-                    }
-                    ws.rhs[ia] -= acc * ws.sc_p[ia];
-                }
-                __syncthreads();
-                ok = chol_solve(ws.S, NP, ws.rhs, ws.y, &sh_flag);
+                // reduced system in global memory (W = 20): tiled Schur SYRK + blocked Cholesky with shared panels
+                double *wt = sm_dyn;
+                build_reduced_global(s, ws, nl, mu, wt);
+                ok = chol_solve_blocked_global(ws.S, NP, ws.rhs, ws.y, &sh_flag, sm_dyn);
               }
                 __syncthreads();
                 if (ok) {
