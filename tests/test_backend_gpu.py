@@ -284,8 +284,14 @@ def test_marginalisation_eigen_paths(api, abi, synth, eig, slow, exact):
                 # b = H (x - x0) + ... amplifies the state differences of later windows
                 assert rel_err(gp["b"], rp["b"]) < (1e-7 if k == W else 1e-3), f"kf {k}: prior b {rel_err(gp['b'], rp['b'])}"
                 # c0 = b^T A_r^+ b divides by the small eigenvalues of A_r, which no eigensolver (Eigen's included) resolves to better than
-                # eps * |A_r|: it agrees to a few 1e-3 between solvers; it is a constant of the cost and does not influence the step
-                assert abs(gp["c0"] - rp["c0"]) <= 5e-3 * max(1.0, abs(rp["c0"])), f"kf {k}: c0 {gp['c0']} vs {rp['c0']}"
+                # eps * |A_r|: it agrees to a few 1e-3 between solvers; it is a constant of the cost and does not influence the step.
+                # When an eigenvalue of A_r sits AT the pseudo-inverse cut (1e-8, marginalization_factor.cpp:283-284) its 1/lambda term is in
+                # or out depending on round-off -- also from one run of the reference build to another -- and c0 is defined only up to that
+                # term: such keyframes are excluded from the c0 comparison (H and b are still compared above).
+                ev = np.concatenate([np.linalg.eigvalsh(rp["H"]), np.linalg.eigvalsh(gp["H"])])
+                at_cut = bool(((ev > 1e-9) & (ev < 1e-7)).any())
+                if not at_cut:
+                    assert abs(gp["c0"] - rp["c0"]) <= 5e-3 * max(1.0, abs(rp["c0"])), f"kf {k}: c0 {gp['c0']} vs {rp['c0']}"
                 e = rel_err(gpu.state()["P"], ref.state()["P"])
                 assert e < (1e-7 if k == W else 1e-4), f"kf {k}: P {e}"
     finally:
