@@ -233,6 +233,30 @@ int vio_prim_projection_factor(const vio_config *cfg, const double pts_i[3], con
                                double *residual /*2*/, double *J /*2x13 row-major: [pi6 pj6 lambda1]*/);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Visual-inertial alignment of the initialisation (the linear-algebra half).
+ * Replaces VisualIMUAlignment (initial_aligment.cpp:222-229) = solveGyroscopeBias (:10-46) + SolveScale (:135-220) +
+ * RefineGravity (:64-133) over the map<double, ImageFrame> VINS::solveInitial hands it (VINS.cpp:889-905), for `batch` streams
+ * at once, one CTA per stream; the IMU pre-integration of every frame interval (IntegrationBase ctor + push_back,
+ * VINS.cpp:340-352) and its re-propagation with the corrected gyroscope bias (integration_base.h:46-61) run on the device.
+ * Host in / out (an initialisation-time call, not on the per-frame path):
+ *   n_frames   [batch]                         frames in all_image_frame (2 .. max_frames)
+ *   R, T       [batch][max_frames][9 | 3]      ImageFrame::R (row-major) and ImageFrame::T of every frame, in map order
+ *   imu_counts [batch][max_frames]             samples of the interval ENDING at frame k (0 .. max_imu); frame 0's are never read
+ *   imu0       [batch][max_frames][6]          acc_0, gyr_0 each interval starts from (the previous sample)
+ *   imu        [batch][max_frames][max_imu][7] dt, acc xyz, gyr xyz
+ *   bg0        [batch][3]                      Bgs[*] before the call
+ *   bgs        [batch][3]                      Bgs[*] after (bg0 + delta_bg)
+ *   g          [batch][3]                      refined gravity in the frame R / T are expressed in
+ *   x          [batch][3 max_frames + 4]       the reference's VectorXd x: body-frame velocity of every frame, then the 2 tangent-plane
+ *                                              steps, then the scale s (already divided by 100) -- 3 n + 3 entries; when SolveScale
+ *                                              itself rejects (|norm(g) - G_NORM| > G_THRESHOLD or s < 0) its 3 n + 4 entries instead
+ *   ok         [batch]                         the bool VisualIMUAlignment returns
+ * VIO_ERR_CAPACITY when a stream has more frames / samples than the maxima. */
+int vio_visual_imu_align(const vio_config *cfg, int batch, int max_frames, int max_imu, const int32_t *n_frames,
+                         const double *R, const double *T, const int32_t *imu_counts, const double *imu0, const double *imu,
+                         const double *bg0, double *bgs, double *g, double *x, int32_t *ok);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Motion-only PnP tracker: FeatureTracker::solveVinsPnP (feature_tracker.cpp:107-160) and the
  * vinsPnP object it drives (vins_pnp.hpp:40-91, vins_pnp.cpp).  `batch` independent 7-frame windows advancing in lock-step.
  * Replaces: vinsPnP::setInit (:63-83), processIMU (:197-233), processImage (:236-256) incl. updateFeatures / solve_ceres /

@@ -44,6 +44,8 @@ def lib():
         L.vref_preintegrate.argtypes = [C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
         L.vref_imu_factor.argtypes = [DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP]
         L.vref_projection_factor.argtypes = [C.c_double, DP, DP, DP, DP, DP, DP, C.c_double, DP, DP]
+        if hasattr(L, "vref_visual_imu_align"):
+            L.vref_visual_imu_align.argtypes = [C.c_int, DP, DP, IP, DP, C.c_int, DP, DP, DP, DP, DP, DP]
         if hasattr(L, "vpnp_create"):
             L.vpnp_create.restype = C.c_void_p
             L.vpnp_create.argtypes = [C.POINTER(_abi.VioConfig)]
@@ -225,3 +227,14 @@ def perspective_factor(obs_xy, pos_xyz, track_num, fx, pose7, ex7):
     lib().vpnp_perspective_factor(_abi.ptr(a[0], C.c_double), _abi.ptr(a[1], C.c_double), int(track_num), float(fx), _abi.ptr(b[0], C.c_double),
                                   _abi.ptr(b[1], C.c_double), *[_abi.ptr(x, C.c_double) for x in (res, Jp, Je)])
     return res, Jp, Je
+
+
+def visual_imu_align(n, R, T, counts, imu0, imu, bg0, tic):
+    """The reference's VisualIMUAlignment (initial_aligment.cpp:222-229, compiled unmodified) on ONE stream.
+    R [n][3][3], T [n][3], counts [n], imu0 [n][6], imu [n][M][7], bg0 [3], tic [3] -> (bgs [3], g [3], x [3 n + 3], ok)."""
+    R, T, imu0, imu, bg0, tic = (_d(a) for a in (R, T, imu0, imu, bg0, tic))
+    counts = np.ascontiguousarray(counts, np.int32)
+    bgs = np.zeros(3); g = np.zeros(3); x = np.zeros(3 * n + 3)
+    p = lambda a: a.ctypes.data_as(DP)
+    ok = lib().vref_visual_imu_align(n, p(R), p(T), counts.ctypes.data_as(IP), p(imu0), imu.shape[1], p(imu), p(bg0), p(tic), p(bgs), p(g), p(x))
+    return bgs, g, x, int(ok)

@@ -99,6 +99,7 @@ def lib():
             L.vio_prim_preintegrate.argtypes = [cfgp, C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
             L.vio_prim_imu_factor.argtypes = [cfgp, DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP]
             L.vio_prim_projection_factor.argtypes = [cfgp, DP, DP, DP, DP, C.c_double, DP, DP]
+            L.vio_visual_imu_align.argtypes = [cfgp, C.c_int, C.c_int, C.c_int, IP, DP, DP, IP, DP, DP, DP, DP, DP, DP, IP]
         _lib = L
     return _lib
 
@@ -434,6 +435,22 @@ def prim_projection_factor(cfg, pts_i, pts_j, pi, pj, inv_dep):
     p = lambda x: ptr(x, C.c_double)
     _check(lib().vio_prim_projection_factor(C.byref(cfg), *[p(x) for x in a], float(inv_dep), p(res), p(J)), "vio_prim_projection_factor")
     return res, J
+
+
+def visual_imu_align(cfg, n_frames, R, T, imu_counts, imu0, imu, bg0):
+    """Batched VisualIMUAlignment (initial_aligment.cpp:222-229).  R [B][F][3][3], T [B][F][3], imu_counts [B][F], imu0 [B][F][6],
+    imu [B][F][M][7] (dt, acc, gyr), bg0 [B][3]  ->  (bgs [B][3], g [B][3], x [B][3 F + 4], ok [B])."""
+    d = lambda a: np.ascontiguousarray(a, np.float64)
+    n_frames = np.ascontiguousarray(n_frames, np.int32); imu_counts = np.ascontiguousarray(imu_counts, np.int32)
+    R, T, imu0, imu, bg0 = d(R), d(T), d(imu0), d(imu), d(bg0)
+    B, F = imu_counts.shape
+    M = imu.shape[2]
+    assert R.shape == (B, F, 3, 3) and T.shape == (B, F, 3) and imu0.shape == (B, F, 6) and imu.shape == (B, F, M, 7) and bg0.shape == (B, 3)
+    bgs = np.zeros((B, 3)); g = np.zeros((B, 3)); x = np.zeros((B, 3 * F + 4)); ok = np.zeros(B, np.int32)
+    p = lambda a: ptr(a, C.c_double)
+    _check(lib().vio_visual_imu_align(C.byref(cfg), B, F, M, ptr(n_frames, C.c_int32), p(R), p(T), ptr(imu_counts, C.c_int32), p(imu0), p(imu),
+                                      p(bg0), p(bgs), p(g), p(x), ptr(ok, C.c_int32)), "vio_visual_imu_align")
+    return bgs, g, x, ok
 
 
 class PnP:

@@ -636,6 +636,71 @@ extern "C" int vio_prim_projection_factor(const vio_config *cfg, const double pt
     return VIO_OK;
 }
 
+// ================================================================== visual-inertial alignment (linear half)
+#include "be_align.cuh"
+
+extern "C" int vio_visual_imu_align(const vio_config *cfg, int batch, int max_frames, int max_imu, const int32_t *n_frames, const double *R,
+                                    const double *T, const int32_t *imu_counts, const double *imu0, const double *imu, const double *bg0,
+                                    double *bgs, double *g, double *x, int32_t *ok) {
+    if (!cfg || !n_frames || !R || !T || !imu_counts || !imu0 || !imu || !bg0 || !bgs || !g || !x || !ok) return VIO_ERR_ARG;
+    if (batch <= 0 || max_frames < 2 || max_frames > 256 || max_imu <= 0) return VIO_ERR_ARG;
+    for (int b = 0; b < batch; b++) {
+        if (n_frames[b] < 2 || n_frames[b] > max_frames) return VIO_ERR_CAPACITY;
+        for (int k = 0; k < n_frames[b]; k++)
+            if (imu_counts[(size_t)b * max_frames + k] < 0 || imu_counts[(size_t)b * max_frames + k] > max_imu) return VIO_ERR_CAPACITY;
+    }
+    VIO_CUDA_TRY(cudaSetDevice(cfg->device));
+    AlignArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = batch; a.F = max_frames; a.MAXIMU = max_imu; a.NS = 3 * max_frames + 4;
+    const size_t B = batch, F = max_frames, NS = a.NS;
+    // one allocation: inputs, scratch, outputs (doubles first, then ints)
+    const size_t nd_in = B * F * 9 + B * F * 3 + B * F * 6 + B * F * max_imu * 7 + B * 3;
+    const size_t nd_scr = B * F * PR_STRIDE + 2 * B * NS * NS + B * NS + B * F * 110 + 2 * B * NS;
+    const size_t nd_out = B * 3 + B * 3 + B * NS;
+    const size_t ni = B + B * F + B * NS + B;
+    double *d = nullptr;
+    VIO_CUDA_TRY(cudaMalloc((void **)&d, (nd_in + nd_scr + nd_out) * sizeof(double) + ni * sizeof(int)));
+    double *p = d;
+    double *dR = p; p += B * F * 9;
+    double *dT = p; p += B * F * 3;
+    double *dI0 = p; p += B * F * 6;
+    double *dI = p; p += B * F * max_imu * 7;
+    double *dBg = p; p += B * 3;
+    a.pre = p; p += B * F * PR_STRIDE;
+    a.A = p; p += B * NS * NS;
+    a.Aw = p; p += B * NS * NS;
+    a.rhs = p; p += B * NS;
+    a.pairs = p; p += B * F * 110;
+    a.xs = p; p += 2 * B * NS;
+    a.bgs_out = p; p += B * 3;
+    a.g_out = p; p += B * 3;
+    a.x_out = p; p += B * NS;
+    int *q = reinterpret_cast<int *>(p);
+    int *dN = q; q += B;
+    int *dC = q; q += B * F;
+    a.perm = q; q += B * NS;
+    a.ok = q;
+    a.n_frames = dN; a.counts = dC; a.R = dR; a.T = dT; a.imu0 = dI0; a.imu = dI; a.bg0 = dBg;
+    memcpy(a.tic, cfg->tic, 24);
+    a.g_norm = cfg->gravity;             // G_NORM, global_param.hpp:50
+    a.g_thr = 3.0;                       // G_THRESHOLD, global_param.hpp:49
+    a.noise[0] = a.noise[2] = cfg->acc_n * cfg->acc_n; a.noise[1] = a.noise[3] = cfg->gyr_n * cfg->gyr_n;
+    a.noise[4] = cfg->acc_w * cfg->acc_w; a.noise[5] = cfg->gyr_w * cfg->gyr_w;
+    cudaMemcpy(dR, R, B * F * 9 * 8, cudaMemcpyHostToDevice); cudaMemcpy(dT, T, B * F * 3 * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(dI0, imu0, B * F * 6 * 8, cudaMemcpyHostToDevice); cudaMemcpy(dI, imu, B * F * max_imu * 7 * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(dBg, bg0, B * 3 * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(dN, n_frames, B * 4, cudaMemcpyHostToDevice); cudaMemcpy(dC, imu_counts, B * F * 4, cudaMemcpyHostToDevice);
+    cudaMemset(a.x_out, 0, B * NS * 8); cudaMemset(a.g_out, 0, B * 3 * 8); cudaMemset(a.bgs_out, 0, B * 3 * 8);
+    visual_imu_align_kernel<<<batch, ALIGN_THREADS>>>(a);
+    cudaMemcpy(bgs, a.bgs_out, B * 3 * 8, cudaMemcpyDeviceToHost); cudaMemcpy(g, a.g_out, B * 3 * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(x, a.x_out, B * NS * 8, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(ok, a.ok, B * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d);
+    return e == cudaSuccess ? VIO_OK : VIO_ERR_CUDA;
+}
+
 // ================================================================== motion-only PnP tracker
 #include "be_pnp.cuh"
 
