@@ -228,6 +228,14 @@ int vio_prim_imu_factor(const vio_config *cfg, const double *delta_pqv, const do
                         double sum_dt, const double lin_ba[3], const double lin_bg[3],
                         const double pose_i[7], const double sb_i[9], const double pose_j[7], const double sb_j[9],
                         double *residual /*15*/, double *J /*15x30 row-major, local: [pi6 sbi9 pj6 sbj9]*/);
+/* Same factor with the 15x15 weighting matrix made explicit: sqrt_info_in (row-major, upper triangular; NULL = form it on the device
+ * from `covariance` as imu_factor.h:72 does) and sqrt_info_out (NULL or 225 doubles: the matrix that was used).  The covariance has
+ * condition ~1e8, so the parity tests check the weighting matrix on its own (entry-wise and through U^T U cov = I) and the rest of
+ * IMUFactor::Evaluate (imu_factor.h:27-184) with the reference's matrix passed in. */
+int vio_prim_imu_factor_sqi(const vio_config *cfg, const double *delta_pqv, const double *jacobian, const double *covariance,
+                            double sum_dt, const double lin_ba[3], const double lin_bg[3],
+                            const double pose_i[7], const double sb_i[9], const double pose_j[7], const double sb_j[9],
+                            const double *sqrt_info_in, double *sqrt_info_out, double *residual /*15*/, double *J /*15x30*/);
 int vio_prim_projection_factor(const vio_config *cfg, const double pts_i[3], const double pts_j[3],
                                const double pose_i[7], const double pose_j[7], double inv_dep,
                                double *residual /*2*/, double *J /*2x13 row-major: [pi6 pj6 lambda1]*/);

@@ -43,6 +43,8 @@ def lib():
         L.vref_get_loop_result.argtypes = [C.c_void_p, DP]
         L.vref_preintegrate.argtypes = [C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
         L.vref_imu_factor.argtypes = [DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP]
+        if hasattr(L, "vref_imu_sqrt_info"):
+            L.vref_imu_sqrt_info.argtypes = [DP, DP]
         L.vref_projection_factor.argtypes = [C.c_double, DP, DP, DP, DP, DP, DP, C.c_double, DP, DP]
         if hasattr(L, "vref_visual_imu_align"):
             L.vref_visual_imu_align.argtypes = [C.c_int, DP, DP, IP, DP, C.c_int, DP, DP, DP, DP, DP, DP]
@@ -166,6 +168,13 @@ def imu_factor(pqv, jac, cov, sum_dt, lba, lbg, pi, sbi, pj, sbj):
     p = lambda x: _abi.ptr(x, C.c_double)
     lib().vref_imu_factor(p(a[0]), p(a[1]), p(a[2]), float(sum_dt), *[p(x) for x in b], p(res), p(J))
     return res, J
+
+
+def imu_sqrt_info(cov):
+    """LLT(cov^-1).matrixL()^T as imu_factor.h:72 computes it (Eigen 3.3, the oracle's compiler flags)."""
+    cov = _d(cov); U = np.zeros((15, 15))
+    lib().vref_imu_sqrt_info(_abi.ptr(cov, C.c_double), _abi.ptr(U, C.c_double))
+    return U
 
 
 def projection_factor(fx, tic, ric, pts_i, pts_j, pi, pj, inv_dep):

@@ -735,6 +735,13 @@ void vref_imu_factor(const double *pqv, const double *jac, const double *cov, do
         for (int c = 0; c < 9; c++) { J[r * 30 + 6 + c] = j1[r * 9 + c]; J[r * 30 + 21 + c] = j3[r * 9 + c]; }
     }
 }
+// sqrt_info exactly as IMUFactor::Evaluate forms it (imu_factor.h:72), row-major 15 x 15 (upper triangular)
+void vref_imu_sqrt_info(const double *cov, double *U) {
+    Matrix<double, 15, 15> covariance = Map<const Matrix<double, 15, 15, RowMajor>>(cov);
+    Matrix<double, 15, 15> sqrt_info = LLT<Matrix<double, 15, 15>>(covariance.inverse()).matrixL().transpose();
+    Map<Matrix<double, 15, 15, RowMajor>> out(U);
+    out = sqrt_info;
+}
 void vref_projection_factor(double fx, const double *tic, const double *ric, const double *pts_i, const double *pts_j,
                             const double *pi, const double *pj, double inv_dep, double *res, double *J) {
     ProjectionFactor::sqrt_info = fx / 1.5 * Matrix2d::Identity();

@@ -99,6 +99,7 @@ def lib():
             L.vio_prim_preintegrate.argtypes = [cfgp, C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
             L.vio_prim_imu_factor.argtypes = [cfgp, DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP]
             L.vio_prim_projection_factor.argtypes = [cfgp, DP, DP, DP, DP, C.c_double, DP, DP]
+            L.vio_prim_imu_factor_sqi.argtypes = [cfgp, DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
             L.vio_visual_imu_align.argtypes = [cfgp, C.c_int, C.c_int, C.c_int, IP, DP, DP, IP, DP, DP, DP, DP, DP, DP, IP]
         _lib = L
     return _lib
@@ -426,6 +427,18 @@ def prim_imu_factor(cfg, pqv, jac, cov, sum_dt, lba, lbg, pi, sbi, pj, sbj):
     p = lambda x: ptr(x, C.c_double)
     _check(lib().vio_prim_imu_factor(C.byref(cfg), p(a[0]), p(a[1]), p(a[2]), float(sum_dt), *[p(x) for x in b], p(res), p(J)), "vio_prim_imu_factor")
     return res, J
+
+
+def prim_imu_factor_sqi(cfg, pqv, jac, cov, sum_dt, lba, lbg, pi, sbi, pj, sbj, sqrt_info=None):
+    """IMUFactor::Evaluate with the weighting matrix explicit: returns (residual, J, sqrt_info used); `sqrt_info` overrides the device's own."""
+    d = lambda a: np.ascontiguousarray(a, np.float64)
+    a = [d(x) for x in (pqv, jac, cov)]; b = [d(x) for x in (lba, lbg, pi, sbi, pj, sbj)]
+    res = np.zeros(15); J = np.zeros((15, 30)); U = np.zeros((15, 15))
+    p = lambda x: ptr(x, C.c_double)
+    sin = d(sqrt_info) if sqrt_info is not None else None
+    _check(lib().vio_prim_imu_factor_sqi(C.byref(cfg), p(a[0]), p(a[1]), p(a[2]), float(sum_dt), *[p(x) for x in b],
+                                         p(sin) if sin is not None else None, p(U), p(res), p(J)), "vio_prim_imu_factor_sqi")
+    return res, J, U
 
 
 def prim_projection_factor(cfg, pts_i, pts_j, pi, pj, inv_dep):

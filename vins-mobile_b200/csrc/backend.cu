@@ -569,10 +569,10 @@ extern "C" int vio_prim_preintegrate(const vio_config *cfg, int n, const double 
     return VIO_OK;
 }
 
-__global__ void prim_imu_factor_kernel(double *pr, double g, const double *x, double *res, double *J) {
+__global__ void prim_imu_factor_kernel(double *pr, double g, const double *x, double *res, double *J, int sqi_given) {
     if (threadIdx.x != 0) return;
     double rr[15], Jr[450];
-    imu_sqrt_info(pr + PR_COV, pr + PR_SQI);
+    if (!sqi_given) imu_sqrt_info(pr + PR_COV, pr + PR_SQI);
     imu_residual(pr, g, x, x + 7, x + 16, x + 23, rr, Jr);
     const double *U = pr + PR_SQI;
     for (int r = 0; r < 15; r++) {
@@ -583,23 +583,31 @@ __global__ void prim_imu_factor_kernel(double *pr, double g, const double *x, do
     }
 }
 
-extern "C" int vio_prim_imu_factor(const vio_config *cfg, const double *pqv, const double *jac, const double *cov, double sum_dt, const double lba[3],
-                                   const double lbg[3], const double pi[7], const double sbi[9], const double pj[7], const double sbj[9], double *res,
-                                   double *J) {
+extern "C" int vio_prim_imu_factor_sqi(const vio_config *cfg, const double *pqv, const double *jac, const double *cov, double sum_dt,
+                                       const double lba[3], const double lbg[3], const double pi[7], const double sbi[9], const double pj[7],
+                                       const double sbj[9], const double *sqrt_info_in, double *sqrt_info_out, double *res, double *J) {
     VIO_CUDA_TRY(cudaSetDevice(cfg->device));
     std::vector<double> h(PR_STRIDE, 0.0);
     memcpy(&h[PR_DP], pqv, 80); memcpy(&h[PR_LBA], lba, 24); memcpy(&h[PR_LBG], lbg, 24); h[PR_SUMDT] = sum_dt; h[PR_VALID] = 1;
     memcpy(&h[PR_JAC], jac, 225 * 8); memcpy(&h[PR_COV], cov, 225 * 8);
+    if (sqrt_info_in) memcpy(&h[PR_SQI], sqrt_info_in, 225 * 8);
     double x[32];
     memcpy(x, pi, 56); memcpy(x + 7, sbi, 72); memcpy(x + 16, pj, 56); memcpy(x + 23, sbj, 72);
     double *d;
     VIO_CUDA_TRY(cudaMalloc((void **)&d, (PR_STRIDE + 32 + 15 + 450) * 8));
     cudaMemcpy(d, h.data(), PR_STRIDE * 8, cudaMemcpyHostToDevice); cudaMemcpy(d + PR_STRIDE, x, sizeof(x), cudaMemcpyHostToDevice);
-    prim_imu_factor_kernel<<<1, 32>>>(d, cfg->gravity, d + PR_STRIDE, d + PR_STRIDE + 32, d + PR_STRIDE + 47);
+    prim_imu_factor_kernel<<<1, 32>>>(d, cfg->gravity, d + PR_STRIDE, d + PR_STRIDE + 32, d + PR_STRIDE + 47, sqrt_info_in ? 1 : 0);
     cudaMemcpy(res, d + PR_STRIDE + 32, 15 * 8, cudaMemcpyDeviceToHost);
+    if (sqrt_info_out) cudaMemcpy(sqrt_info_out, d + PR_SQI, 225 * 8, cudaMemcpyDeviceToHost);
     cudaError_t e = cudaMemcpy(J, d + PR_STRIDE + 47, 450 * 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     return e == cudaSuccess ? VIO_OK : VIO_ERR_CUDA;
+}
+
+extern "C" int vio_prim_imu_factor(const vio_config *cfg, const double *pqv, const double *jac, const double *cov, double sum_dt, const double lba[3],
+                                   const double lbg[3], const double pi[7], const double sbi[9], const double pj[7], const double sbj[9], double *res,
+                                   double *J) {
+    return vio_prim_imu_factor_sqi(cfg, pqv, jac, cov, sum_dt, lba, lbg, pi, sbi, pj, sbj, nullptr, nullptr, res, J);
 }
 
 __global__ void prim_proj_kernel(ProjConst K, const double *in, double *out) {
