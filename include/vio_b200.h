@@ -264,6 +264,19 @@ int vio_visual_imu_align(const vio_config *cfg, int batch, int max_frames, int m
                          const double *R, const double *T, const int32_t *imu_counts, const double *imu0, const double *imu,
                          const double *bg0, double *bgs, double *g, double *x, int32_t *ok);
 
+/* The same alignment inside the estimator: VINS::visualInitialAlign (VINS.cpp:1022-1102) on the back end's own window.
+ * vio_backend_set_init_sfm hands over what VINS::solveInitial has after the global SfM (VINS.cpp:889-905) -- ImageFrame::R [batch][W+1][9]
+ * (row-major) and ImageFrame::T [batch][W+1][3] of the window's frames -- and the vio_backend_process_image call that fills the window
+ * then runs, per stream and on the device: VisualIMUAlignment over the window's own IMU buffers; on success Ps / Rs from the SfM,
+ * clearDepth + triangulate on the camera poses, repropagate with the new Bgs, metric scale, Vs, gravity-aligned frame, then the
+ * first solve exactly as VINS.cpp:415-447; on failure Bgs keep the corrected bias and the window only slides (solveInitial == false).
+ * Supported case: all_image_frame holds exactly the window's frames, i.e. no MARGIN_SECOND_NEW slide happened since the stream
+ * (re)started; otherwise the attempt counts as failed and VIO_ERR_STATE is latched for the stream (use vio_visual_imu_align with the
+ * full frame list and vio_backend_set_init_window instead).  The SfM itself (relativePose / GlobalSFM) is NOT part of this library.
+ * vio_backend_get_init_result: ok = 1 / 0 of the stream's last alignment (-1: none yet), g = vins.g after it, scale = the metric scale. */
+int vio_backend_set_init_sfm(vio_backend *be, const double *R, const double *T);
+int vio_backend_get_init_result(vio_backend *be, int s, int32_t *ok, double g[3], double *scale);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Motion-only PnP tracker: FeatureTracker::solveVinsPnP (feature_tracker.cpp:107-160) and the
  * vinsPnP object it drives (vins_pnp.hpp:40-91, vins_pnp.cpp).  `batch` independent 7-frame windows advancing in lock-step.

@@ -46,6 +46,9 @@ def lib():
         if hasattr(L, "vref_imu_sqrt_info"):
             L.vref_imu_sqrt_info.argtypes = [DP, DP]
         L.vref_projection_factor.argtypes = [C.c_double, DP, DP, DP, DP, DP, DP, C.c_double, DP, DP]
+        if hasattr(L, "vref_set_init_sfm"):
+            L.vref_set_init_sfm.argtypes = [C.c_void_p, DP, DP]
+            L.vref_get_init_result.argtypes = [C.c_void_p, IP, DP, DP]
         if hasattr(L, "vref_visual_imu_align"):
             L.vref_visual_imu_align.argtypes = [C.c_int, DP, DP, IP, DP, C.c_int, DP, DP, DP, DP, DP, DP]
         if hasattr(L, "vpnp_create"):
@@ -111,6 +114,17 @@ class RefEstimator:
     def set_init_window(self, P, Q, V, Ba, Bg):
         arrs = [_d(x) for x in (P, Q, V, Ba, Bg)]
         lib().vref_set_init_window(self.h, *[_abi.ptr(x, C.c_double) for x in arrs])
+
+    def set_init_sfm(self, R, T):
+        """ImageFrame::R / T of the window's W + 1 frames as solveInitial leaves them (VINS.cpp:889-905); consumed by the process_image
+        call that fills the window: visualInitialAlign (VINS.cpp:1022-1102) + the first solve."""
+        R, T = _d(R), _d(T)
+        lib().vref_set_init_sfm(self.h, _abi.ptr(R, C.c_double), _abi.ptr(T, C.c_double))
+
+    def init_result(self):
+        ok = np.zeros(1, np.int32); g = np.zeros(3); sc = np.zeros(1)
+        lib().vref_get_init_result(self.h, _abi.ptr(ok, C.c_int32), _abi.ptr(g, C.c_double), _abi.ptr(sc, C.c_double))
+        return int(ok[0]), g, float(sc[0])
 
     def process_image(self, ids, xyz, header):
         ids = np.ascontiguousarray(ids, np.int32)

@@ -86,6 +86,11 @@ struct Est {
     int failure_occur = 0;
     Matrix3d last_R, last_R_old, back_R0;
     Vector3d last_P, last_P_old, back_P0;
+    // initialisation from SfM poses (vref_set_init_sfm): visualInitialAlign restated around the reference's own VisualIMUAlignment
+    bool sfm_pending = false, all_key = true;       // all_key: no MARGIN_SECOND_NEW slide since (re)start => all_image_frame == window
+    std::vector<Matrix3d> sR; std::vector<Vector3d> sT;
+    std::vector<Vector3d> abg;                       // bias the all_image_frame copy of each frame's pre-integration is linearised at
+    Vector3d g_init = Vector3d::Zero(); int align_ok = -1; double scale_init = 0;
     // external initialisation
     bool init_pending = false;
     std::vector<Vector3d> iP, iV; std::vector<Quaterniond> iQ; Vector3d iBa, iBg;
@@ -141,6 +146,7 @@ void clear_state(Est &e) {           // VINS::clearState, VINS.cpp:35-80
     e.tic = Vector3d(e.c.tic[0], e.c.tic[1], e.c.tic[2]);
     e.ric = Map<const Matrix<double, 3, 3, RowMajor>>(e.c.ric);
     e.frame_count = 0; e.first_imu = false; e.solver_flag = 0;
+    e.abg.assign(n, Vector3d::Zero()); e.all_key = true; e.sfm_pending = false;     // all_image_frame.clear(), VINS.cpp:62-68
     delete e.last_marg; e.last_marg = nullptr; e.last_marg_blocks.clear();
     e.feat.clear();
 }
@@ -214,6 +220,49 @@ void triangulate(Est &e) {            // FeatureManager::triangulate, feature_ma
         t.depth = v[2] / v[3];
         if (t.depth < 0.1) t.depth = e.c.init_depth;
     }
+}
+
+}  // namespace
+// oracle/init_ref.cpp: builds map<double, ImageFrame> from the arrays and calls the reference's VisualIMUAlignment (initial_aligment.cpp:222-229)
+bool vref_align_frames(int n, const double *headers, const Eigen::Matrix3d *R, const Eigen::Vector3d *T, IntegrationBase **pre,
+                       Eigen::Vector3d *Bgs, Eigen::Vector3d &g, Eigen::VectorXd &x);
+namespace {
+
+// VINS::visualInitialAlign (VINS.cpp:1022-1102) for the case all_image_frame == the window's frames (no MARGIN_SECOND_NEW slide since the
+// stream started, so every frame of the map is a keyframe; ImageFrame::R / T come from the caller's SfM, VINS.cpp:889-905).
+bool visual_initial_align(Est &e) {
+    const int W = e.W, n = W + 1;
+    // all_image_frame's pre-integrations are separate objects (tmp_pre_integration, VINS.cpp:396-398: zero biases at creation) that
+    // keep the bias of the last alignment attempt (solveGyroscopeBias repropagates them, initial_aligment.cpp:41-45)
+    std::vector<IntegrationBase *> tmp(n);
+    for (int i = 0; i < n; i++) if (!e.pre[i]) { e.align_ok = 0; return false; }   // no IMU sample ever arrived for a frame (the reference would dereference NULL)
+    for (int i = 0; i < n; i++) {
+        IntegrationBase *src = e.pre[i];
+        tmp[i] = new IntegrationBase{src->linearized_acc, src->linearized_gyr, Vector3d::Zero(), e.abg[i]};
+        for (size_t k = 0; k < src->dt_buf.size(); k++) tmp[i]->push_back(src->dt_buf[k], src->acc_buf[k], src->gyr_buf[k]);
+    }
+    TIC_X = e.tic.x(); TIC_Y = e.tic.y(); TIC_Z = e.tic.z();      // initial_aligment.cpp reads the globals (global_param.cpp:37-39 sets them per device)
+    Vector3d g; VectorXd x;
+    const bool ok = vref_align_frames(n, e.Headers.data(), e.sR.data(), e.sT.data(), tmp.data(), e.Bgs.data(), g, x);
+    for (int i = 0; i < n; i++) { e.abg[i] = e.Bgs[0]; delete tmp[i]; }
+    e.align_ok = ok ? 1 : 0;
+    if (!ok) return false;
+    for (int i = 0; i <= e.frame_count; i++) { e.Ps[i] = e.sT[i]; e.Rs[i] = e.sR[i]; }
+    for (auto &t : e.feat) t.depth = -1.0;                       // clearDepth(-1)
+    { const Vector3d keep = e.tic; e.tic.setZero(); triangulate(e); e.tic = keep; }      // "triangulat on cam pose, no tic"
+    const double s = (x.tail<1>())(0);
+    e.scale_init = s;
+    for (int i = 0; i <= W; i++) e.pre[i]->repropagate(Vector3d::Zero(), e.Bgs[i]);
+    for (int i = e.frame_count; i >= 0; i--) e.Ps[i] = s * e.Ps[i] - e.Rs[i] * e.tic - (s * e.Ps[0] - e.Rs[0] * e.tic);
+    for (int kv = 0; kv < n; kv++) e.Vs[kv] = e.sR[kv] * x.segment<3>(kv * 3);
+    for (auto &t : e.feat) { if (!in_solve(e, t)) continue; t.depth *= s; }
+    Matrix3d R0 = Utility::g2R(g);
+    const double yaw0 = Utility::R2ypr(R0).x();
+    R0 = Utility::ypr2R(Vector3d{-yaw0, 0, 0}) * R0;
+    g = R0 * g;
+    e.g_init = g;
+    for (int i = 0; i <= e.frame_count; i++) { e.Ps[i] = R0 * e.Ps[i]; e.Rs[i] = R0 * e.Rs[i]; e.Vs[i] = R0 * e.Vs[i]; }
+    return true;
 }
 
 int feature_count(Est &e) { int s = 0; for (auto &t : e.feat) s += in_solve(e, t); return s; }
@@ -456,6 +505,8 @@ void slide_window(Est &e) {          // VINS.cpp:1149-1273 + feature_manager.cpp
         }
         e.Headers[W] = e.Headers[W - 1]; e.Ps[W] = e.Ps[W - 1]; e.Vs[W] = e.Vs[W - 1]; e.Rs[W] = e.Rs[W - 1];
         e.Bas[W] = e.Bas[W - 1]; e.Bgs[W] = e.Bgs[W - 1];          // Q9: Bas/Bgs are NOT shifted for i < W
+        for (int i = 0; i < W; i++) e.abg[i] = e.abg[i + 1];       // all_image_frame.erase(begin, Headers[0]), VINS.cpp:1186-1193
+        e.abg[W] = Vector3d::Zero();                                // the next tmp_pre_integration starts from zero biases
         delete e.pre[W];
         e.pre[W] = new IntegrationBase{e.acc_0, e.gyr_0, e.Bas[W], e.Bgs[W]};
         e.dt_buf[W].clear(); e.acc_buf[W].clear(); e.gyr_buf[W].clear();
@@ -493,6 +544,7 @@ void slide_window(Est &e) {          // VINS.cpp:1149-1273 + feature_manager.cpp
             e.acc_buf[W - 1].push_back(e.acc_buf[W][i]);
             e.gyr_buf[W - 1].push_back(e.gyr_buf[W][i]);
         }
+        if (e.solver_flag == 0) e.all_key = false;                  // the dropped frame stays in all_image_frame as a non-keyframe
         e.Headers[W - 1] = e.Headers[W]; e.Ps[W - 1] = e.Ps[W]; e.Vs[W - 1] = e.Vs[W]; e.Rs[W - 1] = e.Rs[W];
         e.Bas[W - 1] = e.Bas[W]; e.Bgs[W - 1] = e.Bgs[W];
         delete e.pre[W];
@@ -522,7 +574,25 @@ int process_image(Est &e, int n, const int *ids, const double *xyz, double heade
     if (e.solver_flag == 0) {
         if (e.frame_count == e.W) {
             if (e.last_track_num < 20) { clear_state(e); return 2; }      // VINS.cpp:401-405
-            if (e.init_pending) {
+            if (e.sfm_pending) {                            // solveInitial() from the SfM poses on: VINS.cpp:1022-1102, then :415-447
+                e.sfm_pending = false;
+                if (e.all_key && visual_initial_align(e)) {
+                    solve(e);
+                    if (e.cost1 > 200) {
+                        delete e.last_marg; e.last_marg = nullptr;
+                        e.solver_flag = 0;
+                        slide_window(e);
+                    } else {
+                        e.failure_occur = 0;
+                        e.solver_flag = 1;
+                        slide_window(e);
+                        remove_failures(e);
+                        e.last_R = e.Rs[e.W]; e.last_P = e.Ps[e.W]; e.last_R_old = e.Rs[0]; e.last_P_old = e.Ps[0];
+                    }
+                } else {
+                    slide_window(e);
+                }
+            } else if (e.init_pending) {
                 e.init_pending = false;
                 for (int i = 0; i <= e.W; i++) { e.Ps[i] = e.iP[i]; e.Rs[i] = e.iQ[i].normalized().toRotationMatrix(); e.Vs[i] = e.iV[i]; e.Bas[i] = e.iBa; e.Bgs[i] = e.iBg; }
                 for (auto &t : e.feat) t.depth = -1.0;       // clearDepth(-1), VINS.cpp:1047-1050
@@ -625,6 +695,20 @@ void vref_set_init_window(void *h, const double *P, const double *Q, const doubl
     }
     e.iBa = Vector3d(Ba[0], Ba[1], Ba[2]); e.iBg = Vector3d(Bg[0], Bg[1], Bg[2]);
     e.init_pending = true;
+}
+void vref_set_init_sfm(void *h, const double *R, const double *T) {
+    Est &e = *(Est *)h;
+    e.sR.clear(); e.sT.clear();
+    for (int i = 0; i <= e.W; i++) {
+        e.sR.push_back(Map<const Matrix<double, 3, 3, RowMajor>>(R + 9 * i));
+        e.sT.emplace_back(T[3 * i], T[3 * i + 1], T[3 * i + 2]);
+    }
+    e.sfm_pending = true;
+}
+void vref_get_init_result(void *h, int *ok, double *g, double *scale) {
+    Est &e = *(Est *)h;
+    *ok = e.align_ok; *scale = e.scale_init;
+    for (int i = 0; i < 3; i++) g[i] = e.g_init[i];
 }
 int vref_process_image(void *h, int n, const int *ids, const double *xyz, double header) {
     const auto t0 = std::chrono::steady_clock::now();

@@ -10,6 +10,26 @@
 #include <fcntl.h>
 #include "initial_aligment.hpp"
 
+// Used by oracle/backend_ref.cpp (visual_initial_align): the window's frames as all_image_frame, then the reference's VisualIMUAlignment.
+// pre[k] are the all_image_frame pre-integration objects (owned by the caller); Bgs has WINDOW_SIZE + 1 entries.
+bool vref_align_frames(int n, const double *headers, const Eigen::Matrix3d *R, const Eigen::Vector3d *T, IntegrationBase **pre,
+                       Eigen::Vector3d *Bgs, Eigen::Vector3d &g, Eigen::VectorXd &x) {
+    std::map<double, ImageFrame> all;
+    for (int k = 0; k < n; k++) {
+        std::map<int, Eigen::Vector3d> pts;
+        ImageFrame f(pts, headers[k]);
+        f.R = R[k]; f.T = T[k]; f.pre_integration = pre[k];
+        all.insert(std::make_pair(headers[k], f));
+    }
+    fflush(stdout);
+    const int saved = dup(1), nul = open("/dev/null", O_WRONLY);
+    dup2(nul, 1);
+    const bool ok = VisualIMUAlignment(all, Bgs, g, x);
+    std::cout.flush(); fflush(stdout);
+    dup2(saved, 1); close(nul); close(saved);
+    return ok;
+}
+
 extern "C" {
 
 // n frames; R [n][9] row-major (ImageFrame::R), T [n][3] (ImageFrame::T); counts [n] samples of the interval ENDING at frame k

@@ -133,3 +133,52 @@ def align_case(sid, n, scale=2.5, gyro_bias=(0.01, -0.02, 0.015), rot_noise=2e-3
             imu0[k, :3] = tr["acc"][j]; imu0[k, 3:] = tr["gyr"][j] + np.asarray(gyro_bias)
     g_c0 = Rc0 @ np.array([0.0, 0.0, 9.805])
     return dict(n=n, R=R, T=T, counts=counts, imu0=imu0, imu=imu, tic=cfg_tic, scale=scale, g=g_c0, gyro_bias=np.asarray(gyro_bias))
+
+
+def sfm_window(tr, k, W, scale=2.5, seed=5, mirrored=False):
+    """What VINS::solveInitial holds after the global SfM (VINS.cpp:889-905) for the window ending at keyframe k: ImageFrame::R (body
+    attitude in the SfM frame c0) and ImageFrame::T (camera position in c0, unknown scale) of keyframes k-W..k, from the synthetic ground
+    truth; c0 is rotated at random against the world.  mirrored=True negates T (a reflected reconstruction: the alignment must reject it)."""
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    w, x, y, z = q
+    Rc0 = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                    [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                    [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    tic = np.array([0.0, 0.092, 0.01])
+    fr = list(range(k - W, k + 1))
+    R = np.stack([Rc0 @ tr["R"][i] for i in fr])
+    Pc = np.stack([tr["P"][i] + tr["R"][i] @ tic for i in fr])
+    T = (Pc - Pc[0]) @ Rc0.T / scale
+    return R, (-T if mirrored else T)
+
+
+def drive_sfm(est, tr, k, W, sfm=None):
+    """Like drive(), but the stream initialises from SfM poses (set_init_sfm) instead of a supplied window; one IMU sample precedes the
+    first image (as on a device: the reference creates pre_integrations[0] from it, VINS.cpp:340-346).  sfm = (R, T) or None."""
+    per = tr["per"]
+    batched = hasattr(est, "B")
+    if k == 0:
+        if batched:
+            est.process_imu(np.array([[0.005]]), tr["acc"][:1][:, None, :], tr["gyr"][:1][:, None, :])
+        else:
+            est.process_imu(0.005, tr["acc"][0], tr["gyr"][0])
+    else:
+        sl = slice((k - 1) * per, k * per)
+        dts = np.diff(np.concatenate([[tr["t_kf"][k - 1]], tr["imu_t"][sl]]))
+        if batched:
+            est.process_imu(dts[:, None], tr["acc"][sl][:, None, :], tr["gyr"][sl][:, None, :])
+        else:
+            for d, a, g in zip(dts, tr["acc"][sl], tr["gyr"][sl]):
+                est.process_imu(d, a, g)
+    if sfm is not None:
+        R, T = sfm
+        if batched:
+            est.set_init_sfm(R[None], T[None])
+        else:
+            est.set_init_sfm(R, T)
+    ids, xyz = tr["frames"][k]
+    if batched:
+        est.process_image_single(ids, xyz, tr["t_kf"][k])
+    else:
+        est.process_image(ids, xyz, tr["t_kf"][k])

@@ -393,6 +393,90 @@ def test_failure_detection_clears_and_stream_recovers(api, cfg, synth):
         ref.close(); gpu.close()
 
 
+def test_initialisation_from_sfm_poses_matches_reference(api, cfg, synth):
+    """VINS::visualInitialAlign (VINS.cpp:1022-1102) on the device: the stream gets only IMU, image_msg and -- when the window is full -- the
+    SfM poses of its frames (ImageFrame::R / T, VINS.cpp:889-905).  First attempt: a mirrored reconstruction, VisualIMUAlignment must
+    reject it (scale < 0): the window slides, Bgs keep the corrected bias.  Second attempt: accepted -- scale, gravity-aligned window,
+    velocities, re-triangulated depths -- and the first solve follows; both estimators stay in step afterwards."""
+    from be_common import drive_sfm, sfm_window
+    W = cfg.window_size
+    for sid in (0, 2):
+        tr = synth.make_tracks(sid, 20, max_cnt=cfg.max_cnt)
+        ref, gpu = bo.RefEstimator(cfg), api.BackEnd(cfg)
+        try:
+            for k in range(18):
+                sfm = None
+                if k == W:
+                    sfm = sfm_window(tr, k, W, mirrored=True)
+                if k == W + 1:
+                    sfm = sfm_window(tr, k, W)
+                with Quiet():
+                    drive_sfm(ref, tr, k, W, sfm)
+                drive_sfm(gpu, tr, k, W, sfm)
+                ri, gi = ref.info(), gpu.info()
+                for key in ("solver_flag", "marg_flag", "frame_count", "failure", "last_track_num"):
+                    assert ri[key] == gi[key], f"stream {sid} kf {k}: {key} {ri[key]} vs {gi[key]}"
+                assert gpu.error() == 0
+                if k >= W:
+                    rok, rg, rsc = ref.init_result()
+                    gok, gg, gsc = gpu.init_result()
+                    assert rok == gok == (0 if k == W else 1), (k, rok, gok)
+                    rs, gs = ref.state(), gpu.state()
+                    if k == W:                                       # rejected attempt: Bgs += delta_bg and nothing else
+                        assert rel_err(gs["Bg"], rs["Bg"]) < 1e-9, (k, gs["Bg"][0], rs["Bg"][0])
+                    else:                                            # after a solve: the (weakly observable, ~1e-4) bias to 1e-6 absolute
+                        assert np.abs(gs["Bg"] - rs["Bg"]).max() < 1e-6, (k, gs["Bg"][0], rs["Bg"][0])
+                    if k > W:
+                        assert rel_err(gg, rg) < 1e-9 and abs(gsc / rsc - 1) < 1e-9 and abs(gsc / 2.5 - 1) < 0.2
+                        print(f"[init] stream {sid} kf {k}: P {rel_err(gs['P'], rs['P']):.2e} V {rel_err(gs['V'], rs['V']):.2e} Q {quat_err(gs['Q'], rs['Q']):.2e}")
+                        _same_window(rs, gs, 1e-6 if k == W + 1 else 1e-4)
+                        rf, gf = ref.features(), gpu.features()
+                        assert np.array_equal(rf["ids"], gf["ids"])
+                        assert rel_err(gf["depth"], rf["depth"]) < (1e-5 if k == W + 1 else 1e-3)
+            assert gpu.info()["solver_flag"] == 1
+            # and the initialised window is the physical one: metric displacement over the window against the ground truth
+            gs = gpu.state()
+            kf = [int(np.argmin(np.abs(tr["t_kf"] - h))) for h in gs["headers"]]
+            d_est = np.linalg.norm(gs["P"][W] - gs["P"][0]); d_true = np.linalg.norm(tr["P"][kf[W]] - tr["P"][kf[0]])
+            assert abs(d_est / d_true - 1) < 0.1, (d_est, d_true)
+        finally:
+            ref.close(); gpu.close()
+
+
+def test_initialisation_from_sfm_needs_all_keyframes(api, cfg, synth):
+    """The device path covers all_image_frame == window frames.  After a MARGIN_SECOND_NEW slide in the INITIAL phase a non-keyframe stays in
+    the reference's map, which the back end does not keep: the attempt is refused (VIO_ERR_STATE latched, window slides)."""
+    from be_common import drive_sfm, sfm_window
+    W = cfg.window_size
+    tr = synth.make_tracks(1, 16, max_cnt=cfg.max_cnt)
+    gpu = api.BackEnd(cfg)
+    try:
+        for k in range(W + 1):
+            drive_sfm(gpu, tr, k, W, None)                       # window full, no initialisation supplied: slides
+        # the newest keyframe's measurements twice more: the parallax test compares the second and third newest frames
+        # (feature_manager.cpp:150-160), so the second repetition gives zero parallax -> MARGIN_SECOND_NEW
+        ids, xyz = tr["frames"][W]
+        per = tr["per"]
+
+        def imu_of(k):
+            sl = slice((k - 1) * per, k * per)
+            dts = np.diff(np.concatenate([[tr["t_kf"][k - 1]], tr["imu_t"][sl]]))
+            gpu.process_imu(dts[:, None], tr["acc"][sl][:, None, :], tr["gyr"][sl][:, None, :])
+
+        for k in (W + 1, W + 2):
+            imu_of(k)
+            gpu.process_image_single(ids, xyz, tr["t_kf"][k])
+        assert gpu.info()["marg_flag"] == 1 and gpu.info()["solver_flag"] == 0
+        imu_of(W + 3)
+        R, T = sfm_window(tr, W + 3, W)
+        gpu.set_init_sfm(R[None], T[None])
+        gpu.process_image_single(*tr["frames"][W + 3], tr["t_kf"][W + 3])
+        assert gpu.error(clear=True) == 3                      # VIO_ERR_STATE
+        assert gpu.info()["solver_flag"] == 0 and gpu.init_result()[0] == 0
+    finally:
+        gpu.close()
+
+
 def test_initialisation_rejected_above_cost_200(api, cfg, synth):
     """VINS.cpp:415-425: when the first solve ends with final_cost > 200 the initialisation is discarded -- prior deleted, solver_flag stays
     INITIAL, the window only slides.  A grossly wrong initial window provokes it; a good one on the next full window succeeds."""

@@ -100,6 +100,8 @@ def lib():
             L.vio_prim_imu_factor.argtypes = [cfgp, DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP]
             L.vio_prim_projection_factor.argtypes = [cfgp, DP, DP, DP, DP, C.c_double, DP, DP]
             L.vio_prim_imu_factor_sqi.argtypes = [cfgp, DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
+            L.vio_backend_set_init_sfm.argtypes = [vp, DP, DP]
+            L.vio_backend_get_init_result.argtypes = [vp, C.c_int, IP, DP, DP]
             L.vio_visual_imu_align.argtypes = [cfgp, C.c_int, C.c_int, C.c_int, IP, DP, DP, IP, DP, DP, DP, DP, DP, DP, IP]
         _lib = L
     return _lib
@@ -402,6 +404,18 @@ class BackEnd:
     def solve(self):
         """VINS::solve_ceres() alone on the current window of every NON_LINEAR stream"""
         _check(lib().vio_backend_solve(self.h), "vio_backend_solve")
+
+    def set_init_sfm(self, R, T):
+        """ImageFrame::R [B][W+1][3][3] / T [B][W+1][3] after the global SfM (VINS.cpp:889-905); visualInitialAlign then runs on the device
+        inside the process_image call that fills the window."""
+        R = np.ascontiguousarray(R, np.float64); T = np.ascontiguousarray(T, np.float64)
+        assert R.shape == (self.B, self.W + 1, 3, 3) and T.shape == (self.B, self.W + 1, 3)
+        _check(lib().vio_backend_set_init_sfm(self.h, ptr(R, C.c_double), ptr(T, C.c_double)), "vio_backend_set_init_sfm")
+
+    def init_result(self, s=0):
+        ok = np.zeros(1, np.int32); g = np.zeros(3); sc = np.zeros(1)
+        _check(lib().vio_backend_get_init_result(self.h, s, ptr(ok, C.c_int32), ptr(g, C.c_double), ptr(sc, C.c_double)), "vio_backend_get_init_result")
+        return int(ok[0]), g, float(sc[0])
 
     def error(self, s=0, clear=False):
         """latched per-stream error code (VIO_ERR_CAPACITY ...), optionally cleared"""

@@ -4,6 +4,7 @@
 // step is a fixed sequence of kernels with one CTA per stream -- no host round trip inside processImage.
 // No CPU fallback.
 #include "be_marg.cuh"
+#include "be_align.cuh"
 
 #include <algorithm>
 #include <new>
@@ -29,6 +30,8 @@ struct vio_backend {
     int be_threads;
     cudaEvent_t evt_ready, evt_consumed;
     bool consumed_valid, record_consumed;
+    // initialisation from SfM poses (vio_backend_set_init_sfm): alignment arguments over the back end's own arrays + scratch, lazily allocated
+    AlignArgs align; bool sfm_armed;
 };
 
 template <typename T>
@@ -261,6 +264,74 @@ extern "C" int vio_backend_set_init_window(vio_backend *be, const double *P, con
     return e == cudaSuccess ? VIO_OK : VIO_ERR_CUDA;
 }
 
+__global__ void set_sfm_pending_kernel(BeState s) {
+    if (threadIdx.x == 0) S_iv(s, blockIdx.x)[IV_INIT_PENDING] = 2;
+}
+
+// ImageFrame::R / T of the window's W + 1 frames as VINS::solveInitial leaves them after the global SfM (VINS.cpp:889-905: R = body attitude
+// in the SfM frame, T = camera position in it, unknown scale).  Consumed by the vio_backend_process_image call that fills the window:
+// VisualIMUAlignment + the rest of visualInitialAlign (VINS.cpp:1022-1102) run on the device, then the first solve (VINS.cpp:415-447).
+extern "C" int vio_backend_set_init_sfm(vio_backend *be, const double *R, const double *T) {
+    if (!be || !R || !T) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    BeState &s = be->s;
+    const size_t B = s.B, NF = s.NF, NS = 3 * NF + 4;
+    if (!s.init_sfm) {
+        int rc = dalloc(be, &s.init_sfm, B * NF * 12);
+        AlignArgs &a = be->align;
+        memset(&a, 0, sizeof(a));
+        a.B = s.B; a.F = s.NF; a.MAXIMU = s.MAXIMU; a.NS = (int)NS;
+        double *scr = nullptr; int *iscr = nullptr;
+        const size_t nd = B * NF * PR_STRIDE + 2 * B * NS * NS + B * NS + B * NF * 110 + 2 * B * NS + B * 3 + B * 3 + B * NS;
+        if (!rc) rc = dalloc(be, &scr, nd);
+        if (!rc) rc = dalloc(be, &iscr, B * NS + B);
+        if (rc) { s.init_sfm = nullptr; return rc; }
+        double *p = scr;
+        a.pre = p; p += B * NF * PR_STRIDE;
+        a.A = p; p += B * NS * NS;
+        a.Aw = p; p += B * NS * NS;
+        a.rhs = p; p += B * NS;
+        a.pairs = p; p += B * NF * 110;
+        a.xs = p; p += 2 * B * NS;
+        a.bgs_out = p; p += B * 3;
+        a.g_out = p; p += B * 3;
+        a.x_out = p; p += B * NS;
+        a.perm = iscr; a.ok = iscr + B * NS;
+        a.R = s.init_sfm; a.T = s.init_sfm + B * NF * 9;
+        a.counts = s.imu_cnt; a.imu = s.imu_buf;
+        a.imu0 = s.pre + PR_LIN_ACC; a.imu0_stride = PR_STRIDE;
+        a.bg0 = s.Bgs; a.bg0_stride = (int)(3 * NF);
+        a.abg = s.pre + PR_ABG; a.abg_stride = PR_STRIDE;
+        memcpy(a.tic, be->cfg.tic, 24);
+        a.g_norm = be->cfg.gravity; a.g_thr = 3.0;          // G_NORM, G_THRESHOLD (global_param.hpp:49-50)
+        memcpy(a.noise, s.noise, sizeof(a.noise));
+    }
+    VIO_CUDA_TRY(cudaMemcpyAsync(s.init_sfm, R, B * NF * 9 * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(s.init_sfm + B * NF * 9, T, B * NF * 3 * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    set_sfm_pending_kernel<<<s.B, 32, 0, be->stream>>>(s);
+    be->launches++;
+    be->sfm_armed = true;
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));        // R / T are the caller's (pageable) memory
+    return VIO_OK;
+}
+
+// Outcome of the last VisualIMUAlignment of stream s: ok = 1 / 0 (-1: none yet since the stream started), g = gravity in the window's frame
+// after the alignment (vins.g, VINS.cpp:1086-1091; ~ (0, 0, G_NORM)), scale = the metric scale applied to the SfM.
+extern "C" int vio_backend_get_init_result(vio_backend *be, int sidx, int32_t *ok, double g[3], double *scale) {
+    if (!be || !ok || !g || !scale || sidx < 0 || sidx >= be->s.B) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    int iv[IV_COUNT];
+    VIO_CUDA_TRY(cudaMemcpy(iv, be->s.iv + (size_t)sidx * IV_COUNT, sizeof(iv), cudaMemcpyDeviceToHost));
+    *ok = iv[IV_ALIGN_OK]; g[0] = g[1] = g[2] = 0; *scale = 0;
+    if (be->s.init_sfm && iv[IV_ALIGN_OK] >= 0) {
+        const AlignArgs &a = be->align;
+        VIO_CUDA_TRY(cudaMemcpy(g, a.g_out + 3 * sidx, 24, cudaMemcpyDeviceToHost));
+        VIO_CUDA_TRY(cudaMemcpy(scale, a.x_out + (size_t)sidx * a.NS + 3 * be->s.NF + 2, 8, cudaMemcpyDeviceToHost));
+    }
+    return VIO_OK;
+}
+
 __global__ void clear_init_pending_kernel(BeState s) {
     int *iv = S_iv(s, blockIdx.x);
     if (threadIdx.x == 0 && iv[IV_ACTION] == ACT_INIT_SOLVE) iv[IV_INIT_PENDING] = 0;
@@ -271,6 +342,10 @@ static int run_process_image(vio_backend *be, const int32_t *counts, const int32
     cudaStream_t st = be->stream;
     VIO_LAUNCH(be->timer, st, "addfeat_kernel", (addfeat_kernel<<<s.B, 256, 0, st>>>(s, counts, ids, xyz, headers_dev)));
     if (be->record_consumed) { cudaEventRecord(be->evt_consumed, st); be->consumed_valid = true; be->record_consumed = false; }   // image_msg fully read
+    if (be->sfm_armed) {        // VINS::visualInitialAlign for the streams whose window fills with SfM poses pending; a no-op for the others
+        VIO_LAUNCH(be->timer, st, "init_align_kernel", (init_align_kernel<<<s.B, ALIGN_THREADS, 0, st>>>(s, be->align)));
+        be->launches += 1;
+    }
     VIO_LAUNCH(be->timer, st, "triangulate_kernel", (triangulate_kernel<<<s.B, 128, 0, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "prepare_kernel", (prepare_kernel<<<s.B, 256, 0, st>>>(s)));
     VIO_LAUNCH(be->timer, st, "solve_kernel", (solve_kernel<<<s.B, be->be_threads, be->solve_smem, st>>>(s, be->use_smem_solve, be->solve_vec_off)));
@@ -645,7 +720,6 @@ extern "C" int vio_prim_projection_factor(const vio_config *cfg, const double pt
 }
 
 // ================================================================== visual-inertial alignment (linear half)
-#include "be_align.cuh"
 
 extern "C" int vio_visual_imu_align(const vio_config *cfg, int batch, int max_frames, int max_imu, const int32_t *n_frames, const double *R,
                                     const double *T, const int32_t *imu_counts, const double *imu0, const double *imu, const double *bg0,
@@ -690,6 +764,7 @@ extern "C" int vio_visual_imu_align(const vio_config *cfg, int batch, int max_fr
     a.perm = q; q += B * NS;
     a.ok = q;
     a.n_frames = dN; a.counts = dC; a.R = dR; a.T = dT; a.imu0 = dI0; a.imu = dI; a.bg0 = dBg;
+    a.imu0_stride = 6; a.bg0_stride = 3; a.abg = nullptr; a.abg_stride = 0;
     memcpy(a.tic, cfg->tic, 24);
     a.g_norm = cfg->gravity;             // G_NORM, global_param.hpp:50
     a.g_thr = 3.0;                       // G_THRESHOLD, global_param.hpp:49

@@ -10,7 +10,7 @@
 //   A.ldlt().solve(b)      Eigen 3.3 Cholesky/LDLT.h:277-374 (unblocked, diagonal pivoting, lower) and :545-580 (solve)
 //   IntegrationBase::repropagate                          integration_base.h:46-61 (be_factors.cuh: pre_init + pre_propagate_warp)
 #pragma once
-#include "be_factors.cuh"
+#include "be_kernels.cuh"
 
 namespace be {
 
@@ -19,7 +19,9 @@ constexpr int ALIGN_THREADS = 128;
 struct AlignArgs {
     int B, F, MAXIMU, NS;                       // NS = 3 F + 4: leading dimension of the normal matrix
     const int *n_frames, *counts;               // [B], [B][F]
-    const double *R, *T, *imu0, *imu, *bg0;     // [B][F][9], [B][F][3], [B][F][6], [B][F][MAXIMU][7], [B][3]
+    const double *R, *T, *imu0, *imu, *bg0;     // [B][F][9], [B][F][3], [B][F][imu0_stride] (acc_0, gyr_0 first), [B][F][MAXIMU][7], [B][bg0_stride]
+    int imu0_stride, bg0_stride;                // 6 and 3 for the stand-alone entry; PR_STRIDE and 3 NF when the arrays are the back end's own
+    const double *abg; int abg_stride;          // optional [B][F][abg_stride]: bias each frame's FIRST integration uses (nullptr: bg0 for all)
     double tic[3], g_norm, g_thr, noise[6];
     double *pre, *A, *Aw, *rhs, *pairs, *xs;    // scratch: [B][F][PR_STRIDE], [B][NS NS], [B][NS NS], [B][NS], [B][F][110], [B][2 NS]
     int *perm;                                  // [B][NS] transpositions
@@ -101,12 +103,13 @@ __device__ inline void align_ldlt_solve(double *M, int ld, int n, const double *
 }
 
 // pre-integrate (or re-propagate) every frame's interval with gyroscope bias bg; warps take frames round-robin
-__device__ inline void align_integrate(const AlignArgs &a, int b, int n, V3 bg, PreScratch *scr) {
+__device__ inline void align_integrate(const AlignArgs &a, int b, int n, V3 bg, bool per_frame_bias, PreScratch *scr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = warp; k < n; k += ALIGN_THREADS / 32) {
         double *pr = a.pre + ((size_t)b * a.F + k) * PR_STRIDE;
-        const double *i0 = a.imu0 + ((size_t)b * a.F + k) * 6;
-        if (lane == 0) pre_init(pr, ld3(i0), ld3(i0 + 3), v3(0, 0, 0), bg);
+        const double *i0 = a.imu0 + ((size_t)b * a.F + k) * a.imu0_stride;
+        const V3 bgk = (per_frame_bias && a.abg) ? ld3(a.abg + ((size_t)b * a.F + k) * a.abg_stride) : bg;
+        if (lane == 0) pre_init(pr, ld3(i0), ld3(i0 + 3), v3(0, 0, 0), bgk);
         __syncwarp();
         const int cnt = min(a.counts[(size_t)b * a.F + k], a.MAXIMU);
         const double *e = a.imu + ((size_t)b * a.F + k) * a.MAXIMU * 7;
@@ -189,19 +192,17 @@ __device__ inline void align_gather(const AlignArgs &a, int b, int n, int m, int
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(ALIGN_THREADS) visual_imu_align_kernel(AlignArgs a) {
-    __shared__ PreScratch scr[ALIGN_THREADS / 32];
-    __shared__ double sh[16];
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const int n = min(a.n_frames[b], a.F);
+// VisualIMUAlignment for stream b with n frames; whole CTA; results in a.bgs_out / g_out / x_out / ok.  Returns ok.
+__device__ inline int align_core(const AlignArgs &a, int b, int n, PreScratch *scr, double *sh) {
+    const int tid = threadIdx.x;
     double *A = a.A + (size_t)b * a.NS * a.NS, *Aw = a.Aw + (size_t)b * a.NS * a.NS, *rhs = a.rhs + (size_t)b * a.NS;
     double *x = a.xs + (size_t)b * 2 * a.NS, *temp = x + a.NS;
     int *trn = a.perm + (size_t)b * a.NS;
     double *pairs = a.pairs + (size_t)b * a.F * 110;
     if (tid == 0) a.ok[b] = 0;
-    if (n < 2) return;
-    V3 bg = ld3(a.bg0 + 3 * b);
-    align_integrate(a, b, n, bg, scr);
+    if (n < 2) return 0;
+    V3 bg = ld3(a.bg0 + (size_t)b * a.bg0_stride);
+    align_integrate(a, b, n, bg, true, scr);
 
     // ---- solveGyroscopeBias
     if (tid == 0) {
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS) visual_imu_align_kernel(AlignAr
     bg = bg + v3(x[0], x[1], x[2]);
     __syncthreads();
     if (tid == 0) st3(a.bgs_out + 3 * b, bg);
-    align_integrate(a, b, n, bg, scr);
+    align_integrate(a, b, n, bg, false, scr);
 
     // ---- SolveScale
     int ns = 3 * n + 4;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS) visual_imu_align_kernel(AlignAr
     V3 g = v3(x[ns - 4], x[ns - 3], x[ns - 2]);
     double sc = x[ns - 1] / 100.0;
     __syncthreads();
-    if (fabs(norm(g) - a.g_norm) > a.g_thr || sc < 0) { if (tid == 0) st3(a.g_out + 3 * b, g); return; }
+    if (fabs(norm(g) - a.g_norm) > a.g_thr || sc < 0) { if (tid == 0) st3(a.g_out + 3 * b, g); __syncthreads(); return 0; }
 
     // ---- RefineGravity
     ns = 3 * n + 3;
@@ -284,6 +285,106 @@ __global__ void __launch_bounds__(ALIGN_THREADS) visual_imu_align_kernel(AlignAr
     sc = x[ns - 1] / 100.0;
     for (int e = tid; e < a.NS; e += ALIGN_THREADS) xo[e] = e < ns - 1 ? x[e] : (e == ns - 1 ? sc : 0.0);
     if (tid == 0) { st3(a.g_out + 3 * b, g0); a.ok[b] = sc > 0.0 ? 1 : 0; }
+    __syncthreads();
+    return sc > 0.0 ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(ALIGN_THREADS) visual_imu_align_kernel(AlignArgs a) {
+    __shared__ PreScratch scr[ALIGN_THREADS / 32];
+    __shared__ double sh[16];
+    align_core(a, blockIdx.x, min(a.n_frames[blockIdx.x], a.F), scr, sh);
+}
+
+// ---- VINS::visualInitialAlign (VINS.cpp:1022-1102) on the back end's own state --------------------------------------------------
+// Runs before triangulate_kernel when the host has supplied the SfM poses of the window's frames (vio_backend_set_init_sfm,
+// IV_INIT_PENDING == 2) and the feature kernel decided ACT_INIT_SOLVE.  Supported case: all_image_frame holds exactly the window's
+// frames (no MARGIN_SECOND_NEW slide since the stream started -- IV_ALLKEY), so every frame of the map is a keyframe.
+//   alignment fails  -> Bgs keep the corrected bias (solveGyroscopeBias has already added it), action becomes ACT_SLIDE_ONLY
+//   alignment passes -> Ps / Rs from the SfM, depths re-triangulated on the camera poses (tic = 0), pre-integrations re-propagated with the
+//                       new Bgs, metric scale, velocities, gravity-aligned frame; IV_INIT_PENDING = 3 tells triangulate_kernel that the window
+//                       is ready and the solve follows as in the reference (VINS.cpp:415-447).
+__device__ inline M3 g2R_dev(V3 g) {                  // Utility::g2R, utility.cpp:8-19 (Quaterniond::FromTwoVectors(ng1, e_z))
+    const double ng = norm(g);
+    const V3 v0 = v3(g.x / ng, g.y / ng, g.z / ng), v1 = v3(0, 0, 1);
+    const double c = dot(v1, v0);
+    Q4 q;
+    if (c < -1.0 + 1e-12) q = q4(1, 0, 0, 0);         // antiparallel: Eigen picks an orthogonal axis by SVD; any half turn about one maps g to +z
+    else {
+        const V3 axis = cross(v0, v1);
+        const double sq = sqrt((1.0 + c) * 2.0), invs = 1.0 / sq;
+        q = q4(axis.x * invs, axis.y * invs, axis.z * invs, sq * 0.5);
+    }
+    M3 R0 = q2R(q);
+    const double yaw = R2ypr(R0).x;
+    R0 = ypr2R(v3(-yaw, 0, 0)) * R0;
+    R0 = ypr2R(v3(-90, 0, 0)) * R0;
+    return R0;
+}
+
+__global__ void __launch_bounds__(ALIGN_THREADS) init_align_kernel(BeState s, AlignArgs a) {
+    __shared__ PreScratch scr[ALIGN_THREADS / 32];
+    __shared__ double sh[16];
+    __shared__ int sh_bad;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int *iv = S_iv(s, b);
+    if (iv[IV_ACTION] != ACT_INIT_SOLVE || iv[IV_INIT_PENDING] != 2) return;
+    const int n = s.NF, W = s.W;
+    if (tid == 0) { sh_bad = iv[IV_ALLKEY] ? 0 : 1; }
+    __syncthreads();
+    for (int i = tid; i < n; i += ALIGN_THREADS) if (S_pre(s, b, i)[PR_VALID] == 0.0) sh_bad = 2;   // a frame never saw an IMU sample
+    __syncthreads();
+    if (sh_bad) {
+        if (tid == 0) { if (sh_bad == 1) iv[IV_ERR] = VIO_ERR_STATE; iv[IV_ALIGN_OK] = 0; iv[IV_ACTION] = ACT_SLIDE_ONLY; iv[IV_INIT_PENDING] = 0; }
+        return;
+    }
+    const int ok = align_core(a, b, n, scr, sh);
+    const V3 bgs = ld3(a.bgs_out + 3 * b);
+    const V3 dbg = bgs - ld3(S_Bgs(s, b, 0));
+    __syncthreads();
+    for (int i = tid; i < n; i += ALIGN_THREADS) {                        // Bgs[i] += delta_bg; the map's pre-integrations now sit at Bgs[0]
+        st3(S_Bgs(s, b, i), ld3(S_Bgs(s, b, i)) + dbg);
+        st3(S_pre(s, b, i) + PR_ABG, bgs);
+    }
+    if (tid == 0) iv[IV_ALIGN_OK] = ok;
+    if (!ok) { if (tid == 0) { iv[IV_ACTION] = ACT_SLIDE_ONLY; iv[IV_INIT_PENDING] = 0; } return; }
+    const size_t fo = (size_t)b * s.FCAP;
+    const int nf = iv[IV_NFEAT];
+    for (int i = tid; i < n; i += ALIGN_THREADS) {
+        st3(S_Ps(s, b, i), ld3(a.T + ((size_t)b * a.F + i) * 3));
+        stm(S_Rs(s, b, i), ldm(a.R + ((size_t)b * a.F + i) * 9));
+    }
+    for (int k = tid; k < nf; k += ALIGN_THREADS) s.f_depth[fo + k] = -1.0;          // clearDepth(-1)
+    __syncthreads();
+    triangulate_stream(s, b, v3(0, 0, 0), tid, ALIGN_THREADS);                        // "triangulat on cam pose, no tic"
+    // pre_integrations[i]->repropagate(0, Bgs[i]): the alignment's second pass did exactly that (same samples, same start, same bias)
+    for (int i = 0; i < n; i++) {
+        double *d = S_pre(s, b, i); const double *sr = a.pre + ((size_t)b * a.F + i) * PR_STRIDE;
+        for (int k = tid; k < PR_ABG; k += ALIGN_THREADS) d[k] = sr[k];
+    }
+    __syncthreads();
+    const double *x = a.x_out + (size_t)b * a.NS;
+    const double sc = x[3 * n + 2];
+    const V3 tic = ld3(S_dv(s, b) + DV_TIC);
+    if (tid == 0) {
+        const V3 P0 = ld3(S_Ps(s, b, 0));
+        const V3 off = sc * P0 - ldm(S_Rs(s, b, 0)) * tic;
+        for (int i = W; i >= 0; i--) st3(S_Ps(s, b, i), sc * ld3(S_Ps(s, b, i)) - ldm(S_Rs(s, b, i)) * tic - off);
+    }
+    for (int i = tid; i < n; i += ALIGN_THREADS) st3(S_Vs(s, b, i), ldm(S_Rs(s, b, i)) * v3(x[3 * i], x[3 * i + 1], x[3 * i + 2]));
+    for (int k = tid; k < nf; k += ALIGN_THREADS)
+        if (in_solve(s, s.f_nobs[fo + k], s.f_start[fo + k])) s.f_depth[fo + k] *= sc;
+    __syncthreads();
+    const V3 g = ld3(a.g_out + 3 * b);
+    M3 R0 = g2R_dev(g);
+    const double yaw0 = R2ypr(R0).x;
+    R0 = ypr2R(v3(-yaw0, 0, 0)) * R0;
+    for (int i = tid; i < n; i += ALIGN_THREADS) {
+        st3(S_Ps(s, b, i), R0 * ld3(S_Ps(s, b, i)));
+        stm(S_Rs(s, b, i), R0 * ldm(S_Rs(s, b, i)));
+        st3(S_Vs(s, b, i), R0 * ld3(S_Vs(s, b, i)));
+    }
+    __syncthreads();
+    if (tid == 0) { st3(a.g_out + 3 * b, R0 * g); iv[IV_INIT_PENDING] = 3; }
 }
 
 }  // namespace be

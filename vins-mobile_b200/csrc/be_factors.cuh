@@ -13,13 +13,16 @@ namespace be {
 // ---- pre-integration record layout (doubles) ------------------------------------------------------------
 constexpr int PR_DP = 0, PR_DQ = 3, PR_DV = 7, PR_LBA = 10, PR_LBG = 13, PR_SUMDT = 16, PR_ACC0 = 17, PR_GYR0 = 20, PR_VALID = 23,
               PR_SQI_OK = 24;     // 1 when PR_SQI matches PR_COV (cleared by every propagation step, set by prepare_kernel)
+constexpr int PR_LIN_ACC = 25, PR_LIN_GYR = 28;   // linearized_acc / linearized_gyr: the acc_0, gyr_0 the interval started from (repropagate needs them)
 constexpr int PR_JAC = 32, PR_COV = PR_JAC + 225, PR_SQI = PR_COV + 225, PR_STRIDE = PR_SQI + 225 + 7;   // 714
+constexpr int PR_ABG = PR_SQI + 225;              // 3: gyroscope bias the frame's all_image_frame copy is linearised at (initialisation only)
 
 // IntegrationBase ctor (integration_base.h:26-44): called by one lane
 __device__ inline void pre_init(double *pr, V3 acc0, V3 gyr0, V3 ba, V3 bg) {
     st3(pr + PR_DP, v3(0, 0, 0)); stq(pr + PR_DQ, q4(0, 0, 0, 1)); st3(pr + PR_DV, v3(0, 0, 0));
     st3(pr + PR_LBA, ba); st3(pr + PR_LBG, bg); pr[PR_SUMDT] = 0;
     st3(pr + PR_ACC0, acc0); st3(pr + PR_GYR0, gyr0); pr[PR_VALID] = 1; pr[PR_SQI_OK] = 0;
+    st3(pr + PR_LIN_ACC, acc0); st3(pr + PR_LIN_GYR, gyr0); st3(pr + PR_ABG, v3(0, 0, 0));
     for (int i = 0; i < 225; i++) { pr[PR_JAC + i] = (i % 16 == 0) ? 1.0 : 0.0; pr[PR_COV + i] = 0.0; }
 }
 

@@ -208,31 +208,14 @@ __device__ inline void smallest_right_sv4(double *A, int rows, double out[4]) {
     for (int r = 0; r < 4; r++) out[r] = V[4 * r + best];
 }
 
-__global__ void __launch_bounds__(128) triangulate_kernel(BeState s) {
-    VIO_POISON(4u);
-    const int b = blockIdx.x, tid = threadIdx.x;
-    int *iv = S_iv(s, b);
-    const int act = iv[IV_ACTION];
-    if (act != ACT_INIT_SOLVE && act != ACT_NL_SOLVE) return;
+// FeatureManager::triangulate (feature_manager.cpp:190-257) for one stream: every in-solve landmark without a depth; `nt` threads of the CTA
+__device__ inline void triangulate_stream(const BeState &s, int b, V3 tic, int tid, int nt) {
     const size_t fo = (size_t)b * s.FCAP;
-    const int nf = iv[IV_NFEAT];
-    if (act == ACT_INIT_SOLVE) {
-        // caller-supplied window replaces solveInitial()/visualInitialAlign() (VINS.cpp:833-1102, out of scope)
-        const double *in = s.init_state + (size_t)b * (s.NF * 10 + 6);
-        for (int i = tid; i < s.NF; i += 128) {
-            st3(S_Ps(s, b, i), ld3(in + 10 * i));
-            stm(S_Rs(s, b, i), q2R(qnormalized(ldq(in + 10 * i + 3))));
-            st3(S_Vs(s, b, i), ld3(in + 10 * i + 7));
-            st3(S_Bas(s, b, i), ld3(in + 10 * s.NF)); st3(S_Bgs(s, b, i), ld3(in + 10 * s.NF + 3));
-        }
-        for (int k = tid; k < nf; k += 128) s.f_depth[fo + k] = -1.0;      // clearDepth(-1), VINS.cpp:1047-1050
-        __syncthreads();
-    }
+    const int nf = S_iv(s, b)[IV_NFEAT];
     const double *dv = S_dv(s, b);
-    const V3 tic = ld3(dv + DV_TIC);
     const M3 ric = ldm(dv + DV_RIC);
     double A[4 * 2 * (VIO_MAX_WIN + 1)];
-    for (int k = tid; k < nf; k += 128) {
+    for (int k = tid; k < nf; k += nt) {
         const int st = s.f_start[fo + k], no = s.f_nobs[fo + k];
         if (!in_solve(s, no, st) || s.f_depth[fo + k] > 0) continue;
         const M3 Rs0 = ldm(S_Rs(s, b, st));
@@ -265,6 +248,29 @@ __global__ void __launch_bounds__(128) triangulate_kernel(BeState s) {
         if (dep < 0.1) dep = s.init_depth;
         s.f_depth[fo + k] = dep;
     }
+}
+
+__global__ void __launch_bounds__(128) triangulate_kernel(BeState s) {
+    VIO_POISON(4u);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int *iv = S_iv(s, b);
+    const int act = iv[IV_ACTION];
+    if (act != ACT_INIT_SOLVE && act != ACT_NL_SOLVE) return;
+    const size_t fo = (size_t)b * s.FCAP;
+    const int nf = iv[IV_NFEAT];
+    if (act == ACT_INIT_SOLVE && iv[IV_INIT_PENDING] != 3) {      // 3: init_align_kernel (visualInitialAlign) has already prepared the window
+        // caller-supplied window replaces solveInitial()/visualInitialAlign() (VINS.cpp:833-1102, out of scope)
+        const double *in = s.init_state + (size_t)b * (s.NF * 10 + 6);
+        for (int i = tid; i < s.NF; i += 128) {
+            st3(S_Ps(s, b, i), ld3(in + 10 * i));
+            stm(S_Rs(s, b, i), q2R(qnormalized(ldq(in + 10 * i + 3))));
+            st3(S_Vs(s, b, i), ld3(in + 10 * i + 7));
+            st3(S_Bas(s, b, i), ld3(in + 10 * s.NF)); st3(S_Bgs(s, b, i), ld3(in + 10 * s.NF + 3));
+        }
+        for (int k = tid; k < nf; k += 128) s.f_depth[fo + k] = -1.0;      // clearDepth(-1), VINS.cpp:1047-1050
+        __syncthreads();
+    }
+    triangulate_stream(s, b, ld3(S_dv(s, b) + DV_TIC), tid, 128);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -529,6 +535,7 @@ __device__ inline void clear_state_cta(const BeState &s, int b) {      // VINS::
     }
     if (tid == 0) {
         iv[IV_FRAME_COUNT] = 0; iv[IV_FIRST_IMU] = 0; iv[IV_SOLVER_FLAG] = 0; iv[IV_NFEAT] = 0; iv[IV_PRIOR_VALID] = 0; iv[IV_PRIOR_N] = 0;
+        iv[IV_ALLKEY] = 1; iv[IV_ALIGN_OK] = -1;                         // all_image_frame.clear(), VINS.cpp:62-68
     }
 }
 
@@ -643,6 +650,7 @@ __global__ void __launch_bounds__(256) finish_kernel(BeState s) {
                 nf = sh_total;
             } else {                                         // ---- MARGIN_SECOND_NEW: slideWindow() + slideWindowNew()
                 const int c = s.imu_cnt[(size_t)b * s.NF + W];
+                if (!nonlinear && tid == 0) iv[IV_ALLKEY] = 0;  // the dropped frame stays in all_image_frame as a non-keyframe
                 if (tid < 32) {                              // pre_integrations[W-1]->push_back(every buffered sample of frame W)
                     double *pr = S_pre(s, b, W - 1);
                     const double *buf = S_imu(s, b, W);

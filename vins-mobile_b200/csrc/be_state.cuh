@@ -9,7 +9,9 @@ namespace be {
 // per-stream integer scalars (BeState::iv)
 enum { IV_FRAME_COUNT = 0, IV_FIRST_IMU, IV_SOLVER_FLAG, IV_MARG_FLAG, IV_FAILURE, IV_NFEAT, IV_LAST_TRACK, IV_ACTION, IV_INIT_PENDING,
        IV_PRIOR_VALID, IV_N_LM, IV_N_FAC, IV_ITERS, IV_PRIOR_N, IV_ERR, IV_MARG_FAST, IV_MARG_SWEEPS, IV_MARG_M, IV_CHOL_RETRY,
-       IV_N_FAC_ALL /* IV_N_FAC + loop-closure factors */, IV_LOOP_FRAME /* window frame the loop pose is tied to, -1: none */, IV_LOOP_NFAC, IV_COUNT = 24 };
+       IV_N_FAC_ALL /* IV_N_FAC + loop-closure factors */, IV_LOOP_FRAME /* window frame the loop pose is tied to, -1: none */, IV_LOOP_NFAC,
+       IV_ALLKEY /* no MARGIN_SECOND_NEW slide since the stream (re)started: all_image_frame == the window's frames */,
+       IV_ALIGN_OK /* result of the last VisualIMUAlignment, -1: none yet */, IV_COUNT = 24 };
 // per-stream double scalars (BeState::dv)
 enum { DV_ACC0 = 0, DV_GYR0 = 3, DV_LAST_P = 6, DV_LAST_P_OLD = 9, DV_BACK_P0 = 12, DV_LAST_R = 15, DV_LAST_R_OLD = 24, DV_BACK_R0 = 33,
        DV_COST0 = 42, DV_COST1 = 43, DV_PRIOR_C0 = 44, DV_TIC = 45, DV_RIC = 48, DV_COUNT = 64 };
@@ -39,6 +41,7 @@ struct BeState {
     double *imu_buf; int *imu_cnt;                    // [B][NF][MAXIMU][7], [B][NF]
     int *iv; double *dv;                              // [B][IV_COUNT], [B][DV_COUNT]
     double *init_state;                               // [B][NF*10 + 6]  P3 Q4 V3 per frame, Ba3 Bg3
+    double *init_sfm;                                 // [B][NF][9] ImageFrame::R then [B][NF][3] ImageFrame::T (vio_backend_set_init_sfm), lazily allocated
     // feature table (FeatureManager::feature, in the list's insertion order; compacted order-preservingly)
     int *f_id, *f_start, *f_nobs, *f_flag; double *f_depth; double *f_obs;   // [B][FCAP], obs [B][FCAP][NF][2]
     // prior (MarginalizationInfo in information form, canonical layout [pose_i(6) sb_i(9)]_i ex(6))
