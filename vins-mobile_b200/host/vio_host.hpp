@@ -223,6 +223,19 @@ class VINS {
         check(vio_backend_set_init_window(h_, P, Q, V, Ba, Bg), "vio_backend_set_init_window");
     }
 
+    // The other way in: hand over what solveInitial() holds after the global SfM (VINS.cpp:889-905) -- ImageFrame::R (row-major 3x3) and
+    // ImageFrame::T of the window's WINDOW_SIZE + 1 frames -- and let the device run visualInitialAlign (VINS.cpp:1022-1102:
+    // VisualIMUAlignment, scale, gravity frame, velocities, depths) inside the processImage call that fills the window.
+    void setInitialSfm(const double *R, const double *T) { check(vio_backend_set_init_sfm(h_, R, T), "vio_backend_set_init_sfm"); }
+    // bool result of the last VisualIMUAlignment (-1: none yet), vins.g after it and the metric scale of the SfM
+    int initialAlignment(Vector3d *g = nullptr, double *scale = nullptr) {
+        int32_t ok = -1; double gg[3] = {0, 0, 0}, sc = 0;
+        check(vio_backend_get_init_result(h_, 0, &ok, gg, &sc), "vio_backend_get_init_result");
+        if (g) { g->x = gg[0]; g->y = gg[1]; g->z = gg[2]; }
+        if (scale) *scale = sc;
+        return ok;
+    }
+
     // void processImage(map<int, Vector3d> &image_msg, double header, int buf_num)                             VINS.hpp:163
     // buf_num only scaled the wall-time cap of ceres::Solve (VINS.cpp:648-653); the cap is removed (it made the reference
     // timing-dependent), so buf_num is accepted and ignored.  solve_ceres() runs inside, on the device.
