@@ -407,6 +407,41 @@ def pnp_bench(bn, args, n_frames=40):
             "what": "vinsPnP::processIMU + processImage (5 dogleg iterations on the 7-frame window) through the host C-ABI, host loop included"}
 
 
+def align_bench(bn, args, n=11, reps=5):
+    """vio_visual_imu_align (VisualIMUAlignment, initial_aligment.cpp:222-229) for B streams x n frames through the host C-ABI (copies and
+    scratch allocation inside the call), next to the reference's own code (oracle/_ref) on the first 8 of the same streams, one thread."""
+    B = bn.B
+    cases = [bn.synth.make_align_case(b, n) for b in range(min(B, 16))]
+    pick = [cases[b % len(cases)] for b in range(B)]
+    nf = np.full(B, n, np.int32)
+    R = np.stack([c["R"] for c in pick]); T = np.stack([c["T"] for c in pick]); cnt = np.stack([c["counts"] for c in pick])
+    i0 = np.stack([c["imu0"] for c in pick]); imu = np.stack([c["imu"] for c in pick]); bg0 = np.zeros((B, 3))
+    cfg = bn.abi.default_config(batch=1, device=bn.local)
+    bn.api.visual_imu_align(cfg, nf, R, T, cnt, i0, imu, bg0)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        bgs, g, x, ok = bn.api.visual_imu_align(cfg, nf, R, T, cnt, i0, imu, bg0)
+    gpu_ms = 1e3 * (time.perf_counter() - t0) / reps
+    out = {"streams": B, "frames_per_stream": n, "imu_samples_per_interval": int(cnt[0, 1]), "gpu_ms_all_streams": gpu_ms, "ok": int(ok.sum()),
+           "what": "batched VisualIMUAlignment through the host C-ABI (H2D, one CTA per stream, D2H)"}
+    try:                                   # cpu_baseline leg of this variant (the checker, timed beside): skipped with --no-cpu
+        if args.no_cpu:
+            return out
+        import oracle.backend_oracle as bo
+        if bo.available() and hasattr(bo.lib(), "vref_visual_imu_align"):
+            t0 = time.perf_counter()
+            worst = 0.0
+            for b, c in enumerate(cases[:8]):
+                rb, rg, rx, rok = bo.visual_imu_align(n, c["R"], c["T"], c["counts"], c["imu0"], c["imu"], np.zeros(3), c["tic"])
+                worst = max(worst, float(np.abs(x[b, :3 * n + 3] - rx).max() / np.abs(rx).max()))
+            out["cpu_baseline"] = {"ms_per_stream": 1e3 * (time.perf_counter() - t0) / 8, "cores": 1, "kind": "reference",
+                                   "sample": "the reference's own initial_aligment.cpp (oracle/_ref) on the first 8 of the same streams"}
+            out["max_rel_err_vs_reference"] = worst
+    except Exception as e:
+        out["cpu_reference_error"] = repr(e)
+    return out
+
+
 def run_ours(args):
     import torch
     rank, local, world = _rank_world()
@@ -446,6 +481,11 @@ def run_ours(args):
             extras["pnp_tracker"] = pnp_bench(bn, args)
         except Exception as e:
             extras["pnp_tracker"] = {"error": repr(e)}
+        # (d) the visual-inertial alignment of the initialisation (initial_aligment.cpp), B streams x 11 frames
+        try:
+            extras["visual_imu_align"] = align_bench(bn, args)
+        except Exception as e:
+            extras["visual_imu_align"] = {"error": repr(e)}
     single = None
     configs_extra = {}
     if world == 1 and rank == 0 and not args.no_extras and args.config == "c2":

@@ -319,3 +319,41 @@ def make_pnp_sequence(stream_id: int, n_frames: int = 16, n_lm: int = 60, cam: C
         obs.append(pc[:, :2] / pc[:, 2:3] + rng.normal(0, px_noise / cam.fx, (n_lm, 2)))
     return dict(t=t, P=P, V=V, R=R, X=X, ids=np.arange(n_lm, dtype=np.int32), track_num=np.full(n_lm, 10, np.int32), obs=np.array(obs),
                 imu_t=imu_t, acc=acc, gyr=gyr, lag=lag)
+
+
+def make_align_case(sid, n, scale=2.5, gyro_bias=(0.01, -0.02, 0.015), rot_noise=2e-3, pos_noise=2e-3, max_frames=None, max_imu=None):
+    """Inputs of VisualIMUAlignment (initial_aligment.cpp:222-229) for one synthetic stream: n camera frames as VINS::solveInitial
+    leaves them after the global SfM (VINS.cpp:889-905: ImageFrame::R = body attitude in the SfM frame c0, ImageFrame::T = camera
+    position in c0, up to the unknown scale), the raw IMU samples of every frame interval (constant gyroscope bias added), and the
+    ground truth (scale, gravity in c0).  c0 is rotated at random against the world, so gravity is not axis aligned."""
+    tr = make_tracks(sid, n + 1, max_cnt=8)
+    cfg_tic = np.array([0.0, 0.092, 0.01])
+    rng = np.random.default_rng(1000 + sid)
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    w, x, y, z = q
+    Rc0 = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                    [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                    [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    per = tr["per"]
+    F = max_frames or n
+    M = max_imu or per
+    R = np.zeros((F, 3, 3)); T = np.zeros((F, 3)); counts = np.zeros(F, np.int32); imu0 = np.zeros((F, 6)); imu = np.zeros((F, M, 7))
+    R[:] = np.eye(3)
+    Pc0 = tr["P"][0] + tr["R"][0] @ cfg_tic
+    for k in range(n):
+        th = rng.normal(0, rot_noise, 3)
+        dR = np.eye(3) + np.array([[0, -th[2], th[1]], [th[2], 0, -th[0]], [-th[1], th[0], 0]])
+        u, _, vt = np.linalg.svd(dR)
+        R[k] = Rc0 @ tr["R"][k] @ (u @ vt)
+        T[k] = Rc0 @ (tr["P"][k] + tr["R"][k] @ cfg_tic - Pc0) / scale + rng.normal(0, pos_noise, 3)
+        if k > 0:
+            sl = slice((k - 1) * per, k * per)
+            dts = np.diff(np.concatenate([[tr["t_kf"][k - 1]], tr["imu_t"][sl]]))
+            counts[k] = per
+            imu[k, :per, 0] = dts
+            imu[k, :per, 1:4] = tr["acc"][sl]
+            imu[k, :per, 4:7] = tr["gyr"][sl] + np.asarray(gyro_bias)
+            j = max(0, (k - 1) * per - 1)
+            imu0[k, :3] = tr["acc"][j]; imu0[k, 3:] = tr["gyr"][j] + np.asarray(gyro_bias)
+    g_c0 = Rc0 @ np.array([0.0, 0.0, 9.805])
+    return dict(n=n, R=R, T=T, counts=counts, imu0=imu0, imu=imu, tic=cfg_tic, scale=scale, g=g_c0, gyro_bias=np.asarray(gyro_bias))
