@@ -408,8 +408,8 @@ def pnp_bench(bn, args, n_frames=40):
 
 
 def align_bench(bn, args, n=11, reps=5):
-    """vio_visual_imu_align (VisualIMUAlignment, initial_aligment.cpp:222-229) for B streams x n frames through the host C-ABI (copies and
-    scratch allocation inside the call), next to the reference's own code (oracle/_ref) on the first 8 of the same streams, one thread."""
+    """vio_visual_imu_align (VisualIMUAlignment, initial_aligment.cpp:222-229) for B streams x n frames through the host C-ABI (host copies inside
+    the call), next to the reference's own code (oracle/_ref) on the first 8 of the same streams, one thread."""
     B = bn.B
     cases = [bn.synth.make_align_case(b, n) for b in range(min(B, 16))]
     pick = [cases[b % len(cases)] for b in range(B)]

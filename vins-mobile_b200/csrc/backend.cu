@@ -7,6 +7,7 @@
 #include "be_align.cuh"
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 #include <string.h>
@@ -741,8 +742,22 @@ extern "C" int vio_visual_imu_align(const vio_config *cfg, int batch, int max_fr
     const size_t nd_scr = B * F * PR_STRIDE + 2 * B * NS * NS + B * NS + B * F * 110 + 2 * B * NS;
     const size_t nd_out = B * 3 + B * 3 + B * NS;
     const size_t ni = B + B * F + B * NS + B;
-    double *d = nullptr;
-    VIO_CUDA_TRY(cudaMalloc((void **)&d, (nd_in + nd_scr + nd_out) * sizeof(double) + ni * sizeof(int)));
+    // device scratch: one grow-only buffer per device, kept between calls (cudaMalloc / cudaFree synchronise the whole device and cost
+    // milliseconds next to a running pipeline); calls are serialised by the lock
+    static std::mutex mu;
+    static double *cache[64];
+    static size_t cache_bytes[64];
+    std::lock_guard<std::mutex> lock(mu);
+    const int dev = cfg->device;
+    if (dev < 0 || dev >= 64) return VIO_ERR_ARG;
+    const size_t need = (nd_in + nd_scr + nd_out) * sizeof(double) + ni * sizeof(int);
+    if (cache_bytes[dev] < need) {
+        if (cache[dev]) cudaFree(cache[dev]);
+        cache[dev] = nullptr; cache_bytes[dev] = 0;
+        VIO_CUDA_TRY(cudaMalloc((void **)&cache[dev], need));
+        cache_bytes[dev] = need;
+    }
+    double *d = cache[dev];
     double *p = d;
     double *dR = p; p += B * F * 9;
     double *dT = p; p += B * F * 3;
@@ -780,7 +795,6 @@ extern "C" int vio_visual_imu_align(const vio_config *cfg, int batch, int max_fr
     cudaMemcpy(x, a.x_out, B * NS * 8, cudaMemcpyDeviceToHost);
     cudaError_t e = cudaMemcpy(ok, a.ok, B * 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(d);
     return e == cudaSuccess ? VIO_OK : VIO_ERR_CUDA;
 }
 
