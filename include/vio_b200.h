@@ -270,11 +270,17 @@ int vio_visual_imu_align(const vio_config *cfg, int batch, int max_frames, int m
  * then runs, per stream and on the device: VisualIMUAlignment over the window's own IMU buffers; on success Ps / Rs from the SfM,
  * clearDepth + triangulate on the camera poses, repropagate with the new Bgs, metric scale, Vs, gravity-aligned frame, then the
  * first solve exactly as VINS.cpp:415-447; on failure Bgs keep the corrected bias and the window only slides (solveInitial == false).
- * Supported case: all_image_frame holds exactly the window's frames, i.e. no MARGIN_SECOND_NEW slide happened since the stream
- * (re)started; otherwise the attempt counts as failed and VIO_ERR_STATE is latched for the stream (use vio_visual_imu_align with the
- * full frame list and vio_backend_set_init_window instead).  The SfM itself (relativePose / GlobalSFM) is NOT part of this library.
+ * The alignment runs over all_image_frame as the back end keeps it: every camera frame since the stream (re)started, keyframe or not
+ * (VINS.cpp:392-398), each with its own IMU interval; frames older than the window are dropped as the reference does (VINS.cpp:1186-1193).
+ * vio_backend_get_init_frames returns their headers (at most 3 (W + 1) - 1 are kept; beyond that the list is abandoned until the next
+ * clearState and attempts are refused with VIO_ERR_STATE); vio_backend_set_init_sfm_frames takes R [batch][max_frames][9] / T
+ * [batch][max_frames][3] for exactly those frames (n_frames[b] of them; a mismatch with the device's count refuses the attempt with
+ * VIO_ERR_STATE); vio_backend_set_init_sfm is the common case where every frame is a keyframe (no MARGIN_SECOND_NEW slide since the start):
+ * R / T of the window's W + 1 frames.  The SfM itself (relativePose / GlobalSFM / solvePnP) is NOT part of this library.
  * vio_backend_get_init_result: ok = 1 / 0 of the stream's last alignment (-1: none yet), g = vins.g after it, scale = the metric scale. */
 int vio_backend_set_init_sfm(vio_backend *be, const double *R, const double *T);
+int vio_backend_set_init_sfm_frames(vio_backend *be, const int32_t *n_frames, int max_frames, const double *R, const double *T);
+int vio_backend_get_init_frames(vio_backend *be, int s, int cap, int32_t *n, double *headers);
 int vio_backend_get_init_result(vio_backend *be, int s, int32_t *ok, double g[3], double *scale);
 
 /* ------------------------------------------------------------------------------------------------------------------

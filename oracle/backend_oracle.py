@@ -48,6 +48,8 @@ def lib():
         L.vref_projection_factor.argtypes = [C.c_double, DP, DP, DP, DP, DP, DP, C.c_double, DP, DP]
         if hasattr(L, "vref_set_init_sfm"):
             L.vref_set_init_sfm.argtypes = [C.c_void_p, DP, DP]
+            L.vref_set_init_sfm_frames.argtypes = [C.c_void_p, C.c_int, DP, DP]
+            L.vref_get_init_frames.argtypes = [C.c_void_p, C.c_int, DP]
             L.vref_get_init_result.argtypes = [C.c_void_p, IP, DP, DP]
         if hasattr(L, "vref_visual_imu_align"):
             L.vref_visual_imu_align.argtypes = [C.c_int, DP, DP, IP, DP, C.c_int, DP, DP, DP, DP, DP, DP]
@@ -120,6 +122,15 @@ class RefEstimator:
         call that fills the window: visualInitialAlign (VINS.cpp:1022-1102) + the first solve."""
         R, T = _d(R), _d(T)
         lib().vref_set_init_sfm(self.h, _abi.ptr(R, C.c_double), _abi.ptr(T, C.c_double))
+
+    def set_init_sfm_frames(self, R, T):
+        R, T = _d(R), _d(T)
+        lib().vref_set_init_sfm_frames(self.h, R.shape[0], _abi.ptr(R, C.c_double), _abi.ptr(T, C.c_double))
+
+    def init_frames(self):
+        h = np.zeros(256)
+        n = lib().vref_get_init_frames(self.h, 256, _abi.ptr(h, C.c_double))
+        return h[:n].copy()
 
     def init_result(self):
         ok = np.zeros(1, np.int32); g = np.zeros(3); sc = np.zeros(1)

@@ -87,9 +87,14 @@ struct Est {
     Matrix3d last_R, last_R_old, back_R0;
     Vector3d last_P, last_P_old, back_P0;
     // initialisation from SfM poses (vref_set_init_sfm): visualInitialAlign restated around the reference's own VisualIMUAlignment
-    bool sfm_pending = false, all_key = true;       // all_key: no MARGIN_SECOND_NEW slide since (re)start => all_image_frame == window
-    std::vector<Matrix3d> sR; std::vector<Vector3d> sT;
-    std::vector<Vector3d> abg;                       // bias the all_image_frame copy of each frame's pre-integration is linearised at
+    bool sfm_pending = false;
+    std::vector<Matrix3d> sR; std::vector<Vector3d> sT;      // ImageFrame::R / T of every frame of the map, map order
+    // all_image_frame (VINS.hpp:141; filled while INITIAL, VINS.cpp:392-398): per frame the header and what its tmp_pre_integration was fed --
+    // start values, samples, and the gyroscope bias it is currently linearised at (solveGyroscopeBias repropagates it)
+    struct AllFrame { double hdr = 0; Vector3d acc0 = Vector3d::Zero(), gyr0 = Vector3d::Zero(), abg = Vector3d::Zero();
+                      std::vector<double> dt; std::vector<Vector3d> acc, gyr; };
+    std::vector<AllFrame> all;                               // closed records
+    AllFrame tmp;                                            // the open one (tmp_pre_integration)
     Vector3d g_init = Vector3d::Zero(); int align_ok = -1; double scale_init = 0;
     // external initialisation
     bool init_pending = false;
@@ -146,7 +151,7 @@ void clear_state(Est &e) {           // VINS::clearState, VINS.cpp:35-80
     e.tic = Vector3d(e.c.tic[0], e.c.tic[1], e.c.tic[2]);
     e.ric = Map<const Matrix<double, 3, 3, RowMajor>>(e.c.ric);
     e.frame_count = 0; e.first_imu = false; e.solver_flag = 0;
-    e.abg.assign(n, Vector3d::Zero()); e.all_key = true; e.sfm_pending = false;     // all_image_frame.clear(), VINS.cpp:62-68
+    e.all.clear(); e.tmp = Est::AllFrame(); e.sfm_pending = false;                  // all_image_frame.clear(), VINS.cpp:62-68
     delete e.last_marg; e.last_marg = nullptr; e.last_marg_blocks.clear();
     e.feat.clear();
 }
@@ -157,6 +162,7 @@ void process_imu(Est &e, double dt, const Vector3d &acc, const Vector3d &gyr) { 
     if (!e.pre[j]) e.pre[j] = new IntegrationBase{e.acc_0, e.gyr_0, e.Bas[j], e.Bgs[j]};
     if (j != 0) {
         e.pre[j]->push_back(dt, acc, gyr);
+        if (e.solver_flag != 1) { e.tmp.dt.push_back(dt); e.tmp.acc.push_back(acc); e.tmp.gyr.push_back(gyr); }     // tmp_pre_integration->push_back
         e.dt_buf[j].push_back(dt); e.acc_buf[j].push_back(acc); e.gyr_buf[j].push_back(gyr);
         Vector3d g{0, 0, GRAVITY};
         Vector3d un_acc_0 = e.Rs[j] * (e.acc_0 - e.Bas[j]) - g;
@@ -228,33 +234,40 @@ bool vref_align_frames(int n, const double *headers, const Eigen::Matrix3d *R, c
                        Eigen::Vector3d *Bgs, Eigen::Vector3d &g, Eigen::VectorXd &x);
 namespace {
 
-// VINS::visualInitialAlign (VINS.cpp:1022-1102) for the case all_image_frame == the window's frames (no MARGIN_SECOND_NEW slide since the
-// stream started, so every frame of the map is a keyframe; ImageFrame::R / T come from the caller's SfM, VINS.cpp:889-905).
+// VINS::visualInitialAlign (VINS.cpp:1022-1102).  ImageFrame::R / T of every frame of the map come from the caller's SfM (VINS.cpp:889-958).
 bool visual_initial_align(Est &e) {
-    const int W = e.W, n = W + 1;
-    // all_image_frame's pre-integrations are separate objects (tmp_pre_integration, VINS.cpp:396-398: zero biases at creation) that
-    // keep the bias of the last alignment attempt (solveGyroscopeBias repropagates them, initial_aligment.cpp:41-45)
-    std::vector<IntegrationBase *> tmp(n);
-    for (int i = 0; i < n; i++) if (!e.pre[i]) { e.align_ok = 0; return false; }   // no IMU sample ever arrived for a frame (the reference would dereference NULL)
-    for (int i = 0; i < n; i++) {
-        IntegrationBase *src = e.pre[i];
-        tmp[i] = new IntegrationBase{src->linearized_acc, src->linearized_gyr, Vector3d::Zero(), e.abg[i]};
-        for (size_t k = 0; k < src->dt_buf.size(); k++) tmp[i]->push_back(src->dt_buf[k], src->acc_buf[k], src->gyr_buf[k]);
+    const int W = e.W, n = (int)e.all.size();
+    e.align_ok = 0;
+    if ((int)e.sR.size() != n || n < 2) return false;            // the caller's frame list is not the map's
+    std::vector<int> key(W + 1, -1);                              // map index of window frame i
+    for (int i = 0, k = 0; i <= W; i++) {
+        while (k < n && e.all[k].hdr != e.Headers[i]) k++;
+        if (k >= n) return false;
+        key[i] = k;
     }
+    for (int i = 0; i <= W; i++) if (!e.pre[i]) return false;    // no IMU sample ever arrived for a frame (the reference would dereference NULL)
     TIC_X = e.tic.x(); TIC_Y = e.tic.y(); TIC_Z = e.tic.z();      // initial_aligment.cpp reads the globals (global_param.cpp:37-39 sets them per device)
+    std::vector<IntegrationBase *> tmp(n);
+    std::vector<double> hdrs(n);
+    for (int k = 0; k < n; k++) {
+        const Est::AllFrame &f = e.all[k];
+        hdrs[k] = f.hdr;
+        tmp[k] = new IntegrationBase{f.acc0, f.gyr0, Vector3d::Zero(), f.abg};
+        for (size_t q = 0; q < f.dt.size(); q++) tmp[k]->push_back(f.dt[q], f.acc[q], f.gyr[q]);
+    }
     Vector3d g; VectorXd x;
-    const bool ok = vref_align_frames(n, e.Headers.data(), e.sR.data(), e.sT.data(), tmp.data(), e.Bgs.data(), g, x);
-    for (int i = 0; i < n; i++) { e.abg[i] = e.Bgs[0]; delete tmp[i]; }
+    const bool ok = vref_align_frames(n, hdrs.data(), e.sR.data(), e.sT.data(), tmp.data(), e.Bgs.data(), g, x);
+    for (int k = 0; k < n; k++) { e.all[k].abg = e.Bgs[0]; delete tmp[k]; }
     e.align_ok = ok ? 1 : 0;
     if (!ok) return false;
-    for (int i = 0; i <= e.frame_count; i++) { e.Ps[i] = e.sT[i]; e.Rs[i] = e.sR[i]; }
+    for (int i = 0; i <= e.frame_count; i++) { e.Ps[i] = e.sT[key[i]]; e.Rs[i] = e.sR[key[i]]; }
     for (auto &t : e.feat) t.depth = -1.0;                       // clearDepth(-1)
     { const Vector3d keep = e.tic; e.tic.setZero(); triangulate(e); e.tic = keep; }      // "triangulat on cam pose, no tic"
     const double s = (x.tail<1>())(0);
     e.scale_init = s;
     for (int i = 0; i <= W; i++) e.pre[i]->repropagate(Vector3d::Zero(), e.Bgs[i]);
     for (int i = e.frame_count; i >= 0; i--) e.Ps[i] = s * e.Ps[i] - e.Rs[i] * e.tic - (s * e.Ps[0] - e.Rs[0] * e.tic);
-    for (int kv = 0; kv < n; kv++) e.Vs[kv] = e.sR[kv] * x.segment<3>(kv * 3);
+    for (int kv = 0; kv <= W; kv++) e.Vs[kv] = e.sR[key[kv]] * x.segment<3>(kv * 3);    // indexed by the keyframe counter, as written (VINS.cpp:1066-1075)
     for (auto &t : e.feat) { if (!in_solve(e, t)) continue; t.depth *= s; }
     Matrix3d R0 = Utility::g2R(g);
     const double yaw0 = Utility::R2ypr(R0).x();
@@ -505,8 +518,11 @@ void slide_window(Est &e) {          // VINS.cpp:1149-1273 + feature_manager.cpp
         }
         e.Headers[W] = e.Headers[W - 1]; e.Ps[W] = e.Ps[W - 1]; e.Vs[W] = e.Vs[W - 1]; e.Rs[W] = e.Rs[W - 1];
         e.Bas[W] = e.Bas[W - 1]; e.Bgs[W] = e.Bgs[W - 1];          // Q9: Bas/Bgs are NOT shifted for i < W
-        for (int i = 0; i < W; i++) e.abg[i] = e.abg[i + 1];       // all_image_frame.erase(begin, Headers[0]), VINS.cpp:1186-1193
-        e.abg[W] = Vector3d::Zero();                                // the next tmp_pre_integration starts from zero biases
+        if (e.solver_flag == 0) {                                   // all_image_frame.erase(begin, find(Headers[0])), VINS.cpp:1186-1193
+            size_t m = 0;
+            while (m < e.all.size() && e.all[m].hdr != e.Headers[0]) m++;
+            if (m < e.all.size()) e.all.erase(e.all.begin(), e.all.begin() + m);
+        }
         delete e.pre[W];
         e.pre[W] = new IntegrationBase{e.acc_0, e.gyr_0, e.Bas[W], e.Bgs[W]};
         e.dt_buf[W].clear(); e.acc_buf[W].clear(); e.gyr_buf[W].clear();
@@ -544,7 +560,6 @@ void slide_window(Est &e) {          // VINS.cpp:1149-1273 + feature_manager.cpp
             e.acc_buf[W - 1].push_back(e.acc_buf[W][i]);
             e.gyr_buf[W - 1].push_back(e.gyr_buf[W][i]);
         }
-        if (e.solver_flag == 0) e.all_key = false;                  // the dropped frame stays in all_image_frame as a non-keyframe
         e.Headers[W - 1] = e.Headers[W]; e.Ps[W - 1] = e.Ps[W]; e.Vs[W - 1] = e.Vs[W]; e.Rs[W - 1] = e.Rs[W];
         e.Bas[W - 1] = e.Bas[W]; e.Bgs[W - 1] = e.Bgs[W];
         delete e.pre[W];
@@ -572,11 +587,13 @@ int process_image(Est &e, int n, const int *ids, const double *xyz, double heade
     e.marg_flag = add_feature_check_parallax(e, n, ids, xyz) ? 0 : 1;
     e.Headers[e.frame_count] = header;
     if (e.solver_flag == 0) {
+        e.tmp.hdr = header; e.all.push_back(e.tmp);           // all_image_frame.insert; tmp_pre_integration = new IntegrationBase{acc_0, gyr_0, 0, 0}
+        e.tmp = Est::AllFrame(); e.tmp.acc0 = e.acc_0; e.tmp.gyr0 = e.gyr_0;
         if (e.frame_count == e.W) {
             if (e.last_track_num < 20) { clear_state(e); return 2; }      // VINS.cpp:401-405
             if (e.sfm_pending) {                            // solveInitial() from the SfM poses on: VINS.cpp:1022-1102, then :415-447
                 e.sfm_pending = false;
-                if (e.all_key && visual_initial_align(e)) {
+                if (visual_initial_align(e)) {
                     solve(e);
                     if (e.cost1 > 200) {
                         delete e.last_marg; e.last_marg = nullptr;
@@ -696,14 +713,21 @@ void vref_set_init_window(void *h, const double *P, const double *Q, const doubl
     e.iBa = Vector3d(Ba[0], Ba[1], Ba[2]); e.iBg = Vector3d(Bg[0], Bg[1], Bg[2]);
     e.init_pending = true;
 }
-void vref_set_init_sfm(void *h, const double *R, const double *T) {
+void vref_set_init_sfm_frames(void *h, int n, const double *R, const double *T) {
     Est &e = *(Est *)h;
     e.sR.clear(); e.sT.clear();
-    for (int i = 0; i <= e.W; i++) {
+    for (int i = 0; i < n; i++) {
         e.sR.push_back(Map<const Matrix<double, 3, 3, RowMajor>>(R + 9 * i));
         e.sT.emplace_back(T[3 * i], T[3 * i + 1], T[3 * i + 2]);
     }
     e.sfm_pending = true;
+}
+void vref_set_init_sfm(void *h, const double *R, const double *T) { vref_set_init_sfm_frames(h, ((Est *)h)->W + 1, R, T); }
+int vref_get_init_frames(void *h, int cap, double *headers) {
+    Est &e = *(Est *)h;
+    const int n = (int)e.all.size();
+    for (int i = 0; i < n && i < cap; i++) headers[i] = e.all[i].hdr;
+    return n;
 }
 void vref_get_init_result(void *h, int *ok, double *g, double *scale) {
     Est &e = *(Est *)h;

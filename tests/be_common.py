@@ -120,6 +120,22 @@ def sfm_window(tr, k, W, scale=2.5, seed=5, mirrored=False):
     return R, (-T if mirrored else T)
 
 
+def sfm_frames(tr, headers, scale=2.5, seed=5):
+    """sfm_window for an arbitrary list of frame timestamps (every frame of all_image_frame, keyframe or not): ImageFrame::R / T from the
+    ground truth at those times."""
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    w, x, y, z = q
+    Rc0 = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                    [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                    [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    tic = np.array([0.0, 0.092, 0.01])
+    fr = [int(np.argmin(np.abs(tr["t_kf"] - h))) for h in headers]
+    R = np.stack([Rc0 @ tr["R"][i] for i in fr])
+    Pc = np.stack([tr["P"][i] + tr["R"][i] @ tic for i in fr])
+    return R, (Pc - Pc[0]) @ Rc0.T / scale
+
+
 def drive_sfm(est, tr, k, W, sfm=None):
     """Like drive(), but the stream initialises from SfM poses (set_init_sfm) instead of a supplied window; one IMU sample precedes the
     first image (as on a device: the reference creates pre_integrations[0] from it, VINS.cpp:340-346).  sfm = (R, T) or None."""

@@ -443,38 +443,80 @@ def test_initialisation_from_sfm_poses_matches_reference(api, cfg, synth):
             ref.close(); gpu.close()
 
 
-def test_initialisation_from_sfm_needs_all_keyframes(api, cfg, synth):
-    """The device path covers all_image_frame == window frames.  After a MARGIN_SECOND_NEW slide in the INITIAL phase a non-keyframe stays in
-    the reference's map, which the back end does not keep: the attempt is refused (VIO_ERR_STATE latched, window slides)."""
-    from be_common import drive_sfm, sfm_window
+def test_initialisation_from_sfm_with_a_non_keyframe_in_the_map(api, cfg, synth):
+    """all_image_frame keeps every camera frame since the stream started (VINS.cpp:392-398), also the one a MARGIN_SECOND_NEW slide drops
+    from the window in the INITIAL phase; VisualIMUAlignment then runs over 12 frames of which 11 are the window's keyframes, and Vs are
+    read from x by the keyframe counter (VINS.cpp:1066-1075).  Both estimators keep the same frame list and initialise identically."""
+    from be_common import drive_sfm, sfm_frames
     W = cfg.window_size
-    tr = synth.make_tracks(1, 16, max_cnt=cfg.max_cnt)
-    gpu = api.BackEnd(cfg)
+    tr = synth.make_tracks(1, 20, max_cnt=cfg.max_cnt)
+    ref, gpu = bo.RefEstimator(cfg), api.BackEnd(cfg)
+    per = tr["per"]
+
+    def imu_of(est, k):
+        sl = slice((k - 1) * per, k * per)
+        dts = np.diff(np.concatenate([[tr["t_kf"][k - 1]], tr["imu_t"][sl]]))
+        if hasattr(est, "B"):
+            est.process_imu(dts[:, None], tr["acc"][sl][:, None, :], tr["gyr"][sl][:, None, :])
+        else:
+            for d, a, g in zip(dts, tr["acc"][sl], tr["gyr"][sl]):
+                est.process_imu(d, a, g)
+
     try:
-        for k in range(W + 1):
-            drive_sfm(gpu, tr, k, W, None)                       # window full, no initialisation supplied: slides
-        # the newest keyframe's measurements twice more: the parallax test compares the second and third newest frames
-        # (feature_manager.cpp:150-160), so the second repetition gives zero parallax -> MARGIN_SECOND_NEW
-        ids, xyz = tr["frames"][W]
-        per = tr["per"]
-
-        def imu_of(k):
-            sl = slice((k - 1) * per, k * per)
-            dts = np.diff(np.concatenate([[tr["t_kf"][k - 1]], tr["imu_t"][sl]]))
-            gpu.process_imu(dts[:, None], tr["acc"][sl][:, None, :], tr["gyr"][sl][:, None, :])
-
+        for k in range(W + 1):                                       # window full, no initialisation supplied: slides
+            with Quiet():
+                drive_sfm(ref, tr, k, W, None)
+            drive_sfm(gpu, tr, k, W, None)
+        # frame W + 1 repeats keyframe W's measurements (a camera that did not move in the image); the parallax test compares the second and
+        # third newest frames (feature_manager.cpp:150-160), so it is the NEXT frame that sees zero parallax -> MARGIN_SECOND_NEW drops the
+        # repeated frame from the window (its observations go with it) while all_image_frame keeps it
         for k in (W + 1, W + 2):
-            imu_of(k)
-            gpu.process_image_single(ids, xyz, tr["t_kf"][k])
-        assert gpu.info()["marg_flag"] == 1 and gpu.info()["solver_flag"] == 0
-        imu_of(W + 3)
-        R, T = sfm_window(tr, W + 3, W)
-        gpu.set_init_sfm(R[None], T[None])
-        gpu.process_image_single(*tr["frames"][W + 3], tr["t_kf"][W + 3])
-        assert gpu.error(clear=True) == 3                      # VIO_ERR_STATE
-        assert gpu.info()["solver_flag"] == 0 and gpu.init_result()[0] == 0
+            ids, xyz = tr["frames"][W] if k == W + 1 else tr["frames"][k]
+            for est in (ref, gpu):
+                with Quiet():
+                    imu_of(est, k)
+                    if hasattr(est, "B"):
+                        est.process_image_single(ids, xyz, tr["t_kf"][k])
+                    else:
+                        est.process_image(ids, xyz, tr["t_kf"][k])
+        assert gpu.info()["marg_flag"] == 1 and gpu.info()["solver_flag"] == 0 and ref.info()["marg_flag"] == 1
+        hd = gpu.init_frames()
+        assert np.array_equal(hd, ref.init_frames()) and len(hd) == W + 1
+        assert tr["t_kf"][W + 1] in hd and tr["t_kf"][W + 1] not in gpu.state()["headers"]      # in the map, not in the window
+        k = W + 3
+        R, T = sfm_frames(tr, list(hd) + [tr["t_kf"][k]])            # the frame about to be processed is part of the map by then
+        for est in (ref, gpu):
+            with Quiet():
+                imu_of(est, k)
+                if hasattr(est, "B"):
+                    est.set_init_sfm_frames([len(R)], R[None], T[None])
+                    est.process_image_single(*tr["frames"][k], tr["t_kf"][k])
+                else:
+                    est.set_init_sfm_frames(R, T)
+                    est.process_image(*tr["frames"][k], tr["t_kf"][k])
+        assert gpu.error() == 0
+        rok, rg, rsc = ref.init_result()
+        gok, gg, gsc = gpu.init_result()
+        assert rok == gok == 1 and abs(gsc / rsc - 1) < 1e-9 and rel_err(gg, rg) < 1e-9
+        assert ref.info()["solver_flag"] == gpu.info()["solver_flag"] == 1, (ref.info()["cost1"], gpu.info()["cost1"])
+        rs, gs = ref.state(), gpu.state()
+        print(f"\n[init, 12 frames / 11 keyframes] P {rel_err(gs['P'], rs['P']):.2e} V {rel_err(gs['V'], rs['V']):.2e} Q {quat_err(gs['Q'], rs['Q']):.2e} cost {gpu.info()['cost1']:.3f}")
+        _same_window(rs, gs, 1e-6)
+        # a frame list that is not the map's is refused
+        gpu2 = api.BackEnd(cfg)
+        try:
+            for k in range(W):
+                drive_sfm(gpu2, tr, k, W, None)
+            R, T = sfm_frames(tr, tr["t_kf"][:W])                    # one frame short
+            imu_of(gpu2, W)
+            gpu2.set_init_sfm_frames([W], R[None], T[None])
+            gpu2.process_image_single(*tr["frames"][W], tr["t_kf"][W])
+            assert gpu2.error(clear=True) == 3                       # VIO_ERR_STATE
+            assert gpu2.info()["solver_flag"] == 0 and gpu2.init_result()[0] == 0
+        finally:
+            gpu2.close()
     finally:
-        gpu.close()
+        ref.close(); gpu.close()
 
 
 def test_initialisation_rejected_above_cost_200(api, cfg, synth):

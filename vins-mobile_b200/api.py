@@ -101,6 +101,8 @@ def lib():
             L.vio_prim_projection_factor.argtypes = [cfgp, DP, DP, DP, DP, C.c_double, DP, DP]
             L.vio_prim_imu_factor_sqi.argtypes = [cfgp, DP, DP, DP, C.c_double, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP]
             L.vio_backend_set_init_sfm.argtypes = [vp, DP, DP]
+            L.vio_backend_set_init_sfm_frames.argtypes = [vp, IP, C.c_int, DP, DP]
+            L.vio_backend_get_init_frames.argtypes = [vp, C.c_int, C.c_int, IP, DP]
             L.vio_backend_get_init_result.argtypes = [vp, C.c_int, IP, DP, DP]
             L.vio_visual_imu_align.argtypes = [cfgp, C.c_int, C.c_int, C.c_int, IP, DP, DP, IP, DP, DP, DP, DP, DP, DP, IP]
         _lib = L
@@ -411,6 +413,21 @@ class BackEnd:
         R = np.ascontiguousarray(R, np.float64); T = np.ascontiguousarray(T, np.float64)
         assert R.shape == (self.B, self.W + 1, 3, 3) and T.shape == (self.B, self.W + 1, 3)
         _check(lib().vio_backend_set_init_sfm(self.h, ptr(R, C.c_double), ptr(T, C.c_double)), "vio_backend_set_init_sfm")
+
+    def set_init_sfm_frames(self, n_frames, R, T):
+        """The general form: R [B][F][3][3] / T [B][F][3] of EVERY frame of all_image_frame (init_frames()), n_frames [B] of them per stream."""
+        n_frames = np.ascontiguousarray(n_frames, np.int32)
+        R = np.ascontiguousarray(R, np.float64); T = np.ascontiguousarray(T, np.float64)
+        F = R.shape[1]
+        assert R.shape == (self.B, F, 3, 3) and T.shape == (self.B, F, 3) and n_frames.shape == (self.B,)
+        _check(lib().vio_backend_set_init_sfm_frames(self.h, ptr(n_frames, C.c_int32), F, ptr(R, C.c_double), ptr(T, C.c_double)), "vio_backend_set_init_sfm_frames")
+
+    def init_frames(self, s=0):
+        """headers of the frames in all_image_frame for stream s, oldest first"""
+        cap = 3 * (self.W + 1)
+        n = np.zeros(1, np.int32); h = np.zeros(cap)
+        _check(lib().vio_backend_get_init_frames(self.h, s, cap, ptr(n, C.c_int32), ptr(h, C.c_double)), "vio_backend_get_init_frames")
+        return h[:int(n[0])].copy()
 
     def init_result(self, s=0):
         ok = np.zeros(1, np.int32); g = np.zeros(3); sc = np.zeros(1)

@@ -113,6 +113,12 @@ extern "C" int vio_backend_create(const vio_config *cfg, vio_backend **out) {
     if (!rc) rc = dalloc(be, &s.imu_buf, B * NF * s.MAXIMU * 7);
     if (!rc) rc = dalloc(be, &s.imu_cnt, B * NF);
     if (!rc) rc = dalloc(be, &s.iv, B * IV_COUNT);
+    s.FA = 3 * s.NF;
+    if (!rc) rc = dalloc(be, &s.af_hdr, B * s.FA);
+    if (!rc) rc = dalloc(be, &s.af_imu0, B * s.FA * 6);
+    if (!rc) rc = dalloc(be, &s.af_imu, B * s.FA * (size_t)s.MAXIMU * 7);
+    if (!rc) rc = dalloc(be, &s.af_abg, B * s.FA * 3);
+    if (!rc) rc = dalloc(be, &s.af_cnt, B * s.FA);
     if (!rc) rc = dalloc(be, &s.dv, B * DV_COUNT);
     if (!rc) rc = dalloc(be, &s.init_state, B * (NF * 10 + 6));
     if (!rc) rc = dalloc(be, &s.f_id, B * s.FCAP);
@@ -269,50 +275,81 @@ __global__ void set_sfm_pending_kernel(BeState s) {
     if (threadIdx.x == 0) S_iv(s, blockIdx.x)[IV_INIT_PENDING] = 2;
 }
 
-// ImageFrame::R / T of the window's W + 1 frames as VINS::solveInitial leaves them after the global SfM (VINS.cpp:889-905: R = body attitude
-// in the SfM frame, T = camera position in it, unknown scale).  Consumed by the vio_backend_process_image call that fills the window:
-// VisualIMUAlignment + the rest of visualInitialAlign (VINS.cpp:1022-1102) run on the device, then the first solve (VINS.cpp:415-447).
-extern "C" int vio_backend_set_init_sfm(vio_backend *be, const double *R, const double *T) {
-    if (!be || !R || !T) return VIO_ERR_ARG;
+// ImageFrame::R / T of every frame of all_image_frame as VINS::solveInitial leaves them after the global SfM and the PnP of the
+// non-keyframes (VINS.cpp:889-958: R = body attitude in the SfM frame, T = camera position in it, unknown scale), in map (= time) order;
+// n_frames[b] must equal the number of frames the back end holds for the stream (vio_backend_get_init_frames).  Consumed by the
+// vio_backend_process_image call that fills the window: VisualIMUAlignment + the rest of visualInitialAlign (VINS.cpp:1022-1102) run on
+// the device, then the first solve (VINS.cpp:415-447).
+extern "C" int vio_backend_set_init_sfm_frames(vio_backend *be, const int32_t *n_frames, int max_frames, const double *R, const double *T) {
+    if (!be || !n_frames || !R || !T || max_frames < 2) return VIO_ERR_ARG;
     VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
     BeState &s = be->s;
-    const size_t B = s.B, NF = s.NF, NS = 3 * NF + 4;
+    const size_t B = s.B, NF = s.NF, FA = s.FA, NS = 3 * FA + 4;
+    for (size_t b = 0; b < B; b++) if (n_frames[b] < 0 || n_frames[b] > max_frames || n_frames[b] > (int)FA) return VIO_ERR_CAPACITY;
     if (!s.init_sfm) {
-        int rc = dalloc(be, &s.init_sfm, B * NF * 12);
+        int rc = dalloc(be, &s.init_sfm, B * FA * 12 + (B + 1) / 2 + 1);       // R, T, then B ints
         AlignArgs &a = be->align;
         memset(&a, 0, sizeof(a));
-        a.B = s.B; a.F = s.NF; a.MAXIMU = s.MAXIMU; a.NS = (int)NS;
+        a.B = s.B; a.F = (int)FA; a.MAXIMU = s.MAXIMU; a.NS = (int)NS;
         double *scr = nullptr; int *iscr = nullptr;
-        const size_t nd = B * NF * PR_STRIDE + 2 * B * NS * NS + B * NS + B * NF * 110 + 2 * B * NS + B * 3 + B * 3 + B * NS;
+        const size_t nd = B * FA * PR_STRIDE + 2 * B * NS * NS + B * NS + B * FA * 110 + 2 * B * NS + B * 3 + B * 3 + B * NS;
         if (!rc) rc = dalloc(be, &scr, nd);
         if (!rc) rc = dalloc(be, &iscr, B * NS + B);
         if (rc) { s.init_sfm = nullptr; return rc; }
         double *p = scr;
-        a.pre = p; p += B * NF * PR_STRIDE;
+        a.pre = p; p += B * FA * PR_STRIDE;
         a.A = p; p += B * NS * NS;
         a.Aw = p; p += B * NS * NS;
         a.rhs = p; p += B * NS;
-        a.pairs = p; p += B * NF * 110;
+        a.pairs = p; p += B * FA * 110;
         a.xs = p; p += 2 * B * NS;
         a.bgs_out = p; p += B * 3;
         a.g_out = p; p += B * 3;
         a.x_out = p; p += B * NS;
         a.perm = iscr; a.ok = iscr + B * NS;
-        a.R = s.init_sfm; a.T = s.init_sfm + B * NF * 9;
-        a.counts = s.imu_cnt; a.imu = s.imu_buf;
-        a.imu0 = s.pre + PR_LIN_ACC; a.imu0_stride = PR_STRIDE;
+        a.R = s.init_sfm; a.T = s.init_sfm + B * FA * 9;
+        a.counts = s.af_cnt; a.imu = s.af_imu;
+        a.imu0 = s.af_imu0; a.imu0_stride = 6;
         a.bg0 = s.Bgs; a.bg0_stride = (int)(3 * NF);
-        a.abg = s.pre + PR_ABG; a.abg_stride = PR_STRIDE;
+        a.abg = s.af_abg; a.abg_stride = 3;
         memcpy(a.tic, be->cfg.tic, 24);
         a.g_norm = be->cfg.gravity; a.g_thr = 3.0;          // G_NORM, G_THRESHOLD (global_param.hpp:49-50)
         memcpy(a.noise, s.noise, sizeof(a.noise));
     }
-    VIO_CUDA_TRY(cudaMemcpyAsync(s.init_sfm, R, B * NF * 9 * sizeof(double), cudaMemcpyHostToDevice, be->stream));
-    VIO_CUDA_TRY(cudaMemcpyAsync(s.init_sfm + B * NF * 9, T, B * NF * 3 * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    std::vector<double> h(B * FA * 12, 0.0);
+    for (size_t b = 0; b < B; b++)
+        for (int k = 0; k < n_frames[b]; k++) {
+            memcpy(&h[(b * FA + k) * 9], R + (b * max_frames + k) * 9, 72);
+            memcpy(&h[B * FA * 9 + (b * FA + k) * 3], T + (b * max_frames + k) * 3, 24);
+        }
+    VIO_CUDA_TRY(cudaMemcpyAsync(s.init_sfm, h.data(), B * FA * 12 * sizeof(double), cudaMemcpyHostToDevice, be->stream));
+    VIO_CUDA_TRY(cudaMemcpyAsync(s.init_sfm + B * FA * 12, n_frames, B * sizeof(int), cudaMemcpyHostToDevice, be->stream));
     set_sfm_pending_kernel<<<s.B, 32, 0, be->stream>>>(s);
     be->launches++;
     be->sfm_armed = true;
-    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));        // R / T are the caller's (pageable) memory
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));        // h and n_frames are host memory of this call
+    return VIO_OK;
+}
+
+// The common case: every frame of the map is a keyframe (no MARGIN_SECOND_NEW slide since the stream started), so the map's frames are the
+// window's W + 1 frames.  R [batch][W+1][9], T [batch][W+1][3].
+extern "C" int vio_backend_set_init_sfm(vio_backend *be, const double *R, const double *T) {
+    if (!be) return VIO_ERR_ARG;
+    std::vector<int32_t> n(be->s.B, be->s.NF);
+    return vio_backend_set_init_sfm_frames(be, n.data(), be->s.NF, R, T);
+}
+
+// Headers of the frames the back end holds in all_image_frame for stream s (what the SfM must deliver poses for), oldest first.
+extern "C" int vio_backend_get_init_frames(vio_backend *be, int sidx, int cap, int32_t *n, double *headers) {
+    if (!be || !n || !headers || sidx < 0 || sidx >= be->s.B || cap < 0) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    int an = 0;
+    VIO_CUDA_TRY(cudaMemcpy(&an, be->s.iv + (size_t)sidx * IV_COUNT + IV_AF_N, sizeof(int), cudaMemcpyDeviceToHost));
+    if (an > be->s.FA) return VIO_ERR_CAPACITY;             // the list overflowed (more than 3 (W + 1) - 1 frames without an initialisation)
+    *n = an;
+    if (an > cap) return VIO_ERR_CAPACITY;
+    if (an > 0) VIO_CUDA_TRY(cudaMemcpy(headers, be->s.af_hdr + (size_t)sidx * be->s.FA, an * sizeof(double), cudaMemcpyDeviceToHost));
     return VIO_OK;
 }
 
@@ -325,10 +362,10 @@ extern "C" int vio_backend_get_init_result(vio_backend *be, int sidx, int32_t *o
     int iv[IV_COUNT];
     VIO_CUDA_TRY(cudaMemcpy(iv, be->s.iv + (size_t)sidx * IV_COUNT, sizeof(iv), cudaMemcpyDeviceToHost));
     *ok = iv[IV_ALIGN_OK]; g[0] = g[1] = g[2] = 0; *scale = 0;
-    if (be->s.init_sfm && iv[IV_ALIGN_OK] >= 0) {
-        const AlignArgs &a = be->align;
-        VIO_CUDA_TRY(cudaMemcpy(g, a.g_out + 3 * sidx, 24, cudaMemcpyDeviceToHost));
-        VIO_CUDA_TRY(cudaMemcpy(scale, a.x_out + (size_t)sidx * a.NS + 3 * be->s.NF + 2, 8, cudaMemcpyDeviceToHost));
+    if (iv[IV_ALIGN_OK] >= 0) {
+        double dvh[4];
+        VIO_CUDA_TRY(cudaMemcpy(dvh, be->s.dv + (size_t)sidx * DV_COUNT + DV_INIT_SCALE, sizeof(dvh), cudaMemcpyDeviceToHost));
+        *scale = dvh[0]; g[0] = dvh[1]; g[1] = dvh[2]; g[2] = dvh[3];
     }
     return VIO_OK;
 }

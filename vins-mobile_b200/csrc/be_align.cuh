@@ -297,8 +297,9 @@ __global__ void __launch_bounds__(ALIGN_THREADS) visual_imu_align_kernel(AlignAr
 
 // ---- VINS::visualInitialAlign (VINS.cpp:1022-1102) on the back end's own state --------------------------------------------------
 // Runs before triangulate_kernel when the host has supplied the SfM poses of the window's frames (vio_backend_set_init_sfm,
-// IV_INIT_PENDING == 2) and the feature kernel decided ACT_INIT_SOLVE.  Supported case: all_image_frame holds exactly the window's
-// frames (no MARGIN_SECOND_NEW slide since the stream started -- IV_ALLKEY), so every frame of the map is a keyframe.
+// IV_INIT_PENDING == 2) and the feature kernel decided ACT_INIT_SOLVE.  The alignment runs over all_image_frame as the back end keeps it
+// (the af_* records of be_state.cuh: every camera frame since the stream started, keyframe or not, with its own IMU interval); the
+// window's frames are the map's keyframes, found by their headers.
 //   alignment fails  -> Bgs keep the corrected bias (solveGyroscopeBias has already added it), action becomes ACT_SLIDE_ONLY
 //   alignment passes -> Ps / Rs from the SfM, depths re-triangulated on the camera poses (tic = 0), pre-integrations re-propagated with the
 //                       new Bgs, metric scale, velocities, gravity-aligned frame; IV_INIT_PENDING = 3 tells triangulate_kernel that the window
@@ -325,13 +326,22 @@ __global__ void __launch_bounds__(ALIGN_THREADS) init_align_kernel(BeState s, Al
     __shared__ PreScratch scr[ALIGN_THREADS / 32];
     __shared__ double sh[16];
     __shared__ int sh_bad;
-    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ int key[VIO_MAX_WIN + 1];              // all_image_frame index of window frame i (the keyframes of the map)
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int *iv = S_iv(s, b);
     if (iv[IV_ACTION] != ACT_INIT_SOLVE || iv[IV_INIT_PENDING] != 2) return;
-    const int n = s.NF, W = s.W;
-    if (tid == 0) { sh_bad = iv[IV_ALLKEY] ? 0 : 1; }
-    __syncthreads();
-    for (int i = tid; i < n; i += ALIGN_THREADS) if (S_pre(s, b, i)[PR_VALID] == 0.0) sh_bad = 2;   // a frame never saw an IMU sample
+    const int n = iv[IV_AF_N], W = s.W, NF = s.NF;
+    if (tid == 0) {
+        const int *host_n = reinterpret_cast<const int *>(s.init_sfm + (size_t)s.B * s.FA * 12);
+        int bad = 0;
+        if (n < 2 || n > s.FA || host_n[b] != n) bad = 1;          // the caller's frame list is not the map's (or the map overflowed)
+        for (int i = 0, k = 0; i <= W && !bad; i++) {               // Headers ascend, so does the map: one forward scan
+            while (k < n && s.af_hdr[(size_t)b * s.FA + k] != s.Headers[(size_t)b * NF + i]) k++;
+            if (k >= n) bad = 1; else key[i] = k;
+        }
+        for (int i = 0; i < NF && !bad; i++) if (S_pre(s, b, i)[PR_VALID] == 0.0) bad = 2;   // a frame never saw an IMU sample
+        sh_bad = bad;
+    }
     __syncthreads();
     if (sh_bad) {
         if (tid == 0) { if (sh_bad == 1) iv[IV_ERR] = VIO_ERR_STATE; iv[IV_ALIGN_OK] = 0; iv[IV_ACTION] = ACT_SLIDE_ONLY; iv[IV_INIT_PENDING] = 0; }
@@ -341,25 +351,32 @@ __global__ void __launch_bounds__(ALIGN_THREADS) init_align_kernel(BeState s, Al
     const V3 bgs = ld3(a.bgs_out + 3 * b);
     const V3 dbg = bgs - ld3(S_Bgs(s, b, 0));
     __syncthreads();
-    for (int i = tid; i < n; i += ALIGN_THREADS) {                        // Bgs[i] += delta_bg; the map's pre-integrations now sit at Bgs[0]
-        st3(S_Bgs(s, b, i), ld3(S_Bgs(s, b, i)) + dbg);
-        st3(S_pre(s, b, i) + PR_ABG, bgs);
-    }
+    for (int i = tid; i < NF; i += ALIGN_THREADS) st3(S_Bgs(s, b, i), ld3(S_Bgs(s, b, i)) + dbg);        // Bgs[i] += delta_bg
+    for (int k = tid; k < n; k += ALIGN_THREADS) st3(s.af_abg + ((size_t)b * s.FA + k) * 3, bgs);       // the map's pre-integrations now sit at Bgs[0]
     if (tid == 0) iv[IV_ALIGN_OK] = ok;
-    if (!ok) { if (tid == 0) { iv[IV_ACTION] = ACT_SLIDE_ONLY; iv[IV_INIT_PENDING] = 0; } return; }
+    if (!ok) {
+        if (tid == 0) { iv[IV_ACTION] = ACT_SLIDE_ONLY; iv[IV_INIT_PENDING] = 0; double *dvo = S_dv(s, b); dvo[DV_INIT_SCALE] = 0.0; st3(dvo + DV_INIT_G, ld3(a.g_out + 3 * b)); }
+        return;
+    }
     const size_t fo = (size_t)b * s.FCAP;
     const int nf = iv[IV_NFEAT];
-    for (int i = tid; i < n; i += ALIGN_THREADS) {
-        st3(S_Ps(s, b, i), ld3(a.T + ((size_t)b * a.F + i) * 3));
-        stm(S_Rs(s, b, i), ldm(a.R + ((size_t)b * a.F + i) * 9));
+    for (int i = tid; i < NF; i += ALIGN_THREADS) {
+        st3(S_Ps(s, b, i), ld3(a.T + ((size_t)b * a.F + key[i]) * 3));
+        stm(S_Rs(s, b, i), ldm(a.R + ((size_t)b * a.F + key[i]) * 9));
     }
     for (int k = tid; k < nf; k += ALIGN_THREADS) s.f_depth[fo + k] = -1.0;          // clearDepth(-1)
     __syncthreads();
     triangulate_stream(s, b, v3(0, 0, 0), tid, ALIGN_THREADS);                        // "triangulat on cam pose, no tic"
-    // pre_integrations[i]->repropagate(0, Bgs[i]): the alignment's second pass did exactly that (same samples, same start, same bias)
-    for (int i = 0; i < n; i++) {
-        double *d = S_pre(s, b, i); const double *sr = a.pre + ((size_t)b * a.F + i) * PR_STRIDE;
-        for (int k = tid; k < PR_ABG; k += ALIGN_THREADS) d[k] = sr[k];
+    // pre_integrations[i]->repropagate(0, Bgs[i]) (integration_base.h:46-61) from the window's own sample buffers
+    for (int i = warp; i < NF; i += ALIGN_THREADS / 32) {
+        double *pr = S_pre(s, b, i);
+        const V3 la = ld3(pr + PR_LIN_ACC), lg = ld3(pr + PR_LIN_GYR), bgi = ld3(S_Bgs(s, b, i));
+        __syncwarp();
+        if (lane == 0) pre_init(pr, la, lg, v3(0, 0, 0), bgi);
+        __syncwarp();
+        const int cnt = min(s.imu_cnt[(size_t)b * NF + i], s.MAXIMU);
+        const double *e = S_imu(s, b, i);
+        for (int k = 0; k < cnt; k++) pre_propagate_warp(pr, e[7 * k], ld3(e + 7 * k + 1), ld3(e + 7 * k + 4), s.noise, scr[warp]);
     }
     __syncthreads();
     const double *x = a.x_out + (size_t)b * a.NS;
@@ -370,7 +387,9 @@ __global__ void __launch_bounds__(ALIGN_THREADS) init_align_kernel(BeState s, Al
         const V3 off = sc * P0 - ldm(S_Rs(s, b, 0)) * tic;
         for (int i = W; i >= 0; i--) st3(S_Ps(s, b, i), sc * ld3(S_Ps(s, b, i)) - ldm(S_Rs(s, b, i)) * tic - off);
     }
-    for (int i = tid; i < n; i += ALIGN_THREADS) st3(S_Vs(s, b, i), ldm(S_Rs(s, b, i)) * v3(x[3 * i], x[3 * i + 1], x[3 * i + 2]));
+    // Vs[kv] = R_keyframe * x.segment<3>(kv * 3): the reference indexes x by the KEYFRAME counter, not by the frame's place in the map
+    // (VINS.cpp:1066-1075); identical when every frame is a keyframe, reproduced as written otherwise
+    for (int i = tid; i < NF; i += ALIGN_THREADS) st3(S_Vs(s, b, i), ldm(S_Rs(s, b, i)) * v3(x[3 * i], x[3 * i + 1], x[3 * i + 2]));
     for (int k = tid; k < nf; k += ALIGN_THREADS)
         if (in_solve(s, s.f_nobs[fo + k], s.f_start[fo + k])) s.f_depth[fo + k] *= sc;
     __syncthreads();
@@ -378,13 +397,13 @@ __global__ void __launch_bounds__(ALIGN_THREADS) init_align_kernel(BeState s, Al
     M3 R0 = g2R_dev(g);
     const double yaw0 = R2ypr(R0).x;
     R0 = ypr2R(v3(-yaw0, 0, 0)) * R0;
-    for (int i = tid; i < n; i += ALIGN_THREADS) {
+    for (int i = tid; i < NF; i += ALIGN_THREADS) {
         st3(S_Ps(s, b, i), R0 * ld3(S_Ps(s, b, i)));
         stm(S_Rs(s, b, i), R0 * ldm(S_Rs(s, b, i)));
         st3(S_Vs(s, b, i), R0 * ld3(S_Vs(s, b, i)));
     }
     __syncthreads();
-    if (tid == 0) { st3(a.g_out + 3 * b, R0 * g); iv[IV_INIT_PENDING] = 3; }
+    if (tid == 0) { double *dvo = S_dv(s, b); dvo[DV_INIT_SCALE] = sc; st3(dvo + DV_INIT_G, R0 * g); iv[IV_INIT_PENDING] = 3; }
 }
 
 }  // namespace be

@@ -72,6 +72,17 @@ __global__ void __launch_bounds__(128) imu_kernel(BeState s, int n_samples, cons
                     e[0] = dt; st3(e + 1, acc); st3(e + 4, gyr);
                     cnt++;
                 } else iv[IV_ERR] = VIO_ERR_CAPACITY;
+                if (iv[IV_SOLVER_FLAG] == 0) {               // tmp_pre_integration->push_back (VINS.cpp:352-353): the open all_image_frame record
+                    const int k = iv[IV_AF_N];
+                    if (k < s.FA) {
+                        int &ac = s.af_cnt[(size_t)b * s.FA + k];
+                        if (ac < s.MAXIMU) {
+                            double *e = s.af_imu + (((size_t)b * s.FA + k) * s.MAXIMU + ac) * 7;
+                            e[0] = dt; st3(e + 1, acc); st3(e + 4, gyr);
+                            ac++;
+                        }
+                    }
+                }
                 // mid-point propagation of the newest state (VINS.cpp:359-370)
                 const V3 g = v3(0, 0, s.gravity);
                 const V3 a0 = ld3(dv + DV_ACC0), g0 = ld3(dv + DV_GYR0), ba = ld3(S_Bas(s, b, fc)), bg = ld3(S_Bgs(s, b, fc));
@@ -171,6 +182,20 @@ __global__ void __launch_bounds__(256) addfeat_kernel(BeState s, const int *__re
         iv[IV_NFEAT] = nf2;
         iv[IV_LAST_TRACK] = last_track;
         s.Headers[(size_t)b * s.NF + fc] = headers[b];
+        if (iv[IV_SOLVER_FLAG] == 0) {      // all_image_frame.insert(header -> tmp_pre_integration); tmp = new IntegrationBase{acc_0, gyr_0, 0, 0}  (VINS.cpp:392-398)
+            const int k = iv[IV_AF_N];
+            if (k < s.FA) {
+                s.af_hdr[(size_t)b * s.FA + k] = headers[b];
+                iv[IV_AF_N] = k + 1;
+                if (k + 1 < s.FA) {
+                    const double *dvv = S_dv(s, b);
+                    double *i0 = s.af_imu0 + ((size_t)b * s.FA + k + 1) * 6;
+                    for (int c = 0; c < 3; c++) { i0[c] = dvv[DV_ACC0 + c]; i0[3 + c] = dvv[DV_GYR0 + c]; }
+                    s.af_cnt[(size_t)b * s.FA + k + 1] = 0;
+                    st3(s.af_abg + ((size_t)b * s.FA + k + 1) * 3, v3(0, 0, 0));
+                } else iv[IV_AF_N] = s.FA + 1;  // list full (no room for the open record): poisoned until clearState, initialisation attempts are refused
+            }
+        }
         int act;
         if (iv[IV_SOLVER_FLAG] == 0) {
             if (fc != s.W) act = ACT_ACCUMULATE;
@@ -536,6 +561,9 @@ __device__ inline void clear_state_cta(const BeState &s, int b) {      // VINS::
     if (tid == 0) {
         iv[IV_FRAME_COUNT] = 0; iv[IV_FIRST_IMU] = 0; iv[IV_SOLVER_FLAG] = 0; iv[IV_NFEAT] = 0; iv[IV_PRIOR_VALID] = 0; iv[IV_PRIOR_N] = 0;
         iv[IV_ALLKEY] = 1; iv[IV_ALIGN_OK] = -1;                         // all_image_frame.clear(), VINS.cpp:62-68
+        iv[IV_AF_N] = 0; s.af_cnt[(size_t)b * s.FA] = 0;
+        for (int c = 0; c < 6; c++) s.af_imu0[(size_t)b * s.FA * 6 + c] = 0.0;
+        st3(s.af_abg + (size_t)b * s.FA * 3, v3(0, 0, 0));
     }
 }
 
@@ -620,6 +648,27 @@ __global__ void __launch_bounds__(256) finish_kernel(BeState s) {
                     stm(dv + DV_BACK_R0, backR0); st3(dv + DV_BACK_P0, backP0);
                 }
                 __syncthreads();
+                if (!nonlinear) {                            // all_image_frame.erase(begin, find(Headers[0])), VINS.cpp:1186-1193
+                    const double t0 = s.Headers[(size_t)b * s.NF];
+                    const int an = iv[IV_AF_N];
+                    int m = 0;
+                    while (m < an && s.af_hdr[(size_t)b * s.FA + m] != t0) m++;
+                    if (m > 0 && m < an && an < s.FA) {
+                        const int last = an;                 // the open record moves along
+                        for (int r = m; r <= last; r++) {
+                            const size_t src = (size_t)b * s.FA + r, dst = src - m;
+                            const int c = s.af_cnt[src];
+                            const double *bs = s.af_imu + src * s.MAXIMU * 7; double *bd = s.af_imu + dst * s.MAXIMU * 7;
+                            for (int k = tid; k < 7 * c; k += 256) bd[k] = bs[k];
+                            if (tid < 6) s.af_imu0[dst * 6 + tid] = s.af_imu0[src * 6 + tid];
+                            if (tid < 3) s.af_abg[dst * 3 + tid] = s.af_abg[src * 3 + tid];
+                            if (tid == 0) { s.af_cnt[dst] = c; if (r < an) s.af_hdr[dst] = s.af_hdr[src]; }
+                            __syncthreads();
+                        }
+                        if (tid == 0) iv[IV_AF_N] = an - m;
+                        __syncthreads();
+                    }
+                }
                 // removeBackShiftDepth (NON_LINEAR) / removeBack (INITIAL)
                 const M3 ric = ldm(dv + DV_RIC);
                 const V3 tic = ld3(dv + DV_TIC);

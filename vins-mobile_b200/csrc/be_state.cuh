@@ -11,10 +11,12 @@ enum { IV_FRAME_COUNT = 0, IV_FIRST_IMU, IV_SOLVER_FLAG, IV_MARG_FLAG, IV_FAILUR
        IV_PRIOR_VALID, IV_N_LM, IV_N_FAC, IV_ITERS, IV_PRIOR_N, IV_ERR, IV_MARG_FAST, IV_MARG_SWEEPS, IV_MARG_M, IV_CHOL_RETRY,
        IV_N_FAC_ALL /* IV_N_FAC + loop-closure factors */, IV_LOOP_FRAME /* window frame the loop pose is tied to, -1: none */, IV_LOOP_NFAC,
        IV_ALLKEY /* no MARGIN_SECOND_NEW slide since the stream (re)started: all_image_frame == the window's frames */,
-       IV_ALIGN_OK /* result of the last VisualIMUAlignment, -1: none yet */, IV_COUNT = 24 };
+       IV_ALIGN_OK /* result of the last VisualIMUAlignment, -1: none yet */,
+       IV_AF_N /* frames in all_image_frame (closed records of the af_* list; record IV_AF_N is the open tmp_pre_integration) */, IV_COUNT = 32 };
 // per-stream double scalars (BeState::dv)
 enum { DV_ACC0 = 0, DV_GYR0 = 3, DV_LAST_P = 6, DV_LAST_P_OLD = 9, DV_BACK_P0 = 12, DV_LAST_R = 15, DV_LAST_R_OLD = 24, DV_BACK_R0 = 33,
-       DV_COST0 = 42, DV_COST1 = 43, DV_PRIOR_C0 = 44, DV_TIC = 45, DV_RIC = 48, DV_COUNT = 64 };
+       DV_COST0 = 42, DV_COST1 = 43, DV_PRIOR_C0 = 44, DV_TIC = 45, DV_RIC = 48,
+       DV_INIT_SCALE = 57 /* metric scale of the last accepted alignment */, DV_INIT_G = 58 /* 3: vins.g after the last alignment */, DV_COUNT = 64 };
 // IV_ACTION values decided by the feature kernel (VINS::processImage control flow, VINS.cpp:377-478)
 enum { ACT_ACCUMULATE = 0, ACT_INIT_SOLVE = 1, ACT_SLIDE_ONLY = 2, ACT_NL_SOLVE = 3, ACT_NONE = 4, ACT_CLEAR = 5 /* track_num < 20 at frame_count == W: clearState(), VINS.cpp:401-405 */ };
 
@@ -41,7 +43,13 @@ struct BeState {
     double *imu_buf; int *imu_cnt;                    // [B][NF][MAXIMU][7], [B][NF]
     int *iv; double *dv;                              // [B][IV_COUNT], [B][DV_COUNT]
     double *init_state;                               // [B][NF*10 + 6]  P3 Q4 V3 per frame, Ba3 Bg3
-    double *init_sfm;                                 // [B][NF][9] ImageFrame::R then [B][NF][3] ImageFrame::T (vio_backend_set_init_sfm), lazily allocated
+    double *init_sfm;                                 // [B][FA][9] ImageFrame::R then [B][FA][3] ImageFrame::T then (int) [B] frame counts; lazily allocated
+    // all_image_frame (VINS.hpp:141, filled while solver_flag == INITIAL, VINS.cpp:392-398): one record per camera frame since the stream
+    // (re)started -- header, the IMU samples since the previous frame (tmp_pre_integration), the acc_0 / gyr_0 it started from, and the
+    // gyroscope bias its pre-integration is currently linearised at.  Record IV_AF_N is the open one.
+    int FA;                                           // capacity (3 NF)
+    double *af_hdr, *af_imu0, *af_imu, *af_abg;       // [B][FA], [B][FA][6], [B][FA][MAXIMU][7], [B][FA][3]
+    int *af_cnt;                                      // [B][FA]
     // feature table (FeatureManager::feature, in the list's insertion order; compacted order-preservingly)
     int *f_id, *f_start, *f_nobs, *f_flag; double *f_depth; double *f_obs;   // [B][FCAP], obs [B][FCAP][NF][2]
     // prior (MarginalizationInfo in information form, canonical layout [pose_i(6) sb_i(9)]_i ex(6))

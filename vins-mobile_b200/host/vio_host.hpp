@@ -227,6 +227,19 @@ class VINS {
     // ImageFrame::T of the window's WINDOW_SIZE + 1 frames -- and let the device run visualInitialAlign (VINS.cpp:1022-1102:
     // VisualIMUAlignment, scale, gravity frame, velocities, depths) inside the processImage call that fills the window.
     void setInitialSfm(const double *R, const double *T) { check(vio_backend_set_init_sfm(h_, R, T), "vio_backend_set_init_sfm"); }
+    // The general form: poses of EVERY frame of all_image_frame (keyframes and the frames MARGIN_SECOND_NEW dropped from the window), in
+    // time order, the frame about to be processed last; initialFrames() lists the headers the device holds so far.
+    void setInitialSfmFrames(int n_frames, const double *R, const double *T) {
+        int32_t n = n_frames;
+        check(vio_backend_set_init_sfm_frames(h_, &n, n_frames, R, T), "vio_backend_set_init_sfm_frames");
+    }
+    std::vector<double> initialFrames() {
+        std::vector<double> h(3 * (cfg_.window_size + 1));
+        int32_t n = 0;
+        check(vio_backend_get_init_frames(h_, 0, (int)h.size(), &n, h.data()), "vio_backend_get_init_frames");
+        h.resize(n);
+        return h;
+    }
     // bool result of the last VisualIMUAlignment (-1: none yet), vins.g after it and the metric scale of the SfM
     int initialAlignment(Vector3d *g = nullptr, double *scale = nullptr) {
         int32_t ok = -1; double gg[3] = {0, 0, 0}, sc = 0;
