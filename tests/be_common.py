@@ -165,3 +165,51 @@ def drive_sfm(est, tr, k, W, sfm=None):
         est.process_image_single(ids, xyz, tr["t_kf"][k])
     else:
         est.process_image(ids, xyz, tr["t_kf"][k])
+
+
+def init_scenario(est, cfg, name):
+    """Two scripted initialisations from SfM poses, identical for the reference estimator and the CUDA back end (batch 1):
+    'rejected_then_accepted' (stream 0): mirrored SfM at keyframe W (VisualIMUAlignment rejects it), correct SfM at W + 1;
+    'non_keyframe' (stream 1): no SfM at W, frame W + 1 repeats keyframe W's measurements so that frame W + 2 triggers MARGIN_SECOND_NEW
+    (the repeated frame leaves the window but stays in all_image_frame), SfM for all 12 frames of the map at W + 3."""
+    W = cfg.window_size
+    batched = hasattr(est, "B")
+    if name == "rejected_then_accepted":
+        tr = synth.make_tracks(0, 20, max_cnt=cfg.max_cnt)
+        for k in range(W + 2):
+            sfm = sfm_window(tr, k, W, mirrored=True) if k == W else (sfm_window(tr, k, W) if k == W + 1 else None)
+            drive_sfm(est, tr, k, W, sfm)
+        return tr
+    assert name == "non_keyframe"
+    tr = synth.make_tracks(1, 20, max_cnt=cfg.max_cnt)
+    per = tr["per"]
+
+    def imu_of(k):
+        sl = slice((k - 1) * per, k * per)
+        dts = np.diff(np.concatenate([[tr["t_kf"][k - 1]], tr["imu_t"][sl]]))
+        if batched:
+            est.process_imu(dts[:, None], tr["acc"][sl][:, None, :], tr["gyr"][sl][:, None, :])
+        else:
+            for d, a, g in zip(dts, tr["acc"][sl], tr["gyr"][sl]):
+                est.process_imu(d, a, g)
+
+    def image(k, src):
+        ids, xyz = tr["frames"][src]
+        if batched:
+            est.process_image_single(ids, xyz, tr["t_kf"][k])
+        else:
+            est.process_image(ids, xyz, tr["t_kf"][k])
+
+    for k in range(W + 1):
+        drive_sfm(est, tr, k, W, None)
+    imu_of(W + 1); image(W + 1, W)
+    imu_of(W + 2); image(W + 2, W + 2)
+    hd = est.init_frames()
+    R, T = sfm_frames(tr, list(hd) + [tr["t_kf"][W + 3]])
+    imu_of(W + 3)
+    if batched:
+        est.set_init_sfm_frames([len(R)], R[None], T[None])
+    else:
+        est.set_init_sfm_frames(R, T)
+    image(W + 3, W + 3)
+    return tr

@@ -519,6 +519,27 @@ def test_initialisation_from_sfm_with_a_non_keyframe_in_the_map(api, cfg, synth)
         ref.close(); gpu.close()
 
 
+@pytest.mark.parametrize("name", ["rejected_then_accepted", "non_keyframe"])
+def test_initialisation_from_sfm_matches_golden(api, cfg, name):
+    """The device initialisation against the committed outputs of the reference oracle (tests/golden/init_sfm_golden.npz, made by
+    tests/golden/make_init_golden.py): window right after the accepted alignment + first solve."""
+    import os
+    from be_common import init_scenario
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "init_sfm_golden.npz"))
+    gpu = api.BackEnd(cfg)
+    try:
+        init_scenario(gpu, cfg, name)
+        ok, g, sc = gpu.init_result()
+        assert ok == 1 and gpu.info()["solver_flag"] == 1 and gpu.error() == 0
+        st = gpu.state()
+        assert np.array_equal(st["headers"], z[f"{name}_headers"])
+        assert abs(sc / float(z[f"{name}_scale"]) - 1) < 1e-9 and rel_err(g, z[f"{name}_g"]) < 1e-9
+        assert rel_err(st["P"], z[f"{name}_P"]) < 1e-6 and rel_err(st["V"], z[f"{name}_V"]) < 1e-6 and quat_err(st["Q"], z[f"{name}_Q"]) < 1e-6
+        assert abs(gpu.info()["cost1"] / float(z[f"{name}_cost1"]) - 1) < 1e-6
+    finally:
+        gpu.close()
+
+
 def test_initialisation_rejected_above_cost_200(api, cfg, synth):
     """VINS.cpp:415-425: when the first solve ends with final_cost > 200 the initialisation is discarded -- prior deleted, solver_flag stays
     INITIAL, the window only slides.  A grossly wrong initial window provokes it; a good one on the next full window succeeds."""
