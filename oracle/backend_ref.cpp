@@ -152,6 +152,7 @@ void clear_state(Est &e) {           // VINS::clearState, VINS.cpp:35-80
     e.ric = Map<const Matrix<double, 3, 3, RowMajor>>(e.c.ric);
     e.frame_count = 0; e.first_imu = false; e.solver_flag = 0;
     e.all.clear(); e.tmp = Est::AllFrame(); e.sfm_pending = false;                  // all_image_frame.clear(), VINS.cpp:62-68
+    e.align_ok = -1;
     delete e.last_marg; e.last_marg = nullptr; e.last_marg_blocks.clear();
     e.feat.clear();
 }

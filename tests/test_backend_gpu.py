@@ -519,6 +519,54 @@ def test_initialisation_from_sfm_with_a_non_keyframe_in_the_map(api, cfg, synth)
         ref.close(); gpu.close()
 
 
+def test_initialisation_from_sfm_survives_a_failure_reset(api, cfg, synth):
+    """A stream initialised on the device, driven into failureDetection() -> clearState() (a keyframe with only unseen ids), refills its
+    window and initialises a second time from SfM poses -- all_image_frame starts over with the reset (VINS.cpp:62-68) -- in step with
+    the reference throughout."""
+    from be_common import drive_sfm, sfm_window
+    W = cfg.window_size
+    tr = synth.make_tracks(4, 30, max_cnt=cfg.max_cnt)
+    ref, gpu = bo.RefEstimator(cfg), api.BackEnd(cfg)
+    kfail = 14
+    per = tr["per"]
+    try:
+        for k in range(30):
+            if k == kfail:                                   # 150 points never seen before
+                ids = np.arange(100000, 100000 + cfg.max_cnt, dtype=np.int32)
+                xyz = np.resize(tr["frames"][k][1][:cfg.max_cnt].copy(), (cfg.max_cnt, 3))
+                sl = slice((k - 1) * per, k * per)
+                dts = np.diff(np.concatenate([[tr["t_kf"][k - 1]], tr["imu_t"][sl]]))
+                with Quiet():
+                    for d, a, g in zip(dts, tr["acc"][sl], tr["gyr"][sl]):
+                        ref.process_imu(d, a, g)
+                    ref.process_image(ids, xyz, tr["t_kf"][k])
+                gpu.process_imu(dts[:, None], tr["acc"][sl][:, None, :], tr["gyr"][sl][:, None, :])
+                gpu.process_image_single(ids, xyz, tr["t_kf"][k])
+            else:
+                sfm = sfm_window(tr, k, W) if k in (W, kfail + 1 + W) else None
+                # drive_sfm feeds one IMU sample before keyframe 0 only; after the reset the interval of the first new frame plays that role
+                if k == 0:
+                    with Quiet():
+                        drive_sfm(ref, tr, k, W, sfm)
+                    drive_sfm(gpu, tr, k, W, sfm)
+                else:
+                    with Quiet():
+                        drive_sfm(ref, tr, k, W, sfm)
+                    drive_sfm(gpu, tr, k, W, sfm)
+            ri, gi = ref.info(), gpu.info()
+            for key in ("solver_flag", "marg_flag", "frame_count", "failure", "last_track_num"):
+                assert ri[key] == gi[key], f"kf {k}: {key} {ri[key]} vs {gi[key]}"
+            assert np.array_equal(ref.init_frames(), gpu.init_frames()) or gi["solver_flag"] == 1, k
+            if k == kfail:
+                assert gi["failure"] == 1 and gi["solver_flag"] == 0 and gi["frame_count"] == 0 and len(gpu.init_frames()) == 0
+            if gi["solver_flag"] == 1:
+                _same_window(ref.state(), gpu.state(), 1e-6 if k in (W, kfail + 1 + W) else 1e-4)
+        assert gpu.info()["solver_flag"] == 1 and gpu.init_result()[0] == 1 and gpu.error() == 0
+        assert ref.init_result()[0] == 1
+    finally:
+        ref.close(); gpu.close()
+
+
 @pytest.mark.parametrize("name", ["rejected_then_accepted", "non_keyframe"])
 def test_initialisation_from_sfm_matches_golden(api, cfg, name):
     """The device initialisation against the committed outputs of the reference oracle (tests/golden/init_sfm_golden.npz, made by
