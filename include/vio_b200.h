@@ -195,6 +195,10 @@ int vio_backend_get_info(vio_backend *be, int s, int32_t info[8], double dinfo[4
 /* f_manager.feature of stream s: ids, start_frame, n_obs, estimated_depth, solve_flag; arrays sized `cap`. */
 int vio_backend_get_features(vio_backend *be, int s, int cap, int *n_out, int32_t *ids, int32_t *start_frame,
                              int32_t *n_obs, double *depth, int32_t *solve_flag);
+/* FeaturePerId::feature_per_frame[k].point (x, y; z = 1) of the same features in the same order: obs [cap][window_size + 1][2], entry
+ * k < n_obs valid.  What FeatureManager::getCorresponding (feature_manager.cpp:157-176) and the SfM set-up of VINS::solveInitial
+ * (VINS.cpp:857-886) read from f_manager -- for a caller that keeps relativePose / GlobalSFM on the host. */
+int vio_backend_get_observations(vio_backend *be, int s, int cap, int *n_out, double *obs);
 /* Prior in information form over the canonical local layout [pose0(6) sb0(9) ... poseW sbW ex(6)],
  * n = 15*(W+1)+6:  H[n*n] = J0^T J0, b[n] = J0^T r0, present[2*(W+1)+1] block mask.  For parity tests. */
 int vio_backend_get_prior(vio_backend *be, int s, double *H, double *b, int32_t *present, double *c0);

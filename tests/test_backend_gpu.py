@@ -519,6 +519,32 @@ def test_initialisation_from_sfm_with_a_non_keyframe_in_the_map(api, cfg, synth)
         ref.close(); gpu.close()
 
 
+def test_observations_and_get_corresponding(api, cfg, synth):
+    """vio_backend_get_observations / getCorresponding (feature_manager.cpp:157-176): what a host-side SfM reads from f_manager."""
+    W = cfg.window_size
+    tr = synth.make_tracks(3, W + 1, max_cnt=cfg.max_cnt)
+    gpu = api.BackEnd(cfg)
+    try:
+        for k in range(W):
+            drive(gpu, tr, k, W + 99)                        # fill the window without initialising
+        f, o = gpu.features(), gpu.observations()
+        assert o.shape == (len(f["ids"]), W + 1, 2)
+        seen = {}                                            # id -> {frame: (x, y)} from what was fed
+        for k in range(W):
+            for i, p in zip(*tr["frames"][k]):
+                seen.setdefault(int(i), {})[k] = p[:2] / p[2]
+        for row, (i, st, no) in enumerate(zip(f["ids"], f["start"], f["n_obs"])):
+            for j in range(no):
+                assert np.array_equal(o[row, j], seen[int(i)][st + j])
+        for l in (0, 3, W - 2):
+            ids, a, b = gpu.corresponding(l, W - 1)
+            want = [i for i in f["ids"] if l in seen[int(i)] and (W - 1) in seen[int(i)] and all(k in seen[int(i)] for k in range(l, W))]
+            assert list(ids) == want
+            assert all(np.array_equal(a[n], seen[int(i)][l]) and np.array_equal(b[n], seen[int(i)][W - 1]) for n, i in enumerate(ids))
+    finally:
+        gpu.close()
+
+
 def test_initialisation_from_sfm_survives_a_failure_reset(api, cfg, synth):
     """A stream initialised on the device, driven into failureDetection() -> clearState() (a keyframe with only unseen ids), refills its
     window and initialises a second time from SfM poses -- all_image_frame starts over with the reset (VINS.cpp:62-68) -- in step with

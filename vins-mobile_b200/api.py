@@ -87,6 +87,7 @@ def lib():
             L.vio_backend_state_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64)]
             L.vio_backend_get_info.argtypes = [vp, C.c_int, IP, DP]
             L.vio_backend_get_features.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int), IP, IP, IP, DP, IP]
+            L.vio_backend_get_observations.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int), DP]
             L.vio_backend_get_prior.argtypes = [vp, C.c_int, DP, DP, IP, DP]
             L.vio_backend_get_post_solve.argtypes = [vp, C.c_int, DP]
             L.vio_backend_launch_count.argtypes = [vp]
@@ -352,6 +353,22 @@ class BackEnd:
                                               ptr(dep, C.c_double), ptr(fl, C.c_int32)), "vio_backend_get_features")
         k = n.value
         return dict(ids=ids[:k], start=st[:k], n_obs=no[:k], depth=dep[:k], solve_flag=fl[:k])
+
+    def observations(self, s=0, cap=8192):
+        """feature_per_frame points (x, y) of every feature, [n][W + 1][2], rows beyond n_obs are stale"""
+        n = C.c_int(0)
+        obs = np.zeros((cap, self.W + 1, 2))
+        _check(lib().vio_backend_get_observations(self.h, s, cap, C.byref(n), ptr(obs, C.c_double)), "vio_backend_get_observations")
+        return obs[:n.value]
+
+    def corresponding(self, l, r, s=0):
+        """FeatureManager::getCorresponding(l, r) (feature_manager.cpp:157-176): (a, b) point pairs of the features seen in both frames"""
+        f = self.features(s); o = self.observations(s)
+        sel = (f["start"] <= l) & (f["start"] + f["n_obs"] - 1 >= r)
+        idx = np.nonzero(sel)[0]
+        a = np.stack([o[i, l - f["start"][i]] for i in idx]) if len(idx) else np.zeros((0, 2))
+        b = np.stack([o[i, r - f["start"][i]] for i in idx]) if len(idx) else np.zeros((0, 2))
+        return f["ids"][idx], a, b
 
     def prior(self, s=0):
         N = 15 * (self.W + 1) + 6

@@ -595,6 +595,23 @@ extern "C" int vio_backend_get_features(vio_backend *be, int s, int cap, int *n_
     return nf <= cap ? VIO_OK : VIO_ERR_CAPACITY;
 }
 
+// FeaturePerId::feature_per_frame[k].point (x, y; z = 1) of the first min(n_features, cap) features of stream s, in the order of
+// vio_backend_get_features: obs [cap][W + 1][2], entry k < n_obs valid.  What a host-side SfM (relativePose / GlobalSFM, VINS.cpp:857-886)
+// and FeatureManager::getCorresponding (feature_manager.cpp:157-176) read from f_manager.
+extern "C" int vio_backend_get_observations(vio_backend *be, int s, int cap, int *n_out, double *obs) {
+    if (!be || s < 0 || s >= be->s.B || !n_out || !obs || cap < 0) return VIO_ERR_ARG;
+    VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));
+    int nf = 0;
+    VIO_CUDA_TRY(cudaMemcpyAsync(&nf, be->s.iv + (size_t)s * IV_COUNT + IV_NFEAT, sizeof(int), cudaMemcpyDeviceToHost, be->stream));
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    const int n = std::min(nf, cap);
+    int rc = bd2h(be, obs, be->s.f_obs + (size_t)s * be->s.FCAP * be->s.NF * 2, (size_t)n * be->s.NF * 2);
+    if (rc) return rc;
+    VIO_CUDA_TRY(cudaStreamSynchronize(be->stream));
+    *n_out = nf;
+    return nf <= cap ? VIO_OK : VIO_ERR_CAPACITY;
+}
+
 extern "C" int vio_backend_get_prior(vio_backend *be, int s, double *H, double *b, int32_t *present, double *c0) {
     if (!be || s < 0 || s >= be->s.B) return VIO_ERR_ARG;
     VIO_CUDA_TRY(cudaSetDevice(be->cfg.device));

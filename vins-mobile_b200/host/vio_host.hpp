@@ -223,6 +223,26 @@ class VINS {
         check(vio_backend_set_init_window(h_, P, Q, V, Ba, Bg), "vio_backend_set_init_window");
     }
 
+    // vector<pair<Vector3d, Vector3d>> FeatureManager::getCorresponding(int frame_count_l, int frame_count_r)          feature_manager.cpp:157-176
+    // (f_manager lives on the device: this reads its table back) -- the correspondences relativePose / the SfM set-up work from
+    std::vector<std::pair<Vector3d, Vector3d>> getCorresponding(int frame_count_l, int frame_count_r) {
+        const int cap = cfg_.num_of_f, nfr = cfg_.window_size + 1;
+        std::vector<int32_t> ids(cap), st(cap), no(cap), fl(cap);
+        std::vector<double> dep(cap), obs((size_t)cap * nfr * 2);
+        int n = 0, n2 = 0;
+        check(vio_backend_get_features(h_, 0, cap, &n, ids.data(), st.data(), no.data(), dep.data(), fl.data()), "vio_backend_get_features");
+        check(vio_backend_get_observations(h_, 0, cap, &n2, obs.data()), "vio_backend_get_observations");
+        std::vector<std::pair<Vector3d, Vector3d>> corres;
+        for (int i = 0; i < n && i < n2; i++)
+            if (st[i] <= frame_count_l && st[i] + no[i] - 1 >= frame_count_r) {
+                const double *a = &obs[((size_t)i * nfr + (frame_count_l - st[i])) * 2], *b = &obs[((size_t)i * nfr + (frame_count_r - st[i])) * 2];
+                Vector3d pa, pb;
+                pa.x = a[0]; pa.y = a[1]; pa.z = 1.0; pb.x = b[0]; pb.y = b[1]; pb.z = 1.0;
+                corres.push_back(std::make_pair(pa, pb));
+            }
+        return corres;
+    }
+
     // The other way in: hand over what solveInitial() holds after the global SfM (VINS.cpp:889-905) -- ImageFrame::R (row-major 3x3) and
     // ImageFrame::T of the window's WINDOW_SIZE + 1 frames -- and let the device run visualInitialAlign (VINS.cpp:1022-1102:
     // VisualIMUAlignment, scale, gravity frame, velocities, depths) inside the processImage call that fills the window.
